@@ -1,0 +1,124 @@
+/*
+ * b200_internal.h -- private types of the b200 backend (host side, C).
+ *
+ * Layering:  csinn_* API (reference, unchanged)  ->  callbacks in ops.c / session hooks in
+ * graph.c  ->  b200_op (one device operator: packed weights + tables in the weight arena, a
+ * run function)  ->  include/b200nn.h (CUDA shim).  The same b200_op serves layer mode
+ * (H2D -> convert -> run -> convert -> D2H per call) and graph mode (planned once, replayed
+ * as a CUDA graph).
+ */
+#ifndef B200_INTERNAL_H_
+#define B200_INTERNAL_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b200nn.h"
+#include "csi_nn.h"
+#include "shl_b200.h"
+#include "shl_gref.h"
+#include "shl_utils.h"
+
+/* ---- device context: one per session (graph mode) + one process-wide for layer mode ------ */
+typedef struct b200_ctx {
+    int device;
+    void *stream;
+    /* weight arena: bump allocator over one device allocation (graph mode) or a chain of
+     * chunks (layer mode) */
+    uint8_t *wbase;
+    size_t wcap, wused;
+    int fixed_arena; /* 1: allocation failure instead of chaining a new chunk */
+    int skip_upload; /* 1: allocate but do not copy (weights arrive by NCCL broadcast) */
+} b200_ctx;
+
+b200_ctx *b200_ctx_default(void);                        /* NULL + error if no device */
+b200_ctx *b200_ctx_of(struct csinn_session *sess);       /* session ctx or the default */
+int b200_ctx_init(b200_ctx *ctx, int device);
+void b200_ctx_destroy(b200_ctx *ctx);
+/* device memory for constants, 256-byte aligned; uploads `src` when non-NULL */
+void *b200_warena_put(b200_ctx *ctx, const void *src, size_t bytes);
+void b200_fail(const char *fmt, ...);
+int b200_default_device(void);
+
+/* ---- device tensor (pixel-major [n][h][w][cp], or raw NCHW for a graph input) ------------- */
+typedef struct b200_dt {
+    void *d;
+    int n, c, h, w, cp;
+    int eb;      /* element bytes */
+    int is_nchw; /* 1: raw API layout [n][c][h][w], cp unused */
+} b200_dt;
+size_t b200_dt_bytes(const b200_dt *t);
+/* shape of a csinn tensor as the device sees it; returns 0 on unsupported rank */
+int b200_dt_from_tensor(b200_dt *t, const struct csinn_tensor *src);
+
+/* ---- one device operator ------------------------------------------------------------------ */
+enum b200_op_kind {
+    B200_OPK_CONV = 1, /* 1x1 direct GEMM or im2col + GEMM, groups */
+    B200_OPK_DW,
+    B200_OPK_FC,
+    B200_OPK_ACT,     /* relu / relu6 / requantising identity */
+    B200_OPK_ADD,
+    B200_OPK_POOL,
+    B200_OPK_SOFTMAX,
+    B200_OPK_COPY,    /* reshape / flatten whose memory order is unchanged */
+};
+
+typedef struct b200_op {
+    int kind;
+    int dtype; /* b200_dtype */
+    int eb;
+    const char *kname; /* kernel name reported to the trace profiler */
+    b200_ctx *ctx;
+    /* conv / dw / fc */
+    int cin, o, kh, kw, sh, sw, pt, pl, dh, dw, group;
+    int direct;  /* 1x1 stride-1 unpadded conv or fc: GEMM straight on the activation */
+    int kdim;    /* reduction length per group */
+    int ldk;     /* im2col / weight row pitch (elements) */
+    void *d_w;   /* packed weights */
+    float *d_mult, *d_badd;
+    int32_t *d_ibias;
+    int8_t *d_lut; /* post table or the ACT table */
+    int zp_in, zp_out, act, q6;
+    /* the output qinfo the epilogue quantises to (needed when a relu is fused later) */
+    float s_out;
+    /* eltwise / pool / softmax */
+    float s_in, s_in1;
+    int zp_in1;
+    int pool_avg, pool_global, count_include_pad;
+    /* layer-mode staging buffers, grown on demand */
+    void *stg[8];
+    size_t stg_bytes[8];
+} b200_op;
+
+/* registry params* -> op (ops.c) */
+void b200_op_bind(void *params, b200_op *op);
+b200_op *b200_op_find(void *params);
+
+/* run on device tensors; scratch is im2col space (b200_op_scratch_bytes) */
+size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out);
+int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
+                void *scratch, void *stream);
+/* fuse a following relu / relu6 node (with its own qinfo) into this op's epilogue */
+int b200_op_can_fuse_act(const b200_op *op);
+int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
+                     const struct csinn_tensor *act_out);
+
+/* quant.c */
+int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
+                      const struct csinn_tensor *kernel, const struct csinn_tensor *bias,
+                      const struct csinn_tensor *output, int taps_per_o, int fuse_zp2bias,
+                      int n_out);
+void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
+void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);
+void *b200_pack_fc_weights(b200_op *op, const struct csinn_tensor *weights, size_t *bytes);
+
+/* graph.c */
+typedef struct b200_graph b200_graph;
+typedef struct b200_option {
+    b200_ctx ctx;
+    b200_graph *g;
+} b200_option;
+b200_option *b200_option_of(struct csinn_session *sess);
+
+#endif

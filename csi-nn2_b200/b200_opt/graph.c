@@ -1,0 +1,566 @@
+/*
+ * graph.c -- graph-mode session of the b200 backend (CSINN_RM_CPU_GRAPH with a b200 api id).
+ *
+ * The reference's GREF layer still records the graph (est callbacks shl_gref_<op>,
+ * source/graph_ref/utils.c:75) and owns the I/O bookkeeping; this file replaces what
+ * shl_gref_session_setup / shl_gref_session_run do around it
+ * (source/graph_ref/setup.c:688-856, 1305-1449), because their per-node calloc -> exec -> free
+ * loop with host tensors is exactly what a GPU must not do:
+ *
+ *   setup : init every node through its callback (weights packed once into ONE device weight
+ *           arena), fuse conv/dw/fc/add -> relu/relu6 pairs into the producer's epilogue, plan
+ *           every intermediate tensor into a liveness-shared device activation arena, run the
+ *           step list once eagerly, then capture it as a CUDA graph.
+ *   run   : H2D the graph inputs, replay the CUDA graph, D2H the graph outputs, sync --
+ *           csinn_session_run stays synchronous as the API promises.
+ *
+ * Modelled on how shl_c920_session_setup / sess_op_init override the GREF hooks
+ * (source/c920_opt/setup.c:96-236); nothing of their bodies is reused.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200_internal.h"
+
+#define DEV_CHECK(expr)                                                        \
+    do {                                                                       \
+        int _rc = (expr);                                                      \
+        if (_rc != B200_OK) {                                                  \
+            b200_fail("%s -> %d: %s", #expr, _rc, b200_last_error());          \
+            return CSINN_FALSE;                                                \
+        }                                                                      \
+    } while (0)
+
+typedef struct {
+    struct shl_node *node; /* tensor node (node->data = csinn_tensor) */
+    b200_dt dt;
+    int first_def, last_use; /* step indices */
+    size_t off;              /* offset in the activation arena */
+    int is_input, is_output;
+    void *d_in_nchw;  /* graph inputs that feed a non-conv op: raw NCHW copy, converted per run */
+    void *d_out_nchw; /* graph outputs: compact NCHW copy for D2H */
+    void *h_out;      /* graph outputs: host buffer handed to csinn_get_output */
+} g_tensor;
+
+typedef struct {
+    b200_op *op;
+    int in0, in1, out;
+    size_t scratch;
+    char name[96];
+} g_step;
+
+struct b200_graph {
+    g_tensor *t;
+    int nt;
+    g_step *s;
+    int ns;
+    uint8_t *arena;
+    size_t arena_bytes, scratch_off;
+    void *exec; /* captured CUDA graph */
+    int kernels_per_run;
+};
+
+/* our option struct hangs on gref's target data (include/shl_utils.h:53-57), like
+ * shl_c920_option does (source/c920_opt/setup.c:76-88) */
+#define B200_MAGIC 0xB200B200u
+typedef struct {
+    uint32_t magic;
+    b200_option opt;
+} b200_option_box;
+
+b200_option *b200_option_of(struct csinn_session *sess)
+{
+    if (!sess || !sess->td) return NULL;
+    if (sess->base_run_mode == CSINN_RM_LAYER) return NULL;
+    struct shl_gref_target_data *td = sess->td;
+    b200_option_box *box = td->cpu_option;
+    if (!box || box->magic != B200_MAGIC) return NULL;
+    return &box->opt;
+}
+
+void shl_b200_session_init(struct csinn_session *sess)
+{
+    struct shl_ref_graph *graph = shl_mem_alloc(sizeof(struct shl_ref_graph));
+    struct shl_gref_target_data *td = shl_mem_alloc(sizeof(struct shl_gref_target_data));
+    b200_option_box *box = shl_mem_alloc(sizeof(b200_option_box));
+    td->graph = graph;
+    td->cpu_option = box;
+    sess->td = td;
+    sess->base_layout = CSINN_LAYOUT_NCHW;
+    box->magic = B200_MAGIC;
+    if (b200_ctx_init(&box->opt.ctx, b200_default_device()) != CSINN_TRUE) {
+        /* csinn_session_init returns void (source/nn2/setup.c:153): the failure resurfaces at
+         * session_setup, which refuses to continue without a device */
+        box->opt.ctx.device = -1;
+    }
+}
+
+static void graph_free(b200_graph *g)
+{
+    if (!g) return;
+    if (g->exec) b200_graph_destroy(g->exec);
+    if (g->arena) b200_free(g->arena);
+    for (int i = 0; i < g->nt; i++) {
+        if (g->t[i].d_in_nchw) b200_free(g->t[i].d_in_nchw);
+        if (g->t[i].d_out_nchw) b200_free(g->t[i].d_out_nchw);
+        if (g->t[i].h_out) b200_free_host(g->t[i].h_out);
+    }
+    free(g->t);
+    free(g->s);
+    free(g);
+}
+
+void shl_b200_session_deinit(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    struct shl_ref_graph *graph = shl_gref_get_graph(sess);
+    if (opt) {
+        if (opt->ctx.device >= 0) b200_set_device(opt->ctx.device);
+        if (graph)
+            for (int i = 0; i < graph->layer_index; i++) shl_b200_op_release(graph->layer[i]->data);
+        graph_free(opt->g);
+        opt->g = NULL;
+        if (opt->ctx.device >= 0) b200_ctx_destroy(&opt->ctx);
+    }
+    if (graph) {
+        shl_mem_free(graph->input);
+        shl_mem_free(graph->output);
+        shl_mem_free(graph->layer);
+        shl_mem_free(graph);
+    }
+    struct shl_gref_target_data *td = sess->td;
+    if (td) {
+        shl_mem_free(td->cpu_option);
+        shl_mem_free(td);
+    }
+    sess->td = NULL;
+    shl_mem_free(sess->input);
+    shl_mem_free(sess->output);
+}
+
+/* ---- planning -------------------------------------------------------------------------------- */
+static int tensor_index(b200_graph *g, struct shl_node *n)
+{
+    for (int i = 0; i < g->nt; i++)
+        if (g->t[i].node == n) return i;
+    return -1;
+}
+
+static int tensor_add(b200_graph *g, struct shl_node *n)
+{
+    int i = tensor_index(g, n);
+    if (i >= 0) return i;
+    struct csinn_tensor *ct = n->data;
+    g_tensor *t = &g->t[g->nt];
+    memset(t, 0, sizeof(*t));
+    t->node = n;
+    if (!b200_dt_from_tensor(&t->dt, ct)) {
+        b200_fail("tensor '%s': dtype %d / rank %d not supported on the device", ct->name ? ct->name : "?",
+                  ct->dtype, ct->dim_count);
+        return -1;
+    }
+    t->first_def = -1, t->last_use = -1;
+    return g->nt++;
+}
+
+static int is_act_node(const struct shl_node *n) { return n->type == CSINN_OP_RELU || n->type == CSINN_OP_RELU6; }
+
+/* number of layer nodes that read tensor node `tn` */
+static int consumers(struct shl_ref_graph *graph, struct shl_node *tn, struct shl_node **only)
+{
+    int cnt = 0;
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *l = graph->layer[i];
+        for (int j = 0; j < l->in_num; j++)
+            if (l->in[j] == tn) {
+                cnt++;
+                if (only) *only = l;
+            }
+    }
+    return cnt;
+}
+
+static int is_graph_output(struct shl_ref_graph *graph, struct shl_node *tn)
+{
+    for (int i = 0; i < graph->output_num; i++)
+        if (graph->output[i] == tn) return 1;
+    return 0;
+}
+
+static int init_node(struct shl_node *n)
+{
+    /* what gref's init_op does (source/graph_ref/setup.c:656-680): map the callback with the
+     * run mode forced to LAYER, then call cb->init */
+    struct csinn_params_base *params = n->data;
+    const int org = params->sess->base_run_mode;
+    params->sess->base_run_mode = CSINN_RM_LAYER;
+    struct csinn_callback *cb = shl_gref_best_callback(n);
+    params->sess->base_run_mode = org;
+    if (!cb || !cb->init) {
+        b200_fail("node '%s' (op %d): not implemented by the b200 backend", n->name ? n->name : "?", n->type);
+        return CSINN_FALSE;
+    }
+    int ret = shl_gref_call_layer_func(cb->init, n);
+    if (ret != CSINN_TRUE) {
+        if (!shl_b200_last_error()[0]) b200_fail("node '%s' (op %d): init failed (%d)", n->name, n->type, ret);
+        return CSINN_FALSE;
+    }
+    return CSINN_TRUE;
+}
+
+static size_t weight_bound(struct shl_ref_graph *graph)
+{
+    /* upper bound of what the init callbacks put into the weight arena: packed weights
+     * (depthwise int8 expands 4x, channel padding at most 16x on tiny layers), three per-channel
+     * tables, a 256-byte table, each rounded to 256 bytes */
+    size_t total = 1 << 20;
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *l = graph->layer[i];
+        for (int j = 1; j < l->in_num; j++) {
+            struct csinn_tensor *ct = l->in[j]->data;
+            if (!ct || !ct->is_const) continue;
+            size_t e = csinn_tensor_size(ct);
+            total += e * 8 + (size_t)(ct->dim_count ? ct->dim[0] : 1) * 64 * 4 + 8192;
+        }
+        total += 4096;
+    }
+    return total;
+}
+
+static int plan_memory(b200_graph *g)
+{
+    /* greedy first-fit over liveness intervals, largest tensors first; graph inputs and
+     * outputs live for the whole run (H2D before, D2H after) */
+    int *order = malloc(sizeof(int) * g->nt);
+    for (int i = 0; i < g->nt; i++) order[i] = i;
+    for (int i = 0; i < g->nt; i++)
+        for (int j = i + 1; j < g->nt; j++)
+            if (b200_dt_bytes(&g->t[order[j]].dt) > b200_dt_bytes(&g->t[order[i]].dt)) {
+                int tmp = order[i];
+                order[i] = order[j], order[j] = tmp;
+            }
+    size_t top = 0;
+    int *placed = calloc(g->nt, sizeof(int));
+    for (int oi = 0; oi < g->nt; oi++) {
+        g_tensor *t = &g->t[order[oi]];
+        if (t->is_input) t->first_def = -1;
+        if (t->is_output) t->last_use = g->ns;
+        const size_t sz = (b200_dt_bytes(&t->dt) + 1023) & ~(size_t)1023;
+        size_t off = 0;
+        for (;;) {
+            int moved = 0;
+            for (int k = 0; k < g->nt; k++) {
+                if (!placed[k]) continue;
+                g_tensor *u = &g->t[k];
+                const size_t usz = (b200_dt_bytes(&u->dt) + 1023) & ~(size_t)1023;
+                const int overlap_time = !(u->last_use < t->first_def || t->last_use < u->first_def);
+                const int overlap_mem = off < u->off + usz && u->off < off + sz;
+                if (overlap_time && overlap_mem) {
+                    off = u->off + usz;
+                    moved = 1;
+                }
+            }
+            if (!moved) break;
+        }
+        t->off = off;
+        placed[order[oi]] = 1;
+        if (off + sz > top) top = off + sz;
+    }
+    free(order);
+    free(placed);
+    size_t scratch = 0;
+    for (int i = 0; i < g->ns; i++)
+        if (g->s[i].scratch > scratch) scratch = g->s[i].scratch;
+    g->scratch_off = top;
+    g->arena_bytes = top + ((scratch + 1023) & ~(size_t)1023) + 1024;
+    return CSINN_TRUE;
+}
+
+static int run_steps(b200_graph *g, void *stream)
+{
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        if (!t->is_input || !t->d_in_nchw) continue;
+        DEV_CHECK(b200_nchw_to_nhwc(t->d_in_nchw, t->dt.d, t->dt.n, t->dt.c, t->dt.h, t->dt.w, t->dt.cp,
+                                    t->dt.eb, 0, stream));
+    }
+    for (int i = 0; i < g->ns; i++) {
+        g_step *s = &g->s[i];
+        const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
+        if (b200_op_run(s->op, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
+            CSINN_TRUE) {
+            shl_debug_error("b200: step %d (%s) failed: %s\n", i, s->name, shl_b200_last_error());
+            return CSINN_FALSE;
+        }
+    }
+    /* graph outputs: compact NCHW copies, ready for D2H */
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        if (!t->is_output) continue;
+        DEV_CHECK(b200_nhwc_to_nchw(t->dt.d, t->d_out_nchw, t->dt.n, t->dt.c, t->dt.h, t->dt.w, t->dt.cp,
+                                    t->dt.eb, stream));
+    }
+    return CSINN_TRUE;
+}
+
+int shl_b200_session_setup(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    struct shl_ref_graph *graph = shl_gref_get_graph(sess);
+    if (!opt || !graph) {
+        b200_fail("session_setup without a b200 session_init");
+        return CSINN_FALSE;
+    }
+    if (opt->ctx.device < 0) {
+        b200_fail("no usable CUDA device: the b200 backend has no CPU fallback (%s)", b200_last_error());
+        return CSINN_FALSE;
+    }
+    b200_ctx *ctx = &opt->ctx;
+    b200_set_device(ctx->device);
+
+    /* one contiguous weight arena for the whole network */
+    ctx->wcap = weight_bound(graph);
+    ctx->wused = 0;
+    ctx->fixed_arena = 1;
+    ctx->skip_upload = getenv("SHL_B200_SKIP_WEIGHT_UPLOAD") != NULL;
+    void *wb = NULL;
+    DEV_CHECK(b200_malloc(&wb, ctx->wcap));
+    ctx->wbase = wb;
+
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *n = graph->layer[i];
+        if (n->type < 0 || n->type >= CSINN_OP_SIZE) {
+            b200_fail("layer %d: subgraph / unknown node type %d is not supported", i, n->type);
+            return CSINN_FALSE;
+        }
+        n->subgraph_idx = i;
+        if (init_node(n) != CSINN_TRUE) return CSINN_FALSE;
+    }
+
+    b200_graph *g = calloc(1, sizeof(*g));
+    g->t = calloc((size_t)graph->layer_index * 2 + graph->input_num + graph->output_num + 4, sizeof(g_tensor));
+    g->s = calloc((size_t)graph->layer_index + 1, sizeof(g_step));
+    opt->g = g;
+
+    for (int i = 0; i < graph->input_num; i++) {
+        int ti = tensor_add(g, graph->input[i]);
+        if (ti < 0) return CSINN_FALSE;
+        g->t[ti].is_input = 1;
+    }
+
+    /* step list with relu / relu6 fused into the producing op when it is the only consumer */
+    char *skip = calloc(graph->layer_index + 1, 1);
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *n = graph->layer[i];
+        if (skip[i]) continue;
+        b200_op *op = b200_op_find(n->data);
+        if (!op) {
+            b200_fail("layer %d '%s': no device operator after init", i, n->name ? n->name : "?");
+            free(skip);
+            return CSINN_FALSE;
+        }
+        struct shl_node *out_tn = n->out[0];
+        snprintf(g->s[g->ns].name, sizeof(g->s[g->ns].name), "%s", n->name ? n->name : op->kname);
+        if (b200_op_can_fuse_act(op) && !is_graph_output(graph, out_tn)) {
+            struct shl_node *next = NULL;
+            if (consumers(graph, out_tn, &next) == 1 && next && is_act_node(next) && next->in[0] == out_tn) {
+                const int act = next->type == CSINN_OP_RELU ? B200_ACT_RELU : B200_ACT_RELU6;
+                if (b200_op_fuse_act(op, act, next->in[0]->data, next->out[0]->data) == CSINN_TRUE) {
+                    for (int k = i + 1; k < graph->layer_index; k++)
+                        if (graph->layer[k] == next) skip[k] = 1;
+                    out_tn = next->out[0];
+                    strncat(g->s[g->ns].name, "+act", sizeof(g->s[g->ns].name) - strlen(g->s[g->ns].name) - 1);
+                }
+            }
+        }
+        g_step *s = &g->s[g->ns];
+        s->op = op;
+        s->in0 = tensor_add(g, n->in[0]);
+        s->in1 = -1;
+        if (op->kind == B200_OPK_ADD) s->in1 = tensor_add(g, n->in[1]);
+        s->out = tensor_add(g, out_tn);
+        if (s->in0 < 0 || s->out < 0 || (op->kind == B200_OPK_ADD && s->in1 < 0)) {
+            free(skip);
+            return CSINN_FALSE;
+        }
+        g_tensor *ti = &g->t[s->in0], *to = &g->t[s->out];
+        if (ti->first_def < 0 && !ti->is_input) {
+            b200_fail("layer %d '%s' reads a tensor no earlier layer produced", i, n->name ? n->name : "?");
+            free(skip);
+            return CSINN_FALSE;
+        }
+        ti->last_use = g->ns;
+        if (s->in1 >= 0) g->t[s->in1].last_use = g->ns;
+        if (to->first_def < 0) to->first_def = g->ns;
+        to->last_use = g->ns;
+        g->ns++;
+    }
+    free(skip);
+
+    for (int i = 0; i < graph->output_num; i++) {
+        int ti = tensor_index(g, graph->output[i]);
+        if (ti < 0) {
+            b200_fail("graph output %d is not produced by any b200 step", i);
+            return CSINN_FALSE;
+        }
+        g->t[ti].is_output = 1;
+    }
+    /* a graph input read only by im2col convs stays in the API's NCHW layout on the device
+     * (the gather reads it directly); any other input is converted once per run */
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        if (!t->is_input) continue;
+        int direct_ok = 1;
+        for (int k = 0; k < g->ns; k++) {
+            if (g->s[k].in1 == i) direct_ok = 0;
+            if (g->s[k].in0 == i && !(g->s[k].op->kind == B200_OPK_CONV && g->s[k].op->group == 1)) direct_ok = 0;
+        }
+        if (t->is_output) direct_ok = 0;
+        t->dt.is_nchw = direct_ok;
+    }
+    for (int k = 0; k < g->ns; k++)
+        g->s[k].scratch = b200_op_scratch_bytes(g->s[k].op, &g->t[g->s[k].in0].dt, &g->t[g->s[k].out].dt);
+
+    if (plan_memory(g) != CSINN_TRUE) return CSINN_FALSE;
+    void *arena = NULL;
+    DEV_CHECK(b200_malloc(&arena, g->arena_bytes));
+    g->arena = arena;
+    DEV_CHECK(b200_memset(g->arena, 0, g->arena_bytes, ctx->stream));
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        t->dt.d = g->arena + t->off;
+        if (t->is_input && !t->dt.is_nchw) {
+            const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+            DEV_CHECK(b200_malloc(&t->d_in_nchw, raw));
+        }
+        if (t->is_output) {
+            const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+            DEV_CHECK(b200_malloc(&t->d_out_nchw, raw));
+            DEV_CHECK(b200_malloc_host(&t->h_out, raw));
+            struct csinn_tensor *ct = t->node->data;
+            ct->data = t->h_out; /* what csinn_get_output hands back (graph_ref/setup.c:37-42) */
+            ct->mtype = CSINN_MEM_TYPE_CPU_ACC;
+        }
+    }
+
+    /* ref-count bookkeeping gref's own setup would have done (graph_ref/setup.c:774-795), so
+     * that reference tools walking the graph afterwards see consistent counts */
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *n = graph->layer[i];
+        for (int j = 0; j < n->in_num; j++)
+            if (n->in[j]->ref_count_init > 0) n->in[j]->ref_count_init++;
+        for (int k = 0; k < n->out_num; k++) n->out[k]->ref_count_init++;
+    }
+    for (int i = 0; i < graph->output_num; i++) graph->output[i]->ref_count_init++;
+
+    /* one eager pass (surfaces launch errors with a step name, sets function attributes),
+     * then capture the same launches as a CUDA graph */
+    uint64_t before = b200_launch_count();
+    if (run_steps(g, ctx->stream) != CSINN_TRUE) return CSINN_FALSE;
+    DEV_CHECK(b200_stream_sync(ctx->stream));
+    g->kernels_per_run = (int)(b200_launch_count() - before);
+    if (!getenv("SHL_B200_NO_CUDA_GRAPH")) {
+        DEV_CHECK(b200_graph_begin(ctx->stream));
+        int rc = run_steps(g, ctx->stream);
+        void *exec = NULL;
+        int rc2 = b200_graph_end(ctx->stream, &exec);
+        if (rc != CSINN_TRUE || rc2 != B200_OK) {
+            b200_fail("CUDA graph capture failed: %s", b200_last_error());
+            return CSINN_FALSE;
+        }
+        g->exec = exec;
+    }
+    return CSINN_TRUE;
+}
+
+int shl_b200_session_launch(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g) {
+        b200_fail("session_launch before session_setup");
+        return CSINN_FALSE;
+    }
+    b200_set_device(opt->ctx.device);
+    if (opt->g->exec) {
+        DEV_CHECK(b200_graph_launch(opt->g->exec, opt->ctx.stream));
+        return CSINN_TRUE;
+    }
+    return run_steps(opt->g, opt->ctx.stream);
+}
+
+int shl_b200_session_sync(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt) return CSINN_FALSE;
+    DEV_CHECK(b200_stream_sync(opt->ctx.stream));
+    return CSINN_TRUE;
+}
+
+void *shl_b200_session_stream(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    return opt ? opt->ctx.stream : NULL;
+}
+
+int shl_b200_session_run(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g) {
+        b200_fail("session_run before session_setup");
+        return CSINN_FALSE;
+    }
+    b200_graph *g = opt->g;
+    b200_set_device(opt->ctx.device);
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        if (!t->is_input) continue;
+        struct csinn_tensor *ct = t->node->data;
+        if (!ct->data || ct->data == (void *)t->node) {
+            b200_fail("graph input '%s' has no data: call csinn_update_input first", ct->name ? ct->name : "?");
+            return CSINN_FALSE;
+        }
+        const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+        DEV_CHECK(b200_memcpy_h2d(t->d_in_nchw ? t->d_in_nchw : t->dt.d, ct->data, raw, opt->ctx.stream));
+    }
+    if (shl_b200_session_launch(sess) != CSINN_TRUE) return CSINN_FALSE;
+    for (int i = 0; i < g->nt; i++) {
+        g_tensor *t = &g->t[i];
+        if (!t->is_output) continue;
+        const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+        DEV_CHECK(b200_memcpy_d2h(t->h_out, t->d_out_nchw, raw, opt->ctx.stream));
+    }
+    DEV_CHECK(b200_stream_sync(opt->ctx.stream));
+    return CSINN_TRUE;
+}
+
+int shl_b200_session_num_kernels(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    return opt && opt->g ? opt->g->kernels_per_run : 0;
+}
+
+int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g || !buf || buflen <= 0) return 0;
+    b200_graph *g = opt->g;
+    int n = snprintf(buf, buflen, "steps=%d tensors=%d kernels_per_run=%d activation_arena=%zu weight_arena=%zu/%zu cuda_graph=%d\n",
+                     g->ns, g->nt, g->kernels_per_run, g->arena_bytes, opt->ctx.wused, opt->ctx.wcap,
+                     g->exec != NULL);
+    for (int i = 0; i < g->ns && n < buflen; i++) {
+        const b200_dt *o = &g->t[g->s[i].out].dt;
+        n += snprintf(buf + n, buflen - n, "%3d %-28s %s -> [%d,%d,%d,%d]\n", i, g->s[i].op->kname, g->s[i].name,
+                      o->n, o->c, o->h, o->w);
+    }
+    return n < buflen ? n : buflen - 1;
+}
+
+int shl_b200_session_weight_arena(struct csinn_session *sess, void **dev_ptr, uint64_t *bytes)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->ctx.wbase) return CSINN_FALSE;
+    if (dev_ptr) *dev_ptr = opt->ctx.wbase;
+    if (bytes) *bytes = opt->ctx.wused;
+    return CSINN_TRUE;
+}

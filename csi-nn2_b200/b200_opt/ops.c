@@ -1,0 +1,894 @@
+/*
+ * ops.c -- operator callbacks of the b200 backend: the init / exec pairs the reference's
+ * front ends call (source/nn2/convolution.c:26-86, depthwise_conv2d.c, fullyconnected.c,
+ * relu.c, add.c, maxpool.c, averagepool.c, global_avgpool.c, softmax.c, reshape.c, flatten.c).
+ *
+ *   init : validate, pack weights + per-channel tables into the device weight arena, build the
+ *          b200_op, bind it to the params struct, set cb->exec.  Host kernel / bias buffers are
+ *          left untouched (the RVV back end rewrites them in place,
+ *          source/thead_rvv/int8/convolution.c:172-190).
+ *   exec : layer mode (CSINN_RM_LAYER).  Synchronous by contract -- the caller reads
+ *          output->data right after return (source/nn2/convolution.c:79) -- so it stages
+ *          H2D -> NCHW->pixel-major -> kernels -> pixel-major->NCHW -> D2H -> stream sync.
+ *          Graph mode never goes through exec: graph.c plans the same b200_ops once and
+ *          replays them as a CUDA graph.
+ * There is no CPU path: every failure returns CSINN_FALSE / a negative status after logging
+ * through shl_debug_error, and shl_b200_last_error() keeps the message.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200_internal.h"
+
+/* ---- errors --------------------------------------------------------------------------- */
+/* The reference's front ends discard what init / exec return (source/nn2/convolution.c:50-55,
+ * 64-86 always answer CSINN_TRUE), so a status code alone would be silent.  Every failure is
+ * therefore (1) written to stderr unconditionally, (2) kept for shl_b200_last_error(), (3)
+ * counted (shl_b200_error_count()), and (4) fatal when SHL_B200_ABORT_ON_ERROR is set. */
+static char g_err[640];
+static int g_err_count;
+void b200_fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    g_err_count++;
+    fprintf(stderr, "[shl_b200 ERROR] %s\n", g_err);
+    if (getenv("SHL_B200_ABORT_ON_ERROR")) abort();
+}
+const char *shl_b200_last_error(void) { return g_err; }
+int shl_b200_error_count(void) { return g_err_count; }
+void shl_b200_clear_error(void) { g_err[0] = 0; }
+
+#define DEV_CHECK(expr)                                                        \
+    do {                                                                       \
+        int _rc = (expr);                                                      \
+        if (_rc != B200_OK) {                                                  \
+            b200_fail("%s -> %d: %s", #expr, _rc, b200_last_error());          \
+            return CSINN_FALSE;                                                \
+        }                                                                      \
+    } while (0)
+
+/* ---- context --------------------------------------------------------------------------- */
+static int g_device = -1;
+int shl_b200_set_device(int device)
+{
+    g_device = device;
+    return CSINN_TRUE;
+}
+int b200_default_device(void)
+{
+    if (g_device >= 0) return g_device;
+    const char *e = getenv("SHL_B200_DEVICE");
+    if (!e) e = getenv("LOCAL_RANK");
+    return e ? atoi(e) : 0;
+}
+
+int b200_ctx_init(b200_ctx *ctx, int device)
+{
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    int rc = b200_set_device(device);
+    if (rc != B200_OK) {
+        b200_fail("cannot use CUDA device %d: %s", device, b200_last_error());
+        return CSINN_FALSE;
+    }
+    DEV_CHECK(b200_stream_create(&ctx->stream));
+    return CSINN_TRUE;
+}
+
+void b200_ctx_destroy(b200_ctx *ctx)
+{
+    if (ctx->stream) b200_stream_destroy(ctx->stream);
+    /* arena chunks of the default context live for the process; a session's fixed arena is
+     * released here */
+    if (ctx->fixed_arena && ctx->wbase) b200_free(ctx->wbase);
+    memset(ctx, 0, sizeof(*ctx));
+}
+
+static b200_ctx g_ctx;
+static int g_ctx_ready;
+b200_ctx *b200_ctx_default(void)
+{
+    if (!g_ctx_ready) {
+        if (b200_ctx_init(&g_ctx, b200_default_device()) != CSINN_TRUE) return NULL;
+        g_ctx_ready = 1;
+    }
+    b200_set_device(g_ctx.device);
+    return &g_ctx;
+}
+
+b200_ctx *b200_ctx_of(struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (opt) {
+        b200_set_device(opt->ctx.device);
+        return &opt->ctx;
+    }
+    return b200_ctx_default();
+}
+
+void *b200_warena_put(b200_ctx *ctx, const void *src, size_t bytes)
+{
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (!ctx->wbase || ctx->wused + need > ctx->wcap) {
+        if (ctx->fixed_arena) {
+            b200_fail("weight arena exhausted (%zu + %zu > %zu)", ctx->wused, need, ctx->wcap);
+            return NULL;
+        }
+        size_t cap = (size_t)64 << 20;
+        if (cap < need) cap = need;
+        void *p = NULL;
+        if (b200_malloc(&p, cap) != B200_OK) {
+            b200_fail("weight arena allocation of %zu bytes failed: %s", cap, b200_last_error());
+            return NULL;
+        }
+        ctx->wbase = p, ctx->wcap = cap, ctx->wused = 0;
+    }
+    void *dst = ctx->wbase + ctx->wused;
+    ctx->wused += need;
+    if (src && !ctx->skip_upload) {
+        /* pageable source: the runtime stages it, the call returns once the copy is queued
+         * from a private staging buffer -- sync so the caller may free `src` at once */
+        if (b200_memcpy_h2d(dst, src, bytes, ctx->stream) != B200_OK ||
+            b200_stream_sync(ctx->stream) != B200_OK) {
+            b200_fail("weight upload failed: %s", b200_last_error());
+            return NULL;
+        }
+    } else if (b200_memset(dst, 0, need, ctx->stream) != B200_OK) {
+        b200_fail("weight arena clear failed: %s", b200_last_error());
+        return NULL;
+    }
+    return dst;
+}
+
+/* ---- device tensors --------------------------------------------------------------------- */
+size_t b200_dt_bytes(const b200_dt *t)
+{
+    if (t->is_nchw) return (size_t)t->n * t->c * t->h * t->w * t->eb;
+    return (size_t)t->n * t->h * t->w * t->cp * t->eb;
+}
+
+int b200_dt_from_tensor(b200_dt *t, const struct csinn_tensor *src)
+{
+    memset(t, 0, sizeof(*t));
+    if (src->dtype == CSINN_DTYPE_INT8)
+        t->eb = 1;
+    else if (src->dtype == CSINN_DTYPE_FLOAT16)
+        t->eb = 2;
+    else
+        return 0;
+    switch (src->dim_count) {
+        case 4:
+            t->n = src->dim[0], t->c = src->dim[1], t->h = src->dim[2], t->w = src->dim[3];
+            break;
+        case 3:
+            t->n = src->dim[0], t->c = src->dim[1], t->h = 1, t->w = src->dim[2];
+            break;
+        case 2:
+            t->n = src->dim[0], t->c = src->dim[1], t->h = 1, t->w = 1;
+            break;
+        case 1:
+            t->n = 1, t->c = src->dim[0], t->h = 1, t->w = 1;
+            break;
+        default:
+            return 0;
+    }
+    if (t->n <= 0 || t->c <= 0 || t->h <= 0 || t->w <= 0) return 0;
+    t->cp = b200_round_channels(t->c, t->eb);
+    return 1;
+}
+
+/* ---- params -> op registry (open addressing, grows; tombstones on release) --------------- */
+#define REG_TOMB ((void *)1)
+static struct reg_slot {
+    void *key;
+    b200_op *op;
+} *g_reg;
+static size_t g_reg_cap, g_reg_used;
+
+static size_t reg_hash(void *p, size_t cap) { return (size_t)(((uintptr_t)p >> 4) * 2654435761u) & (cap - 1); }
+
+static void reg_grow(void)
+{
+    const size_t ncap = g_reg_cap ? g_reg_cap * 2 : 1024;
+    struct reg_slot *n = calloc(ncap, sizeof(*n));
+    if (!n) return;
+    for (size_t i = 0; i < g_reg_cap; i++) {
+        if (!g_reg[i].key || g_reg[i].key == REG_TOMB) continue;
+        size_t h = reg_hash(g_reg[i].key, ncap);
+        while (n[h].key) h = (h + 1) & (ncap - 1);
+        n[h] = g_reg[i];
+    }
+    size_t live = 0;
+    for (size_t i = 0; i < ncap; i++) live += n[i].key != NULL;
+    free(g_reg);
+    g_reg = n, g_reg_cap = ncap, g_reg_used = live;
+}
+
+void b200_op_bind(void *params, b200_op *op)
+{
+    if ((g_reg_used + 1) * 2 > g_reg_cap) reg_grow();
+    if (!g_reg) {
+        b200_fail("out of host memory growing the operator registry");
+        return;
+    }
+    size_t h = reg_hash(params, g_reg_cap), tomb = (size_t)-1;
+    while (g_reg[h].key && g_reg[h].key != params) {
+        if (g_reg[h].key == REG_TOMB && tomb == (size_t)-1) tomb = h;
+        h = (h + 1) & (g_reg_cap - 1);
+    }
+    if (!g_reg[h].key) {
+        if (tomb != (size_t)-1)
+            h = tomb;
+        else
+            g_reg_used++;
+    }
+    g_reg[h].key = params;
+    g_reg[h].op = op; /* re-init of the same params replaces the op (constants stay in the arena) */
+}
+
+b200_op *b200_op_find(void *params)
+{
+    if (!g_reg) return NULL;
+    size_t h = reg_hash(params, g_reg_cap);
+    while (g_reg[h].key) {
+        if (g_reg[h].key == params) return g_reg[h].op;
+        h = (h + 1) & (g_reg_cap - 1);
+    }
+    return NULL;
+}
+
+/* The reference API has no per-operator deinit (its back ends leak kernel_tm, see the FIXME at
+ * source/thead_rvv/int8/convolution_gemm_int8.c:50); this addition lets long-running hosts and
+ * the test harness drop an operator's staging buffers. */
+void shl_b200_op_release(void *params)
+{
+    if (!g_reg) return;
+    size_t h = reg_hash(params, g_reg_cap);
+    while (g_reg[h].key) {
+        if (g_reg[h].key == params) {
+            b200_op *op = g_reg[h].op;
+            g_reg[h].key = REG_TOMB, g_reg[h].op = NULL;
+            if (op) {
+                b200_set_device(op->ctx->device);
+                for (int i = 0; i < 8; i++)
+                    if (op->stg[i]) b200_free(op->stg[i]);
+                free(op);
+            }
+            return;
+        }
+        h = (h + 1) & (g_reg_cap - 1);
+    }
+}
+
+static b200_op *op_new(struct csinn_params_base *base, int kind, int csinn_dtype, const char *kname)
+{
+    int dt;
+    if (csinn_dtype == CSINN_DTYPE_INT8)
+        dt = B200_I8;
+    else if (csinn_dtype == CSINN_DTYPE_FLOAT16)
+        dt = B200_F16;
+    else {
+        b200_fail("dtype %d not supported by the b200 backend (int8 and float16 only)", csinn_dtype);
+        return NULL;
+    }
+    b200_ctx *ctx = b200_ctx_of(base->sess);
+    if (!ctx) return NULL;
+    b200_op *op = calloc(1, sizeof(*op));
+    if (!op) return NULL;
+    op->kind = kind, op->dtype = dt, op->eb = dt == B200_I8 ? 1 : 2;
+    op->kname = kname, op->ctx = ctx;
+    return op;
+}
+
+static void fill_epilogue(const b200_op *op, b200_epilogue *ep)
+{
+    memset(ep, 0, sizeof(*ep));
+    ep->mult = op->d_mult, ep->badd = op->d_badd, ep->ibias = op->d_ibias;
+    ep->post_lut = op->kind == B200_OPK_ACT ? NULL : op->d_lut;
+    ep->zp_out = op->zp_out, ep->act = op->act, ep->q6 = op->q6;
+}
+
+/* ---- running one op on device tensors ------------------------------------------------------ */
+size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
+{
+    if (op->kind != B200_OPK_CONV || (op->direct && !in0->is_nchw)) return 0;
+    return (size_t)out->n * out->h * out->w * op->ldk * op->eb;
+}
+
+static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *scratch, void *stream)
+{
+    const int og = op->o / op->group, cg = op->cin / op->group;
+    const int m = out->n * out->h * out->w;
+    b200_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.dtype = op->dtype, g.m = m, g.k = op->kdim, g.ldw = op->ldk, g.ldo = out->cp;
+    fill_epilogue(op, &g.ep);
+    for (int grp = 0; grp < op->group; grp++) {
+        if (op->direct && !in->is_nchw) {
+            g.a = in->d, g.lda = in->cp;
+        } else {
+            b200_im2col_desc c;
+            memset(&c, 0, sizeof(c));
+            c.dtype = op->dtype, c.n = in->n, c.h = in->h, c.w = in->w, c.cp_in = in->cp;
+            c.in_nchw = in->is_nchw, c.c_total = in->c, c.c_off = grp * cg, c.cg = cg;
+            c.oh = out->h, c.ow = out->w, c.kh = op->kh, c.kw = op->kw;
+            c.stride_h = op->sh, c.stride_w = op->sw, c.pad_top = op->pt, c.pad_left = op->pl;
+            c.dil_h = op->dh, c.dil_w = op->dw, c.ldk = op->ldk, c.pad_value = op->zp_in;
+            c.in = in->d, c.col = scratch;
+            DEV_CHECK(b200_im2col(&c, stream));
+            g.a = scratch, g.lda = op->ldk;
+        }
+        g.n = og;
+        g.w = (const uint8_t *)op->d_w + (size_t)grp * og * op->ldk * op->eb;
+        g.out = (uint8_t *)out->d + (size_t)grp * og * op->eb;
+        if (op->group > 1) {
+            /* each group writes its own column window of the pixel-major output */
+            g.ldo = out->cp;
+            g.ep.mult = op->d_mult ? op->d_mult + grp * og : NULL;
+            g.ep.badd = op->d_badd ? op->d_badd + grp * og : NULL;
+            g.ep.ibias = op->d_ibias ? op->d_ibias + grp * og : NULL;
+        }
+        DEV_CHECK(b200_gemm(&g, stream));
+    }
+    return CSINN_TRUE;
+}
+
+int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
+                void *scratch, void *stream)
+{
+    switch (op->kind) {
+        case B200_OPK_CONV:
+            return run_conv(op, in0, out, scratch, stream);
+        case B200_OPK_FC: {
+            b200_gemm_desc g;
+            memset(&g, 0, sizeof(g));
+            g.dtype = op->dtype, g.m = in0->n * in0->h * in0->w, g.n = op->o, g.k = op->kdim;
+            g.a = in0->d, g.lda = in0->cp, g.w = op->d_w, g.ldw = op->ldk;
+            g.out = out->d, g.ldo = out->cp;
+            fill_epilogue(op, &g.ep);
+            DEV_CHECK(b200_gemm(&g, stream));
+            return CSINN_TRUE;
+        }
+        case B200_OPK_DW: {
+            b200_dwconv_desc d;
+            memset(&d, 0, sizeof(d));
+            d.dtype = op->dtype, d.n = in0->n, d.c = in0->c, d.cp = in0->cp;
+            d.h = in0->h, d.w = in0->w, d.oh = out->h, d.ow = out->w;
+            d.kh = op->kh, d.kw = op->kw, d.stride_h = op->sh, d.stride_w = op->sw;
+            d.pad_top = op->pt, d.pad_left = op->pl, d.dil_h = op->dh, d.dil_w = op->dw;
+            d.in = in0->d, d.wt = op->d_w, d.out = out->d, d.zp_in = op->zp_in;
+            fill_epilogue(op, &d.ep);
+            DEV_CHECK(b200_dwconv2d(&d, stream));
+            return CSINN_TRUE;
+        }
+        case B200_OPK_ACT:
+            if (op->dtype == B200_I8)
+                DEV_CHECK(b200_lut_i8(in0->d, out->d, b200_dt_bytes(out), op->d_lut, stream));
+            else
+                DEV_CHECK(b200_relu_f16(in0->d, out->d, b200_dt_bytes(out) / 2, op->act, stream));
+            return CSINN_TRUE;
+        case B200_OPK_ADD:
+            DEV_CHECK(b200_add(op->dtype, in0->d, in1->d, out->d, b200_dt_bytes(out) / op->eb,
+                               op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out, op->zp_out,
+                               op->d_lut, op->act, stream));
+            return CSINN_TRUE;
+        case B200_OPK_POOL: {
+            b200_pool_desc p;
+            memset(&p, 0, sizeof(p));
+            p.dtype = op->dtype, p.n = in0->n, p.c = in0->c, p.cp = in0->cp, p.h = in0->h, p.w = in0->w;
+            p.oh = out->h, p.ow = out->w;
+            p.kh = op->pool_global ? in0->h : op->kh, p.kw = op->pool_global ? in0->w : op->kw;
+            p.stride_h = op->pool_global ? 1 : op->sh, p.stride_w = op->pool_global ? 1 : op->sw;
+            p.pad_top = op->pool_global ? 0 : op->pt, p.pad_left = op->pool_global ? 0 : op->pl;
+            p.is_avg = op->pool_avg, p.count_include_pad = op->count_include_pad;
+            p.s_in = op->s_in, p.zp_in = op->zp_in, p.s_out = op->s_out, p.zp_out = op->zp_out;
+            p.in = in0->d, p.out = out->d;
+            DEV_CHECK(b200_pool2d(&p, stream));
+            return CSINN_TRUE;
+        }
+        case B200_OPK_SOFTMAX:
+            DEV_CHECK(b200_softmax(op->dtype, in0->d, out->d, in0->n, in0->c, in0->cp, out->cp,
+                                   op->s_in, op->zp_in, op->s_out, op->zp_out, stream));
+            return CSINN_TRUE;
+        case B200_OPK_COPY:
+            if (b200_dt_bytes(in0) != b200_dt_bytes(out)) {
+                b200_fail("reshape changes the device footprint (%zu -> %zu bytes)", b200_dt_bytes(in0),
+                          b200_dt_bytes(out));
+                return CSINN_FALSE;
+            }
+            DEV_CHECK(b200_memcpy_d2d(out->d, in0->d, b200_dt_bytes(out), stream));
+            return CSINN_TRUE;
+    }
+    b200_fail("unknown op kind %d", op->kind);
+    return CSINN_FALSE;
+}
+
+int b200_op_can_fuse_act(const b200_op *op)
+{
+    return (op->kind == B200_OPK_CONV || op->kind == B200_OPK_DW || op->kind == B200_OPK_FC ||
+            op->kind == B200_OPK_ADD) &&
+           op->d_lut == NULL;
+}
+
+static int8_t *upload_lut(b200_ctx *ctx, int act, float s_in, int zp_in, float s_out, int zp_out)
+{
+    int8_t lut[256];
+    b200_build_requant_lut(lut, act, s_in, zp_in, s_out, zp_out);
+    return b200_warena_put(ctx, lut, 256);
+}
+
+int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
+                     const struct csinn_tensor *act_out)
+{
+    if (op->dtype == B200_F16) {
+        /* relu on top of an already fused relu6 etc. is not produced by the planner */
+        if (op->act != B200_ACT_NONE) return CSINN_FALSE;
+        op->act = act;
+        return CSINN_TRUE;
+    }
+    op->d_lut = upload_lut(op->ctx, act, act_in->qinfo->scale, act_in->qinfo->zero_point,
+                           act_out->qinfo->scale, act_out->qinfo->zero_point);
+    return op->d_lut ? CSINN_TRUE : CSINN_FALSE;
+}
+
+/* ---- layer-mode execution ------------------------------------------------------------------ */
+static void *stage(b200_op *op, int slot, size_t bytes)
+{
+    if (op->stg_bytes[slot] < bytes) {
+        if (op->stg[slot]) b200_free(op->stg[slot]);
+        op->stg[slot] = NULL, op->stg_bytes[slot] = 0;
+        if (b200_malloc(&op->stg[slot], bytes) != B200_OK) {
+            b200_fail("staging allocation of %zu bytes failed: %s", bytes, b200_last_error());
+            return NULL;
+        }
+        op->stg_bytes[slot] = bytes;
+    }
+    return op->stg[slot];
+}
+
+static int upload_nchw(b200_op *op, int slot, const struct csinn_tensor *t, b200_dt *dt, void *stream)
+{
+    if (!b200_dt_from_tensor(dt, t)) {
+        b200_fail("unsupported tensor (dtype %d, rank %d)", t->dtype, t->dim_count);
+        return CSINN_FALSE;
+    }
+    if (!t->data) {
+        b200_fail("tensor '%s' has no host data", t->name ? t->name : "?");
+        return CSINN_FALSE;
+    }
+    const size_t raw = (size_t)dt->n * dt->c * dt->h * dt->w * dt->eb;
+    void *d_raw = stage(op, slot, raw);
+    void *d_pm = stage(op, slot + 1, b200_dt_bytes(dt));
+    if (!d_raw || !d_pm) return CSINN_FALSE;
+    DEV_CHECK(b200_memcpy_h2d(d_raw, t->data, raw, stream));
+    DEV_CHECK(b200_nchw_to_nhwc(d_raw, d_pm, dt->n, dt->c, dt->h, dt->w, dt->cp, dt->eb, 0, stream));
+    dt->d = d_pm;
+    return CSINN_TRUE;
+}
+
+static int layer_exec(void *params, struct csinn_tensor *in0, struct csinn_tensor *in1,
+                      struct csinn_tensor *output)
+{
+    b200_op *op = b200_op_find(params);
+    if (!op) {
+        b200_fail("exec before init: no b200 operator bound to these params");
+        return CSINN_FALSE;
+    }
+    b200_set_device(op->ctx->device);
+    void *stream = op->ctx->stream;
+    b200_dt d0, d1, dout;
+    memset(&d1, 0, sizeof(d1));
+    if (upload_nchw(op, 0, in0, &d0, stream) != CSINN_TRUE) return CSINN_FALSE;
+    if (in1 && upload_nchw(op, 2, in1, &d1, stream) != CSINN_TRUE) return CSINN_FALSE;
+    if (!b200_dt_from_tensor(&dout, output) || !output->data) {
+        b200_fail("unsupported or unallocated output tensor");
+        return CSINN_FALSE;
+    }
+    const size_t raw = (size_t)dout.n * dout.c * dout.h * dout.w * dout.eb;
+    dout.d = stage(op, 4, b200_dt_bytes(&dout));
+    void *d_raw = stage(op, 5, raw);
+    if (!dout.d || !d_raw) return CSINN_FALSE;
+    void *scratch = NULL;
+    const size_t sb = b200_op_scratch_bytes(op, &d0, &dout);
+    if (sb && !(scratch = stage(op, 6, sb))) return CSINN_FALSE;
+    if (b200_op_run(op, &d0, in1 ? &d1 : NULL, &dout, scratch, stream) != CSINN_TRUE) return CSINN_FALSE;
+    DEV_CHECK(b200_nhwc_to_nchw(dout.d, d_raw, dout.n, dout.c, dout.h, dout.w, dout.cp, dout.eb, stream));
+    DEV_CHECK(b200_memcpy_d2h(output->data, d_raw, raw, stream));
+    DEV_CHECK(b200_stream_sync(stream));
+    return CSINN_TRUE;
+}
+
+/* ---- conv2d ---------------------------------------------------------------------------------- */
+static int conv_act_of(struct csinn_params_base *base, int op_relu, int op_relu6)
+{
+    /* the front end does not pass the op enum to init; CONV2D_RELU / _RELU6 are registered with
+     * their own init wrappers below */
+    (void)base;
+    (void)op_relu;
+    (void)op_relu6;
+    return B200_ACT_NONE;
+}
+
+static int conv_init_common(struct csinn_tensor *input, struct csinn_tensor *output,
+                            struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                            struct csinn_conv2d_params *params, int act)
+{
+    (void)conv_act_of;
+    if (input->dim_count != 4 || kernel->dim_count != 4) {
+        b200_fail("conv2d: expected 4-D NCHW input and OIHW kernel");
+        return CSINN_UNSUPPORT_LAYOUT;
+    }
+    if (params->base.layout != CSINN_LAYOUT_NCHW && params->base.layout != 0) {
+        b200_fail("conv2d: only CSINN_LAYOUT_NCHW tensors are supported (got %d)", params->base.layout);
+        return CSINN_UNSUPPORT_LAYOUT;
+    }
+    const int C = input->dim[1], O = kernel->dim[0], cg = kernel->dim[1];
+    const int kh = kernel->dim[2], kw = kernel->dim[3];
+    int group = params->group > 0 ? params->group : 1;
+    const int is_dw = group == C && cg == 1 && group > 1;
+    if (!is_dw && (C % group || O % group || cg != C / group)) {
+        b200_fail("conv2d: inconsistent group=%d for C=%d O=%d kernel I=%d", group, C, O, cg);
+        return CSINN_FALSE;
+    }
+    int dh = params->dilation_height, dw = params->dilation_width;
+    if (kh == 1) dh = 1;
+    if (kw == 1) dw = 1;
+    if (dh < 1 || dw < 1 || params->stride_height < 1 || params->stride_width < 1) {
+        b200_fail("conv2d: stride %dx%d / dilation %dx%d must be >= 1", params->stride_height,
+                  params->stride_width, params->dilation_height, params->dilation_width);
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(&params->base, is_dw ? B200_OPK_DW : B200_OPK_CONV, input->dtype,
+                         is_dw ? "b200_dwconv2d" : "b200_im2col_gemm_tcgen05");
+    if (!op) return CSINN_FALSE;
+    op->cin = C, op->o = O, op->kh = kh, op->kw = kw;
+    op->sh = params->stride_height, op->sw = params->stride_width;
+    op->pt = params->pad_top, op->pl = params->pad_left, op->dh = dh, op->dw = dw;
+    op->group = is_dw ? 1 : group;
+    op->act = act;
+    int rc;
+    size_t wbytes = 0;
+    if (is_dw) {
+        if (O != C) {
+            b200_fail("depthwise conv2d: depth multiplier %d/%d != 1 is not supported", O, C);
+            free(op);
+            return CSINN_FALSE;
+        }
+        const int cp = b200_round_channels(C, op->eb);
+        rc = b200_make_requant(op, input, kernel, bias, output, kh * kw, params->conv_extra.fuse_zp2bias, O);
+        if (rc == CSINN_TRUE && !(op->d_w = b200_pack_dw_weights(op, kernel, cp, &wbytes))) rc = CSINN_FALSE;
+    } else {
+        const int og = O / group;
+        if (group > 1 && (og * op->eb) % 16) {
+            b200_fail("group conv2d: %d output channels per group is not a multiple of %d", og, 16 / op->eb);
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->kdim = cg * kh * kw;
+        op->ldk = b200_round_channels(op->kdim, op->eb);
+        op->direct = kh == 1 && kw == 1 && op->sh == 1 && op->sw == 1 && op->pt == 0 && op->pl == 0 &&
+                     params->pad_down == 0 && params->pad_right == 0 && group == 1;
+        if (op->direct) op->kname = "b200_gemm_tcgen05";
+        rc = b200_make_requant(op, input, kernel, bias, output, op->kdim, params->conv_extra.fuse_zp2bias, O);
+        if (rc == CSINN_TRUE && !(op->d_w = b200_pack_conv_weights(op, kernel, &wbytes))) rc = CSINN_FALSE;
+    }
+    if (rc != CSINN_TRUE) {
+        free(op);
+        return rc;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = is_dw ? (int (*)())shl_b200_depthwise_conv2d : (int (*)())shl_b200_conv2d;
+    return CSINN_TRUE;
+}
+
+int shl_b200_conv2d_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                         struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                         struct csinn_conv2d_params *params)
+{
+    return conv_init_common(input, output, kernel, bias, params, B200_ACT_NONE);
+}
+static int conv2d_relu_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                            struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                            struct csinn_conv2d_params *params)
+{
+    return conv_init_common(input, output, kernel, bias, params, B200_ACT_RELU);
+}
+static int conv2d_relu6_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                             struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                             struct csinn_conv2d_params *params)
+{
+    return conv_init_common(input, output, kernel, bias, params, B200_ACT_RELU6);
+}
+void *shl_b200_conv2d_relu_init_fn(void) { return (void *)conv2d_relu_init; }
+void *shl_b200_conv2d_relu6_init_fn(void) { return (void *)conv2d_relu6_init; }
+
+int shl_b200_conv2d(struct csinn_tensor *input, struct csinn_tensor *output,
+                    struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                    struct csinn_conv2d_params *params)
+{
+    (void)kernel;
+    (void)bias;
+    return layer_exec(params, input, NULL, output);
+}
+
+int shl_b200_depthwise_conv2d_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                                   struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                                   struct csinn_conv2d_params *params)
+{
+    return conv_init_common(input, output, kernel, bias, params, B200_ACT_NONE);
+}
+int shl_b200_depthwise_conv2d(struct csinn_tensor *input, struct csinn_tensor *output,
+                              struct csinn_tensor *kernel, struct csinn_tensor *bias,
+                              struct csinn_conv2d_params *params)
+{
+    (void)kernel;
+    (void)bias;
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- fullyconnected ---------------------------------------------------------------------------- */
+int shl_b200_fullyconnected_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                                 struct csinn_tensor *weights, struct csinn_tensor *bias,
+                                 struct csinn_fc_params *params)
+{
+    if (weights->dim_count != 2) {
+        b200_fail("fullyconnected: expected [out][in] weights");
+        return CSINN_FALSE;
+    }
+    b200_dt din;
+    if (!b200_dt_from_tensor(&din, input) || din.h * din.w != 1 || din.c != weights->dim[1]) {
+        /* source/reference/fullyconnected.c:21 flattens any leading dims in NCHW order; on the
+         * pixel-major device layout that only coincides when H*W == 1 */
+        b200_fail("fullyconnected: input must be [batch][%d] (or N x %d x 1 x 1)", weights->dim[1], weights->dim[1]);
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(&params->base, B200_OPK_FC, input->dtype, "b200_gemm_tcgen05");
+    if (!op) return CSINN_FALSE;
+    op->o = weights->dim[0], op->cin = weights->dim[1], op->kdim = weights->dim[1];
+    op->ldk = b200_round_channels(op->kdim, op->eb);
+    op->group = 1, op->direct = 1;
+    size_t wbytes = 0;
+    int rc = b200_make_requant(op, input, weights, bias, output, op->kdim, params->fc_extra.fuse_zp2bias, op->o);
+    if (rc == CSINN_TRUE && !(op->d_w = b200_pack_fc_weights(op, weights, &wbytes))) rc = CSINN_FALSE;
+    if (rc != CSINN_TRUE) {
+        free(op);
+        return rc;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_fullyconnected;
+    return CSINN_TRUE;
+}
+int shl_b200_fullyconnected(struct csinn_tensor *input, struct csinn_tensor *output,
+                            struct csinn_tensor *weights, struct csinn_tensor *bias,
+                            struct csinn_fc_params *params)
+{
+    (void)weights;
+    (void)bias;
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- relu / relu6 -------------------------------------------------------------------------------- */
+static int act_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params, int act)
+{
+    struct csinn_params_base *base = params;
+    b200_op *op = op_new(base, B200_OPK_ACT, input->dtype, act == B200_ACT_RELU ? "b200_relu" : "b200_relu6");
+    if (!op) return CSINN_FALSE;
+    op->act = act;
+    if (op->dtype == B200_I8) {
+        if (!input->qinfo || !output->qinfo) {
+            b200_fail("relu: int8 tensors without qinfo");
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->d_lut = upload_lut(op->ctx, act, input->qinfo->scale, input->qinfo->zero_point,
+                               output->qinfo->scale, output->qinfo->zero_point);
+        if (!op->d_lut) {
+            free(op);
+            return CSINN_FALSE;
+        }
+    }
+    b200_op_bind(params, op);
+    base->cb->exec = (int (*)())shl_b200_relu;
+    return CSINN_TRUE;
+}
+int shl_b200_relu_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                       struct csinn_relu_params *params)
+{
+    return act_init(input, output, params, B200_ACT_RELU);
+}
+static int relu6_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                      struct csinn_relu_params *params)
+{
+    return act_init(input, output, params, B200_ACT_RELU6);
+}
+void *shl_b200_relu6_init_fn(void) { return (void *)relu6_init; }
+int shl_b200_relu(struct csinn_tensor *input, struct csinn_tensor *output,
+                  struct csinn_relu_params *params)
+{
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- add -------------------------------------------------------------------------------------------- */
+int shl_b200_add_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
+                      struct csinn_tensor *output, struct csinn_diso_params *params)
+{
+    if (input0->dim_count != input1->dim_count) {
+        b200_fail("add: broadcasting is not supported (ranks %d vs %d)", input0->dim_count, input1->dim_count);
+        return CSINN_FALSE;
+    }
+    for (int i = 0; i < input0->dim_count; i++)
+        if (input0->dim[i] != input1->dim[i]) {
+            b200_fail("add: broadcasting is not supported (dim %d: %d vs %d)", i, input0->dim[i], input1->dim[i]);
+            return CSINN_FALSE;
+        }
+    if (input1->is_const) {
+        b200_fail("add: constant second operand is not supported");
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, "b200_add");
+    if (!op) return CSINN_FALSE;
+    if (op->dtype == B200_I8) {
+        if (!input0->qinfo || !input1->qinfo || !output->qinfo) {
+            b200_fail("add: int8 tensors without qinfo");
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->s_in = input0->qinfo->scale, op->zp_in = input0->qinfo->zero_point;
+        op->s_in1 = input1->qinfo->scale, op->zp_in1 = input1->qinfo->zero_point;
+        op->s_out = output->qinfo->scale, op->zp_out = output->qinfo->zero_point;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_add;
+    return CSINN_TRUE;
+}
+int shl_b200_add(struct csinn_tensor *input0, struct csinn_tensor *input1,
+                 struct csinn_tensor *output, struct csinn_diso_params *params)
+{
+    return layer_exec(params, input0, input1, output);
+}
+
+/* ---- pooling ------------------------------------------------------------------------------------------ */
+static int pool_init_common(struct csinn_tensor *input, struct csinn_tensor *output,
+                            struct csinn_pool_params *params, int avg, int global)
+{
+    if (input->dim_count != 4) {
+        b200_fail("pool2d: expected a 4-D NCHW input");
+        return CSINN_UNSUPPORT_LAYOUT;
+    }
+    b200_op *op = op_new(&params->base, B200_OPK_POOL, input->dtype,
+                         global ? "b200_global_avgpool" : (avg ? "b200_avgpool" : "b200_maxpool"));
+    if (!op) return CSINN_FALSE;
+    op->pool_avg = avg, op->pool_global = global;
+    op->kh = params->filter_height, op->kw = params->filter_width;
+    op->sh = params->stride_height, op->sw = params->stride_width;
+    op->pt = params->pad_top, op->pl = params->pad_left;
+    op->count_include_pad = params->count_include_pad ? 1 : 0;
+    if (!global && (op->kh < 1 || op->kw < 1 || op->sh < 1 || op->sw < 1)) {
+        b200_fail("pool2d: filter %dx%d / stride %dx%d must be >= 1", op->kh, op->kw, op->sh, op->sw);
+        free(op);
+        return CSINN_FALSE;
+    }
+    if (op->dtype == B200_I8) {
+        if (!input->qinfo || !output->qinfo) {
+            b200_fail("pool2d: int8 tensors without qinfo");
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->s_in = input->qinfo->scale, op->zp_in = input->qinfo->zero_point;
+        op->s_out = output->qinfo->scale, op->zp_out = output->qinfo->zero_point;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_pool2d;
+    return CSINN_TRUE;
+}
+int shl_b200_pool2d_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                         struct csinn_pool_params *params)
+{
+    return pool_init_common(input, output, params, 0, 0); /* maxpool */
+}
+static int avgpool_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                        struct csinn_pool_params *params)
+{
+    return pool_init_common(input, output, params, 1, 0);
+}
+static int global_avgpool_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                               struct csinn_pool_params *params)
+{
+    return pool_init_common(input, output, params, 1, 1);
+}
+void *shl_b200_avgpool_init_fn(void) { return (void *)avgpool_init; }
+void *shl_b200_global_avgpool_init_fn(void) { return (void *)global_avgpool_init; }
+int shl_b200_pool2d(struct csinn_tensor *input, struct csinn_tensor *output,
+                    struct csinn_pool_params *params)
+{
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- softmax -------------------------------------------------------------------------------------------- */
+int shl_b200_softmax_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                          struct csinn_softmax_params *params)
+{
+    b200_dt din;
+    int axis = params->axis < 0 ? params->axis + input->dim_count : params->axis;
+    if (!b200_dt_from_tensor(&din, input) || din.h * din.w != 1 || axis != 1) {
+        b200_fail("softmax: only axis 1 of an [N][C] (or N x C x 1 x 1) tensor is supported");
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(&params->base, B200_OPK_SOFTMAX, input->dtype, "b200_softmax");
+    if (!op) return CSINN_FALSE;
+    if (op->dtype == B200_I8) {
+        if (!input->qinfo || !output->qinfo) {
+            b200_fail("softmax: int8 tensors without qinfo");
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->s_in = input->qinfo->scale, op->zp_in = input->qinfo->zero_point;
+        op->s_out = output->qinfo->scale, op->zp_out = output->qinfo->zero_point;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_softmax;
+    return CSINN_TRUE;
+}
+int shl_b200_softmax(struct csinn_tensor *input, struct csinn_tensor *output,
+                     struct csinn_softmax_params *params)
+{
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- reshape / flatten ------------------------------------------------------------------------------------ */
+int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params)
+{
+    struct csinn_params_base *base = params;
+    b200_dt din, dout;
+    if (!b200_dt_from_tensor(&din, input) || !b200_dt_from_tensor(&dout, output) ||
+        din.h * din.w != 1 || dout.h * dout.w != 1 || din.n != dout.n || din.c != dout.c) {
+        /* with H*W > 1 an NCHW reshape permutes the pixel-major buffer */
+        b200_fail("reshape/flatten: only N x C x 1 x 1 <-> N x C is supported on the device layout");
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(base, B200_OPK_COPY, input->dtype, "b200_reshape_copy");
+    if (!op) return CSINN_FALSE;
+    b200_op_bind(params, op);
+    base->cb->exec = (int (*)())shl_b200_reshape;
+    return CSINN_TRUE;
+}
+int shl_b200_reshape(struct csinn_tensor *input, struct csinn_tensor *output, void *params)
+{
+    return layer_exec(params, input, NULL, output);
+}
+
+/* ---- perf callbacks: kernel name for the trace profiler ------------------------------------------------ */
+/* gref calls perf with the op's own argument list plus a trailing csinn_perf_info*
+ * (source/graph_ref/setup.c:509-540), hence one function per arity. */
+static int perf_set(void *params, struct csinn_perf_info *perf_info)
+{
+    b200_op *op = b200_op_find(params);
+    if (perf_info) perf_info->kernel_name = (char *)(op ? op->kname : "b200");
+    return CSINN_TRUE;
+}
+int shl_b200_perf(struct csinn_tensor *input, struct csinn_tensor *output,
+                  struct csinn_tensor *kernel, struct csinn_tensor *bias, void *params,
+                  struct csinn_perf_info *perf_info)
+{
+    (void)input, (void)output, (void)kernel, (void)bias;
+    return perf_set(params, perf_info);
+}
+int shl_b200_perf_siso(struct csinn_tensor *input, struct csinn_tensor *output, void *params,
+                       struct csinn_perf_info *perf_info)
+{
+    (void)input, (void)output;
+    return perf_set(params, perf_info);
+}
+int shl_b200_perf_diso(struct csinn_tensor *input0, struct csinn_tensor *input1,
+                       struct csinn_tensor *output, void *params,
+                       struct csinn_perf_info *perf_info)
+{
+    (void)input0, (void)input1, (void)output;
+    return perf_set(params, perf_info);
+}

@@ -1,0 +1,199 @@
+/*
+ * quant.c -- init-time host work of the b200 backend: per-channel requantisation tables and
+ * weight packing.  Does what shl_rvv_conv2d_init_int8 does at init
+ * (source/thead_rvv/int8/convolution.c:161-190: per-channel multiplier, zero-point fold) and
+ * what shl_rvv_conv_im2col_gemm_reorder_kernel_int8 / shl_rvv_fc_gemm_reorder_weight_int8 do
+ * (convolution_gemm_int8.c:21, fullyconnected_int8.c:79), but for the epilogue contract of
+ * include/b200nn.h and the K-major tile layout the tcgen05 GEMM reads; unlike the RVV back end
+ * it never mutates the caller's kernel / bias buffers.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200_internal.h"
+
+static float f16_to_f32(uint16_t h)
+{
+    uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 0x1F, man = h & 0x3FF, u;
+    if (exp == 0) {
+        if (man == 0) {
+            u = sign;
+        } else {
+            int e = -1;
+            do {
+                man <<= 1;
+                e++;
+            } while (!(man & 0x400));
+            u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FF) << 13);
+        }
+    } else if (exp == 31) {
+        u = sign | 0x7F800000u | (man << 13);
+    } else {
+        u = sign | ((exp + 112) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int has_bias(const struct csinn_tensor *bias)
+{
+    return bias && bias->data && bias->dim_count != 0 && csinn_tensor_size((struct csinn_tensor *)bias) != 0;
+}
+
+int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
+                      const struct csinn_tensor *kernel, const struct csinn_tensor *bias,
+                      const struct csinn_tensor *output, int taps_per_o, int fuse_zp2bias,
+                      int n_out)
+{
+    const int n_alloc = round_up(n_out, 16);
+    float *mult = calloc(n_alloc, sizeof(float));
+    float *badd = calloc(n_alloc, sizeof(float));
+    int32_t *ibias = calloc(n_alloc, sizeof(int32_t));
+    int rc = CSINN_TRUE;
+    if (!mult || !badd || !ibias) {
+        b200_fail("out of host memory building requant tables");
+        rc = CSINN_FALSE;
+        goto done;
+    }
+    if (op->dtype == B200_F16) {
+        if (has_bias(bias)) {
+            const uint16_t *b = bias->data;
+            for (int o = 0; o < n_out; o++) badd[o] = f16_to_f32(b[o]);
+        }
+        op->d_mult = NULL;
+        op->d_ibias = NULL;
+        op->d_badd = b200_warena_put(op->ctx, badd, n_alloc * sizeof(float));
+        if (!op->d_badd) rc = CSINN_FALSE;
+        goto done;
+    }
+    if (!input->qinfo || !kernel->qinfo || !output->qinfo) {
+        b200_fail("int8 op without qinfo on input / kernel / output");
+        rc = CSINN_FALSE;
+        goto done;
+    }
+    const double s_in = input->qinfo->scale, s_out = output->qinfo->scale;
+    const int zp_in = input->qinfo->zero_point;
+    const int8_t *w = kernel->data;
+    const int32_t *b = has_bias(bias) ? bias->data : NULL;
+    for (int o = 0; o < n_out; o++) {
+        const int qi = kernel->quant_channel > 1 ? o : 0;
+        if (kernel->qinfo[qi].zero_point != 0) {
+            /* same restriction as the reference's accelerated int8 path, which only takes
+             * CSINN_QUANT_INT8_ASYM_W_SYM (thead_rvv/int8/convolution.c:40-43) -- but with no
+             * CPU fallback behind it */
+            b200_fail("weight zero_point %d != 0 (channel %d): only symmetric weights are supported",
+                      kernel->qinfo[qi].zero_point, o);
+            rc = CSINN_UNSUPPORT_DTYPE;
+            goto done;
+        }
+        const double sw = kernel->qinfo[qi].scale;
+        double sb = s_in * sw;
+        if (b && bias->qinfo) {
+            const int bi = bias->quant_channel > 1 ? o : 0;
+            if (bias->qinfo[bi].scale != 0) sb = bias->qinfo[bi].scale;
+        }
+        int64_t wsum = 0;
+        for (int t = 0; t < taps_per_o; t++) wsum += w[(int64_t)o * taps_per_o + t];
+        int64_t bq = b ? b[o] : 0;
+        if (fuse_zp2bias) bq += (int64_t)zp_in * wsum; /* un-fold, cf. reference/convolution.c:375-395 */
+        mult[o] = (float)(s_in * sw / s_out);
+        badd[o] = (float)((double)bq * sb / s_out);
+        ibias[o] = (int32_t)(-(int64_t)zp_in * wsum);
+        const double bound = (double)taps_per_o * 128.0 * 255.0 * fabs(mult[o]) + fabs(badd[o]);
+        if (!(bound < 4194304.0)) {
+            b200_fail("channel %d: |acc*mult+bias| may reach %.3g >= 2^22; qinfo out of the supported range",
+                      o, bound);
+            rc = CSINN_FALSE;
+            goto done;
+        }
+    }
+    op->zp_in = zp_in;
+    op->zp_out = output->qinfo->zero_point;
+    op->s_out = output->qinfo->scale;
+    {
+        /* quantised 6.0 in the output domain (CONV2D_RELU6: convolution_relu6.c:21) */
+        float t = 6.0f / output->qinfo->scale;
+        float v = (float)(nearbyint((double)t) + (double)op->zp_out);
+        op->q6 = v > 127 ? 127 : (v < -128 ? -128 : (int)v);
+    }
+    op->d_mult = b200_warena_put(op->ctx, mult, n_alloc * sizeof(float));
+    op->d_badd = b200_warena_put(op->ctx, badd, n_alloc * sizeof(float));
+    op->d_ibias = b200_warena_put(op->ctx, ibias, n_alloc * sizeof(int32_t));
+    if (!op->d_mult || !op->d_badd || !op->d_ibias) rc = CSINN_FALSE;
+done:
+    free(mult);
+    free(badd);
+    free(ibias);
+    return rc;
+}
+
+/* OIHW -> [O][kh][kw][Cg] rows of pitch ldk: k = (ky, kx, ci), ci fastest = im2col's order */
+void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes)
+{
+    const int O = kernel->dim[0], cg = kernel->dim[1], kh = kernel->dim[2], kw = kernel->dim[3];
+    const int eb = op->eb;
+    const size_t total = (size_t)O * op->ldk * eb;
+    uint8_t *buf = calloc(1, total ? total : 16);
+    if (!buf) return NULL;
+    const uint8_t *src = kernel->data;
+    for (int o = 0; o < O; o++)
+        for (int ci = 0; ci < cg; ci++)
+            for (int ky = 0; ky < kh; ky++)
+                for (int kx = 0; kx < kw; kx++) {
+                    const size_t s = ((((size_t)o * cg + ci) * kh + ky) * kw + kx) * eb;
+                    const size_t d = ((size_t)o * op->ldk + ((size_t)ky * kw + kx) * cg + ci) * eb;
+                    memcpy(buf + d, src + s, eb);
+                }
+    void *dev = b200_warena_put(op->ctx, buf, total);
+    free(buf);
+    *bytes = total;
+    return dev;
+}
+
+/* O1HW -> tap-major [kh*kw][cp]; int8 entries are expanded to one 32-bit word per channel with
+ * the weight in byte lane (c & 3) so that dp4a against a 4-channel activation word yields the
+ * single per-channel product */
+void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes)
+{
+    const int C = kernel->dim[0], taps = kernel->dim[2] * kernel->dim[3];
+    const size_t esz = op->dtype == B200_I8 ? 4 : 2;
+    const size_t total = (size_t)taps * cp * esz;
+    uint8_t *buf = calloc(1, total ? total : 16);
+    if (!buf) return NULL;
+    if (op->dtype == B200_I8) {
+        const int8_t *src = kernel->data;
+        uint32_t *dst = (uint32_t *)buf;
+        for (int c = 0; c < C; c++)
+            for (int t = 0; t < taps; t++)
+                dst[(size_t)t * cp + c] = (uint32_t)(uint8_t)src[(size_t)c * taps + t] << (8 * (c & 3));
+    } else {
+        const uint16_t *src = kernel->data;
+        uint16_t *dst = (uint16_t *)buf;
+        for (int c = 0; c < C; c++)
+            for (int t = 0; t < taps; t++) dst[(size_t)t * cp + c] = src[(size_t)c * taps + t];
+    }
+    void *dev = b200_warena_put(op->ctx, buf, total);
+    free(buf);
+    *bytes = total;
+    return dev;
+}
+
+/* [O][I] -> rows of pitch ldk */
+void *b200_pack_fc_weights(b200_op *op, const struct csinn_tensor *weights, size_t *bytes)
+{
+    const int O = weights->dim[0], I = weights->dim[1];
+    const int eb = op->eb;
+    const size_t total = (size_t)O * op->ldk * eb;
+    uint8_t *buf = calloc(1, total ? total : 16);
+    if (!buf) return NULL;
+    const uint8_t *src = weights->data;
+    for (int o = 0; o < O; o++) memcpy(buf + (size_t)o * op->ldk * eb, src + (size_t)o * I * eb, (size_t)I * eb);
+    void *dev = b200_warena_put(op->ctx, buf, total);
+    free(buf);
+    *bytes = total;
+    return dev;
+}

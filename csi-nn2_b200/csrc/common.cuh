@@ -1,0 +1,314 @@
+// common.cuh -- sm_100a PTX wrappers and shared helpers for the b200nn kernels.
+// Everything here is hand-written inline PTX (mbarrier, TMA, tcgen05/TMEM); no CUTLASS.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200nn.h"
+
+namespace b200 {
+
+// ---- host side error plumbing -------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+#define B200_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                            cudaGetErrorString(_e));                                       \
+            return B200_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+#define B200_LAUNCH_CHECK()                                                                \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            b200::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,              \
+                            cudaGetErrorString(_e));                                       \
+            return B200_ERR_CUDA;                                                          \
+        }                                                                                  \
+        b200::count_launch();                                                              \
+    } while (0)
+
+int sm_count();
+// 2-D tiled tensor map, SWIZZLE_128B, zero fill out of bounds (runtime.cu)
+int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
+                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+
+// ---- device helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// mbarrier ------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// TMA -----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
+{
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
+                                            int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
+                                            int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0,
+                                             int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::
+                     "l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+// tcgen05 / TMEM ------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before()
+{
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after()
+{
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+// arrives on `bar` once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+            smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait()
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, rows of 128 bytes:
+// 8-row x 128-byte swizzle atoms stacked every 1024 bytes (SBO); LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                     // LBO (ignored), bits [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;             // SBO = 1024 B, bits [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(2) << 61;                     // layout: SWIZZLE_128B
+    return d;
+}
+
+// UMMA instruction descriptor (32-bit), dense, K-major A and B.
+//   c_fmt: 1 = F32, 2 = S32;  ab_fmt: kind::i8 -> 1 = S8;  kind::f16 -> 0 = F16, 1 = BF16
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t c_fmt, uint32_t ab_fmt, uint32_t m,
+                                                  uint32_t n)
+{
+    return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ---- quantised epilogue (device copy of b200_epilogue) ---------------------------
+struct EpiScalars {
+    const float *mult;
+    const float *badd;
+    const int32_t *ibias;
+    const int8_t *post_lut;
+    int32_t zp_out, act, q6;
+};
+inline EpiScalars make_epi(const b200_epilogue &e)
+{
+    EpiScalars s;
+    s.mult = e.mult;
+    s.badd = e.badd;
+    s.ibias = e.ibias;
+    s.post_lut = e.post_lut;
+    s.zp_out = e.zp_out;
+    s.act = e.act;
+    s.q6 = e.q6;
+    return s;
+}
+
+__device__ __forceinline__ int clamp_i8(int v) { return max(-128, min(127, v)); }
+
+// int8 epilogue for one accumulator (ibias already added); contract in b200nn.h.
+// __float2int_rn is cvt.rni (round half even) and saturates, the host bounds |f| < 2^22.
+__device__ __forceinline__ int requant_i8(int acc, float mult, float badd, int zp_out, int act,
+                                          int q6)
+{
+    float f = fmaf(static_cast<float>(acc), mult, badd);
+    int q = clamp_i8(__float2int_rn(f) + zp_out);
+    if (act != B200_ACT_NONE) q = max(q, zp_out);
+    if (act == B200_ACT_RELU6) q = min(q, q6);
+    return q;
+}
+
+__device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d)
+{
+    return (static_cast<uint32_t>(a) & 0xFF) | ((static_cast<uint32_t>(b) & 0xFF) << 8) |
+           ((static_cast<uint32_t>(c) & 0xFF) << 16) | ((static_cast<uint32_t>(d) & 0xFF) << 24);
+}
+
+__device__ __forceinline__ float act_f(float v, int act)
+{
+    if (act != B200_ACT_NONE) v = v > 0.f ? v : 0.f;
+    if (act == B200_ACT_RELU6) v = fminf(v, 6.f);
+    return v;
+}
+
+// exact restatement of source/nn2/utils.c:550 float_to_int8_base on the device:
+// IEEE division, round half even, clamp.  Used by add / pool / softmax.
+__device__ __forceinline__ int quant_i8_exact(float x, float s, int zp)
+{
+    float t = __fadd_rn(rintf(__fdiv_rn(x, s)), static_cast<float>(zp));
+    t = fminf(fmaxf(t, -128.f), 127.f);
+    return static_cast<int>(t);
+}
+__device__ __forceinline__ float dequant_i8(int q, float s, int zp)
+{
+    return __fmul_rn(__fsub_rn(static_cast<float>(q), static_cast<float>(zp)), s);
+}
+
+}  // namespace b200

@@ -1,0 +1,243 @@
+// dwconv.cu -- depthwise conv2d on pixel-major tensors (HBM-bound stencil).
+//
+// One thread owns 16 bytes of channels (16 int8 / 8 fp16) of kTW consecutive output pixels of
+// one row, so every global access is a 128-bit vector and a warp covers 512 contiguous bytes of
+// the channel axis (or several pixels when C is small).  int8 products use dp4a against
+// "expanded" weights (one weight byte per 32-bit word, the other three zero), which gives the
+// exact per-channel int32 product without unpacking the activations; accumulation is int32 and
+// the epilogue is the contract of include/b200nn.h.  fp16 accumulates in fp32 like the
+// reference (source/reference/convolution.c:206-269).
+//
+// Replaces shl_rvv_dwconv3x3s1_int8 / s2 (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31)
+// and the fp16 twins; any kernel size / stride / dilation is covered by the same kernel.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kTW = 4;  // output pixels per thread along W
+
+struct DwArgs {
+    int n, c, cp, h, w, oh, ow;
+    int kh, kw, sh, sw, pt, pl, dh, dw;
+    const void *in;
+    const void *wt;  // int8: expanded [kh*kw][cp] words ; fp16: [kh*kw][cp] halves
+    void *out;
+    int zp_in;
+    EpiScalars ep;
+};
+
+__global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
+{
+    __shared__ int8_t s_lut[256];
+    if (a.ep.post_lut != nullptr)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.ep.post_lut[i];
+    __syncthreads();
+
+    const int chunks = a.cp / 16;
+    const int xgroups = (a.ow + kTW - 1) / kTW;
+    const long long total = static_cast<long long>(a.n) * a.oh * xgroups * chunks;
+    const int8_t *in = static_cast<const int8_t *>(a.in);
+    const uint32_t *wexp = static_cast<const uint32_t *>(a.wt);
+    int8_t *out = static_cast<int8_t *>(a.out);
+    const uint32_t padw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
+
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % chunks);
+        const int xg = static_cast<int>((i / chunks) % xgroups);
+        const int oy = static_cast<int>((i / (static_cast<long long>(chunks) * xgroups)) % a.oh);
+        const int b = static_cast<int>(i / (static_cast<long long>(chunks) * xgroups * a.oh));
+        const int c0 = ch * 16;
+        const int ox0 = xg * kTW;
+
+        int acc[kTW][16];
+#pragma unroll
+        for (int p = 0; p < kTW; p++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[p][j] = 0;
+
+        for (int ky = 0; ky < a.kh; ky++) {
+            const int iy = oy * a.sh - a.pt + ky * a.dh;
+            const bool yok = iy >= 0 && iy < a.h;
+            for (int kx = 0; kx < a.kw; kx++) {
+                // 16 expanded weight words for this tap and these 16 channels
+                const uint4 *wp = reinterpret_cast<const uint4 *>(
+                    wexp + (static_cast<long long>(ky * a.kw + kx) * a.cp + c0));
+                uint32_t wv[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint4 t = __ldg(wp + q);
+                    wv[q * 4 + 0] = t.x, wv[q * 4 + 1] = t.y, wv[q * 4 + 2] = t.z, wv[q * 4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int p = 0; p < kTW; p++) {
+                    const int ix = (ox0 + p) * a.sw - a.pl + kx * a.dw;
+                    uint4 x = make_uint4(padw, padw, padw, padw);
+                    if (yok && ix >= 0 && ix < a.w && ox0 + p < a.ow)
+                        x = __ldg(reinterpret_cast<const uint4 *>(
+                            in + ((static_cast<long long>(b) * a.h + iy) * a.w + ix) * a.cp + c0));
+                    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            acc[p][q * 4 + e] = __dp4a(static_cast<int>(xw[q]),
+                                                       static_cast<int>(wv[q * 4 + e]),
+                                                       acc[p][q * 4 + e]);
+                }
+            }
+        }
+
+        // epilogue: per-channel parameters once per thread, reused for the kTW pixels
+        float mu[16], ba[16];
+        int ib[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4 *>(a.ep.mult + c0) + q);
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.ep.badd + c0) + q);
+            const int4 i4 = __ldg(reinterpret_cast<const int4 *>(a.ep.ibias + c0) + q);
+            mu[q * 4] = m4.x, mu[q * 4 + 1] = m4.y, mu[q * 4 + 2] = m4.z, mu[q * 4 + 3] = m4.w;
+            ba[q * 4] = b4.x, ba[q * 4 + 1] = b4.y, ba[q * 4 + 2] = b4.z, ba[q * 4 + 3] = b4.w;
+            ib[q * 4] = i4.x, ib[q * 4 + 1] = i4.y, ib[q * 4 + 2] = i4.z, ib[q * 4 + 3] = i4.w;
+        }
+#pragma unroll
+        for (int p = 0; p < kTW; p++) {
+            if (ox0 + p >= a.ow) break;
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int v[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int j = q * 4 + e;
+                    int qv = requant_i8(acc[p][j] + ib[j], mu[j], ba[j], a.ep.zp_out, a.ep.act,
+                                        a.ep.q6);
+                    if (a.ep.post_lut != nullptr) qv = s_lut[qv + 128];
+                    v[e] = c0 + j < a.c ? qv : 0;
+                }
+                pk[q] = pack4_i8(v[0], v[1], v[2], v[3]);
+            }
+            *reinterpret_cast<uint4 *>(
+                out + ((static_cast<long long>(b) * a.oh + oy) * a.ow + ox0 + p) * a.cp + c0) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
+{
+    const int chunks = a.cp / 8;
+    const int xgroups = (a.ow + kTW - 1) / kTW;
+    const long long total = static_cast<long long>(a.n) * a.oh * xgroups * chunks;
+    const __half *in = static_cast<const __half *>(a.in);
+    const __half *wt = static_cast<const __half *>(a.wt);
+    __half *out = static_cast<__half *>(a.out);
+
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % chunks);
+        const int xg = static_cast<int>((i / chunks) % xgroups);
+        const int oy = static_cast<int>((i / (static_cast<long long>(chunks) * xgroups)) % a.oh);
+        const int b = static_cast<int>(i / (static_cast<long long>(chunks) * xgroups * a.oh));
+        const int c0 = ch * 8;
+        const int ox0 = xg * kTW;
+
+        float acc[kTW][8];
+#pragma unroll
+        for (int p = 0; p < kTW; p++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[p][j] = 0.f;
+
+        for (int ky = 0; ky < a.kh; ky++) {
+            const int iy = oy * a.sh - a.pt + ky * a.dh;
+            const bool yok = iy >= 0 && iy < a.h;
+            for (int kx = 0; kx < a.kw; kx++) {
+                const uint4 wraw = __ldg(reinterpret_cast<const uint4 *>(
+                    wt + static_cast<long long>(ky * a.kw + kx) * a.cp + c0));
+                const __half2 *wh = reinterpret_cast<const __half2 *>(&wraw);
+                float wf[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float2 f = __half22float2(wh[q]);
+                    wf[q * 2] = f.x, wf[q * 2 + 1] = f.y;
+                }
+#pragma unroll
+                for (int p = 0; p < kTW; p++) {
+                    const int ix = (ox0 + p) * a.sw - a.pl + kx * a.dw;
+                    if (yok && ix >= 0 && ix < a.w && ox0 + p < a.ow) {
+                        const uint4 xraw = __ldg(reinterpret_cast<const uint4 *>(
+                            in + ((static_cast<long long>(b) * a.h + iy) * a.w + ix) * a.cp + c0));
+                        const __half2 *xh = reinterpret_cast<const __half2 *>(&xraw);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float2 f = __half22float2(xh[q]);
+                            acc[p][q * 2] = fmaf(wf[q * 2], f.x, acc[p][q * 2]);
+                            acc[p][q * 2 + 1] = fmaf(wf[q * 2 + 1], f.y, acc[p][q * 2 + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        float ba[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) ba[j] = a.ep.badd ? __ldg(a.ep.badd + c0 + j) : 0.f;
+#pragma unroll
+        for (int p = 0; p < kTW; p++) {
+            if (ox0 + p >= a.ow) break;
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float f0 = act_f(acc[p][q * 2] + ba[q * 2], a.ep.act);
+                float f1 = act_f(acc[p][q * 2 + 1] + ba[q * 2 + 1], a.ep.act);
+                f0 = c0 + q * 2 < a.c ? f0 : 0.f;
+                f1 = c0 + q * 2 + 1 < a.c ? f1 : 0.f;
+                __half2 hv = __floats2half2_rn(f0, f1);
+                pk[q] = *reinterpret_cast<uint32_t *>(&hv);
+            }
+            *reinterpret_cast<uint4 *>(
+                out + ((static_cast<long long>(b) * a.oh + oy) * a.ow + ox0 + p) * a.cp + c0) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
+{
+    if (!d || !d->in || !d->wt || !d->out) {
+        set_error("b200_dwconv2d: null descriptor field");
+        return B200_ERR_ARG;
+    }
+    if (d->dtype != B200_I8 && d->dtype != B200_F16) {
+        set_error("b200_dwconv2d: dtype %d unsupported", d->dtype);
+        return B200_ERR_UNSUPPORTED;
+    }
+    const int eb = d->dtype == B200_I8 ? 1 : 2;
+    if (d->n <= 0 || d->c <= 0 || d->cp < d->c || (d->cp * eb) % 16 || d->kh <= 0 || d->kw <= 0 ||
+        d->stride_h <= 0 || d->stride_w <= 0 || d->dil_h <= 0 || d->dil_w <= 0 || d->oh <= 0 ||
+        d->ow <= 0 || (d->dtype == B200_I8 && (!d->ep.mult || !d->ep.badd || !d->ep.ibias))) {
+        set_error("b200_dwconv2d: bad descriptor (c=%d cp=%d k=%dx%d)", d->c, d->cp, d->kh, d->kw);
+        return B200_ERR_ARG;
+    }
+    DwArgs a;
+    a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
+    a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;
+    a.pt = d->pad_top, a.pl = d->pad_left, a.dh = d->dil_h, a.dw = d->dil_w;
+    a.in = d->in, a.wt = d->wt, a.out = d->out, a.zp_in = d->zp_in;
+    a.ep = make_epi(d->ep);
+    const int vec = 16 / eb;
+    const long long total = static_cast<long long>(d->n) * d->oh * ((d->ow + kTW - 1) / kTW) *
+                            (d->cp / vec);
+    long long g = (total + 127) / 128;
+    const long long cap = static_cast<long long>(sm_count()) * 32;
+    const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+    if (d->dtype == B200_I8)
+        dwconv_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else
+        dwconv_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

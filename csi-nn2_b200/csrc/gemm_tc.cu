@@ -1,0 +1,364 @@
+// gemm_tc.cu -- the tensor-core half of the hot path: out[m][o] = epilogue(sum_k a[m][k]*w[o][k])
+// on tcgen05 (kind::i8 with s32 accumulators, kind::f16 with f32 accumulators), operands staged
+// by TMA into 128B-swizzled shared memory, accumulators double-buffered in TMEM, the per-channel
+// requantise / bias / relu epilogue fused (contract in include/b200nn.h).
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      tcgen05.mma issuer (one elected lane) + TMEM allocation
+//   warps 2..9  epilogue: tcgen05.ld -> requantise -> 16-byte global stores
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
+// static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n-tile fastest so that
+// CTAs running side by side share the A tile through L2).
+//
+// Replaces shl_rvv_gemm_4x16_int8 / shl_rvv_conv1x1s1_gemm_int8 / shl_rvv_fullyconnected_int8
+// (source/thead_rvv/int8/gemm_int8.c:37, convolution_1x1_int8.c:56, fullyconnected_int8.c:94)
+// and the fp16 twins (source/thead_rvv/fp16/gemm_fp16.c); nothing of them is ported.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128;        // UMMA M (cta_group::1)
+constexpr int kBKBytes = 128;   // one swizzle atom of K per stage
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kMaxStages = 12;
+constexpr size_t kSmemLimit = 226 * 1024;
+
+struct GemmArgs {
+    int m, n;
+    int k_blocks;      // ceil(K bytes / 128)
+    int bn;            // tile N, multiple of 16, <= 256
+    int num_m_tiles, num_n_tiles;
+    int stages;
+    int ldo;           // elements
+    void *out;
+    uint32_t idesc;
+    EpiScalars ep;
+};
+
+struct __align__(16) EpiParams {
+    float mult[256];
+    float badd[256];
+    int32_t ibias[256];
+    int8_t lut[256];
+};
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t *smem = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int stages = args.stages;
+    const uint32_t a_stage_bytes = kBM * kBKBytes;
+    const uint32_t b_stage_bytes = args.bn * kBKBytes;
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + stages * a_stage_bytes;
+    EpiParams *epi = reinterpret_cast<EpiParams *>(smem_b + stages * b_stage_bytes);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + 1);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    uint64_t *tmem_full = empty_bar + kMaxStages;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < stages; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], kEpiWarps);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    if (warp >= 2 && args.ep.post_lut != nullptr) {
+        const int t = threadIdx.x - 64;
+        if (t < 256) epi->lut[t] = args.ep.post_lut[t];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / args.num_n_tiles) * kBM;
+                const int n0 = (tile % args.num_n_tiles) * args.bn;
+                for (int kb = 0; kb < args.k_blocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
+                    tma_load_2d(smem_a + stage * a_stage_bytes, &tma_a, &full_bar[stage],
+                                kb * k_elems, m0);
+                    tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage],
+                                kb * k_elems, n0);
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                for (int kb = 0; kb < args.k_blocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
+#pragma unroll
+                    for (int k = 0; k < kBKBytes / 32; k++) {
+                        // advance 32 bytes of K inside the swizzle atom: +2 in 16-byte units
+                        if (DT == B200_I8)
+                            tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
+                        else
+                            tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc,
+                                       (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int ew = warp - 2;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;           // which alternate 32-column chunks it owns
+        const int et = threadIdx.x - 64;    // 0..255
+        const EpiScalars &ep = args.ep;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int m0 = (tile / args.num_n_tiles) * kBM;
+            const int n0 = (tile % args.num_n_tiles) * args.bn;
+            // stage this n-tile's per-channel parameters
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (et < args.bn) {
+                const int col = n0 + et;
+                const bool ok = col < args.n;
+                epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
+                epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
+                epi->ibias[et] = (ok && ep.ibias) ? ep.ibias[col] : 0;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < args.m;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   acc * kAccStride;
+            for (int c0 = half * 32; c0 < args.bn; c0 += 64) {
+                uint32_t r[32];
+                const int ncols = min(32, args.bn - c0);  // 32 or 16
+                if (ncols == 32) {
+                    tmem_ld_32x32(taddr + c0, r);
+                } else {
+                    uint32_t r16[16];
+                    tmem_ld_32x16(taddr + c0, r16);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) r[j] = r16[j];
+#pragma unroll
+                    for (int j = 16; j < 32; j++) r[j] = 0;
+                }
+                tmem_ld_wait();
+                if (DT == B200_I8) {
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c0 + j4 * 4]);
+                        const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c0 + j4 * 4]);
+                        const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c0 + j4 * 4]);
+                        int q0 = requant_i8(static_cast<int>(r[j4 * 4 + 0]) + ib.x, mu.x, ba.x,
+                                            ep.zp_out, ep.act, ep.q6);
+                        int q1 = requant_i8(static_cast<int>(r[j4 * 4 + 1]) + ib.y, mu.y, ba.y,
+                                            ep.zp_out, ep.act, ep.q6);
+                        int q2 = requant_i8(static_cast<int>(r[j4 * 4 + 2]) + ib.z, mu.z, ba.z,
+                                            ep.zp_out, ep.act, ep.q6);
+                        int q3 = requant_i8(static_cast<int>(r[j4 * 4 + 3]) + ib.w, mu.w, ba.w,
+                                            ep.zp_out, ep.act, ep.q6);
+                        if (ep.post_lut != nullptr) {
+                            q0 = epi->lut[q0 + 128];
+                            q1 = epi->lut[q1 + 128];
+                            q2 = epi->lut[q2 + 128];
+                            q3 = epi->lut[q3 + 128];
+                        }
+                        const int cb = n0 + c0 + j4 * 4;
+                        q0 = cb + 0 < args.n ? q0 : 0;
+                        q1 = cb + 1 < args.n ? q1 : 0;
+                        q2 = cb + 2 < args.n ? q2 : 0;
+                        q3 = cb + 3 < args.n ? q3 : 0;
+                        packed[j4] = pack4_i8(q0, q1, q2, q3);
+                    }
+                    if (row_ok) {
+                        int8_t *dst = static_cast<int8_t *>(args.out) +
+                                      static_cast<size_t>(row) * args.ldo + n0 + c0;
+#pragma unroll
+                        for (int v = 0; v < 2; v++) {
+                            if (v * 16 < ncols && n0 + c0 + v * 16 < args.ldo)
+                                *reinterpret_cast<uint4 *>(dst + v * 16) =
+                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
+                                               packed[v * 4 + 3]);
+                        }
+                    }
+                } else {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j2 = 0; j2 < 16; j2++) {
+                        const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
+                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, ep.act);
+                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, ep.act);
+                        const int cb = n0 + c0 + j2 * 2;
+                        f0 = cb < args.n ? f0 : 0.f;
+                        f1 = cb + 1 < args.n ? f1 : 0.f;
+                        __half2 h = __floats2half2_rn(f0, f1);
+                        packed[j2] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    if (row_ok) {
+                        __half *dst = static_cast<__half *>(args.out) +
+                                      static_cast<size_t>(row) * args.ldo + n0 + c0;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
+                                *reinterpret_cast<uint4 *>(dst + v * 8) =
+                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
+                                               packed[v * 4 + 3]);
+                        }
+                    }
+                }
+            }
+            // this warp has drained its part of the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t gemm_smem_bytes(int stages, int bn)
+{
+    return 1024 + static_cast<size_t>(stages) * (kBM * kBKBytes + bn * kBKBytes) + sizeof(EpiParams) +
+           (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+}
+
+static int pick_bn(int n)
+{
+    // one n-tile when the whole output width fits (<= 256), otherwise the multiple of 16 that
+    // splits n most evenly into the fewest tiles
+    const int n16 = (n + 15) / 16 * 16;
+    if (n16 <= 256) return n16;
+    const int tiles = (n16 + 255) / 256;
+    return ((n16 + tiles - 1) / tiles + 15) / 16 * 16;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
+{
+    if (!d || !d->a || !d->w || !d->out) {
+        set_error("b200_gemm: null descriptor field");
+        return B200_ERR_ARG;
+    }
+    if (d->dtype != B200_I8 && d->dtype != B200_F16) {
+        set_error("b200_gemm: dtype %d unsupported", d->dtype);
+        return B200_ERR_UNSUPPORTED;
+    }
+    const int eb = d->dtype == B200_I8 ? 1 : 2;
+    if (d->m <= 0 || d->n <= 0 || d->k <= 0 || d->ldo < d->n || (d->lda * eb) % 16 ||
+        (d->ldw * eb) % 16 || (d->ldo * eb) % 16 || d->lda < d->k || d->ldw < d->k ||
+        (reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->w) & 15) ||
+        (reinterpret_cast<uintptr_t>(d->out) & 15)) {
+        set_error("b200_gemm: bad sizes m=%d n=%d k=%d lda=%d ldw=%d ldo=%d (pitches and bases must be 16-byte aligned)",
+                  d->m, d->n, d->k, d->lda, d->ldw, d->ldo);
+        return B200_ERR_ARG;
+    }
+    GemmArgs args;
+    args.m = d->m;
+    args.n = d->n;
+    args.k_blocks = (d->k * eb + kBKBytes - 1) / kBKBytes;
+    args.bn = pick_bn(d->n);
+    args.num_m_tiles = (d->m + kBM - 1) / kBM;
+    args.num_n_tiles = (d->n + args.bn - 1) / args.bn;
+    args.ldo = d->ldo;
+    args.out = d->out;
+    args.ep = make_epi(d->ep);
+    args.idesc = d->dtype == B200_I8 ? umma_idesc(2 /*S32*/, 1 /*S8*/, kBM, args.bn)
+                                     : umma_idesc(1 /*F32*/, 0 /*F16*/, kBM, args.bn);
+    // as many stages as fit: the ring also prefetches the next tiles' operands while the
+    // epilogue drains, which is what keeps HBM busy on the short-K (memory-bound) layers
+    int stages = kMaxStages;
+    while (stages > 2 && gemm_smem_bytes(stages, args.bn) > kSmemLimit) stages--;
+    args.stages = stages;
+    const size_t smem = gemm_smem_bytes(stages, args.bn);
+
+    alignas(64) CUtensorMap ta, tb;
+    const int box_k = kBKBytes / eb;
+    int rc = encode_tmap_2d(&ta, eb, d->a, d->k, d->m, static_cast<uint64_t>(d->lda) * eb, box_k, kBM);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
+    if (rc) return rc;
+
+    const int grid = min(args.num_m_tiles * args.num_n_tiles, sm_count());
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    static bool attr_set[64][2] = {};
+    if (dev >= 0 && dev < 64 && !attr_set[dev][d->dtype]) {
+        if (d->dtype == B200_I8)
+            B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<B200_I8>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kSmemLimit));
+        else
+            B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<B200_F16>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kSmemLimit));
+        attr_set[dev][d->dtype] = true;
+    }
+    if (d->dtype == B200_I8)
+        gemm_tc_kernel<B200_I8><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, args);
+    else
+        gemm_tc_kernel<B200_F16><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, args);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

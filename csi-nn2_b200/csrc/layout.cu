@@ -1,0 +1,215 @@
+// layout.cu -- layout conversion at the API boundary and im2col.
+//   b200_nchw_to_nhwc / b200_nhwc_to_nchw : the API's NCHW tensors <-> the device's pixel-major
+//     [N][H][W][Cp] (stand-ins for the NCHW <-> NC1HWC0 reorders of source/thead_rvv/data_convert.c)
+//   b200_im2col : the gather half of "im2col + GEMM conv2d" (k order = (ky, kx, ci), ci fastest,
+//     so that one tap is a contiguous run of channels in the pixel-major input).
+// All three are pure data movement: coalesced along the contiguous axis of whichever side is
+// wider, 16-byte vectors on the pixel-major side.
+#include "common.cuh"
+
+namespace b200 {
+
+// one thread: 16 bytes of channels of one pixel.  Adjacent threads = adjacent pixels, so the
+// strided NCHW side is coalesced across the warp (one byte / half per lane per channel).
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T *__restrict__ src, T *__restrict__ dst, int n, int c,
+                                    int hw, int cp, T pad)
+{
+    constexpr int V = 16 / sizeof(T);
+    const int chunks = cp / V;
+    const long long total = static_cast<long long>(n) * chunks * hw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % hw);
+        const int ch = static_cast<int>((i / hw) % chunks);
+        const int b = static_cast<int>(i / (static_cast<long long>(hw) * chunks));
+        alignas(16) T v[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const int cc = ch * V + j;
+            v[j] = cc < c ? src[(static_cast<long long>(b) * c + cc) * hw + p] : pad;
+        }
+        *reinterpret_cast<uint4 *>(dst + (static_cast<long long>(b) * hw + p) * cp + ch * V) =
+            *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, T *__restrict__ dst, int n, int c,
+                                    int hw, int cp)
+{
+    constexpr int V = 16 / sizeof(T);
+    const int chunks = cp / V;
+    const long long total = static_cast<long long>(n) * chunks * hw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % hw);
+        const int ch = static_cast<int>((i / hw) % chunks);
+        const int b = static_cast<int>(i / (static_cast<long long>(hw) * chunks));
+        alignas(16) T v[V];
+        *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(
+            src + (static_cast<long long>(b) * hw + p) * cp + ch * V);
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const int cc = ch * V + j;
+            if (cc < c) dst[(static_cast<long long>(b) * c + cc) * hw + p] = v[j];
+        }
+    }
+}
+
+struct Im2colArgs {
+    int n, h, w, cp_in, in_nchw, c_total, c_off, cg;
+    int oh, ow, kh, kw, sh, sw, pt, pl, dh, dw;
+    int ldk;
+    const void *in;
+    void *col;
+};
+
+// one thread: one 16-byte vector of one im2col row.
+template <typename T>
+__global__ void im2col_kernel(const Im2colArgs a, T pad)
+{
+    constexpr int V = 16 / sizeof(T);
+    const int vecs = a.ldk / V;
+    const int kvalid = a.kh * a.kw * a.cg;
+    const long long rows = static_cast<long long>(a.n) * a.oh * a.ow;
+    const long long total = rows * vecs;
+    const T *in = static_cast<const T *>(a.in);
+    T *col = static_cast<T *>(a.col);
+    const bool fast = !a.in_nchw && (a.cg % V == 0) && (a.c_off % V == 0);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int vec = static_cast<int>(i % vecs);
+        const long long m = i / vecs;
+        const int ox = static_cast<int>(m % a.ow);
+        const int oy = static_cast<int>((m / a.ow) % a.oh);
+        const int b = static_cast<int>(m / (static_cast<long long>(a.ow) * a.oh));
+        alignas(16) T v[V];
+        const int k0 = vec * V;
+        if (fast) {
+            // the vector lies inside one tap: a contiguous run of channels
+            if (k0 < kvalid) {
+                const int tap = k0 / a.cg, ci = k0 % a.cg;
+                const int iy = oy * a.sh - a.pt + (tap / a.kw) * a.dh;
+                const int ix = ox * a.sw - a.pl + (tap % a.kw) * a.dw;
+                if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+                    *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(
+                        in + ((static_cast<long long>(b) * a.h + iy) * a.w + ix) * a.cp_in + a.c_off +
+                        ci);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; j++) v[j] = pad;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; j++) v[j] = pad;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const int k = k0 + j;
+                T x = pad;
+                if (k < kvalid) {
+                    const int tap = k / a.cg, ci = k % a.cg;
+                    const int iy = oy * a.sh - a.pt + (tap / a.kw) * a.dh;
+                    const int ix = ox * a.sw - a.pl + (tap % a.kw) * a.dw;
+                    if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+                        x = a.in_nchw
+                                ? in[((static_cast<long long>(b) * a.c_total + a.c_off + ci) * a.h + iy) *
+                                         a.w + ix]
+                                : in[((static_cast<long long>(b) * a.h + iy) * a.w + ix) * a.cp_in +
+                                     a.c_off + ci];
+                    }
+                }
+                v[j] = x;
+            }
+        }
+        *reinterpret_cast<uint4 *>(col + m * a.ldk + k0) = *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+static int grid_for(long long total, int block)
+{
+    long long g = (total + block - 1) / block;
+    const long long cap = static_cast<long long>(sm_count()) * 16;
+    return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_nchw_to_nhwc(const void *src, void *dst, int n, int c, int h, int w, int cp,
+                                 int elem_bytes, int pad, void *stream)
+{
+    if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || cp < c ||
+        (elem_bytes != 1 && elem_bytes != 2) || (cp * elem_bytes) % 16) {
+        set_error("b200_nchw_to_nhwc: bad arguments (n=%d c=%d h=%d w=%d cp=%d elem=%d)", n, c, h, w,
+                  cp, elem_bytes);
+        return B200_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(n) * h * w * (cp * elem_bytes / 16);
+    const int grid = grid_for(total, 256);
+    if (elem_bytes == 1)
+        nchw_to_nhwc_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const int8_t *>(src), static_cast<int8_t *>(dst), n, c, h * w, cp,
+            static_cast<int8_t>(pad));
+    else
+        nchw_to_nhwc_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), n, c, h * w, cp,
+            static_cast<uint16_t>(pad));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_nhwc_to_nchw(const void *src, void *dst, int n, int c, int h, int w, int cp,
+                                 int elem_bytes, void *stream)
+{
+    if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || cp < c ||
+        (elem_bytes != 1 && elem_bytes != 2) || (cp * elem_bytes) % 16) {
+        set_error("b200_nhwc_to_nchw: bad arguments (n=%d c=%d h=%d w=%d cp=%d elem=%d)", n, c, h, w,
+                  cp, elem_bytes);
+        return B200_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(n) * h * w * (cp * elem_bytes / 16);
+    const int grid = grid_for(total, 256);
+    if (elem_bytes == 1)
+        nhwc_to_nchw_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const int8_t *>(src), static_cast<int8_t *>(dst), n, c, h * w, cp);
+    else
+        nhwc_to_nchw_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), n, c, h * w, cp);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_im2col(const b200_im2col_desc *d, void *stream)
+{
+    if (!d || !d->in || !d->col) {
+        set_error("b200_im2col: null descriptor field");
+        return B200_ERR_ARG;
+    }
+    const int eb = d->dtype == B200_I8 ? 1 : 2;
+    if ((d->dtype != B200_I8 && d->dtype != B200_F16) || d->n <= 0 || d->cg <= 0 || d->kh <= 0 ||
+        d->kw <= 0 || d->oh <= 0 || d->ow <= 0 || d->stride_h <= 0 || d->stride_w <= 0 ||
+        d->dil_h <= 0 || d->dil_w <= 0 || (d->ldk * eb) % 16 || d->ldk < d->kh * d->kw * d->cg ||
+        (!d->in_nchw && (d->cp_in * eb) % 16)) {
+        set_error("b200_im2col: bad descriptor (cg=%d k=%dx%d ldk=%d cp_in=%d)", d->cg, d->kh, d->kw,
+                  d->ldk, d->cp_in);
+        return B200_ERR_ARG;
+    }
+    Im2colArgs a;
+    a.n = d->n, a.h = d->h, a.w = d->w, a.cp_in = d->cp_in, a.in_nchw = d->in_nchw;
+    a.c_total = d->c_total, a.c_off = d->c_off, a.cg = d->cg;
+    a.oh = d->oh, a.ow = d->ow, a.kh = d->kh, a.kw = d->kw;
+    a.sh = d->stride_h, a.sw = d->stride_w, a.pt = d->pad_top, a.pl = d->pad_left;
+    a.dh = d->dil_h, a.dw = d->dil_w, a.ldk = d->ldk, a.in = d->in, a.col = d->col;
+    const long long total = static_cast<long long>(d->n) * d->oh * d->ow * (d->ldk * eb / 16);
+    const int grid = grid_for(total, 256);
+    if (eb == 1)
+        im2col_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(a, static_cast<int8_t>(d->pad_value));
+    else
+        im2col_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(a, static_cast<uint16_t>(0));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -1,0 +1,164 @@
+// pool.cu -- maxpool / avgpool / global avgpool on pixel-major tensors.
+// One thread owns 16 bytes of channels of one output pixel and walks the window in (y, x)
+// order with one f32 accumulator per channel, which is exactly the reference's sequence
+// (source/reference/averagepool.c:71-121, maxpool.c:64-105, global_averagepool.c:21 through
+// siso_callback_base utils.c:609: dequantise -> f32 op -> requantise), so int8 results are
+// bit-exact.  Adjacent threads own adjacent channel chunks: every load is a coalesced
+// 128-bit vector.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+struct PoolArgs {
+    int n, c, cp, h, w, oh, ow, kh, kw, sh, sw, pt, pl;
+    int is_avg, count_include_pad;
+    float s_in, s_out;
+    int zp_in, zp_out;
+    const void *in;
+    void *out;
+};
+
+__global__ void __launch_bounds__(128) pool_i8_kernel(const PoolArgs a)
+{
+    const int chunks = a.cp / 16;
+    const long long total = static_cast<long long>(a.n) * a.oh * a.ow * chunks;
+    const int8_t *in = static_cast<const int8_t *>(a.in);
+    int8_t *out = static_cast<int8_t *>(a.out);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % chunks);
+        const int ox = static_cast<int>((i / chunks) % a.ow);
+        const int oy = static_cast<int>((i / (static_cast<long long>(chunks) * a.ow)) % a.oh);
+        const int b = static_cast<int>(i / (static_cast<long long>(chunks) * a.ow * a.oh));
+        const int x0 = ox * a.sw - a.pl, y0 = oy * a.sh - a.pt;
+        const int fx0 = max(0, -x0), fx1 = min(a.kw, a.w - x0);
+        const int fy0 = max(0, -y0), fy1 = min(a.kh, a.h - y0);
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = a.is_avg ? 0.f : -FLT_MAX;
+        float cnt = 0.f;
+        for (int fy = fy0; fy < fy1; fy++) {
+            for (int fx = fx0; fx < fx1; fx++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(
+                    in + ((static_cast<long long>(b) * a.h + y0 + fy) * a.w + x0 + fx) * a.cp +
+                    ch * 16));
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float f =
+                            dequant_i8(static_cast<int8_t>(wv[q] >> (8 * e)), a.s_in, a.zp_in);
+                        float &t = acc[q * 4 + e];
+                        t = a.is_avg ? __fadd_rn(t, f) : fmaxf(t, f);
+                    }
+                cnt += 1.f;
+            }
+        }
+        if (a.count_include_pad) cnt = static_cast<float>(a.kh * a.kw);
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int j = q * 4 + e;
+                const float r = a.is_avg ? __fdiv_rn(acc[j], cnt) : acc[j];
+                v[e] = ch * 16 + j < a.c ? quant_i8_exact(r, a.s_out, a.zp_out) : 0;
+            }
+            pk[q] = pack4_i8(v[0], v[1], v[2], v[3]);
+        }
+        *reinterpret_cast<uint4 *>(
+            out + ((static_cast<long long>(b) * a.oh + oy) * a.ow + ox) * a.cp + ch * 16) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+__global__ void __launch_bounds__(128) pool_f16_kernel(const PoolArgs a)
+{
+    const int chunks = a.cp / 8;
+    const long long total = static_cast<long long>(a.n) * a.oh * a.ow * chunks;
+    const __half *in = static_cast<const __half *>(a.in);
+    __half *out = static_cast<__half *>(a.out);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % chunks);
+        const int ox = static_cast<int>((i / chunks) % a.ow);
+        const int oy = static_cast<int>((i / (static_cast<long long>(chunks) * a.ow)) % a.oh);
+        const int b = static_cast<int>(i / (static_cast<long long>(chunks) * a.ow * a.oh));
+        const int x0 = ox * a.sw - a.pl, y0 = oy * a.sh - a.pt;
+        const int fx0 = max(0, -x0), fx1 = min(a.kw, a.w - x0);
+        const int fy0 = max(0, -y0), fy1 = min(a.kh, a.h - y0);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = a.is_avg ? 0.f : -FLT_MAX;
+        float cnt = 0.f;
+        for (int fy = fy0; fy < fy1; fy++) {
+            for (int fx = fx0; fx < fx1; fx++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(
+                    in + ((static_cast<long long>(b) * a.h + y0 + fy) * a.w + x0 + fx) * a.cp +
+                    ch * 8));
+                const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float2 f = __half22float2(h[q]);
+                    acc[q * 2] = a.is_avg ? acc[q * 2] + f.x : fmaxf(acc[q * 2], f.x);
+                    acc[q * 2 + 1] = a.is_avg ? acc[q * 2 + 1] + f.y : fmaxf(acc[q * 2 + 1], f.y);
+                }
+                cnt += 1.f;
+            }
+        }
+        if (a.count_include_pad) cnt = static_cast<float>(a.kh * a.kw);
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float f0 = a.is_avg ? acc[q * 2] / cnt : acc[q * 2];
+            float f1 = a.is_avg ? acc[q * 2 + 1] / cnt : acc[q * 2 + 1];
+            f0 = ch * 8 + q * 2 < a.c ? f0 : 0.f;
+            f1 = ch * 8 + q * 2 + 1 < a.c ? f1 : 0.f;
+            __half2 hv = __floats2half2_rn(f0, f1);
+            pk[q] = *reinterpret_cast<uint32_t *>(&hv);
+        }
+        *reinterpret_cast<uint4 *>(
+            out + ((static_cast<long long>(b) * a.oh + oy) * a.ow + ox) * a.cp + ch * 8) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_pool2d(const b200_pool_desc *d, void *stream)
+{
+    if (!d || !d->in || !d->out) {
+        set_error("b200_pool2d: null descriptor field");
+        return B200_ERR_ARG;
+    }
+    const int eb = d->dtype == B200_I8 ? 1 : 2;
+    if ((d->dtype != B200_I8 && d->dtype != B200_F16) || d->n <= 0 || d->c <= 0 || d->cp < d->c ||
+        (d->cp * eb) % 16 || d->kh <= 0 || d->kw <= 0 || d->stride_h <= 0 || d->stride_w <= 0 ||
+        d->oh <= 0 || d->ow <= 0) {
+        set_error("b200_pool2d: bad descriptor (c=%d cp=%d k=%dx%d)", d->c, d->cp, d->kh, d->kw);
+        return B200_ERR_ARG;
+    }
+    PoolArgs a;
+    a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
+    a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;
+    a.pt = d->pad_top, a.pl = d->pad_left;
+    a.is_avg = d->is_avg, a.count_include_pad = d->count_include_pad;
+    a.s_in = d->s_in, a.s_out = d->s_out, a.zp_in = d->zp_in, a.zp_out = d->zp_out;
+    a.in = d->in, a.out = d->out;
+    const long long total = static_cast<long long>(d->n) * d->oh * d->ow * (d->cp * eb / 16);
+    long long g = (total + 127) / 128;
+    const long long cap = static_cast<long long>(sm_count()) * 32;
+    const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+    if (d->dtype == B200_I8)
+        pool_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else
+        pool_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

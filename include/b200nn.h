@@ -1,0 +1,228 @@
+/*
+ * b200nn.h -- C-ABI of the B200 (sm_100a) operator shim behind the CSI-NN2 API.
+ *
+ * This is the device-side half of the drop-in boundary for the hot path named in
+ * BASELINE.json: csinn_conv2d (im2col + GEMM), csinn_depthwise_conv2d,
+ * csinn_fullyconnected and the bandwidth-bound ops around them.  Everything is
+ * `extern "C"`, plain pointers and sizes: no csinn_* type and no torch type
+ * crosses this line.  The C host side (csi-nn2_b200/b200_opt/ -- the code that
+ * registers in the reference's backend registry, see include/shl_b200.h) is the
+ * only caller in the product; tests call the same symbols through ctypes.
+ *
+ * Each entry point cites the reference interface it stands in for
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - Device activations are "pixel-major": [N][H][W][Cp] with Cp = channel
+ *     stride in elements, Cp*elem a multiple of 16 bytes (b200_round_channels()).
+ *     The API-side NCHW tensors of the reference
+ *     (include/csinn/csinn_data_structure.h:505) are converted at the boundary by
+ *     b200_nchw_to_nhwc / b200_nhwc_to_nchw.
+ *   - dtype: B200_I8 (CSINN_DTYPE_INT8) or B200_F16 (CSINN_DTYPE_FLOAT16).
+ *   - All functions return 0 on success, a negative b200_status otherwise, and
+ *     never fall back to the CPU.  b200_last_error() gives the message.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Launches are asynchronous on `stream`; descriptors are copied at launch.
+ *
+ * Quantised epilogue (the one arithmetic contract; oracle/oracle_int.c restates it):
+ *     acc  = sum_k x~[k] * w[o][k]                        (int32, exact; x~ = zp_in at pads)
+ *     acc += ibias[o]                                     (int32: -zp_in * sum_k w[o][k])
+ *     f    = fmaf((float)acc, mult[o], badd[o])           (one rounding)
+ *     q    = clamp((int)rintf(f) + zp_out, -128, 127)     (round-half-even, like nearbyint in
+ *                                                          source/nn2/utils.c:550 float_to_int8_base)
+ *     act  : B200_ACT_RELU  -> q = max(q, zp_out);  B200_ACT_RELU6 -> also min(q, q6)
+ *     post : optional 256-entry table applied last, q = post_lut[q + 128].  It holds a
+ *            standalone relu / relu6 node with its own qinfo evaluated exactly as
+ *            source/reference/relu.c:39 does through utils.c:609 siso_callback_base:
+ *              r = ((float)q - zp_in) * s_in ; r = act(r) ; q' = clamp(nearbyint(r / s_out) + zp_out)
+ *            (b200_build_requant_lut builds it on the host).
+ *   fp16:  f = acc_f32 + badd[o] ; act(f) ; __float2half_rn.
+ */
+#ifndef B200NN_H_
+#define B200NN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NN_ABI_VERSION 2
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_CUDA = -1,        /* a CUDA runtime/driver call failed */
+    B200_ERR_UNSUPPORTED = -2, /* shape / dtype outside what the kernels cover */
+    B200_ERR_ARG = -3,         /* malformed descriptor */
+    B200_ERR_NO_DEVICE = -4,   /* no sm_100 device visible: there is NO cpu fallback */
+} b200_status;
+
+typedef enum { B200_I8 = 0, B200_F16 = 1 } b200_dtype;
+typedef enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_RELU6 = 2 } b200_act;
+
+/* Requantisation / epilogue parameters shared by conv, depthwise, fc.
+ * For B200_F16 only `badd` (bias as float, may be NULL) and `act` are used. */
+typedef struct {
+    const float *mult;      /* device [O]  s_in*s_w[o]/s_out                          */
+    const float *badd;      /* device [O]  bias_q[o]*s_bias[o]/s_out (f16: bias)      */
+    const int32_t *ibias;   /* device [O]  integer addend (zero-point fold), or NULL  */
+    const int8_t *post_lut; /* device [256] or NULL                                   */
+    int32_t zp_out;
+    int32_t act; /* b200_act */
+    int32_t q6;  /* quantised value of 6.0 in the output domain (RELU6)                */
+} b200_epilogue;
+
+/* ---- device / memory plumbing ------------------------------------------------ */
+int b200_abi_version(void);
+const char *b200_last_error(void);
+int b200_device_count(void);
+int b200_set_device(int dev);
+int b200_sm_count(void);
+int b200_malloc(void **dptr, size_t bytes);
+int b200_free(void *dptr);
+int b200_malloc_host(void **hptr, size_t bytes); /* pinned */
+int b200_free_host(void *hptr);
+int b200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int b200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int b200_memset(void *dst, int value, size_t bytes, void *stream);
+int b200_stream_create(void **stream);
+int b200_stream_destroy(void *stream);
+int b200_stream_sync(void *stream);
+int b200_device_sync(void);
+/* CUDA events on `stream` (bench.py times kernels on the launching stream) */
+int b200_event_create(void **ev);
+int b200_event_destroy(void *ev);
+int b200_event_record(void *ev, void *stream);
+int b200_event_sync(void *ev);
+int b200_event_elapsed_ms(void *start, void *stop, float *ms);
+/* make `stream` wait for an event recorded on another stream (copy/compute overlap) */
+int b200_stream_wait_event(void *stream, void *ev);
+/* CUDA-graph capture of a launch sequence (graph-mode session_run) */
+int b200_graph_begin(void *stream);
+int b200_graph_end(void *stream, void **graph_exec);
+int b200_graph_launch(void *graph_exec, void *stream);
+int b200_graph_destroy(void *graph_exec);
+/* number of kernels this library has launched since load (bench.py "gpu_launches");
+ * launches replayed through a CUDA graph are counted per replay */
+uint64_t b200_launch_count(void);
+/* evict L2: overwrite an internal >L2-sized scratch buffer (bench.py timing hygiene) */
+int b200_flush_l2(void *stream);
+
+static inline int b200_round_channels(int c, int elem_bytes)
+{
+    int per16 = 16 / elem_bytes;
+    return (c + per16 - 1) / per16 * per16;
+}
+
+/* host helper: the 256-entry requantisation table described above (index = q + 128) */
+void b200_build_requant_lut(int8_t lut[256], int act, float s_in, int zp_in, float s_out,
+                            int zp_out);
+
+/* ---- layout conversion at the API boundary ----------------------------------- */
+/* NCHW [N][C][H][W] -> pixel-major [N][H][W][Cp]; pad channels are written as `pad`.
+ * Stands in for the NCHW<->NC1HWC0 reorders of the RVV back end
+ * (source/thead_rvv/data_convert.c, source/c920_opt/setup.c:316-352). */
+int b200_nchw_to_nhwc(const void *src, void *dst, int n, int c, int h, int w, int cp,
+                      int elem_bytes, int pad, void *stream);
+int b200_nhwc_to_nchw(const void *src, void *dst, int n, int c, int h, int w, int cp,
+                      int elem_bytes, void *stream);
+
+/* ---- GEMM on tcgen05: 1x1 conv2d, fullyconnected, and the GEMM half of im2col conv */
+/* out[m][o] = epilogue( sum_k a[m][k] * w[o][k] ),  m = pixel (N*H*W) or fc batch row.
+ * Replaces shl_rvv_conv1x1s1_gemm_int8 (source/thead_rvv/int8/convolution_1x1_int8.c:56),
+ * shl_rvv_gemm_4x16_int8 under shl_rvv_conv_im2col_gemm_int8
+ * (source/thead_rvv/int8/convolution_gemm_int8.c:173, gemm_int8.c:37),
+ * shl_rvv_fullyconnected_int8 (source/thead_rvv/int8/fullyconnected_int8.c:94) and their
+ * fp16 twins; semantics follow shl_ref_conv2d_quant (source/reference/convolution.c:370)
+ * and shl_ref_fullyconnected_quant (source/reference/fullyconnected.c:54). */
+typedef struct {
+    int32_t dtype;   /* B200_I8 | B200_F16 */
+    int32_t m, n, k; /* logical sizes: rows, output channels, reduction length      */
+    const void *a;   /* device [m][lda]                                             */
+    int32_t lda;     /* elements, lda*elem % 16 == 0                                */
+    const void *w;   /* device [n][ldw]   (OIHW with H=W=1, or fc weight [O][I])    */
+    int32_t ldw;     /* elements, ldw*elem % 16 == 0                                */
+    void *out;       /* device [m][ldo]; columns [n, ldo) are written as zero       */
+    int32_t ldo;     /* elements, ldo*elem % 16 == 0, ldo >= n                      */
+    b200_epilogue ep;
+} b200_gemm_desc;
+int b200_gemm(const b200_gemm_desc *d, void *stream);
+
+/* ---- im2col (the other half of "im2col + GEMM conv2d") ------------------------- */
+/* col[m][k], m = (b, oy, ox), k = (ky, kx, ci) with ci fastest, row pitch ldk elements;
+ * padded taps and k >= kh*kw*cg are written as `pad_value` (= zp_in for int8) / 0.
+ * in_nchw != 0: `in` is the API-side NCHW tensor (a network's first layer reads it
+ * directly); otherwise pixel-major with channel stride cp_in.  `c_off` selects the
+ * first channel of a group.  Replaces the im2col loop of
+ * shl_rvv_conv_im2col_gemm_int8 (convolution_gemm_int8.c:106-134) and
+ * conv_im2col_sgemm_avx's (source/reference/conv_avx.h:109). */
+typedef struct {
+    int32_t dtype;
+    int32_t n, h, w, cp_in, in_nchw, c_total; /* c_total: channels of `in` (NCHW indexing) */
+    int32_t c_off, cg;                         /* channel window gathered                  */
+    int32_t oh, ow, kh, kw, stride_h, stride_w, pad_top, pad_left, dil_h, dil_w;
+    int32_t ldk;
+    int32_t pad_value;
+    const void *in;
+    void *col;
+} b200_im2col_desc;
+int b200_im2col(const b200_im2col_desc *d, void *stream);
+
+/* ---- depthwise conv2d (HBM-bound stencil) ------------------------------------ */
+/* Replaces shl_rvv_dwconv3x3s1_int8 / s2 (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31 )
+ * and the fp16 twins; semantics: shl_ref_depthwise_conv2d_quant (source/reference/convolution.c:416).
+ * Weights are tap-major [kh][kw][cp] (packed once at init from O1HW). depth_multiplier == 1. */
+typedef struct {
+    int32_t dtype;
+    int32_t n, c, cp; /* batch, channels, channel stride (elements)          */
+    int32_t h, w, oh, ow;
+    int32_t kh, kw, stride_h, stride_w, pad_top, pad_left, dil_h, dil_w;
+    const void *in;  /* device [n][h][w][cp]                                */
+    const void *wt;  /* device [kh][kw][cp]  int8 | f16                     */
+    void *out;       /* device [n][oh][ow][cp]                              */
+    int32_t zp_in;   /* int8: value of a padded tap                         */
+    b200_epilogue ep;
+} b200_dwconv_desc;
+int b200_dwconv2d(const b200_dwconv_desc *d, void *stream);
+
+/* ---- bandwidth-bound ops ------------------------------------------------------ */
+/* q' = lut[q + 128] over `count` bytes: relu / relu6 / requantising identity with per-tensor
+ * qinfo (source/reference/relu.c:39, relu6.c:42); count % 16 == 0 on pixel-major tensors. */
+int b200_lut_i8(const void *in, void *out, size_t count, const int8_t *lut_dev, void *stream);
+/* fp16 relu / relu6 */
+int b200_relu_f16(const void *in, void *out, size_t count, int act, void *stream);
+/* elementwise add, same shapes, per-tensor qinfo (source/reference/add.c:36 through
+ * diso_callback_base utils.c:622): r = (qa-zpa)*sa + (qb-zpb)*sb ; q = quant(r) ; optional
+ * fused relu expressed as a post table (as in b200_epilogue). */
+int b200_add(int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
+             float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
+             void *stream);
+
+/* maxpool / avgpool on pixel-major tensors; reference: source/reference/maxpool.c:64,
+ * averagepool.c:71 (sequential f32 sum in (y,x) order, divided by the valid-tap count unless
+ * count_include_pad). global average pool = kh=h, kw=w (global_averagepool.c:21). */
+typedef struct {
+    int32_t dtype;
+    int32_t n, c, cp, h, w, oh, ow;
+    int32_t kh, kw, stride_h, stride_w, pad_top, pad_left;
+    int32_t is_avg, count_include_pad;
+    float s_in;
+    int32_t zp_in;
+    float s_out;
+    int32_t zp_out;
+    const void *in;
+    void *out;
+} b200_pool_desc;
+int b200_pool2d(const b200_pool_desc *d, void *stream);
+
+/* softmax over the channel axis of [rows][cp] (axis=1 of an NCHW tensor with H=W=1);
+ * source/reference/softmax.c:20-66 (double exp, f32 accumulate in channel order). */
+int b200_softmax(int dtype, const void *in, void *out, int rows, int c, int cp_in, int cp_out,
+                 float s_in, int zp_in, float s_out, int zp_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NN_H_ */

@@ -1,0 +1,348 @@
+"""ctypes front end used by tests, bench.py and __graft_entry__.smoke().
+
+Two things live here, and they are kept apart on purpose:
+
+* ``Harness`` drives the CSI-NN2 public API (csinn_*_init / csinn_* / csinn_session_*) through
+  tests/harness/csinn_harness.c, against either the product (``Harness("b200")`` ->
+  csi-nn2_b200/lib/libshl_b200.so) or the unmodified reference built from its own sources
+  (``Harness("ref")`` / ``Harness("ref_noavx")`` -> oracle/_ref/libshl_ref_x86*.so).
+* ``Oracle`` is the plain-C restatement oracle/liboracle_int.so (TEST INFRASTRUCTURE: the checker,
+  never the thing measured or shipped).
+
+Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# enum values of include/csinn/csinn_data_structure.h:37-51, 94-115, 118-121
+DT_INT8, DT_INT32, DT_F16, DT_F32 = 3, 7, 8, 10
+API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
+RM_LAYER, RM_GRAPH = 0, 1
+
+(H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE) = range(14)
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+
+
+class HLayer(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("in0", C.c_int32), ("in1", C.c_int32),
+        ("out_dims", C.c_int32 * 4), ("out_rank", C.c_int32),
+        ("s_out", C.c_float), ("zp_out", C.c_int32),
+        ("o", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("pt", C.c_int32), ("pl", C.c_int32), ("pd", C.c_int32), ("pr", C.c_int32),
+        ("dh", C.c_int32), ("dw", C.c_int32), ("group", C.c_int32), ("fuse_zp2bias", C.c_int32),
+        ("w", C.c_void_p), ("b", C.c_void_p), ("s_w", C.c_void_p), ("zp_w", C.c_void_p),
+        ("w_channels", C.c_int32), ("s_b", C.c_void_p),
+        ("count_include_pad", C.c_int32), ("ceil_mode", C.c_int32), ("axis", C.c_int32),
+    ]
+
+
+@dataclass
+class Layer:
+    """One operator of a network, in API terms (NCHW shapes, OIHW weights)."""
+    kind: int
+    out_shape: Sequence[int]
+    in0: int = -1            # tensor id (0 = network input, i+1 = output of layer i); -1 = previous
+    in1: int = -1
+    s_out: float = 1.0
+    zp_out: int = 0
+    w: Optional[np.ndarray] = None       # int8 / float16 / float32, OIHW | O1HW | OI
+    b: Optional[np.ndarray] = None       # int32 / float16 / float32
+    s_w: Optional[np.ndarray] = None     # float32 [O] or [1]
+    zp_w: Optional[np.ndarray] = None
+    s_b: Optional[np.ndarray] = None
+    stride: Sequence[int] = (1, 1)
+    pad: Sequence[int] = (0, 0, 0, 0)    # top, left, down, right
+    dilation: Sequence[int] = (1, 1)
+    group: int = 1
+    fuse_zp2bias: int = 0
+    kernel: Sequence[int] = (1, 1)       # pooling window
+    count_include_pad: int = 0
+    ceil_mode: int = 0
+    axis: int = 1
+    _keep: list = field(default_factory=list, repr=False)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _np_dtype(dt: int):
+    return {DT_INT8: np.int8, DT_F16: np.float16, DT_F32: np.float32}[dt]
+
+
+_LIBS = {
+    "b200": os.path.join(ROOT, "tests", "harness", "lib", "libharness_b200.so"),
+    "ref": os.path.join(ROOT, "tests", "harness", "lib", "libharness_ref.so"),
+    "ref_noavx": os.path.join(ROOT, "tests", "harness", "lib", "libharness_ref_noavx.so"),
+}
+
+
+class Harness:
+    """The CSI-NN2 API as a user calls it, bound to one library build."""
+
+    def __init__(self, which: str):
+        path = _LIBS[which]
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: run __graft_entry__.build() in the build container")
+        self.which = which
+        self.lib = C.CDLL(path, mode=os.RTLD_LOCAL if hasattr(os, "RTLD_LOCAL") else 0)
+        L = self.lib
+        L.h_net_create.restype = C.c_void_p
+        L.h_net_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_float,
+                                   C.c_int, C.POINTER(HLayer), C.c_int]
+        L.h_net_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.h_net_output_bytes.restype = C.c_longlong
+        L.h_net_output_bytes.argtypes = [C.c_void_p]
+        L.h_net_destroy.argtypes = [C.c_void_p]
+        L.h_net_session.restype = C.c_void_p
+        L.h_net_session.argtypes = [C.c_void_p]
+        L.h_net_update_input.argtypes = [C.c_void_p, C.c_void_p]
+        L.h_net_session_run.argtypes = [C.c_void_p]
+        L.h_net_get_output.restype = C.c_void_p
+        L.h_net_get_output.argtypes = [C.c_void_p]
+        L.h_last_error.restype = C.c_char_p
+        assert L.h_layer_sizeof() == C.sizeof(HLayer), "h_layer layout mismatch"
+        self.default_api = API_RVV if which == "b200" else API_REF
+
+    def error(self) -> str:
+        msg = self.lib.h_last_error().decode()
+        if self.which == "b200":
+            try:
+                shl = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libshl_b200.so"))
+                shl.shl_b200_last_error.restype = C.c_char_p
+                msg += " | " + shl.shl_b200_last_error().decode()
+            except OSError:
+                pass
+        return msg
+
+    def create(self, dtype: int, in_shape: Sequence[int], layers: Sequence[Layer], *, s_in=1.0, zp_in=0,
+               run_mode=RM_LAYER, api: Optional[int] = None) -> "Net":
+        return Net(self, dtype, in_shape, layers, s_in, zp_in, run_mode, self.default_api if api is None else api)
+
+    def run(self, dtype, in_shape, layers, x, **kw) -> np.ndarray:
+        net = self.create(dtype, in_shape, layers, **kw)
+        try:
+            return net(x)
+        finally:
+            net.close()
+
+
+class Net:
+    def __init__(self, h: Harness, dtype, in_shape, layers, s_in, zp_in, run_mode, api):
+        self.h, self.dtype, self.in_shape = h, dtype, tuple(int(d) for d in in_shape)
+        self.layers = list(layers)
+        n = len(self.layers)
+        arr = (HLayer * n)()
+        self._keep = []
+        for i, l in enumerate(self.layers):
+            a = arr[i]
+            a.kind = l.kind
+            a.in0 = i if l.in0 < 0 else l.in0
+            a.in1 = max(l.in1, 0)
+            a.out_rank = len(l.out_shape)
+            for j, d in enumerate(l.out_shape):
+                a.out_dims[j] = int(d)
+            a.s_out, a.zp_out = float(l.s_out), int(l.zp_out)
+            if l.w is not None:
+                w = np.ascontiguousarray(l.w)
+                a.o = w.shape[0]
+                if w.ndim == 4:
+                    a.kh, a.kw = w.shape[2], w.shape[3]
+                s_w = np.ascontiguousarray(l.s_w if l.s_w is not None else np.ones(1), dtype=np.float32)
+                zp_w = np.ascontiguousarray(l.zp_w if l.zp_w is not None else np.zeros(s_w.size), dtype=np.int32)
+                b = None if l.b is None else np.ascontiguousarray(l.b)
+                s_b = None if l.s_b is None else np.ascontiguousarray(l.s_b, dtype=np.float32)
+                self._keep += [w, s_w, zp_w, b, s_b]
+                a.w, a.b, a.s_w, a.zp_w, a.s_b = _ptr(w), _ptr(b), _ptr(s_w), _ptr(zp_w), _ptr(s_b)
+                a.w_channels = s_w.size
+            else:
+                a.kh, a.kw = int(l.kernel[0]), int(l.kernel[1])
+            a.sh, a.sw = int(l.stride[0]), int(l.stride[1])
+            a.pt, a.pl, a.pd, a.pr = (int(p) for p in l.pad)
+            a.dh, a.dw = int(l.dilation[0]), int(l.dilation[1])
+            a.group, a.fuse_zp2bias = int(l.group), int(l.fuse_zp2bias)
+            a.count_include_pad, a.ceil_mode, a.axis = int(l.count_include_pad), int(l.ceil_mode), int(l.axis)
+        dims = (C.c_int32 * len(self.in_shape))(*self.in_shape)
+        self._arr = arr
+        self.handle = h.lib.h_net_create(api, dtype, run_mode, dims, len(self.in_shape), float(s_in), int(zp_in),
+                                         arr, n)
+        if not self.handle:
+            raise RuntimeError(f"[{h.which}] network creation failed: {h.error()}")
+        self.out_shape = tuple(int(d) for d in self.layers[-1].out_shape)
+
+    @property
+    def session(self) -> int:
+        return self.h.lib.h_net_session(self.handle)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=_np_dtype(self.dtype))
+        assert x.shape == self.in_shape, (x.shape, self.in_shape)
+        out = np.empty(self.out_shape, dtype=_np_dtype(self.dtype))
+        assert out.nbytes == self.h.lib.h_net_output_bytes(self.handle)
+        rc = self.h.lib.h_net_run(self.handle, _ptr(x), _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"[{self.h.which}] run failed: {self.h.error()}")
+        return out
+
+    def close(self):
+        if self.handle:
+            self.h.lib.h_net_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle (TEST INFRASTRUCTURE ONLY)
+# ------------------------------------------------------------------------------------------------
+class OConv(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("o", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("stride_h", C.c_int32), ("stride_w", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32),
+        ("dil_h", C.c_int32), ("dil_w", C.c_int32), ("group", C.c_int32),
+        ("s_in", C.c_float), ("zp_in", C.c_int32), ("s_w", C.c_void_p), ("w_channels", C.c_int32),
+        ("s_b", C.c_void_p), ("s_out", C.c_float), ("zp_out", C.c_int32), ("fuse_zp2bias", C.c_int32),
+        ("act", C.c_int32), ("post", C.c_int32), ("post_act", C.c_int32), ("post_s_out", C.c_float),
+        ("post_zp_out", C.c_int32),
+    ]
+
+
+class OPool(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n", "c", "h", "w", "oh", "ow", "kh", "kw", "stride_h", "stride_w",
+                                         "pad_top", "pad_left", "count_include_pad")] + \
+               [("s_in", C.c_float), ("zp_in", C.c_int32), ("s_out", C.c_float), ("zp_out", C.c_int32)]
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "liboracle_int.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: run __graft_entry__.build()")
+        self.lib = C.CDLL(path)
+
+    def _conv_params(self, x_shape, w, out_shape, *, stride, pad, dilation, group, s_in, zp_in, s_w, s_b, s_out,
+                     zp_out, fuse_zp2bias=0, act=ACT_NONE, post=None):
+        p = OConv()
+        if len(x_shape) == 4:
+            p.n, p.c, p.h, p.w = x_shape
+        else:
+            p.n, p.c, p.h, p.w = x_shape[0], x_shape[1], 1, 1
+        p.o = w.shape[0]
+        p.kh, p.kw = (w.shape[2], w.shape[3]) if w.ndim == 4 else (1, 1)
+        p.oh, p.ow = (out_shape[2], out_shape[3]) if len(out_shape) == 4 else (1, 1)
+        p.stride_h, p.stride_w = stride
+        p.pad_top, p.pad_left = pad[0], pad[1]
+        p.dil_h, p.dil_w = dilation
+        p.group = group
+        p.s_in, p.zp_in = s_in, zp_in
+        self._sw = np.ascontiguousarray(s_w if s_w is not None else np.ones(1), dtype=np.float32)
+        p.s_w, p.w_channels = _ptr(self._sw), self._sw.size
+        self._sb = None if s_b is None else np.ascontiguousarray(s_b, dtype=np.float32)
+        p.s_b = _ptr(self._sb)
+        p.s_out, p.zp_out, p.fuse_zp2bias, p.act = s_out, zp_out, fuse_zp2bias, act
+        if post is not None:
+            p.post, p.post_act, p.post_s_out, p.post_zp_out = 1, post[0], post[1], post[2]
+        return p
+
+    def conv2d_i8(self, x, w, b, out_shape, *, depthwise=False, **kw):
+        p = self._conv_params(x.shape, w, out_shape, **kw)
+        x, w = np.ascontiguousarray(x, np.int8), np.ascontiguousarray(w, np.int8)
+        b = None if b is None else np.ascontiguousarray(b, np.int32)
+        out = np.empty(out_shape, np.int8)
+        fn = self.lib.oracle_dwconv2d_i8 if depthwise else self.lib.oracle_conv2d_i8
+        rc = fn(C.byref(p), _ptr(x), _ptr(w), _ptr(b), _ptr(out))
+        if rc != 0:
+            raise RuntimeError("oracle: requant bound check failed")
+        return out
+
+    def fc_i8(self, x, w, b, **kw):
+        out_shape = (x.shape[0], w.shape[0])
+        kw.setdefault("stride", (1, 1)), kw.setdefault("pad", (0, 0, 0, 0)), kw.setdefault("dilation", (1, 1))
+        kw.setdefault("group", 1)
+        p = self._conv_params((x.shape[0], x.shape[1]), w, out_shape, **kw)
+        x, w = np.ascontiguousarray(x, np.int8), np.ascontiguousarray(w, np.int8)
+        b = None if b is None else np.ascontiguousarray(b, np.int32)
+        out = np.empty(out_shape, np.int8)
+        if self.lib.oracle_fc_i8(C.byref(p), _ptr(x), _ptr(w), _ptr(b), _ptr(out)) != 0:
+            raise RuntimeError("oracle: requant bound check failed")
+        return out
+
+    def conv2d_f32(self, x, w, b, out_shape, *, depthwise=False, fc=False, stride=(1, 1), pad=(0, 0, 0, 0),
+                   dilation=(1, 1), group=1, act=ACT_NONE):
+        p = self._conv_params(x.shape, w, out_shape, stride=stride, pad=pad, dilation=dilation, group=group,
+                              s_in=1.0, zp_in=0, s_w=None, s_b=None, s_out=1.0, zp_out=0, act=act)
+        x, w = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(w, np.float32)
+        b = None if b is None else np.ascontiguousarray(b, np.float32)
+        out = np.empty(out_shape, np.float32)
+        fn = self.lib.oracle_fc_f32 if fc else (self.lib.oracle_dwconv2d_f32 if depthwise else self.lib.oracle_conv2d_f32)
+        fn(C.byref(p), _ptr(x), _ptr(w), _ptr(b), _ptr(out))
+        return out
+
+    def relu_i8(self, x, act, s_in, zp_in, s_out, zp_out):
+        x = np.ascontiguousarray(x, np.int8)
+        out = np.empty_like(x)
+        self.lib.oracle_relu_i8(_ptr(x), _ptr(out), C.c_int64(x.size), act, C.c_float(s_in), zp_in,
+                                C.c_float(s_out), zp_out)
+        return out
+
+    def add_i8(self, a, b, s_a, zp_a, s_b, zp_b, s_out, zp_out):
+        a, b = np.ascontiguousarray(a, np.int8), np.ascontiguousarray(b, np.int8)
+        out = np.empty_like(a)
+        self.lib.oracle_add_i8(_ptr(a), _ptr(b), _ptr(out), C.c_int64(a.size), C.c_float(s_a), zp_a,
+                               C.c_float(s_b), zp_b, C.c_float(s_out), zp_out)
+        return out
+
+    def pool_i8(self, x, out_shape, *, avg, kernel, stride, pad, count_include_pad, s_in, zp_in, s_out, zp_out):
+        p = OPool()
+        p.n, p.c, p.h, p.w = x.shape
+        p.oh, p.ow = out_shape[2], out_shape[3]
+        p.kh, p.kw = kernel
+        p.stride_h, p.stride_w = stride
+        p.pad_top, p.pad_left = pad[0], pad[1]
+        p.count_include_pad = count_include_pad
+        p.s_in, p.zp_in, p.s_out, p.zp_out = s_in, zp_in, s_out, zp_out
+        x = np.ascontiguousarray(x, np.int8)
+        out = np.empty(out_shape, np.int8)
+        (self.lib.oracle_avgpool_i8 if avg else self.lib.oracle_maxpool_i8)(C.byref(p), _ptr(x), _ptr(out))
+        return out
+
+    def softmax_i8(self, x, s_in, zp_in, s_out, zp_out):
+        x = np.ascontiguousarray(x, np.int8)
+        out = np.empty_like(x)
+        self.lib.oracle_softmax_i8(_ptr(x), _ptr(out), x.shape[0], x.shape[1], C.c_float(s_in), zp_in,
+                                   C.c_float(s_out), zp_out)
+        return out
+
+
+def conv_out_hw(h, w, kh, kw, stride, pad, dilation=(1, 1)):
+    oh = (h + pad[0] + pad[2] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    ow = (w + pad[1] + pad[3] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    return oh, ow
+
+
+def synth_conv_i8(rng, c_in, o, kh, kw, *, group=1, depthwise=False, s_in=0.02):
+    """Synthetic per-channel-symmetric int8 conv parameters."""
+    cg = 1 if depthwise else c_in // group
+    w = rng.integers(-127, 128, size=(o, cg, kh, kw), dtype=np.int8)
+    s_w = (1e-3 * (1.0 + np.arange(o) / o)).astype(np.float32)
+    b = rng.integers(-10000, 10001, size=(o,), dtype=np.int32)
+    k = cg * kh * kw
+    # acc ~ N(0, sqrt(k)*74*73): put 3.2 sigma at the int8 range so that < 0.2 % saturate
+    s_out = np.float32(s_in * 1.5e-3 * np.sqrt(k) * 74.0 * 73.0 / 40.0)
+    return w, s_w, b, float(s_out)
