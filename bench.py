@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- MobileNetV1 int8 inferences/sec through the CSI-NN2 API on the b200 backend.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic images: the example graph of the
+reference (example/c906_mobilenetv1_f16.c shapes: conv3x3 s2, 13 x (depthwise 3x3 + pointwise 1x1),
+global avgpool, 1x1 classifier, softmax; the 27 relu nodes fused into their producers), int8 with
+per-channel symmetric weights, batch 256 per GPU (BASELINE.json north star), random-init weights,
+synthetic inputs.  Multi-GPU = batch sharding: every rank owns an independent session on its GPU
+(weak scaling, global batch = 256 x N), weights are packed on rank 0 only and broadcast ONCE with
+NCCL over NVLink into the other ranks' weight arenas; the inference path has no collective.
+
+Numbers on the JSON line:
+  value     whole-job images/s, inputs resident in HBM, CUDA-graph replay timed with CUDA events on
+            the session stream, max over ranks
+  e2e       the same metric through csinn_update_input + csinn_session_run + csinn_get_output with
+            pinned HOST buffers: H2D of the batch and D2H of the class scores inside the timed region
+  roofline  the dominant kernel of the step (by share of device time, measured live with CUDA events
+            per step): algorithmic bytes / time against the measured HBM peak of MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference (oracle/_ref, built from its own sources) on the host cores,
+            rank 0, a bounded sample of the same workload.  Reported baseline, not the target.
+--impl reference times that CPU implementation alone, as the reference arm of the same line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "MobileNetV1 int8 inferences/sec"
+UNIT = "images/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(nb1, images, repeat_input):
+    """images/s of the unmodified reference (GREF graph mode, batch 1 per inference: its AVX conv is
+    batch-1 only, source/reference/conv_avx.h:109-135) on the host cores"""
+    from shl import DT_INT8, RM_GRAPH, Harness
+    ref = Harness("ref")
+    with ref.create(DT_INT8, nb1.in_shape, nb1.layers, s_in=nb1.s_in, zp_in=nb1.zp_in, run_mode=RM_GRAPH) as net:
+        net(repeat_input)  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(images):
+            net(repeat_input)
+        dt = time.perf_counter() - t0
+    return images / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-images", type=int, default=48, help="images of the bounded CPU-baseline sample")
+    ap.add_argument("--profile-out", default=None, help="write the per-step device profile (json) here")
+    args = ap.parse_args()
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+
+    import nets
+    from shl import API_C906, DT_INT8, RM_GRAPH, Harness
+
+    nb1 = nets.mobilenet_v1(DT_INT8, batch=1)
+    x1 = nb1.input_batch()
+    config = {"workload": f"MobileNetV1 int8 per-channel symmetric weights, NCHW 3x224x224, batch {args.batch} per GPU "
+                          "(example/c906_mobilenetv1_f16.c graph shapes)",
+              "global_batch": args.batch * world, "parallelism": f"batch-shard x{world}, no per-step collective",
+              "l2": "activations per step (>1 GB at batch 256) exceed the 126 MB L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        per_step = 4  # images per step: a bounded sample of the batch-256 workload
+        for _ in range(warmup):
+            cpu_reference_rate(nb1, 1, x1)
+        t0 = time.perf_counter()
+        rate, _ = cpu_reference_rate(nb1, per_step * steps, x1)
+        wall = time.perf_counter() - t0
+        line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": 1e3 * per_step / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 (float-simulated: f32 accumulate, source/reference/utils.c:639)", "data": "synthetic",
+                "impl": "reference", "config": config,
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": min(8, ncores), "kind": "reference",
+                                 "sample": f"{per_step * steps} images, batch 1 per inference, GREF graph mode, "
+                                           f"oracle/_ref/libshl_ref_x86.so (AVX+OpenMP 8 threads in conv, {ncores} host cores), "
+                                           f"{wall:.1f} s"},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ b200 arm
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["SHL_B200_DEVICE"] = str(local_rank)
+    if world > 1 and rank != 0:
+        os.environ["SHL_B200_SKIP_WEIGHT_UPLOAD"] = "1"  # weights arrive by NCCL broadcast below
+
+    shim = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libb200nn.so"))
+    shl = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libshl_b200.so"))
+    shim.b200_last_error.restype = C.c_char_p
+    shim.b200_launch_count.restype = C.c_uint64
+    shl.shl_b200_session_stream.restype = C.c_void_p
+    shl.shl_b200_session_stream.argtypes = [C.c_void_p]
+    shl.shl_b200_session_launch.argtypes = [C.c_void_p]
+    shl.shl_b200_session_sync.argtypes = [C.c_void_p]
+    shl.shl_b200_session_num_kernels.argtypes = [C.c_void_p]
+    shl.shl_b200_session_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    shl.shl_b200_session_weight_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    shl.shl_b200_session_profile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+    if shim.b200_device_count() <= 0:
+        sys.exit("bench.py: no CUDA device visible -- the b200 backend has no CPU fallback")
+
+    b200 = Harness("b200")
+    nb = nets.mobilenet_v1(DT_INT8, batch=args.batch)
+    x = nb.input_batch(seed=1 + rank)
+    net = b200.create(DT_INT8, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH, api=API_C906)
+    sess = net.session
+    stream = shl.shl_b200_session_stream(sess)
+
+    # one-time weight broadcast over NVLink (rank 0 holds the packed weights + tables)
+    bcast_ms = None
+    if dist is not None:
+        import torch
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        assert shl.shl_b200_session_weight_arena(sess, C.byref(ptr), C.byref(nbytes)) == 1
+
+        class Raw:
+            __cuda_array_interface__ = {"shape": (int(nbytes.value),), "typestr": "|u1",
+                                        "data": (int(ptr.value), False), "version": 2}
+        arena = torch.as_tensor(Raw(), device=torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.broadcast(arena, src=0)
+        torch.cuda.synchronize()
+        bcast_ms = 1e3 * (time.perf_counter() - t0)
+
+    # pinned host buffers for the end-to-end path
+    hin = C.c_void_p()
+    assert shim.b200_malloc_host(C.byref(hin), C.c_size_t(x.nbytes)) == 0, shim.b200_last_error()
+    C.memmove(hin, x.ctypes.data, x.nbytes)
+    out_bytes = args.batch * 1000
+
+    def e2e_step():
+        assert b200.lib.h_net_update_input(net.handle, hin) == 0
+        assert b200.lib.h_net_session_run(net.handle) == 0, b200.error()
+        p = b200.lib.h_net_get_output(net.handle)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(out_bytes,))
+
+    # correctness gate before timing: image 0 of this rank against the oracle chain
+    y = e2e_step().reshape(args.batch, 1000).copy()
+    want0 = nets.oracle_forward(nb1, x[0:1]).reshape(1, 1000)
+    if not np.array_equal(y[0:1], want0):
+        sys.exit(f"bench.py: rank {rank}: GPU result differs from the oracle "
+                 f"({np.count_nonzero(y[0:1] != want0)}/1000) -- refusing to time a wrong kernel")
+
+    def barrier():
+        shl.shl_b200_session_sync(sess)
+        if dist is not None:
+            dist.barrier()
+
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    shim.b200_event_create(C.byref(ev0)), shim.b200_event_create(C.byref(ev1))
+
+    # ---- device-resident throughput: CUDA-graph replays, CUDA events on the session stream
+    for _ in range(warmup):
+        shl.shl_b200_session_launch(sess)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = shim.b200_launch_count()
+    shim.b200_event_record(ev0, C.c_void_p(stream))
+    for _ in range(steps):
+        assert shl.shl_b200_session_launch(sess) == 1
+    shim.b200_event_record(ev1, C.c_void_p(stream))
+    shl.shl_b200_session_sync(sess)
+    launches = int(shim.b200_launch_count() - launches0)
+    ms = C.c_float()
+    shim.b200_event_elapsed_ms(ev0, ev1, C.byref(ms))
+    dev_ms = float(ms.value)
+    barrier()
+
+    # ---- end to end through the public API (host buffers, H2D + D2H inside)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s * 1e3], device=torch.device("cuda", local_rank), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    # ---- per-step device profile (rank 0): dominant kernel and its roofline
+    roofline, per_kernel, layerwise = None, {}, None
+    if rank == 0:
+        cap = 128
+        pms, pby, pop = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        nsteps = shl.shl_b200_session_profile(sess, 2, 5, pms, pby, pop, cap)
+        buf = C.create_string_buffer(16384)
+        shl.shl_b200_session_describe(sess, buf, len(buf))
+        desc = buf.value.decode().splitlines()
+        names = [ln.split()[1] for ln in desc[1:1 + nsteps]]
+        hbm, tflops, peak_src = load_peaks()
+        for i in range(nsteps):
+            k = per_kernel.setdefault(names[i], {"ms": 0.0, "bytes": 0.0, "ops": 0.0, "launches": 0})
+            k["ms"] += pms[i]
+            k["bytes"] += pby[i]
+            k["ops"] += pop[i]
+            k["launches"] += 1
+        total = sum(k["ms"] for k in per_kernel.values())
+        top = max(per_kernel, key=lambda n: per_kernel[n]["ms"])
+        k = per_kernel[top]
+        achieved = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                    "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": k["ms"] / total, "launches_per_step": k["launches"],
+                    "avg_launch_ms": k["ms"] / k["launches"], "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
+                    "tensor_tops": k["ops"] / (k["ms"] * 1e-3) / 1e12}
+        lw_ms = sum(max(pby[i] / (hbm * 1e9), pop[i] / (2 * tflops * 1e12)) for i in range(nsteps)) * 1e3
+        layerwise = {"sum_of_steps_ms": total, "layerwise_roofline_ms": lw_ms, "frac": lw_ms / total,
+                     "note": "sum over steps of max(bytes/HBM peak, ops/(2 x bf16 peak))"}
+        if args.profile_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+            with open(args.profile_out, "w") as f:
+                json.dump({"steps": [{"i": i, "kernel": names[i], "name": desc[1 + i].split()[2], "ms": pms[i],
+                                      "bytes": pby[i], "ops": pop[i], "GBps": pby[i] / pms[i] / 1e6,
+                                      "TOPS": pop[i] / pms[i] / 1e9} for i in range(nsteps)],
+                           "per_kernel": per_kernel, "describe": desc[0]}, f, indent=1)
+
+    # ---- CPU baseline beside it (rank 0 only)
+    cpu = None
+    if rank == 0 and args.cpu_images > 0:
+        rate, dt = cpu_reference_rate(nb1, args.cpu_images, x1)
+        cpu = {"value": rate, "unit": UNIT, "cores": min(8, ncores), "kind": "reference",
+               "sample": f"{args.cpu_images} images of the same graph, batch 1 per inference, GREF graph mode, "
+                         f"unmodified reference oracle/_ref/libshl_ref_x86.so (OpenMP 8 threads in conv, {ncores} host "
+                         f"cores), {dt:.1f} s"}
+
+    if rank == 0:
+        images = args.batch * world * steps
+        value = images / (dev_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 (s32 accumulate on tcgen05 kind::i8, f32 requantise)", "data": "synthetic", "impl": "b200",
+                "config": config, "clocks": clocks,
+                "e2e": {"value": images / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                        "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": out_bytes,
+                        "api": "csinn_update_input + csinn_session_run + csinn_get_output, pinned host buffers"},
+                "gpu_launches": launches, "kernels_per_step": shl.shl_b200_session_num_kernels(sess),
+                "roofline": roofline, "layerwise_roofline": layerwise, "cpu_baseline": cpu,
+                "tensor_tops": 2 * nets.mobilenet_v1_macs() * images / (dev_ms * 1e-3) / 1e12,
+                "weight_broadcast_ms": bcast_ms}
+        print(json.dumps(line))
+    net.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -556,6 +556,66 @@ int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen)
     return n < buflen ? n : buflen - 1;
 }
 
+/* Per-step device time (CUDA events on the session stream, eager launches, averaged over
+ * `iters` after `warmup`) with the algorithmic bytes and ops of each step
+ * (bytes = N*e*(C*H*W + O*OH*OW) + e*O*(C/g)*KH*KW + 4*O ; ops = 2*N*O*OH*OW*(C/g)*KH*KW,
+ * the formula of the reference's own GOPS print, source/utils/debug.c:1084).  What
+ * sess->profiler_level = CSINN_PROFILER_LEVEL_TIMER + shl_benchmark_layer
+ * (source/graph_ref/setup.c:1383-1392) give on the CPU, measured on the device instead of with a
+ * host clock around asynchronous launches.  Returns the number of steps. */
+int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, double *ms, double *bytes,
+                             double *ops, int cap)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g || iters <= 0) return 0;
+    b200_graph *g = opt->g;
+    void *stream = opt->ctx.stream;
+    b200_set_device(opt->ctx.device);
+    const int n = g->ns < cap ? g->ns : cap;
+    void **ev = calloc((size_t)g->ns + 1, sizeof(void *));
+    for (int i = 0; i <= g->ns; i++)
+        if (b200_event_create(&ev[i]) != B200_OK) return 0;
+    for (int i = 0; i < n; i++) ms[i] = 0;
+    for (int it = 0; it < warmup + iters; it++) {
+        for (int i = 0; i < g->ns; i++) {
+            g_step *s = &g->s[i];
+            b200_event_record(ev[i], stream);
+            const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
+            if (b200_op_run(s->op, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
+                CSINN_TRUE)
+                return 0;
+        }
+        b200_event_record(ev[g->ns], stream);
+        if (b200_stream_sync(stream) != B200_OK) return 0;
+        if (it < warmup) continue;
+        for (int i = 0; i < n; i++) {
+            float t = 0;
+            b200_event_elapsed_ms(ev[i], ev[i + 1], &t);
+            ms[i] += t / iters;
+        }
+    }
+    for (int i = 0; i <= g->ns; i++) b200_event_destroy(ev[i]);
+    free(ev);
+    for (int i = 0; i < n; i++) {
+        const g_step *s = &g->s[i];
+        const b200_dt *a = &g->t[s->in0].dt, *o = &g->t[s->out].dt;
+        const double e = a->eb;
+        double by = e * ((double)a->n * a->c * a->h * a->w + (double)o->n * o->c * o->h * o->w), op = 0;
+        if (s->in1 >= 0) by += e * (double)a->n * a->c * a->h * a->w;
+        const b200_op *p = s->op;
+        if (p->kind == B200_OPK_CONV || p->kind == B200_OPK_FC) {
+            by += e * (double)p->o * p->kdim + 4.0 * p->o;
+            op = 2.0 * o->n * o->h * o->w * (double)p->o * p->kdim;
+        } else if (p->kind == B200_OPK_DW) {
+            by += e * (double)p->o * p->kh * p->kw + 4.0 * p->o;
+            op = 2.0 * o->n * o->h * o->w * (double)p->o * p->kh * p->kw;
+        }
+        if (bytes) bytes[i] = by;
+        if (ops) ops[i] = op;
+    }
+    return n;
+}
+
 int shl_b200_session_weight_arena(struct csinn_session *sess, void **dev_ptr, uint64_t *bytes)
 {
     b200_option *opt = b200_option_of(sess);

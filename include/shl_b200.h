@@ -116,6 +116,11 @@ void *shl_b200_session_stream(struct csinn_session *sess);
 /* number of device kernels one session_run launches, and the fused step list for inspection */
 int shl_b200_session_num_kernels(struct csinn_session *sess);
 int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen);
+/* per-step device time (ms, CUDA events on the session stream) with the algorithmic bytes / ops of
+ * each step; the device-side counterpart of shl_benchmark_layer (source/utils/debug.c:1037).
+ * Returns the number of steps written (<= cap). */
+int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, double *ms, double *bytes,
+                             double *ops, int cap);
 /* Weight arena of a set-up session (packed weights + per-channel tables, one contiguous
  * device allocation): exposed so that multi-GPU launchers can broadcast it once over NCCL
  * instead of re-uploading per rank. */

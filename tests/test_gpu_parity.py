@@ -1,0 +1,332 @@
+"""GPU parity tests proper (-m gpu): every case goes through the CSI-NN2 public API into
+libshl_b200.so (registry -> b200_opt -> C-ABI shim -> sm_100a kernels) and is compared with the
+oracle on the same seeded inputs.
+
+Bar: int8 results are BIT-EXACT against oracle/oracle_int.c (the arithmetic contract in
+include/b200nn.h) and within the reference's own f32-noise band (|d| <= 1 on <= 2e-4 of outputs,
+see tests/test_oracle.py) against the unmodified reference library; fp16 is within 1e-3 relative
+(|d| / max(|want|, 1), the north-star tolerance) of f32-accumulated math.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import nets
+from shl import (ACT_NONE, ACT_RELU, ACT_RELU6, API_C906, API_C920, API_RVV, DT_F16, DT_INT8, H_ADD, H_AVGPOOL,
+                 H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_FLATTEN, H_GAP, H_MAXPOOL, H_RELU, H_RELU6,
+                 H_SOFTMAX, RM_GRAPH, RM_LAYER, Layer, conv_out_hw, synth_conv_i8)
+
+pytestmark = pytest.mark.gpu
+F16_TOL = 1e-3
+
+
+def f16_close(got, want, tol=F16_TOL):
+    g, w = got.astype(np.float32), np.asarray(want, np.float32)
+    err = np.abs(g - w) / np.maximum(np.abs(w), 1.0)
+    assert err.max() <= tol, f"max relative error {err.max():.3e} > {tol}"
+
+
+def ref_band(got, want):
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and np.count_nonzero(d) <= max(2e-4 * d.size, 2), (d.max(), np.count_nonzero(d), d.size)
+
+
+CONV_CASES = [
+    # n, c, h, w, o, k, stride, pad, group, depthwise, zp_in, kind
+    (1, 128, 8, 16, 64, 1, 1, 0, 1, False, 0, H_CONV),       # one GEMM tile
+    (1, 32, 8, 16, 64, 1, 1, 0, 1, False, 0, H_CONV),        # K shorter than a k-block
+    (1, 16, 8, 16, 16, 1, 1, 0, 1, False, 0, H_CONV),        # smallest tile
+    (1, 64, 10, 10, 64, 1, 1, 0, 1, False, 0, H_CONV),       # ragged M
+    (1, 64, 8, 16, 40, 1, 1, 0, 1, False, 0, H_CONV),        # ragged N
+    (1, 72, 8, 16, 64, 1, 1, 0, 1, False, 0, H_CONV),        # ragged K
+    (1, 20, 9, 9, 24, 1, 1, 0, 1, False, -3, H_CONV),        # channels not a multiple of 16
+    (1, 1024, 7, 7, 128, 1, 1, 0, 1, False, -128, H_CONV),   # 8 k-blocks, extreme zero point
+    (2, 1024, 1, 1, 1000, 1, 1, 0, 1, False, 0, H_CONV),     # MobileNetV1 classifier: 4 n-tiles
+    (2, 128, 56, 56, 128, 1, 1, 0, 1, False, 0, H_CONV),     # many tiles per CTA (double-buffered TMEM)
+    (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 0, H_CONV_RELU),
+    (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 3, H_CONV_RELU6),
+    (1, 32, 14, 14, 48, 3, 1, 1, 1, False, -7, H_CONV),      # im2col path, asymmetric pad value
+    (2, 3, 32, 32, 32, 3, 2, 1, 1, False, 5, H_CONV),        # first-layer shape
+    (1, 3, 40, 40, 64, 7, 2, 3, 1, False, 0, H_CONV),        # ResNet stem shape
+    (1, 64, 13, 13, 64, 1, 2, 0, 1, False, 0, H_CONV),       # strided 1x1 (ResNet downsample)
+    (1, 64, 12, 12, 64, 3, 1, 1, 4, False, 0, H_CONV),       # group conv
+    (2, 32, 20, 20, 32, 3, 1, 1, 1, True, -7, H_CONV),       # depthwise via csinn_conv2d
+    (1, 64, 21, 21, 64, 3, 2, 1, 1, True, 0, H_DWCONV),      # depthwise via csinn_depthwise_conv2d
+    (1, 24, 9, 11, 24, 3, 1, 1, 1, True, 2, H_CONV),         # depthwise, ragged channels / width
+    (1, 16, 12, 12, 16, 5, 1, 2, 1, True, 4, H_CONV),        # depthwise 5x5
+    (1, 512, 14, 14, 512, 3, 1, 1, 1, True, -128, H_CONV),   # MobileNetV1 depthwise shape
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d_dw%d_zp%d_op%d" % c)
+def test_conv_int8_bit_exact(case, b200, oracle, rng):
+    n, c, h, w, o, k, stride, pad, group, dw, zp_in, kind = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, group=group, depthwise=dw)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layer = Layer(kind, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                  pad=(pad,) * 4, group=c if dw else group)
+    act = {H_CONV_RELU: ACT_RELU, H_CONV_RELU6: ACT_RELU6}.get(kind, ACT_NONE)
+    got = b200.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), depthwise=dw, stride=(stride, stride), pad=(pad,) * 4,
+                            dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out,
+                            zp_out=3, act=act)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} outputs differ from the oracle"
+
+
+def test_conv_int8_against_the_reference_library(b200, ref, rng):
+    """the same API calls against the unmodified reference: inside its own f32-noise band"""
+    for (n, c, h, w, o, k, stride, pad, dw, zp_in) in [(1, 128, 28, 28, 128, 1, 1, 0, False, 0),
+                                                      (1, 64, 14, 14, 96, 3, 1, 1, False, -7),
+                                                      (1, 64, 28, 28, 64, 3, 2, 1, True, -7)]:
+        x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+        wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, depthwise=dw)
+        oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+        layer = Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                      pad=(pad,) * 4, group=c if dw else 1)
+        got = b200.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in)
+        want = ref.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in)
+        ref_band(got, want)
+
+
+@pytest.mark.parametrize("api", [API_RVV, API_C906, API_C920])
+def test_registered_api_ids_reach_the_gpu(api, b200, oracle, rng):
+    """b200 answers under the ids of the back ends it replaces (north star: thead_rvv, c9*_opt)"""
+    x = rng.integers(-128, 128, size=(1, 32, 6, 6), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, 32, 32, 1, 1)
+    layer = Layer(H_CONV, (1, 32, 6, 6), s_out=s_out, w=wt, b=b, s_w=s_w)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, api=api)
+    want = oracle.conv2d_i8(x, wt, b, x.shape, stride=(1, 1), pad=(0,) * 4, dilation=(1, 1), group=1, s_in=0.02,
+                            zp_in=0, s_w=s_w, s_b=None, s_out=s_out, zp_out=0)
+    assert np.array_equal(got, want)
+
+
+def test_fuse_zp2bias_and_per_tensor_weights(b200, oracle, rng):
+    n, c, h, w, o, zp_in = 1, 32, 10, 10, 48, -9
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 3, 3)
+    kw = dict(stride=(1, 1), pad=(1,) * 4, dilation=(1, 1), group=1, s_in=0.02, zp_in=zp_in, s_out=s_out, zp_out=1)
+    folded = (b.astype(np.int64) - zp_in * wt.astype(np.int64).sum(axis=(1, 2, 3))).astype(np.int32)
+    layer = Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=1, w=wt, b=folded, s_w=s_w, pad=(1,) * 4, fuse_zp2bias=1)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=zp_in)
+    assert np.array_equal(got, oracle.conv2d_i8(x, wt, b, (n, o, h, w), s_w=s_w, s_b=None, **kw))
+    # per-tensor weight scale (quant_channel == 1) and no bias
+    s1 = np.float32([1.5e-3])
+    layer = Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=1, w=wt, b=None, s_w=s1, pad=(1,) * 4)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=zp_in)
+    assert np.array_equal(got, oracle.conv2d_i8(x, wt, None, (n, o, h, w), s_w=s1, s_b=None, **kw))
+
+
+def test_asymmetric_weights_are_refused_loudly(b200, rng):
+    x = rng.integers(-128, 128, size=(1, 16, 4, 4), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, 16, 16, 1, 1)
+    layer = Layer(H_CONV, (1, 16, 4, 4), s_out=s_out, w=wt, b=b, s_w=s_w, zp_w=np.full(16, 3, np.int32))
+    with pytest.raises(RuntimeError, match="symmetric weights"):
+        b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02)
+
+
+@pytest.mark.parametrize("batch,cin,units", [(1, 1024, 1000), (8, 31, 17), (300, 2048, 100)])
+def test_fc_int8_bit_exact(batch, cin, units, b200, oracle, rng):
+    x = rng.integers(-128, 128, size=(batch, cin), dtype=np.int8)
+    wt4, s_w, b, s_out = synth_conv_i8(rng, cin, units, 1, 1)
+    wt = wt4.reshape(units, cin)
+    layer = Layer(H_FC, (batch, units), s_out=s_out, zp_out=-5, w=wt, b=b, s_w=s_w)
+    got = b200.run(DT_INT8, (batch, cin), [layer], x, s_in=0.02, zp_in=7)
+    assert np.array_equal(got, oracle.fc_i8(x, wt, b, s_in=0.02, zp_in=7, s_w=s_w, s_b=None, s_out=s_out, zp_out=-5))
+
+
+@pytest.mark.parametrize("kind,act", [(H_RELU, ACT_RELU), (H_RELU6, ACT_RELU6)])
+def test_relu_int8_bit_exact(kind, act, b200, oracle, rng):
+    x = rng.integers(-128, 128, size=(2, 24, 9, 11), dtype=np.int8)
+    for s_in, zp_in, s_out, zp_out in [(0.037, -3, 0.0181, -128), (0.11, 5, 0.0235, -128), (0.05, 0, 0.05, 0)]:
+        got = b200.run(DT_INT8, x.shape, [Layer(kind, x.shape, s_out=s_out, zp_out=zp_out)], x, s_in=s_in, zp_in=zp_in)
+        assert np.array_equal(got, oracle.relu_i8(x, act, s_in, zp_in, s_out, zp_out))
+
+
+def test_add_int8_bit_exact(b200, oracle, rng):
+    shape = (2, 24, 9, 11)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128), Layer(H_ADD, shape, in0=0, in1=1, s_out=0.06, zp_out=-11)]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    want = oracle.add_i8(x, r, 0.04, 3, 0.021, -128, 0.06, -11)
+    for mode in (RM_LAYER, RM_GRAPH):
+        got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=mode)
+        assert np.array_equal(got, want), mode
+
+
+POOLS = [(H_MAXPOOL, 16, 13, 15, 3, 2, 1, 0), (H_MAXPOOL, 8, 12, 12, 2, 2, 0, 0), (H_AVGPOOL, 16, 13, 15, 3, 2, 1, 0),
+         (H_AVGPOOL, 8, 9, 9, 3, 1, 1, 1), (H_GAP, 40, 7, 7, 7, 1, 0, 0), (H_GAP, 1024, 7, 7, 7, 1, 0, 0)]
+
+
+@pytest.mark.parametrize("case", POOLS, ids=lambda c: "op%d_c%d_%dx%d_k%d_s%d_p%d_cip%d" % c)
+def test_pool_int8_bit_exact(case, b200, oracle, rng):
+    kind, c, h, w, k, stride, pad, cip = case
+    x = rng.integers(-128, 128, size=(2, c, h, w), dtype=np.int8)
+    if kind == H_GAP:
+        oh = ow = 1
+        kernel, st, pd = (h, w), (1, 1), (0,) * 4
+    else:
+        oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+        kernel, st, pd = (k, k), (stride, stride), (pad,) * 4
+    layer = Layer(kind, (2, c, oh, ow), s_out=0.043, zp_out=-20, kernel=kernel, stride=st, pad=pd, count_include_pad=cip)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.05, zp_in=9)
+    want = oracle.pool_i8(x, (2, c, oh, ow), avg=kind != H_MAXPOOL, kernel=kernel, stride=st, pad=pd,
+                          count_include_pad=cip, s_in=0.05, zp_in=9, s_out=0.043, zp_out=-20)
+    assert np.array_equal(got, want)
+
+
+def test_softmax_int8_bit_exact(b200, oracle, rng):
+    x = rng.integers(-128, 128, size=(5, 1000), dtype=np.int8)
+    layer = Layer(H_SOFTMAX, x.shape, s_out=1.0 / 256, zp_out=-128, axis=1)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.08, zp_in=10)
+    assert np.array_equal(got, oracle.softmax_i8(x, 0.08, 10, 1.0 / 256, -128))
+
+
+def test_golden_vectors_of_the_reference(golden, b200):
+    """the reference's own known answers, through the GPU path: fp16 conv / dw / fc / pools / relu
+    (tests/unit_test/valid_data/*.dat) and the int8 maxpool + relu vectors it ships"""
+    def run(kind, xk, outk, **kw):
+        x, want = golden[xk], golden[outk]
+        got = b200.run(DT_F16 if x.dtype == np.float16 else DT_INT8, x.shape, [Layer(kind, want.shape, **kw)], x)
+        return got, want
+
+    for name, k, s, p in (("maxpool2x2s2", 2, 2, 0), ("maxpool3x3s2_p1", 3, 2, 1), ("maxpool3x3s1_p1", 3, 1, 1)):
+        got, want = run(H_MAXPOOL, f"{name}_int8_in", f"{name}_int8_out", kernel=(k, k), stride=(s, s), pad=(p,) * 4)
+        assert np.array_equal(got, want), name
+    tol = 3e-2  # the fp16 goldens were accumulated in fp16 (see tests/test_oracle.py)
+    g = golden
+    got = b200.run(DT_F16, g["conv1x1_fp16_in"].shape, [Layer(H_CONV, (1, 19, 4, 5), w=g["conv1x1_fp16_ker"],
+                                                              b=g["conv1x1_fp16_bias"])], g["conv1x1_fp16_in"])
+    f16_close(got, g["conv1x1_fp16_out"], tol)
+    got = b200.run(DT_F16, g["conv3x3_fp16_in"].shape, [Layer(H_CONV, (1, 19, 4, 5), w=g["conv3x3_fp16_ker"],
+                                                              b=g["conv3x3_fp16_bias"], pad=(1,) * 4)], g["conv3x3_fp16_in"])
+    f16_close(got, g["conv3x3_fp16_out"], tol)
+    got = b200.run(DT_F16, g["dw3x3s1_fp16_in"].shape, [Layer(H_CONV, (1, 2, 4, 10), w=g["dw3x3s1_fp16_ker"],
+                                                              b=g["dw3x3s1_fp16_bias"], pad=(1,) * 4, group=2)], g["dw3x3s1_fp16_in"])
+    f16_close(got, g["dw3x3s1_fp16_out"], tol)
+    got = b200.run(DT_F16, g["dw3x3s2_fp16_in"].shape, [Layer(H_CONV, (1, 2, 3, 9), w=g["dw3x3s2_fp16_ker"],
+                                                              b=g["dw3x3s2_fp16_bias"], pad=(1,) * 4, stride=(2, 2), group=2)],
+                   g["dw3x3s2_fp16_in"])
+    f16_close(got, g["dw3x3s2_fp16_out"], tol)
+    got = b200.run(DT_F16, (1, 17), [Layer(H_FC, (1, 31), w=g["fc_fp16_weight"], b=g["fc_fp16_bias"])], g["fc_fp16_in"])
+    f16_close(got, g["fc_fp16_out"], tol)
+    got, want = run(H_AVGPOOL, "avgpool2x2s2_fp16_in", "avgpool2x2s2_fp16_out", kernel=(2, 2), stride=(2, 2))
+    f16_close(got, want, 2e-3)
+    got, want = run(H_AVGPOOL, "avgpool3x3s2_fp16_in", "avgpool3x3s2_fp16_out", kernel=(3, 3), stride=(2, 2))
+    f16_close(got, want, 2e-3)
+    got, want = run(H_GAP, "global_avgpool_fp16_in", "global_avgpool_fp16_out")
+    f16_close(got, want, 2e-3)
+    got, want = run(H_MAXPOOL, "maxpool2x2s2_fp16_in", "maxpool2x2s2_fp16_out", kernel=(2, 2), stride=(2, 2))
+    assert np.array_equal(got, want)
+
+
+F16_CASES = [(1, 64, 8, 16, 64, 1, 1, 0, False), (1, 512, 9, 9, 200, 1, 1, 0, False), (1, 3, 32, 32, 32, 3, 2, 1, False),
+             (2, 48, 14, 14, 56, 3, 1, 1, False), (1, 32, 14, 14, 32, 3, 1, 1, True), (1, 128, 15, 15, 128, 3, 2, 1, True)]
+
+
+@pytest.mark.parametrize("case", F16_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_dw%d" % c)
+def test_conv_fp16_within_tolerance(case, b200, oracle, rng):
+    n, c, h, w, o, k, stride, pad, dw = case
+    x = rng.standard_normal((n, c, h, w)).astype(np.float16)
+    cg = 1 if dw else c
+    wt = (rng.standard_normal((o, cg, k, k)) / np.sqrt(cg * k * k)).astype(np.float16)
+    b = rng.standard_normal(o).astype(np.float16)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layer = Layer(H_CONV, (n, o, oh, ow), w=wt, b=b, stride=(stride, stride), pad=(pad,) * 4, group=c if dw else 1)
+    got = b200.run(DT_F16, (n, c, h, w), [layer], x)
+    want = oracle.conv2d_f32(x.astype(np.float32), wt.astype(np.float32), b.astype(np.float32), (n, o, oh, ow),
+                             depthwise=dw, stride=(stride, stride), pad=(pad,) * 4)
+    f16_close(got, want)
+
+
+def test_conv_fp16_against_the_reference_library(b200, ref, rng):
+    n, c, h, w, o = 1, 64, 14, 14, 96
+    x = rng.standard_normal((n, c, h, w)).astype(np.float16)
+    wt = (rng.standard_normal((o, c, 3, 3)) / np.sqrt(c * 9)).astype(np.float16)
+    b = rng.standard_normal(o).astype(np.float16)
+    layer = Layer(H_CONV, (n, o, h, w), w=wt, b=b, pad=(1,) * 4)
+    f16_close(b200.run(DT_F16, x.shape, [layer], x), ref.run(DT_F16, x.shape, [layer], x))
+
+
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_mobilenet_v1_int8_narrow_bit_exact(mode, b200):
+    """a whole (narrow, 64x64) MobileNetV1: conv3x3 s2 from NCHW, 13 dw + 13 pw with relu fused in
+    graph mode, global avgpool, 1x1 classifier, softmax; batch 3 so that image boundaries matter"""
+    nb = nets.mobilenet_v1(DT_INT8, batch=3, res=64, width=0.25, classes=100)
+    x = nb.input_batch()
+    got = b200.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=mode)
+    want = nets.oracle_forward(nb, x)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+
+
+def test_mobilenet_v1_int8_full_size_graph(b200, ref):
+    """BASELINE.json configs[1]: MobileNetV1 int8, NCHW batch 1, example graph shapes -- bit-exact
+    against the oracle chain, and within the reference's noise band against the reference itself
+    run through GREF (source/graph_ref/setup.c:1305) on the same tensors"""
+    nb = nets.mobilenet_v1(DT_INT8, batch=1)
+    x = nb.input_batch()
+    with b200.create(DT_INT8, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH, api=API_C906) as net:
+        got = net(x)
+        again = net(x)
+    want = nets.oracle_forward(nb, x)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+    assert np.array_equal(got, again), "replaying the CUDA graph is not idempotent"
+    got_ref = ref.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
+    d = np.abs(got.astype(int) - got_ref.astype(int))
+    assert d.max() <= 1 and np.count_nonzero(d) <= 5, (d.max(), np.count_nonzero(d))
+    assert len(np.unique(got)) > 3, "degenerate output"
+
+
+def test_mobilenet_v1_int8_batch_properties(b200):
+    """BASELINE.json's headline size (batch 256) is too slow for the scalar oracle, so it is checked
+    through properties: every image of a batch equals the same image run alone (images are
+    independent units -- the property batch sharding rests on), replay is idempotent, and one image
+    is checked against the oracle chain."""
+    batch = 256
+    nb = nets.mobilenet_v1(DT_INT8, batch=batch)
+    x = nb.input_batch()
+    x[7] = x[200]  # two equal images inside the batch must give equal outputs
+    with b200.create(DT_INT8, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH) as net:
+        y = net(x)
+        y2 = net(x)
+    assert np.array_equal(y, y2)
+    assert np.array_equal(y[7], y[200])
+    nb1 = nets.mobilenet_v1(DT_INT8, batch=1)
+    with b200.create(DT_INT8, nb1.in_shape, nb1.layers, s_in=nb1.s_in, zp_in=nb1.zp_in, run_mode=RM_GRAPH) as net1:
+        for i in (0, 7, 255):
+            assert np.array_equal(net1(x[i:i + 1])[0], y[i]), f"image {i}: batched != alone"
+    assert np.array_equal(y[3:4], nets.oracle_forward(nb1, x[3:4]))
+
+
+def test_mobilenet_v1_fp16_graph(b200):
+    """BASELINE.json configs[2] shapes (c906_mobilenetv1_f16.c), fp16, at a size the oracle finishes"""
+    nb = nets.mobilenet_v1(DT_F16, batch=2, res=96, width=0.5, classes=200)
+    x = nb.input_batch()
+    got = b200.run(DT_F16, nb.in_shape, nb.layers, x, run_mode=RM_GRAPH, api=API_C906)
+    want = nets.oracle_forward(nb, x)
+    # softmax probabilities: absolute tolerance scaled like the relative one
+    assert np.max(np.abs(got.astype(np.float32) - want.astype(np.float32))) < 2e-3
+    assert abs(float(got.astype(np.float32).sum()) - 2.0) < 2e-2
+
+
+def test_resnet50_int8_narrow_bit_exact(b200):
+    """BASELINE.json configs[4] structure (7x7 s2 stem, maxpool, bottlenecks with strided 1x1
+    shortcuts, add + relu, global avgpool, flatten, fullyconnected), narrow and small"""
+    nb = nets.resnet50(DT_INT8, batch=2, res=64, width=0.25, classes=50)
+    x = nb.input_batch()
+    got = b200.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
+    want = nets.oracle_forward(nb, x)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+
+
+def test_dwconv_sweep_shapes(b200, oracle, rng):
+    """BASELINE.json configs[3] (depthwise 3x3 int8, H=W=56) at batch 1 per channel count"""
+    for c in (32, 64, 128, 256, 512, 1024):
+        x = rng.integers(-128, 128, size=(1, c, 56, 56), dtype=np.int8)
+        wt, s_w, b, s_out = synth_conv_i8(rng, c, c, 3, 3, depthwise=True)
+        layer = Layer(H_CONV, (1, c, 56, 56), s_out=s_out, zp_out=-4, w=wt, b=b, s_w=s_w, pad=(1,) * 4, group=c)
+        got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=-7)
+        want = oracle.conv2d_i8(x, wt, b, x.shape, depthwise=True, stride=(1, 1), pad=(1,) * 4, dilation=(1, 1),
+                                group=1, s_in=0.02, zp_in=-7, s_w=s_w, s_b=None, s_out=s_out, zp_out=-4)
+        assert np.array_equal(got, want), c

@@ -1,0 +1,241 @@
+"""Pins the oracle (oracle/oracle_int.c) before anything trusts it:
+
+* against the UNMODIFIED reference compiled from its own sources (oracle/_ref/libshl_ref_x86*.so),
+  driven through the reference's public API exactly as its own layer tests do
+  (tests/validation_layer/testutil.h:845-889);
+* against the reference's committed known-answer vectors (tests/golden/unit_kat.npz, made by
+  tests/golden/make_golden.py from tests/unit_test/valid_data/*.dat).
+
+int8 contraction ops: the reference accumulates dequantised f32 products
+(source/reference/utils.c:639-655), the oracle accumulates exact int32, so they may differ by one
+LSB where the real value sits within f32 noise of a rounding tie.  The bound asserted here
+(|d| <= 1, at most 2e-4 of the outputs) is also what the reference's own AVX and non-AVX builds
+satisfy against each other (test_reference_builds_disagree_like_the_oracle).  Elementwise and
+pooling ops are restated float-op by float-op and must match bit for bit.
+"""
+import numpy as np
+import pytest
+
+from shl import (ACT_NONE, ACT_RELU, ACT_RELU6, DT_F16, DT_F32, DT_INT8, H_ADD, H_AVGPOOL, H_CONV, H_CONV_RELU,
+                 H_CONV_RELU6, H_DWCONV, H_FC, H_GAP, H_MAXPOOL, H_RELU, H_RELU6, H_SOFTMAX, RM_GRAPH, Layer,
+                 conv_out_hw, synth_conv_i8)
+
+TIE_RATE = 2e-4
+
+
+def close_int8(got, want, what):
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1, f"{what}: max |d| = {d.max()}"
+    rate = np.count_nonzero(d) / d.size
+    assert rate <= max(TIE_RATE, 2.0 / d.size), f"{what}: {np.count_nonzero(d)}/{d.size} outputs differ"
+    return rate
+
+
+CONV_CASES = [
+    # n, c, h, w, o, k, stride, pad, group, depthwise, zp_in, kind
+    (1, 128, 28, 28, 128, 1, 1, 0, 1, False, 0, H_CONV),        # MobileNetV1 pointwise
+    (1, 3, 64, 64, 32, 3, 2, 1, 1, False, 5, H_CONV),           # first layer shape, asymmetric input
+    (1, 64, 14, 14, 96, 3, 1, 1, 1, False, -7, H_CONV),
+    (1, 3, 40, 40, 64, 7, 2, 3, 1, False, 0, H_CONV),           # ResNet stem shape
+    (1, 32, 16, 16, 64, 3, 1, 1, 4, False, 0, H_CONV),          # group conv
+    (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 0, H_CONV_RELU),
+    (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 3, H_CONV_RELU6),
+    (2, 32, 20, 20, 32, 3, 1, 1, 1, True, -7, H_CONV),          # depthwise through csinn_conv2d
+    (1, 64, 21, 21, 64, 3, 2, 1, 1, True, 0, H_DWCONV),         # depthwise through csinn_depthwise_conv2d
+    (1, 16, 12, 12, 16, 5, 1, 2, 1, True, 4, H_CONV),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d_dw%d_zp%d_op%d" % c)
+def test_conv_int8_against_reference(case, ref, ref_noavx, oracle, rng):
+    n, c, h, w, o, k, stride, pad, group, dw, zp_in, kind = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, group=group, depthwise=dw)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layer = Layer(kind, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                  pad=(pad,) * 4, group=c if dw else group)
+    act = {H_CONV_RELU: ACT_RELU, H_CONV_RELU6: ACT_RELU6}.get(kind, ACT_NONE)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), depthwise=dw, stride=(stride, stride), pad=(pad,) * 4,
+                            dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out,
+                            zp_out=3, act=act)
+    # the AVX build of the reference computes batch 0 only (source/reference/conv_avx.h:109-135)
+    libs = [ref_noavx] + ([ref] if n == 1 or dw else [])
+    for lib in libs:
+        got = lib.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in)
+        close_int8(got, want, lib.which)
+    assert (np.mean((want == 127) | (want == -128))) < 0.05  # the case is not degenerate
+
+
+def test_reference_builds_disagree_like_the_oracle(ref, ref_noavx, oracle, rng):
+    """The +-1 LSB band is the reference's own f32 accumulation noise: its two builds (AVX im2col
+    sgemm, conv_avx.h:109, vs the scalar NHWC loop, convolution.c:28-89) differ from each other
+    the same way they differ from exact integer accumulation."""
+    n, c, h, w, o = 1, 256, 28, 28, 256
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 1, 1)
+    layer = Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=0, w=wt, b=b, s_w=s_w)
+    a = ref.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02)
+    bb = ref_noavx.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, h, w), stride=(1, 1), pad=(0,) * 4, dilation=(1, 1), group=1,
+                            s_in=0.02, zp_in=0, s_w=s_w, s_b=None, s_out=s_out, zp_out=0)
+    r_ab = close_int8(a, bb, "avx vs non-avx reference")
+    r_a = close_int8(a, want, "avx reference vs oracle")
+    r_b = close_int8(bb, want, "non-avx reference vs oracle")
+    print(f"tie rates: avx-vs-noavx {r_ab:.2e}, avx-vs-oracle {r_a:.2e}, noavx-vs-oracle {r_b:.2e}")
+
+
+def test_fuse_zp2bias_is_unfolded_like_the_reference(ref_noavx, oracle, rng):
+    """A bias that already carries -zp_in*sum(w) (what the RVV init leaves behind,
+    thead_rvv/int8/convolution.c:172-190) gives the same result as the plain bias."""
+    n, c, h, w, o, zp_in = 1, 32, 10, 10, 48, -9
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 3, 3)
+    folded = (b.astype(np.int64) - zp_in * wt.astype(np.int64).sum(axis=(1, 2, 3))).astype(np.int32)
+    kw = dict(stride=(1, 1), pad=(1,) * 4, dilation=(1, 1), group=1, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None,
+              s_out=s_out, zp_out=1)
+    plain = oracle.conv2d_i8(x, wt, b, (n, o, h, w), **kw)
+    unf = oracle.conv2d_i8(x, wt, folded, (n, o, h, w), fuse_zp2bias=1, **kw)
+    assert np.array_equal(plain, unf)
+    layer = Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=1, w=wt, b=folded, s_w=s_w, pad=(1,) * 4, fuse_zp2bias=1)
+    got = ref_noavx.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in)
+    close_int8(got, plain, "reference with fuse_zp2bias")
+
+
+@pytest.mark.parametrize("batch,cin,units", [(1, 1024, 1000), (8, 31, 17), (3, 2048, 100)])
+def test_fc_int8_against_reference(batch, cin, units, ref, oracle, rng):
+    x = rng.integers(-128, 128, size=(batch, cin), dtype=np.int8)
+    wt4, s_w, b, s_out = synth_conv_i8(rng, cin, units, 1, 1)
+    wt = wt4.reshape(units, cin)
+    layer = Layer(H_FC, (batch, units), s_out=s_out, zp_out=-5, w=wt, b=b, s_w=s_w)
+    got = ref.run(DT_INT8, (batch, cin), [layer], x, s_in=0.02, zp_in=7)
+    want = oracle.fc_i8(x, wt, b, s_in=0.02, zp_in=7, s_w=s_w, s_b=None, s_out=s_out, zp_out=-5)
+    close_int8(got, want, "fc")
+
+
+@pytest.mark.parametrize("kind,act", [(H_RELU, ACT_RELU), (H_RELU6, ACT_RELU6)])
+def test_relu_bit_exact(kind, act, ref, oracle, rng):
+    x = rng.integers(-128, 128, size=(2, 24, 9, 11), dtype=np.int8)
+    for s_in, zp_in, s_out, zp_out in [(0.037, -3, 0.0181, -128), (0.11, 5, 0.0235, -128), (0.05, 0, 0.05, 0)]:
+        layer = Layer(kind, x.shape, s_out=s_out, zp_out=zp_out)
+        got = ref.run(DT_INT8, x.shape, [layer], x, s_in=s_in, zp_in=zp_in)
+        assert np.array_equal(got, oracle.relu_i8(x, act, s_in, zp_in, s_out, zp_out))
+
+
+def test_add_bit_exact(ref, oracle, rng):
+    shape = (2, 24, 9, 11)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    # second operand = relu(x) with its own qinfo, so both inputs are live tensors
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128), Layer(H_ADD, shape, in0=0, in1=1, s_out=0.06, zp_out=-11)]
+    got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    assert np.array_equal(got, oracle.add_i8(x, r, 0.04, 3, 0.021, -128, 0.06, -11))
+
+
+POOLS = [  # kind, c, h, w, k, stride, pad, count_include_pad
+    (H_MAXPOOL, 16, 13, 15, 3, 2, 1, 0), (H_MAXPOOL, 8, 12, 12, 2, 2, 0, 0), (H_AVGPOOL, 16, 13, 15, 3, 2, 1, 0),
+    (H_AVGPOOL, 8, 9, 9, 3, 1, 1, 1), (H_GAP, 40, 7, 7, 7, 1, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", POOLS, ids=lambda c: "op%d_c%d_%dx%d_k%d_s%d_p%d_cip%d" % c)
+def test_pool_bit_exact(case, ref, oracle, rng):
+    kind, c, h, w, k, stride, pad, cip = case
+    x = rng.integers(-128, 128, size=(2, c, h, w), dtype=np.int8)
+    if kind == H_GAP:
+        oh = ow = 1
+        kernel, st, pd = (h, w), (1, 1), (0,) * 4
+    else:
+        oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+        kernel, st, pd = (k, k), (stride, stride), (pad,) * 4
+    layer = Layer(kind, (2, c, oh, ow), s_out=0.043, zp_out=-20, kernel=kernel, stride=st, pad=pd, count_include_pad=cip)
+    got = ref.run(DT_INT8, x.shape, [layer], x, s_in=0.05, zp_in=9)
+    want = oracle.pool_i8(x, (2, c, oh, ow), avg=kind != H_MAXPOOL, kernel=kernel, stride=st, pad=pd,
+                          count_include_pad=cip, s_in=0.05, zp_in=9, s_out=0.043, zp_out=-20)
+    assert np.array_equal(got, want)
+
+
+def test_softmax_bit_exact(ref, oracle, rng):
+    x = rng.integers(-128, 128, size=(3, 1000), dtype=np.int8)
+    layer = Layer(H_SOFTMAX, x.shape, s_out=1.0 / 256, zp_out=-128, axis=1)
+    got = ref.run(DT_INT8, x.shape, [layer], x, s_in=0.08, zp_in=10)
+    assert np.array_equal(got, oracle.softmax_i8(x, 0.08, 10, 1.0 / 256, -128))
+
+
+def test_f16_conversions_match_reference(ref, oracle, rng):
+    """f32 -> f16 of the reference is round-half-up on the magnitude (source/nn2/utils.c:576-620),
+    not IEEE round-half-even; f16 -> f32 is exact.  Checked through a 1x1 identity conv in f16."""
+    import ctypes as C
+    vals = np.concatenate([rng.standard_normal(4000).astype(np.float32) * 30, np.float32([0, 65504, -65504, 1e-7, 70000])])
+    oracle.lib.oracle_f32_to_f16.restype = C.c_uint16
+    oracle.lib.oracle_f16_to_f32.restype = C.c_float
+    h = np.array([oracle.lib.oracle_f32_to_f16(C.c_float(v)) for v in vals], np.uint16)
+    back = np.array([oracle.lib.oracle_f16_to_f32(C.c_uint16(int(u))) for u in h], np.float32)
+    ieee = vals.astype(np.float16)
+    finite = np.abs(vals) < 65000
+    assert np.array_equal(back[finite], h.view(np.float16).astype(np.float32)[finite])
+    # within one f16 ulp of IEEE everywhere, identical except on ties
+    assert np.max(np.abs(h.view(np.float16).astype(np.float32)[finite] - ieee.astype(np.float32)[finite]) /
+                  np.maximum(np.abs(vals[finite]), 1e-3)) < 1e-3
+
+
+# ---- golden vectors of the reference's own kernel tests ------------------------------------------
+def _f32_close(got, want, tol=1e-4):
+    g, w = got.astype(np.float64).ravel(), want.astype(np.float64).ravel()
+    err = np.abs(g - w) / np.maximum(np.abs(w), 1.0)
+    assert err.max() < tol, err.max()
+    # the reference's own acceptance metric (tests/utils/test_utils.c:722-751), much tightened
+    cos = float(g @ w / (np.linalg.norm(g) * np.linalg.norm(w)))
+    assert cos > 0.99999, cos
+
+
+@pytest.mark.parametrize("tag", ["fp32", "fp16"])
+def test_golden_conv_dw_fc(tag, golden, oracle):
+    """oracle float restatements vs tests/unit_test/valid_data/{conv2d,dwconv2d,fullyconnected}.dat"""
+    # the fp16 goldens carry fp16 accumulation error (K up to 27 at |x| ~ 30): 3e-2 relative to
+    # max(|want|, 1); the reference accepts them at cosine >= 0.99
+    tol = 1e-4 if tag == "fp32" else 3e-2
+    f = lambda k: golden[k].astype(np.float32)  # noqa: E731
+    got = oracle.conv2d_f32(f(f"conv1x1_{tag}_in"), f(f"conv1x1_{tag}_ker"), f(f"conv1x1_{tag}_bias"), (1, 19, 4, 5))
+    _f32_close(got, f(f"conv1x1_{tag}_out"), tol)
+    got = oracle.conv2d_f32(f(f"conv3x3_{tag}_in"), f(f"conv3x3_{tag}_ker"), f(f"conv3x3_{tag}_bias"), (1, 19, 4, 5),
+                            pad=(1,) * 4)
+    _f32_close(got, f(f"conv3x3_{tag}_out"), tol)
+    got = oracle.conv2d_f32(f(f"dw3x3s1_{tag}_in"), f(f"dw3x3s1_{tag}_ker"), f(f"dw3x3s1_{tag}_bias"), (1, 2, 4, 10),
+                            depthwise=True, pad=(1,) * 4)
+    _f32_close(got, f(f"dw3x3s1_{tag}_out"), tol)
+    got = oracle.conv2d_f32(f(f"dw3x3s2_{tag}_in"), f(f"dw3x3s2_{tag}_ker"), f(f"dw3x3s2_{tag}_bias"), (1, 2, 3, 9),
+                            depthwise=True, stride=(2, 2), pad=(1,) * 4)
+    _f32_close(got, f(f"dw3x3s2_{tag}_out"), tol)
+    got = oracle.conv2d_f32(f(f"fc_{tag}_in"), f(f"fc_{tag}_weight"), f(f"fc_{tag}_bias"), (1, 31), fc=True)
+    _f32_close(got, f(f"fc_{tag}_out"), tol)
+
+
+def test_golden_int8_maxpool_and_relu(golden, oracle):
+    """the int8 known answers the reference does ship (maxpool.dat:112-127,270-288,...; activation.dat)"""
+    for name, k, s, p in (("maxpool2x2s2", 2, 2, 0), ("maxpool3x3s2_p1", 3, 2, 1), ("maxpool3x3s1_p1", 3, 1, 1)):
+        x, want = golden[f"{name}_int8_in"], golden[f"{name}_int8_out"]
+        got = oracle.pool_i8(x, want.shape, avg=False, kernel=(k, k), stride=(s, s), pad=(p,) * 4,
+                             count_include_pad=0, s_in=1.0, zp_in=0, s_out=1.0, zp_out=0)
+        assert np.array_equal(got, want), name
+    x, want = golden["relu_int8_in"], golden["relu_int8_out"]
+    assert np.array_equal(oracle.relu_i8(x, ACT_RELU, 1.0, 0, 1.0, 0), want)
+
+
+def test_golden_reference_library_agrees(golden, ref):
+    """the compiled reference reproduces its own fp32 known answers (sanity of oracle/_ref)"""
+    x, k, b, want = (golden[f"conv3x3_fp32_{s}"] for s in ("in", "ker", "bias", "out"))
+    layer = Layer(H_CONV, want.shape, w=k, b=b, pad=(1,) * 4)
+    got = ref.run(DT_F32, x.shape, [layer], x)
+    _f32_close(got, want)
+
+
+def test_network_oracle_chain_equals_reference_graph(ref, ref_noavx):
+    """A whole (narrow) MobileNetV1 through the reference in graph mode (GREF,
+    source/graph_ref/setup.c:1305) equals the chained oracle ops."""
+    import nets
+    nb = nets.mobilenet_v1(DT_INT8, batch=1, res=64, width=0.25, classes=64)
+    x = nb.input_batch()
+    want = nets.oracle_forward(nb, x)
+    got = ref.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1 and np.count_nonzero(d) <= 2, (d.max(), np.count_nonzero(d))
