@@ -91,7 +91,9 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
             goto done;
         }
         const double sw = kernel->qinfo[qi].scale;
-        double sb = s_in * sw;
+        /* default bias scale: the float product, as it would sit in bias->qinfo[].scale */
+        const float sb_default = input->qinfo->scale * kernel->qinfo[qi].scale;
+        double sb = sb_default;
         if (b && bias->qinfo) {
             const int bi = bias->quant_channel > 1 ? o : 0;
             if (bias->qinfo[bi].scale != 0) sb = bias->qinfo[bi].scale;

@@ -57,7 +57,10 @@ int oracle_requant_tables(const oracle_conv_params *p, const int8_t *wt, const i
     for (int o = 0; o < p->o; o++) {
         int qi = p->w_channels > 1 ? o : 0;
         double sw = p->s_w[qi];
-        double sb = p->s_b ? (double)p->s_b[qi] : (double)p->s_in * sw;
+        /* bias scale defaults to s_in * s_w as a FLOAT product: it lives in the float field
+         * bias->qinfo[].scale (tests/utils/test_utils.c:660 convert_f32_bias) */
+        const float sb_default = p->s_in * p->s_w[qi];
+        double sb = p->s_b ? (double)p->s_b[qi] : (double)sb_default;
         int64_t wsum = 0;
         for (int t = 0; t < taps_per_o; t++) wsum += wt[(int64_t)o * taps_per_o + t];
         int64_t b = bias ? bias[o] : 0;

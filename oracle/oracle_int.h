@@ -24,7 +24,8 @@
  *     acc  += ibias[o] = -zp_in * sum_taps w[o]            (zero-point fold)
  *     f     = fmaf((float)acc, mult[o], badd[o])           (one rounding)
  *             mult[o] = (float)((double)s_in * s_w[o] / s_out)
- *             badd[o] = (float)((double)bias_q[o] * s_b[o] / s_out)
+ *             badd[o] = (float)((double)bias_q[o] * s_b[o] / s_out)   (s_b defaults to the float
+ *                       product s_in * s_w[o], the value a float qinfo field would hold)
  *     q     = clamp((int)rintf(f) + zp_out, -128, 127)     (round half even, as nearbyint in
  *                                                           source/nn2/utils.c:550 float_to_int8_base)
  * The reference itself accumulates dequantised f32 products
