@@ -295,9 +295,18 @@ static void fill_epilogue(const b200_op *op, b200_epilogue *ep)
 }
 
 /* ---- running one op on device tensors ------------------------------------------------------ */
+/* a network's first layer: NCHW input with so few channels that im2col + GEMM loses to the
+ * direct dp4a kernel (csrc/conv_direct.cu) */
+static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
+{
+    return in0->is_nchw && op->dtype == B200_I8 && op->group == 1 && op->kdim <= 160 && op->o <= 256 &&
+           !getenv("SHL_B200_NO_DIRECT_CONV");
+}
+
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
     if (op->kind != B200_OPK_CONV || (op->direct && !in0->is_nchw)) return 0;
+    if (conv_goes_direct(op, in0)) return 0;
     return (size_t)out->n * out->h * out->w * op->ldk * op->eb;
 }
 
@@ -305,6 +314,18 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
 {
     const int og = op->o / op->group, cg = op->cin / op->group;
     const int m = out->n * out->h * out->w;
+    if (conv_goes_direct(op, in)) {
+        b200_conv_direct_desc c;
+        memset(&c, 0, sizeof(c));
+        c.n = in->n, c.c = in->c, c.h = in->h, c.w = in->w;
+        c.o = op->o, c.oh = out->h, c.ow = out->w, c.cp_out = out->cp;
+        c.kh = op->kh, c.kw = op->kw, c.stride_h = op->sh, c.stride_w = op->sw;
+        c.pad_top = op->pt, c.pad_left = op->pl, c.dil_h = op->dh, c.dil_w = op->dw;
+        c.ldw = op->ldk, c.in = in->d, c.wt = op->d_w, c.out = out->d, c.zp_in = op->zp_in;
+        fill_epilogue(op, &c.ep);
+        DEV_CHECK(b200_conv2d_direct(&c, stream));
+        return CSINN_TRUE;
+    }
     b200_gemm_desc g;
     memset(&g, 0, sizeof(g));
     g.dtype = op->dtype, g.m = m, g.k = op->kdim, g.ldw = op->ldk, g.ldo = out->cp;
@@ -362,7 +383,7 @@ int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_
             d.h = in0->h, d.w = in0->w, d.oh = out->h, d.ow = out->w;
             d.kh = op->kh, d.kw = op->kw, d.stride_h = op->sh, d.stride_w = op->sw;
             d.pad_top = op->pt, d.pad_left = op->pl, d.dil_h = op->dh, d.dil_w = op->dw;
-            d.in = in0->d, d.wt = op->d_w, d.out = out->d, d.zp_in = op->zp_in;
+            d.in = in0->d, d.wt = op->d_w, d.wt_col3 = op->d_w2, d.out = out->d, d.zp_in = op->zp_in;
             fill_epilogue(op, &d.ep);
             DEV_CHECK(b200_dwconv2d(&d, stream));
             return CSINN_TRUE;
@@ -563,6 +584,9 @@ static int conv_init_common(struct csinn_tensor *input, struct csinn_tensor *out
         const int cp = b200_round_channels(C, op->eb);
         rc = b200_make_requant(op, input, kernel, bias, output, kh * kw, params->conv_extra.fuse_zp2bias, O);
         if (rc == CSINN_TRUE && !(op->d_w = b200_pack_dw_weights(op, kernel, cp, &wbytes))) rc = CSINN_FALSE;
+        if (rc == CSINN_TRUE && op->dtype == B200_I8 && kh == 3 && kw == 3 &&
+            !(op->d_w2 = b200_pack_dw3x3_cols(op, kernel, cp)))
+            rc = CSINN_FALSE;
     } else {
         const int og = O / group;
         if (group > 1 && (og * op->eb) % 16) {

@@ -285,6 +285,43 @@ __device__ __forceinline__ int requant_i8(int acc, float mult, float badd, int z
     return q;
 }
 
+// ---- fast epilogue pieces ---------------------------------------------------------------
+// Same contract as requant_i8, fewer instructions: the epilogues are issue-bound on the
+// memory-bound layers, so every op per output counts.
+//
+// (q0,q1,q2,q3) -> 4 saturated int8 in one word: two cvt.pack.sat (I2IP) instead of eight
+// min/max plus shifts and ors.  d = {c.lo16, sat(a), sat(b)} with b in byte 0.
+__device__ __forceinline__ uint32_t pack4_sat_i8(int q0, int q1, int q2, int q3)
+{
+    uint32_t hi, d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q3), "r"(q2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(q1), "r"(q0), "r"(hi));
+    return d;
+}
+
+// four requantised values through the post table (shared memory, indexed q + 128) into one word
+__device__ __forceinline__ uint32_t lut4_i8(int q0, int q1, int q2, int q3, const uint8_t *lut)
+{
+    const uint32_t b0 = lut[clamp_i8(q0) + 128], b1 = lut[clamp_i8(q1) + 128];
+    const uint32_t b2 = lut[clamp_i8(q2) + 128], b3 = lut[clamp_i8(q3) + 128];
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
+
+// Exact int <-> float through the 1.5 * 2^23 magic constant, valid while |value| < 2^22 (the
+// host guarantees it: b200_opt/quant.c bounds |acc * mult + bias| and the depthwise / small-K
+// accumulators): an accumulator that was INITIALISED with kMagicI + ibias is turned into
+// float(acc) by one FADD, and round-half-even back to int is one FADD + one IADD.
+constexpr int kMagicI = 0x4B400000;
+constexpr float kMagicF = 12582912.0f;
+__device__ __forceinline__ float magic_to_float(int biased_acc)
+{
+    return __fsub_rn(__int_as_float(biased_acc), kMagicF);
+}
+__device__ __forceinline__ int magic_round(float f, int zp_minus_magic)
+{
+    return __float_as_int(__fadd_rn(f, kMagicF)) + zp_minus_magic;
+}
+
 __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d)
 {
     return (static_cast<uint32_t>(a) & 0xFF) | ((static_cast<uint32_t>(b) & 0xFF) << 8) |

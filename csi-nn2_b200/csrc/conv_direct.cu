@@ -1,0 +1,164 @@
+// conv_direct.cu -- int8 conv2d for a network's FIRST layer: few input channels (K = C*kh*kw
+// <= 160), input still in the API's NCHW layout, output pixel-major.  With K = 27 (3x3x3) or 147
+// (7x7x3) an im2col + GEMM round trip through HBM costs several times the layer's own traffic and
+// the tensor core would multiply mostly zero padding, so this one layer shape is computed
+// directly: one thread per output pixel gathers its K input bytes once (NCHW reads are coalesced
+// across the warp: neighbouring threads own neighbouring pixels), packs them four to a word and
+// runs dp4a against weight words held in shared memory (broadcast reads), 4 output channels per
+// 128-bit shared load.  HBM traffic = input once + output once.
+//
+// k order = (ky, kx, c), the order b200_opt/quant.c packs conv weights in.  Epilogue = the
+// contract of include/b200nn.h.  Replaces, for this shape, the im2col loop + 4x16 GEMM of
+// shl_rvv_conv_im2col_gemm_int8 (source/thead_rvv/int8/convolution_gemm_int8.c:106-170).
+#include "common.cuh"
+
+namespace b200 {
+
+struct DirectArgs {
+    int n, c, h, w, o, oh, ow, cp_out;
+    int kh, kw, sh, sw, pt, pl, dh, dw;
+    int kwords;  // ceil(K / 4)
+    int ldw;     // weight row pitch in bytes (= ldk)
+    const int8_t *in;
+    const int8_t *wt;  // [O][ldw] bytes, k = (ky, kx, c)
+    int8_t *out;
+    int zp_in;
+    EpiScalars ep;
+};
+
+constexpr int kDirectThreads = 128;
+
+__global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_kernel(const DirectArgs a)
+{
+    extern __shared__ uint32_t s_w[];  // [kwords][o4] words, o4 = O rounded up to 4
+    const int o4 = (a.o + 3) & ~3;
+    float *s_mu = reinterpret_cast<float *>(s_w + a.kwords * o4);
+    float *s_ba = s_mu + o4;
+    int *s_ib = reinterpret_cast<int *>(s_ba + o4);
+    uint32_t *s_x = reinterpret_cast<uint32_t *>(s_ib + o4);  // [kwords][threads]: this thread's packed taps
+    __shared__ uint8_t s_lut[256];
+    for (int i = threadIdx.x; i < a.kwords * o4; i += blockDim.x) {
+        const int j = i / o4, o = i % o4;
+        uint32_t wv = 0;
+        if (o < a.o) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = j * 4 + e;
+                const uint32_t byte = k < a.kh * a.kw * a.c ? static_cast<uint8_t>(a.wt[o * a.ldw + k]) : 0;
+                wv |= byte << (8 * e);
+            }
+        }
+        s_w[i] = wv;
+    }
+    for (int o = threadIdx.x; o < o4; o += blockDim.x) {
+        s_mu[o] = o < a.o ? a.ep.mult[o] : 0.f;
+        s_ba[o] = o < a.o ? a.ep.badd[o] : 0.f;
+        s_ib[o] = o < a.o ? a.ep.ibias[o] : 0;
+    }
+    if (a.ep.post_lut != nullptr)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = static_cast<uint8_t>(a.ep.post_lut[i]);
+    __syncthreads();
+    const uint8_t *lut = a.ep.post_lut != nullptr ? s_lut : nullptr;
+
+    const long long total = static_cast<long long>(a.n) * a.oh * a.ow;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(p % a.ow);
+        const int oy = static_cast<int>((p / a.ow) % a.oh);
+        const int b = static_cast<int>(p / (static_cast<long long>(a.ow) * a.oh));
+        // gather: K bytes of this pixel's receptive field, zp_in at padded taps, four to a word
+        const int8_t *img = a.in + static_cast<long long>(b) * a.c * a.h * a.w;
+        {
+            int k = 0;
+            uint32_t cur = 0;
+            for (int ky = 0; ky < a.kh; ky++) {
+                const int iy = oy * a.sh - a.pt + ky * a.dh;
+                for (int kx = 0; kx < a.kw; kx++) {
+                    const int ix = ox * a.sw - a.pl + kx * a.dw;
+                    const bool ok = iy >= 0 && iy < a.h && ix >= 0 && ix < a.w;
+                    for (int c = 0; c < a.c; c++, k++) {
+                        const int v = ok ? img[(static_cast<long long>(c) * a.h + iy) * a.w + ix] : a.zp_in;
+                        cur |= static_cast<uint32_t>(v & 0xFF) << (8 * (k & 3));
+                        if ((k & 3) == 3) {
+                            s_x[(k >> 2) * kDirectThreads + threadIdx.x] = cur;
+                            cur = 0;
+                        }
+                    }
+                }
+            }
+            if (k & 3) s_x[(k >> 2) * kDirectThreads + threadIdx.x] = cur;
+        }
+        int8_t *dst = a.out + p * a.cp_out;
+        for (int ob = 0; ob < o4; ob += 16) {
+            uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int og = 0; og < 4; og++) {
+                const int o = ob + og * 4;
+                if (o >= o4) break;
+                int acc[4];
+                const int4 ib = *reinterpret_cast<const int4 *>(&s_ib[o]);
+                acc[0] = ib.x, acc[1] = ib.y, acc[2] = ib.z, acc[3] = ib.w;
+#pragma unroll 4
+                for (int j = 0; j < a.kwords; j++) {
+                    const int x = static_cast<int>(s_x[j * kDirectThreads + threadIdx.x]);
+                    const uint4 wv = *reinterpret_cast<const uint4 *>(&s_w[j * o4 + o]);
+                    acc[0] = __dp4a(x, static_cast<int>(wv.x), acc[0]);
+                    acc[1] = __dp4a(x, static_cast<int>(wv.y), acc[1]);
+                    acc[2] = __dp4a(x, static_cast<int>(wv.z), acc[2]);
+                    acc[3] = __dp4a(x, static_cast<int>(wv.w), acc[3]);
+                }
+                const float4 mu = *reinterpret_cast<const float4 *>(&s_mu[o]);
+                const float4 ba = *reinterpret_cast<const float4 *>(&s_ba[o]);
+                const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
+                int q[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    q[e] = __float2int_rn(fmaf(static_cast<float>(acc[e]), m4[e], b4[e])) + a.ep.zp_out;
+                    if (a.ep.act != B200_ACT_NONE) q[e] = max(q[e], a.ep.zp_out);
+                    if (a.ep.act == B200_ACT_RELU6) q[e] = min(q[e], a.ep.q6);
+                }
+                pk[og] = lut ? lut4_i8(q[0], q[1], q[2], q[3], lut) : pack4_sat_i8(q[0], q[1], q[2], q[3]);
+            }
+            if (ob < a.cp_out)
+                *reinterpret_cast<uint4 *>(dst + ob) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
+{
+    if (!d || !d->in || !d->wt || !d->out || !d->ep.mult || !d->ep.badd || !d->ep.ibias) {
+        set_error("b200_conv2d_direct: null descriptor field");
+        return B200_ERR_ARG;
+    }
+    const int K = d->c * d->kh * d->kw;
+    if (d->n <= 0 || d->c <= 0 || d->o <= 0 || K > 160 || d->o > 256 || d->cp_out < d->o || d->cp_out % 16 ||
+        d->stride_h < 1 || d->stride_w < 1 || d->dil_h < 1 || d->dil_w < 1 || d->ldw < K) {
+        set_error("b200_conv2d_direct: unsupported shape (C*kh*kw=%d must be <= 160, O=%d <= 256)", K, d->o);
+        return B200_ERR_UNSUPPORTED;
+    }
+    DirectArgs a;
+    a.n = d->n, a.c = d->c, a.h = d->h, a.w = d->w, a.o = d->o, a.oh = d->oh, a.ow = d->ow, a.cp_out = d->cp_out;
+    a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w, a.pt = d->pad_top, a.pl = d->pad_left;
+    a.dh = d->dil_h, a.dw = d->dil_w, a.kwords = (K + 3) / 4, a.ldw = d->ldw;
+    a.in = static_cast<const int8_t *>(d->in), a.wt = static_cast<const int8_t *>(d->wt);
+    a.out = static_cast<int8_t *>(d->out), a.zp_in = d->zp_in, a.ep = make_epi(d->ep);
+    const int o4 = (d->o + 3) & ~3;
+    const size_t smem = static_cast<size_t>(a.kwords) * o4 * 4 + static_cast<size_t>(o4) * 12 +
+                        static_cast<size_t>(a.kwords) * kDirectThreads * 4;
+    const long long total = static_cast<long long>(d->n) * d->oh * d->ow;
+    long long g = (total + 127) / 128;
+    const long long cap = static_cast<long long>(sm_count()) * 16;
+    const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+    if (smem > 48 * 1024) {
+        set_error("b200_conv2d_direct: weights + taps (%zu bytes) exceed the shared-memory budget", smem);
+        return B200_ERR_UNSUPPORTED;
+    }
+    conv_direct_i8_kernel<<<grid, kDirectThreads, smem, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
 
 using namespace b200;
 
+int b200_dwconv3x3_i8_launch(const b200_dwconv_desc *d, const void *wcol, void *stream);  // dwconv3x3.cu
+
 extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
 {
     if (!d || !d->in || !d->wt || !d->out) {
@@ -222,6 +224,9 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         set_error("b200_dwconv2d: bad descriptor (c=%d cp=%d k=%dx%d)", d->c, d->cp, d->kh, d->kw);
         return B200_ERR_ARG;
     }
+    if (d->dtype == B200_I8 && d->wt_col3 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
+        d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2))
+        return b200_dwconv3x3_i8_launch(d, d->wt_col3, stream);
     DwArgs a;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
     a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;

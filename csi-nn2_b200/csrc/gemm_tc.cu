@@ -162,21 +162,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int et = threadIdx.x - 64;    // 0..255
         const EpiScalars &ep = args.ep;
         int local = 0;
+        int staged_n0 = -1;
+        const bool has_lut = ep.post_lut != nullptr;
+        const uint8_t *lut = reinterpret_cast<const uint8_t *>(epi->lut);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int m0 = (tile / args.num_n_tiles) * kBM;
             const int n0 = (tile % args.num_n_tiles) * args.bn;
-            // stage this n-tile's per-channel parameters
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            if (et < args.bn) {
-                const int col = n0 + et;
-                const bool ok = col < args.n;
-                epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
-                epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
-                epi->ibias[et] = (ok && ep.ibias) ? ep.ibias[col] : 0;
+            // stage this n-tile's per-channel parameters (once per CTA when N fits one tile)
+            if (n0 != staged_n0) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                if (et < args.bn) {
+                    const int col = n0 + et;
+                    const bool ok = col < args.n;
+                    epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
+                    epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
+                    epi->ibias[et] = (ok && ep.ibias) ? ep.ibias[col] : 0;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                staged_n0 = n0;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -205,26 +211,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c0 + j4 * 4]);
                         const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c0 + j4 * 4]);
                         const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c0 + j4 * 4]);
-                        int q0 = requant_i8(static_cast<int>(r[j4 * 4 + 0]) + ib.x, mu.x, ba.x,
-                                            ep.zp_out, ep.act, ep.q6);
-                        int q1 = requant_i8(static_cast<int>(r[j4 * 4 + 1]) + ib.y, mu.y, ba.y,
-                                            ep.zp_out, ep.act, ep.q6);
-                        int q2 = requant_i8(static_cast<int>(r[j4 * 4 + 2]) + ib.z, mu.z, ba.z,
-                                            ep.zp_out, ep.act, ep.q6);
-                        int q3 = requant_i8(static_cast<int>(r[j4 * 4 + 3]) + ib.w, mu.w, ba.w,
-                                            ep.zp_out, ep.act, ep.q6);
-                        if (ep.post_lut != nullptr) {
-                            q0 = epi->lut[q0 + 128];
-                            q1 = epi->lut[q1 + 128];
-                            q2 = epi->lut[q2 + 128];
-                            q3 = epi->lut[q3 + 128];
+                        int q[4];
+                        const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
+                        const int i4[4] = {ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float f = fmaf(static_cast<float>(static_cast<int>(r[j4 * 4 + e]) + i4[e]),
+                                                 m4[e], b4[e]);
+                            q[e] = __float2int_rn(f) + ep.zp_out;
+                            if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
+                            if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
                         }
-                        const int cb = n0 + c0 + j4 * 4;
-                        q0 = cb + 0 < args.n ? q0 : 0;
-                        q1 = cb + 1 < args.n ? q1 : 0;
-                        q2 = cb + 2 < args.n ? q2 : 0;
-                        q3 = cb + 3 < args.n ? q3 : 0;
-                        packed[j4] = pack4_i8(q0, q1, q2, q3);
+                        // columns >= n of a partial vector carry unspecified values (never read:
+                        // every consumer takes the true channel count)
+                        packed[j4] = has_lut ? lut4_i8(q[0], q[1], q[2], q[3], lut)
+                                             : pack4_sat_i8(q[0], q[1], q[2], q[3]);
                     }
                     if (row_ok) {
                         int8_t *dst = static_cast<int8_t *>(args.out) +

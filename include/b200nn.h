@@ -144,7 +144,7 @@ typedef struct {
     int32_t lda;     /* elements, lda*elem % 16 == 0                                */
     const void *w;   /* device [n][ldw]   (OIHW with H=W=1, or fc weight [O][I])    */
     int32_t ldw;     /* elements, ldw*elem % 16 == 0                                */
-    void *out;       /* device [m][ldo]; columns [n, ldo) are written as zero       */
+    void *out;       /* device [m][ldo]; columns [n, ldo) hold unspecified values    */
     int32_t ldo;     /* elements, ldo*elem % 16 == 0, ldo >= n                      */
     b200_epilogue ep;
 } b200_gemm_desc;
@@ -170,17 +170,39 @@ typedef struct {
 } b200_im2col_desc;
 int b200_im2col(const b200_im2col_desc *d, void *stream);
 
+/* ---- direct conv2d for a first layer (int8, few input channels, NCHW input) ---- */
+/* The one conv shape where im2col + GEMM loses: K = c*kh*kw <= 160 (3x3x3, 7x7x3 stems) read
+ * straight from the API's NCHW tensor, dp4a against weights in shared memory, pixel-major
+ * output.  Same semantics and epilogue as b200_gemm on the im2col matrix; `wt` is the same packed
+ * [o][ldw] (k = (ky, kx, c)) buffer the GEMM path uses.  Replaces, for this shape,
+ * shl_rvv_conv_im2col_gemm_int8 (source/thead_rvv/int8/convolution_gemm_int8.c:173). */
+typedef struct {
+    int32_t n, c, h, w;      /* NCHW input                                        */
+    int32_t o, oh, ow, cp_out;
+    int32_t kh, kw, stride_h, stride_w, pad_top, pad_left, dil_h, dil_w;
+    int32_t ldw;             /* weight row pitch, bytes                            */
+    const void *in;
+    const void *wt;
+    void *out;               /* device [n][oh][ow][cp_out]                         */
+    int32_t zp_in;
+    b200_epilogue ep;
+} b200_conv_direct_desc;
+int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream);
+
 /* ---- depthwise conv2d (HBM-bound stencil) ------------------------------------ */
 /* Replaces shl_rvv_dwconv3x3s1_int8 / s2 (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31 )
  * and the fp16 twins; semantics: shl_ref_depthwise_conv2d_quant (source/reference/convolution.c:416).
- * Weights are tap-major [kh][kw][cp] (packed once at init from O1HW). depth_multiplier == 1. */
+ * Weights are packed once at init from O1HW (layouts below). depth_multiplier == 1. */
 typedef struct {
     int32_t dtype;
     int32_t n, c, cp; /* batch, channels, channel stride (elements)          */
     int32_t h, w, oh, ow;
     int32_t kh, kw, stride_h, stride_w, pad_top, pad_left, dil_h, dil_w;
     const void *in;  /* device [n][h][w][cp]                                */
-    const void *wt;  /* device [kh][kw][cp]  int8 | f16                     */
+    const void *wt;  /* device, tap-major [kh*kw][cp]: f16 halves, or for int8 one 32-bit word
+                        per (tap, channel) with the weight in byte lane (c & 3), others 0  */
+    const void *wt_col3; /* optional, int8 3x3 only: [3 (kx)][cp] words
+                            (w[0][kx][c], w[1][kx][c], w[2][kx][c], 0) for the dp4a fast path */
     void *out;       /* device [n][oh][ow][cp]                              */
     int32_t zp_in;   /* int8: value of a padded tap                         */
     b200_epilogue ep;

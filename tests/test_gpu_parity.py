@@ -90,6 +90,34 @@ def test_conv_int8_against_the_reference_library(b200, ref, rng):
         ref_band(got, want)
 
 
+FIRST_LAYER = [(2, 3, 32, 32, 32, 3, 2, 1, 5), (1, 3, 40, 40, 64, 7, 2, 3, 0), (1, 4, 17, 19, 24, 3, 1, 1, -9),
+               (1, 1, 16, 16, 8, 5, 1, 2, 3), (3, 3, 224, 224, 32, 3, 2, 1, 0)]
+
+
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "im2col"])
+@pytest.mark.parametrize("case", FIRST_LAYER, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_zp%d" % c)
+def test_first_layer_conv_from_nchw(case, direct, b200, oracle, rng):
+    """graph mode: the network input stays NCHW on the device and the first conv reads it directly,
+    through the dp4a kernel (csrc/conv_direct.cu) or, forced, through the NCHW im2col gather + GEMM;
+    a relu node with its own qinfo rides in the epilogue either way"""
+    n, c, h, w, o, k, stride, pad, zp_in = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layers = [Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=0, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                    pad=(pad,) * 4), Layer(H_RELU, (n, o, oh, ow), s_out=s_out / 2, zp_out=-128)]
+    if not direct:
+        os.environ["SHL_B200_NO_DIRECT_CONV"] = "1"
+    try:
+        got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=zp_in, run_mode=RM_GRAPH)
+    finally:
+        os.environ.pop("SHL_B200_NO_DIRECT_CONV", None)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), stride=(stride, stride), pad=(pad,) * 4, dilation=(1, 1),
+                            group=1, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out, zp_out=0,
+                            post=(ACT_RELU, s_out / 2, -128))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+
+
 @pytest.mark.parametrize("api", [API_RVV, API_C906, API_C920])
 def test_registered_api_ids_reach_the_gpu(api, b200, oracle, rng):
     """b200 answers under the ids of the back ends it replaces (north star: thead_rvv, c9*_opt)"""
@@ -318,6 +346,31 @@ def test_resnet50_int8_narrow_bit_exact(b200):
     got = b200.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
     want = nets.oracle_forward(nb, x)
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+
+
+@pytest.mark.parametrize("rows", [2, 3, 4])
+def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
+    """every rows-per-thread variant of the dp4a depthwise kernel (csrc/dwconv3x3.cu), on shapes that
+    hit ragged rows, ragged strips, both strides, asymmetric pads and a fused relu table"""
+    os.environ["SHL_B200_DW_ROWS"] = str(rows)
+    try:
+        for (n, c, h, w, stride, pad, zp_in) in [(2, 32, 13, 29, 1, 1, -7), (1, 64, 56, 56, 1, 1, 0),
+                                                 (1, 48, 15, 15, 2, 1, 4), (1, 16, 7, 7, 1, 1, -128),
+                                                 (1, 128, 9, 10, 2, 0, 2), (1, 20, 6, 5, 1, 0, 1)]:
+            x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+            wt, s_w, b, s_out = synth_conv_i8(rng, c, c, 3, 3, depthwise=True)
+            oh, ow = conv_out_hw(h, w, 3, 3, (stride, stride), (pad,) * 4)
+            layers = [Layer(H_CONV, (n, c, oh, ow), s_out=s_out, zp_out=2, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                            pad=(pad,) * 4, group=c), Layer(H_RELU, (n, c, oh, ow), s_out=s_out / 2, zp_out=-128)]
+            kw = dict(depthwise=True, stride=(stride, stride), pad=(pad,) * 4, dilation=(1, 1), group=1, s_in=0.02,
+                      zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out, zp_out=2)
+            got = b200.run(DT_INT8, x.shape, layers[:1], x, s_in=0.02, zp_in=zp_in)
+            assert np.array_equal(got, oracle.conv2d_i8(x, wt, b, (n, c, oh, ow), **kw)), (rows, n, c, h, w, stride)
+            got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=zp_in, run_mode=RM_GRAPH)
+            want = oracle.conv2d_i8(x, wt, b, (n, c, oh, ow), post=(ACT_RELU, s_out / 2, -128), **kw)
+            assert np.array_equal(got, want), (rows, n, c, h, w, stride, "fused relu")
+    finally:
+        os.environ.pop("SHL_B200_DW_ROWS", None)
 
 
 def test_dwconv_sweep_shapes(b200, oracle, rng):
