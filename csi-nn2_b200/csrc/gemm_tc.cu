@@ -3,10 +3,13 @@
 // by TMA into 128B-swizzled shared memory, accumulators double-buffered in TMEM, the per-channel
 // requantise / bias / relu epilogue fused (contract in include/b200nn.h).
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      tcgen05.mma issuer (one elected lane) + TMEM allocation
-//   warps 2..9  epilogue: tcgen05.ld -> requantise -> 16-byte global stores
+// One persistent CTA per SM, 18 warps:
+//   warp 0       TMA producer (one elected lane)
+//   warp 1       tcgen05.mma issuer (one elected lane) + TMEM allocation
+//   warps 2..17  epilogue: tcgen05.ld -> requantise -> 16-byte global stores.  On the short-K
+//                (memory-bound) layers the epilogue's instruction stream is the critical path,
+//                so it gets 4 warps per scheduler and a compile-time specialised body
+//                (activation mode, post table, magic-number int<->float) instead of runtime flags.
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
 // static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n-tile fastest so that
 // CTAs running side by side share the A tile through L2).
@@ -20,11 +23,14 @@ namespace b200 {
 
 constexpr int kBM = 128;        // UMMA M (cta_group::1)
 constexpr int kBKBytes = 128;   // one swizzle atom of K per stage
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
+
+// epilogue specialisations
+enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_RELU6 = 2, EPI_LUT = 3, EPI_GENERIC = 4 };
 
 struct GemmArgs {
     int m, n;
@@ -41,19 +47,53 @@ struct GemmArgs {
 struct __align__(16) EpiParams {
     float mult[256];
     float badd[256];
-    int32_t ibias[256];
-    int8_t lut[256];
+    int32_t ibias[256];  // + kMagicI when the kernel converts through the magic constant
+    uint8_t lut[256];
 };
 
-template <int DT>
+// four int8 outputs from four accumulators (already + ibias) -> one packed word
+template <int MODE, bool MAGIC>
+__device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float4 mu, const float4 ba,
+                                             const EpiScalars &ep, const uint8_t *lut, int zp_m,
+                                             int lut_lo)
+{
+    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
+    int q[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float af = MAGIC ? magic_to_float(a[e]) : static_cast<float>(a[e]);
+        const float f = fmaf(af, m4[e], b4[e]);
+        // t = kMagicI + round_half_even(f)   (|f| < 2^22 is guaranteed by the host)
+        const int t = __float_as_int(__fadd_rn(f, kMagicF));
+        if (MODE == EPI_LUT) {
+            q[e] = min(max(t - lut_lo, 0), 255);  // clamp(q, -128, 127) + 128
+        } else {
+            q[e] = t + zp_m;
+            if (MODE == EPI_RELU || MODE == EPI_RELU6) q[e] = max(q[e], ep.zp_out);
+            if (MODE == EPI_RELU6) q[e] = min(q[e], ep.q6);
+            if (MODE == EPI_GENERIC) {
+                if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
+                if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
+            }
+        }
+    }
+    if (MODE == EPI_LUT) {
+        const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
+        return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    }
+    if (MODE == EPI_GENERIC && lut != nullptr) return lut4_i8(q[0], q[1], q[2], q[3], lut);
+    return pack4_sat_i8(q[0], q[1], q[2], q[3]);
+}
+
+template <int DT, int MODE, bool MAGIC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B atoms need 1024-byte alignment
-    uint8_t *smem = reinterpret_cast<uint8_t *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // SWIZZLE_128B atoms need 1024-byte alignment; stay on the shared-memory pointer so that every
+    // access below compiles to LDS/STS rather than generic LD/ST
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int stages = args.stages;
     const uint32_t a_stage_bytes = kBM * kBKBytes;
     const uint32_t b_stage_bytes = args.bn * kBKBytes;
@@ -89,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     if (warp >= 2 && args.ep.post_lut != nullptr) {
         const int t = threadIdx.x - 64;
-        if (t < 256) epi->lut[t] = args.ep.post_lut[t];
+        if (t < 256) epi->lut[t] = static_cast<uint8_t>(args.ep.post_lut[t]);
     }
     tc_fence_before();
     __syncthreads();
@@ -157,14 +197,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
         // ===== epilogue =====
         const int ew = warp - 2;
-        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;           // which alternate 32-column chunks it owns
-        const int et = threadIdx.x - 64;    // 0..255
+        const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+        const int part = ew >> 2;    // 0..3: which column chunks of the tile it owns
+        const int et = threadIdx.x - 64;
         const EpiScalars &ep = args.ep;
+        // column chunk per tcgen05.ld: 32 for wide tiles, 16 when the tile has at most 64 columns
+        // (so that all four warps of a quadrant have work)
+        const int cw = args.bn >= 128 ? 32 : 16;
+        const int zp_m = ep.zp_out - kMagicI;
+        const int lut_lo = kMagicI - ep.zp_out - 128;
+        const uint8_t *lut = ep.post_lut != nullptr ? epi->lut : nullptr;
         int local = 0;
         int staged_n0 = -1;
-        const bool has_lut = ep.post_lut != nullptr;
-        const uint8_t *lut = reinterpret_cast<const uint8_t *>(epi->lut);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
@@ -178,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const bool ok = col < args.n;
                     epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
                     epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
-                    epi->ibias[et] = (ok && ep.ibias) ? ep.ibias[col] : 0;
+                    epi->ibias[et] = ((ok && ep.ibias) ? ep.ibias[col] : 0) + (MAGIC ? kMagicI : 0);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
                 staged_n0 = n0;
@@ -190,9 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const bool row_ok = row < args.m;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    acc * kAccStride;
-            for (int c0 = half * 32; c0 < args.bn; c0 += 64) {
+            for (int c0 = part * cw; c0 < args.bn; c0 += 4 * cw) {
                 uint32_t r[32];
-                const int ncols = min(32, args.bn - c0);  // 32 or 16
+                const int ncols = min(cw, args.bn - c0);  // 32 or 16
                 if (ncols == 32) {
                     tmem_ld_32x32(taddr + c0, r);
                 } else {
@@ -205,46 +249,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 tmem_ld_wait();
                 if (DT == B200_I8) {
-                    uint32_t packed[8];
+                    int8_t *dst = static_cast<int8_t *>(args.out) + static_cast<size_t>(row) * args.ldo +
+                                  n0 + c0;
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c0 + j4 * 4]);
-                        const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c0 + j4 * 4]);
-                        const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c0 + j4 * 4]);
-                        int q[4];
-                        const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
-                        const int i4[4] = {ib.x, ib.y, ib.z, ib.w};
+                    for (int v = 0; v < 2; v++) {
+                        if (v * 16 >= ncols) break;
+                        uint32_t packed[4];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const float f = fmaf(static_cast<float>(static_cast<int>(r[j4 * 4 + e]) + i4[e]),
-                                                 m4[e], b4[e]);
-                            q[e] = __float2int_rn(f) + ep.zp_out;
-                            if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
-                            if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const int c = c0 + v * 16 + j4 * 4;
+                            const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c]);
+                            const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c]);
+                            const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c]);
+                            const int a4[4] = {static_cast<int>(r[v * 16 + j4 * 4 + 0]) + ib.x,
+                                               static_cast<int>(r[v * 16 + j4 * 4 + 1]) + ib.y,
+                                               static_cast<int>(r[v * 16 + j4 * 4 + 2]) + ib.z,
+                                               static_cast<int>(r[v * 16 + j4 * 4 + 3]) + ib.w};
+                            // columns >= n of a partial vector carry unspecified values (never
+                            // read: every consumer takes the true channel count)
+                            packed[j4] = requant4<MODE, MAGIC>(a4, mu, ba, ep, lut, zp_m, lut_lo);
                         }
-                        // columns >= n of a partial vector carry unspecified values (never read:
-                        // every consumer takes the true channel count)
-                        packed[j4] = has_lut ? lut4_i8(q[0], q[1], q[2], q[3], lut)
-                                             : pack4_sat_i8(q[0], q[1], q[2], q[3]);
-                    }
-                    if (row_ok) {
-                        int8_t *dst = static_cast<int8_t *>(args.out) +
-                                      static_cast<size_t>(row) * args.ldo + n0 + c0;
-#pragma unroll
-                        for (int v = 0; v < 2; v++) {
-                            if (v * 16 < ncols && n0 + c0 + v * 16 < args.ldo)
-                                *reinterpret_cast<uint4 *>(dst + v * 16) =
-                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
-                                               packed[v * 4 + 3]);
-                        }
+                        if (row_ok && n0 + c0 + v * 16 < args.ldo)
+                            *reinterpret_cast<uint4 *>(dst + v * 16) =
+                                make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     }
                 } else {
+                    const int act = MODE;  // fp16: MODE is the activation
                     uint32_t packed[16];
 #pragma unroll
                     for (int j2 = 0; j2 < 16; j2++) {
                         const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
-                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, ep.act);
-                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, ep.act);
+                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
+                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
                         const int cb = n0 + c0 + j2 * 2;
                         f0 = cb < args.n ? f0 : 0.f;
                         f1 = cb + 1 < args.n ? f1 : 0.f;
@@ -292,6 +328,23 @@ static int pick_bn(int n)
     return ((n16 + tiles - 1) / tiles + 15) / 16 * 16;
 }
 
+typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
+
+template <int DT, int MODE, bool MAGIC>
+static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &ta,
+                          const CUtensorMap &tb, const GemmArgs &args, int dev)
+{
+    static bool attr_set[64] = {};
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<DT, MODE, MAGIC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kSmemLimit));
+        attr_set[dev] = true;
+    }
+    gemm_tc_kernel<DT, MODE, MAGIC><<<grid, kThreads, smem, stream>>>(ta, tb, args);
+    return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -310,7 +363,8 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     if (d->m <= 0 || d->n <= 0 || d->k <= 0 || d->ldo < d->n || (d->lda * eb) % 16 ||
         (d->ldw * eb) % 16 || (d->ldo * eb) % 16 || d->lda < d->k || d->ldw < d->k ||
         (reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->w) & 15) ||
-        (reinterpret_cast<uintptr_t>(d->out) & 15)) {
+        (reinterpret_cast<uintptr_t>(d->out) & 15) ||
+        (d->dtype == B200_I8 && (!d->ep.mult || !d->ep.badd))) {
         set_error("b200_gemm: bad sizes m=%d n=%d k=%d lda=%d ldw=%d ldo=%d (pitches and bases must be 16-byte aligned)",
                   d->m, d->n, d->k, d->lda, d->ldw, d->ldo);
         return B200_ERR_ARG;
@@ -344,22 +398,40 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     const int grid = min(args.num_m_tiles * args.num_n_tiles, sm_count());
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
-    static bool attr_set[64][2] = {};
-    if (dev >= 0 && dev < 64 && !attr_set[dev][d->dtype]) {
-        if (d->dtype == B200_I8)
-            B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<B200_I8>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)kSmemLimit));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == B200_F16) {
+        switch (d->ep.act) {
+            case B200_ACT_NONE: rc = launch_variant<B200_F16, 0, false>(grid, smem, s, ta, tb, args, dev); break;
+            case B200_ACT_RELU: rc = launch_variant<B200_F16, 1, false>(grid, smem, s, ta, tb, args, dev); break;
+            default: rc = launch_variant<B200_F16, 2, false>(grid, smem, s, ta, tb, args, dev); break;
+        }
+    } else {
+        // |acc + ibias| <= K * 2 * 128 * 127 < 2^22 lets the epilogue convert through the magic
+        // constant (an FADD) instead of I2F
+        const bool magic = d->k <= 128;
+        int mode;
+        if (d->ep.post_lut)
+            mode = d->ep.act == B200_ACT_NONE ? EPI_LUT : EPI_GENERIC;
         else
-            B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<B200_F16>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)kSmemLimit));
-        attr_set[dev][d->dtype] = true;
+            mode = d->ep.act == B200_ACT_NONE ? EPI_PLAIN : (d->ep.act == B200_ACT_RELU ? EPI_RELU : EPI_RELU6);
+#define B200_GEMM_CASE(MODE)                                                                      \
+    case MODE:                                                                                    \
+        rc = magic ? launch_variant<B200_I8, MODE, true>(grid, smem, s, ta, tb, args, dev)        \
+                   : launch_variant<B200_I8, MODE, false>(grid, smem, s, ta, tb, args, dev);      \
+        break;
+        switch (mode) {
+            B200_GEMM_CASE(EPI_PLAIN)
+            B200_GEMM_CASE(EPI_RELU)
+            B200_GEMM_CASE(EPI_RELU6)
+            B200_GEMM_CASE(EPI_LUT)
+            default:
+                rc = magic ? launch_variant<B200_I8, EPI_GENERIC, true>(grid, smem, s, ta, tb, args, dev)
+                           : launch_variant<B200_I8, EPI_GENERIC, false>(grid, smem, s, ta, tb, args, dev);
+                break;
+        }
+#undef B200_GEMM_CASE
     }
-    if (d->dtype == B200_I8)
-        gemm_tc_kernel<B200_I8><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, args);
-    else
-        gemm_tc_kernel<B200_F16><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, args);
+    if (rc) return rc;
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
