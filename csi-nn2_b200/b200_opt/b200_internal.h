@@ -76,7 +76,7 @@ typedef struct b200_op {
     int kdim;    /* reduction length per group */
     int ldk;     /* im2col / weight row pitch (elements) */
     void *d_w;   /* packed weights */
-    void *d_w2;  /* second packing of the same weights (int8 3x3 depthwise: kx-major dp4a words) */
+    void *d_w2;  /* second packing of the same weights (int8 3x3 depthwise: ky-major dp4a words) */
     float *d_mult, *d_badd;
     int32_t *d_ibias;
     int8_t *d_lut; /* post table or the ACT table */
@@ -112,7 +112,7 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
                       int n_out);
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
 void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);
-void *b200_pack_dw3x3_cols(b200_op *op, const struct csinn_tensor *kernel, int cp);
+void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int cp);
 void *b200_pack_fc_weights(b200_op *op, const struct csinn_tensor *weights, size_t *bytes);
 
 /* graph.c */

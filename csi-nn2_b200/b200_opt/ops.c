@@ -383,7 +383,7 @@ int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_
             d.h = in0->h, d.w = in0->w, d.oh = out->h, d.ow = out->w;
             d.kh = op->kh, d.kw = op->kw, d.stride_h = op->sh, d.stride_w = op->sw;
             d.pad_top = op->pt, d.pad_left = op->pl, d.dil_h = op->dh, d.dil_w = op->dw;
-            d.in = in0->d, d.wt = op->d_w, d.wt_col3 = op->d_w2, d.out = out->d, d.zp_in = op->zp_in;
+            d.in = in0->d, d.wt = op->d_w, d.wt_row3 = op->d_w2, d.out = out->d, d.zp_in = op->zp_in;
             fill_epilogue(op, &d.ep);
             DEV_CHECK(b200_dwconv2d(&d, stream));
             return CSINN_TRUE;
@@ -585,7 +585,7 @@ static int conv_init_common(struct csinn_tensor *input, struct csinn_tensor *out
         rc = b200_make_requant(op, input, kernel, bias, output, kh * kw, params->conv_extra.fuse_zp2bias, O);
         if (rc == CSINN_TRUE && !(op->d_w = b200_pack_dw_weights(op, kernel, cp, &wbytes))) rc = CSINN_FALSE;
         if (rc == CSINN_TRUE && op->dtype == B200_I8 && kh == 3 && kw == 3 &&
-            !(op->d_w2 = b200_pack_dw3x3_cols(op, kernel, cp)))
+            !(op->d_w2 = b200_pack_dw3x3_rows(op, kernel, cp)))
             rc = CSINN_FALSE;
     } else {
         const int og = O / group;

@@ -184,19 +184,19 @@ void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int c
     return dev;
 }
 
-/* int8 3x3 depthwise, kx-major for the dp4a kernel: word[kx][c] = (w[0][kx][c], w[1][kx][c],
- * w[2][kx][c], 0) -- one dp4a against the vertical tap triple of a column */
-void *b200_pack_dw3x3_cols(b200_op *op, const struct csinn_tensor *kernel, int cp)
+/* int8 3x3 depthwise, ky-major for the dp4a kernel: word[ky][c] = (w[ky][0][c], w[ky][1][c],
+ * w[ky][2][c], 0) -- one dp4a against the horizontal tap triple of an input row */
+void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int cp)
 {
     const int C = kernel->dim[0];
     uint32_t *buf = calloc((size_t)3 * cp, sizeof(uint32_t));
     if (!buf) return NULL;
     const int8_t *src = kernel->data;
     for (int c = 0; c < C; c++)
-        for (int kx = 0; kx < 3; kx++) {
+        for (int ky = 0; ky < 3; ky++) {
             uint32_t w = 0;
-            for (int ky = 0; ky < 3; ky++) w |= (uint32_t)(uint8_t)src[(size_t)c * 9 + ky * 3 + kx] << (8 * ky);
-            buf[(size_t)kx * cp + c] = w;
+            for (int kx = 0; kx < 3; kx++) w |= (uint32_t)(uint8_t)src[(size_t)c * 9 + ky * 3 + kx] << (8 * kx);
+            buf[(size_t)ky * cp + c] = w;
         }
     void *dev = b200_warena_put(op->ctx, buf, (size_t)3 * cp * sizeof(uint32_t));
     free(buf);

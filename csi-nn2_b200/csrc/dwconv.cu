@@ -10,6 +10,8 @@
 //
 // Replaces shl_rvv_dwconv3x3s1_int8 / s2 (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31)
 // and the fp16 twins; any kernel size / stride / dilation is covered by the same kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
 
 using namespace b200;
 
-int b200_dwconv3x3_i8_launch(const b200_dwconv_desc *d, const void *wcol, void *stream);  // dwconv3x3.cu
+int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream);  // dwconv3x3_tma.cu
 
 extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
 {
@@ -224,9 +226,10 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         set_error("b200_dwconv2d: bad descriptor (c=%d cp=%d k=%dx%d)", d->c, d->cp, d->kh, d->kw);
         return B200_ERR_ARG;
     }
-    if (d->dtype == B200_I8 && d->wt_col3 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
+    if (d->dtype == B200_I8 && d->wt_row3 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
+        !getenv("SHL_B200_DW_GENERIC") &&
         d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2))
-        return b200_dwconv3x3_i8_launch(d, d->wt_col3, stream);
+        return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);
     DwArgs a;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
     a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;

@@ -1,0 +1,368 @@
+// dwconv3x3_tma.cu -- int8 depthwise 3x3 (stride 1 / 2, dilation 1) on pixel-major tensors,
+// TMA-fed.  The HBM-bound half of a MobileNet block.
+//
+// A CTA walks tiles of TH x TW output pixels x CC channels.  A producer warp fetches each tile's
+// input halo ((S*(TH-1)+3) x (S*(TW-1)+3) x CC bytes) with ONE 4-D TMA box into a 3-deep shared
+// memory ring (negative / overhanging coordinates are zero-filled by the hardware and patched to
+// the input zero point, which is what a padded tap holds in the quantised domain); 256 consumer
+// threads never touch global memory for input, so HBM latency is hidden by the ring instead of by
+// registers and occupancy.
+//
+// A consumer thread owns four channels (one 32-bit word) of ONE output column and slides down the
+// tile: per input row it reads the three horizontally adjacent words, permutes them into four
+// "tap words" (x[-1][c], x[0][c], x[+1][c], -) and issues dp4a against weight words
+// (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0): 3 dp4a per output, no unpacking.  Each input row
+// feeds the three output rows it belongs to through rotating accumulator sets (12 registers), so
+// the kernel needs ~60 registers.  Accumulators start at ibias + kMagicI (see common.cuh); the
+// epilogue is the contract of include/b200nn.h, specialised at compile time like the GEMM's.
+//
+// Replaces shl_rvv_dwconv3x3s1_int8 / shl_rvv_dwconv3x3s2_int8
+// (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31,244); semantics
+// shl_ref_depthwise_conv2d_quant (source/reference/convolution.c:416).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+enum { DW_PLAIN = 0, DW_RELU = 1, DW_RELU6 = 2, DW_LUT = 3, DW_GENERIC = 4 };
+constexpr int kDwStages = 3;
+constexpr int kDwConsumers = 256;
+constexpr int kDwThreads = kDwConsumers + 32;
+
+struct DwTmaArgs {
+    int n, c, cp, h, w, oh, ow, pt, pl;
+    int th, thi;            // output rows per tile, input rows per tile
+    int ybands, xbands, cchunks;
+    int stage_bytes;
+    const uint32_t *wrow;   // [3 (ky)][cp] words: (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0)
+    int8_t *out;
+    int zp_in;
+    EpiScalars ep;
+};
+
+template <int MODE>
+__device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const float (&mu)[4], const float (&ba)[4],
+                                                const EpiScalars &ep, const uint8_t *lut, int zp_m, int lut_lo)
+{
+    int q[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float f = fmaf(magic_to_float(acc[e]), mu[e], ba[e]);
+        const int t = __float_as_int(__fadd_rn(f, kMagicF));
+        if (MODE == DW_LUT) {
+            q[e] = min(max(t - lut_lo, 0), 255);
+        } else {
+            q[e] = t + zp_m;
+            if (MODE == DW_RELU || MODE == DW_RELU6) q[e] = max(q[e], ep.zp_out);
+            if (MODE == DW_RELU6) q[e] = min(q[e], ep.q6);
+            if (MODE == DW_GENERIC) {
+                if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
+                if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
+            }
+        }
+    }
+    if (MODE == DW_LUT) {
+        const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
+        return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    }
+    if (MODE == DW_GENERIC && lut != nullptr) return lut4_i8(q[0], q[1], q[2], q[3], lut);
+    return pack4_sat_i8(q[0], q[1], q[2], q[3]);
+}
+
+// tap words of four channels from three horizontally adjacent input words
+__device__ __forceinline__ void taps3(uint32_t a, uint32_t b, uint32_t c, uint32_t (&v)[4])
+{
+    const uint32_t lo = __byte_perm(a, b, 0x5140);  // (a.c0, b.c0, a.c1, b.c1)
+    const uint32_t hi = __byte_perm(a, b, 0x7362);  // (a.c2, b.c2, a.c3, b.c3)
+    v[0] = __byte_perm(lo, c, 0x4410);
+    v[1] = __byte_perm(lo, c, 0x5532);
+    v[2] = __byte_perm(hi, c, 0x6610);
+    v[3] = __byte_perm(hi, c, 0x7732);
+}
+
+__device__ __forceinline__ void dp4(int (&acc)[4], const uint32_t (&v)[4], const uint32_t (&w)[4])
+{
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[e] = __dp4a(static_cast<int>(v[e]), static_cast<int>(w[e]), acc[e]);
+}
+
+template <int S, int CC, int TW, int MODE>
+__global__ void __launch_bounds__(kDwThreads, 2)
+dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
+{
+    constexpr int TWI = S * (TW - 1) + 3;
+    constexpr int WORDS = CC / 4;
+    static_assert(WORDS * TW == kDwConsumers, "tile shape must give 256 consumer threads");
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[kDwStages], empty_bar[kDwStages];
+    __shared__ uint8_t s_lut[256];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < kDwStages; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kDwConsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    if (a.ep.post_lut != nullptr && tid < 256) s_lut[tid] = static_cast<uint8_t>(a.ep.post_lut[tid]);
+    __syncthreads();
+
+    const long long tiles = static_cast<long long>(a.n) * a.ybands * a.xbands * a.cchunks;
+
+    if (warp == kDwConsumers / 32) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int cc = static_cast<int>(t % a.cchunks);
+                const int xb = static_cast<int>((t / a.cchunks) % a.xbands);
+                const int yb = static_cast<int>((t / (static_cast<long long>(a.cchunks) * a.xbands)) % a.ybands);
+                const int b = static_cast<int>(t / (static_cast<long long>(a.cchunks) * a.xbands * a.ybands));
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], a.stage_bytes);
+                tma_load_4d(smem + static_cast<size_t>(stage) * a.stage_bytes, &tmap, &full_bar[stage], cc * CC,
+                            xb * TW * S - a.pl, yb * a.th * S - a.pt, b);
+                if (++stage == kDwStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int cw = tid % WORDS;  // channel word inside the chunk
+    const int x = tid / WORDS;   // output column inside the tile
+    const uint8_t *lut = a.ep.post_lut != nullptr ? s_lut : nullptr;
+    const int zp_m = a.ep.zp_out - kMagicI;
+    const int lut_lo = kMagicI - a.ep.zp_out - 128;
+    const uint32_t padw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int cc = static_cast<int>(t % a.cchunks);
+        const int xb = static_cast<int>((t / a.cchunks) % a.xbands);
+        const int yb = static_cast<int>((t / (static_cast<long long>(a.cchunks) * a.xbands)) % a.ybands);
+        const int b = static_cast<int>(t / (static_cast<long long>(a.cchunks) * a.xbands * a.ybands));
+        const int ch = cc * CC + cw * 4;          // first of this thread's four channels
+        const bool ch_ok = ch < a.cp;
+        const int ox = xb * TW + x;
+        const int oy0 = yb * a.th;
+        const int rows_out = min(a.th, a.oh - oy0);
+        const bool col_ok = ox < a.ow && ch_ok;
+
+        // per-thread constants of this tile's channel chunk (L1 / L2 hits)
+        uint32_t wk[3][4];
+        float mu[4], ba[4];
+        int init[4];
+        {
+            const int chs = ch_ok ? ch : 0;
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(a.wrow + ky * a.cp + chs));
+                wk[ky][0] = wv.x, wk[ky][1] = wv.y, wk[ky][2] = wv.z, wk[ky][3] = wv.w;
+            }
+            const float4 m4 = __ldg(reinterpret_cast<const float4 *>(a.ep.mult + chs));
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.ep.badd + chs));
+            const int4 i4 = __ldg(reinterpret_cast<const int4 *>(a.ep.ibias + chs));
+            mu[0] = m4.x, mu[1] = m4.y, mu[2] = m4.z, mu[3] = m4.w;
+            ba[0] = b4.x, ba[1] = b4.y, ba[2] = b4.z, ba[3] = b4.w;
+            init[0] = i4.x + kMagicI, init[1] = i4.y + kMagicI, init[2] = i4.z + kMagicI, init[3] = i4.w + kMagicI;
+        }
+
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t *tile = smem + static_cast<size_t>(stage) * a.stage_bytes;
+
+        // padded taps hold zp_in in the quantised domain; the TMA zero-filled them
+        const int iy0 = oy0 * S - a.pt, ix0 = xb * TW * S - a.pl;
+        const bool border = iy0 < 0 || ix0 < 0 || iy0 + a.thi > a.h || ix0 + TWI > a.w;
+        if (a.zp_in != 0 && border) {
+            for (int cell = tid; cell < a.thi * TWI; cell += kDwConsumers) {
+                const int r = cell / TWI, cx = cell % TWI;
+                const int iy = iy0 + r, ix = ix0 + cx;
+                if (iy < 0 || iy >= a.h || ix < 0 || ix >= a.w) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(tile + static_cast<size_t>(cell) * CC);
+#pragma unroll
+                    for (int q = 0; q < CC / 16; q++) dst[q] = make_uint4(padw, padw, padw, padw);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
+        }
+
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + x * S * WORDS + cw;
+        int8_t *obase = a.out + ((static_cast<long long>(b) * a.oh + oy0) * a.ow + ox) * a.cp + ch;
+        const long long orow = static_cast<long long>(a.ow) * a.cp;
+
+        auto load_taps = [&](int r, uint32_t (&v)[4]) {
+            const uint32_t *p = tw + r * (TWI * WORDS);
+            taps3(p[0], p[WORDS], p[2 * WORDS], v);
+        };
+        auto finish = [&](int (&acc)[4], int y) {
+            if (y >= 0 && y < rows_out && col_ok)
+                *reinterpret_cast<uint32_t *>(obase + y * orow) =
+                    dw_requant4<MODE>(acc, mu, ba, a.ep, lut, zp_m, lut_lo);
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[e] = init[e];
+        };
+
+        int accA[4], accB[4], accC[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) accA[e] = accB[e] = accC[e] = init[e];
+        uint32_t v[4];
+        if (S == 1) {
+            // input row r feeds output rows r (ky = 0), r - 1 (ky = 1), r - 2 (ky = 2, completes it)
+            const int rows_in = rows_out + 2;
+            for (int r = 0; r < rows_in; r += 3) {
+                load_taps(r, v);
+                dp4(accC, v, wk[0]), dp4(accB, v, wk[1]), dp4(accA, v, wk[2]);
+                finish(accA, r - 2);
+                if (r + 1 >= rows_in) break;
+                load_taps(r + 1, v);
+                dp4(accA, v, wk[0]), dp4(accC, v, wk[1]), dp4(accB, v, wk[2]);
+                finish(accB, r - 1);
+                if (r + 2 >= rows_in) break;
+                load_taps(r + 2, v);
+                dp4(accB, v, wk[0]), dp4(accA, v, wk[1]), dp4(accC, v, wk[2]);
+                finish(accC, r);
+            }
+        } else {
+            // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
+            load_taps(0, v);
+            dp4(accA, v, wk[0]);
+            for (int y = 0; y < rows_out; y += 2) {
+                load_taps(2 * y + 1, v);
+                dp4(accA, v, wk[1]);
+                load_taps(2 * y + 2, v);
+                dp4(accA, v, wk[2]), dp4(accB, v, wk[0]);
+                finish(accA, y);
+                if (y + 1 >= rows_out) break;
+                load_taps(2 * y + 3, v);
+                dp4(accB, v, wk[1]);
+                load_taps(2 * y + 4, v);
+                dp4(accB, v, wk[2]), dp4(accA, v, wk[0]);
+                finish(accB, y + 1);
+            }
+        }
+
+        // hand the slot back: generic-proxy accesses (the zero-point patch) must be ordered before
+        // the next async-proxy (TMA) write into it
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == kDwStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+}
+
+struct DwCfg {
+    int cc, tw;
+};
+
+template <int S, int CC, int TW>
+static int launch_cfg(int mode, int grid, size_t smem, cudaStream_t s, const CUtensorMap &tm, const DwTmaArgs &a,
+                      int dev)
+{
+#define B200_DW_CASE(M)                                                                              \
+    case M: {                                                                                        \
+        static bool attr[64] = {};                                                                   \
+        if (dev >= 0 && dev < 64 && !attr[dev]) {                                                    \
+            B200_CUDA_CHECK(cudaFuncSetAttribute(dw3x3_tma_kernel<S, CC, TW, M>,                     \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+            attr[dev] = true;                                                                        \
+        }                                                                                            \
+        dw3x3_tma_kernel<S, CC, TW, M><<<grid, kDwThreads, smem, s>>>(tm, a);                        \
+        break;                                                                                       \
+    }
+    switch (mode) {
+        B200_DW_CASE(DW_PLAIN)
+        B200_DW_CASE(DW_RELU)
+        B200_DW_CASE(DW_RELU6)
+        B200_DW_CASE(DW_LUT)
+        default:
+            B200_DW_CASE(DW_GENERIC)
+    }
+#undef B200_DW_CASE
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// called by b200_dwconv2d (dwconv.cu) for int8 3x3, dilation 1, stride 1 / 2; `wrow` is the
+// ky-major repack of the depthwise weights built by b200_opt/quant.c
+int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream)
+{
+    const int S = d->stride_h;
+    // tile shape: (CC, TW) with CC/4 * TW = 256 threads; prefer full column use and a thin halo
+    static const DwCfg cfgs[3] = {{32, 32}, {64, 16}, {128, 8}};
+    int best = 0;
+    double best_score = -1;
+    for (int i = 0; i < 3; i++) {
+        const int cc = cfgs[i].cc, tw = cfgs[i].tw;
+        const int xb = (d->ow + tw - 1) / tw, cb = (d->cp + cc - 1) / cc;
+        const int twi = S * (tw - 1) + 3;
+        const double use = (double)d->ow / (xb * tw) * (double)d->cp / (cb * cc);
+        const double halo = (double)(S * tw) / twi;
+        const double score = use * halo;
+        if (score > best_score + 1e-9) best_score = score, best = i;
+    }
+    const int CC = cfgs[best].cc, TW = cfgs[best].tw;
+    const int TWI = S * (TW - 1) + 3;
+    // rows per tile: a ~28 KB halo stage
+    int thi_max = (28 * 1024) / (TWI * CC);
+    if (thi_max > 256) thi_max = 256;  // TMA box limit
+    int th = (thi_max - 3) / S + 1;
+    if (th < 1) th = 1;
+    if (th > d->oh) th = d->oh;
+    const int ybands = (d->oh + th - 1) / th;
+    th = (d->oh + ybands - 1) / ybands;
+    const int thi = S * (th - 1) + 3;
+
+    DwTmaArgs a;
+    a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
+    a.pt = d->pad_top, a.pl = d->pad_left, a.th = th, a.thi = thi;
+    a.ybands = ybands, a.xbands = (d->ow + TW - 1) / TW, a.cchunks = (d->cp + CC - 1) / CC;
+    a.stage_bytes = thi * TWI * CC;
+    a.wrow = static_cast<const uint32_t *>(wrow);
+    a.out = static_cast<int8_t *>(d->out);
+    a.zp_in = d->zp_in;
+    a.ep = make_epi(d->ep);
+
+    alignas(64) CUtensorMap tm;
+    int rc = encode_tmap_nhwc_u8(&tm, d->in, d->n, d->h, d->w, d->cp, CC, TWI, thi);
+    if (rc) return rc;
+
+    const long long tiles = static_cast<long long>(d->n) * a.ybands * a.xbands * a.cchunks;
+    const long long cap = static_cast<long long>(sm_count()) * 2;
+    const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+    const size_t smem = static_cast<size_t>(kDwStages) * a.stage_bytes + 128;
+    int mode;
+    if (d->ep.post_lut)
+        mode = d->ep.act == B200_ACT_NONE ? DW_LUT : DW_GENERIC;
+    else
+        mode = d->ep.act == B200_ACT_NONE ? DW_PLAIN : (d->ep.act == B200_ACT_RELU ? DW_RELU : DW_RELU6);
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (S == 1) {
+        if (best == 0) rc = launch_cfg<1, 32, 32>(mode, grid, smem, s, tm, a, dev);
+        else if (best == 1) rc = launch_cfg<1, 64, 16>(mode, grid, smem, s, tm, a, dev);
+        else rc = launch_cfg<1, 128, 8>(mode, grid, smem, s, tm, a, dev);
+    } else {
+        if (best == 0) rc = launch_cfg<2, 32, 32>(mode, grid, smem, s, tm, a, dev);
+        else if (best == 1) rc = launch_cfg<2, 64, 16>(mode, grid, smem, s, tm, a, dev);
+        else rc = launch_cfg<2, 128, 8>(mode, grid, smem, s, tm, a, dev);
+    }
+    if (rc) return rc;
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -53,8 +53,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
-                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer)
+static encode_tiled_fn encode_entry()
 {
     static encode_tiled_fn fn = nullptr;
     if (!fn) {
@@ -63,10 +62,40 @@ int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t 
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr);
         if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !p) {
             set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-            return B200_ERR_CUDA;
+            return nullptr;
         }
         fn = reinterpret_cast<encode_tiled_fn>(p);
     }
+    return fn;
+}
+
+// pixel-major activation [n][h][w][cp] bytes as a 4-D tiled map (no swizzle, zero fill out of
+// bounds -- negative start coordinates are how a conv halo is fetched)
+int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
+                        int box_w, int box_h)
+{
+    encode_tiled_fn fn = encode_entry();
+    if (!fn) return B200_ERR_CUDA;
+    cuuint64_t gdim[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t gstride[3] = {(cuuint64_t)cp, (cuuint64_t)cp * w, (cuuint64_t)cp * w * h};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(4d) failed: CUresult %d (n %d h %d w %d cp %d box %d x %d x %d)", (int)r,
+                  n, h, w, cp, box_c, box_w, box_h);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
+int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
+                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer)
+{
+    encode_tiled_fn fn = encode_entry();
+    if (!fn) return B200_ERR_CUDA;
     cuuint64_t gdim[2] = {inner, outer};
     cuuint64_t gstride[1] = {pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};

@@ -201,8 +201,8 @@ typedef struct {
     const void *in;  /* device [n][h][w][cp]                                */
     const void *wt;  /* device, tap-major [kh*kw][cp]: f16 halves, or for int8 one 32-bit word
                         per (tap, channel) with the weight in byte lane (c & 3), others 0  */
-    const void *wt_col3; /* optional, int8 3x3 only: [3 (kx)][cp] words
-                            (w[0][kx][c], w[1][kx][c], w[2][kx][c], 0) for the dp4a fast path */
+    const void *wt_row3; /* optional, int8 3x3 only: [3 (ky)][cp] words
+                            (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0) for the TMA-fed dp4a kernel */
     void *out;       /* device [n][oh][ow][cp]                              */
     int32_t zp_in;   /* int8: value of a padded tap                         */
     b200_epilogue ep;

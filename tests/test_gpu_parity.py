@@ -348,15 +348,19 @@ def test_resnet50_int8_narrow_bit_exact(b200):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
 
 
-@pytest.mark.parametrize("rows", [2, 3, 4])
+@pytest.mark.parametrize("rows", ["tma", "generic"])
 def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
-    """every rows-per-thread variant of the dp4a depthwise kernel (csrc/dwconv3x3.cu), on shapes that
-    hit ragged rows, ragged strips, both strides, asymmetric pads and a fused relu table"""
-    os.environ["SHL_B200_DW_ROWS"] = str(rows)
+    """the TMA-fed dp4a depthwise kernel (csrc/dwconv3x3_tma.cu) and the generic one (csrc/dwconv.cu)
+    on shapes that hit ragged rows / columns / channel chunks, both strides, zero-point patching of
+    the halo, unpadded borders and a fused relu table"""
+    if rows == "generic":
+        os.environ["SHL_B200_DW_GENERIC"] = "1"
     try:
         for (n, c, h, w, stride, pad, zp_in) in [(2, 32, 13, 29, 1, 1, -7), (1, 64, 56, 56, 1, 1, 0),
                                                  (1, 48, 15, 15, 2, 1, 4), (1, 16, 7, 7, 1, 1, -128),
-                                                 (1, 128, 9, 10, 2, 0, 2), (1, 20, 6, 5, 1, 0, 1)]:
+                                                 (1, 128, 9, 10, 2, 0, 2), (1, 20, 6, 5, 1, 0, 1),
+                                                 (2, 96, 30, 33, 1, 1, -5), (1, 160, 57, 9, 2, 1, 7),
+                                                 (1, 512, 14, 14, 1, 1, -128), (3, 32, 112, 112, 1, 1, -128)]:
             x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
             wt, s_w, b, s_out = synth_conv_i8(rng, c, c, 3, 3, depthwise=True)
             oh, ow = conv_out_hw(h, w, 3, 3, (stride, stride), (pad,) * 4)
@@ -370,7 +374,7 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
             want = oracle.conv2d_i8(x, wt, b, (n, c, oh, ow), post=(ACT_RELU, s_out / 2, -128), **kw)
             assert np.array_equal(got, want), (rows, n, c, h, w, stride, "fused relu")
     finally:
-        os.environ.pop("SHL_B200_DW_ROWS", None)
+        os.environ.pop("SHL_B200_DW_GENERIC", None)
 
 
 def test_dwconv_sweep_shapes(b200, oracle, rng):
