@@ -34,7 +34,8 @@ struct DwTmaArgs {
     int n, c, cp, h, w, oh, ow, pt, pl;
     int th, thi;            // output rows per tile, input rows per tile
     int ybands, xbands, cchunks;
-    int stage_bytes;
+    int stage_bytes;   // bytes one TMA box delivers
+    int stage_stride;  // distance between ring slots: stage_bytes rounded up to 128 (TMA destination alignment)
     const uint32_t *wrow;   // [3 (ky)][cp] words: (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0)
     int8_t *out;
     int zp_in;
@@ -94,7 +95,9 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     constexpr int TWI = S * (TW - 1) + 3;
     constexpr int WORDS = CC / 4;
     static_assert(WORDS * TW == kDwConsumers, "tile shape must give 256 consumer threads");
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // TMA destinations must be 128-byte aligned; stay on the shared pointer (LDS / STS codegen)
+    uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     __shared__ uint64_t full_bar[kDwStages], empty_bar[kDwStages];
     __shared__ uint8_t s_lut[256];
 
@@ -125,7 +128,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
                 const int b = static_cast<int>(t / (static_cast<long long>(a.cchunks) * a.xbands * a.ybands));
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], a.stage_bytes);
-                tma_load_4d(smem + static_cast<size_t>(stage) * a.stage_bytes, &tmap, &full_bar[stage], cc * CC,
+                tma_load_4d(smem + static_cast<size_t>(stage) * a.stage_stride, &tmap, &full_bar[stage], cc * CC,
                             xb * TW * S - a.pl, yb * a.th * S - a.pt, b);
                 if (++stage == kDwStages) {
                     stage = 0;
@@ -177,7 +180,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
         }
 
         mbar_wait(&full_bar[stage], phase);
-        uint8_t *tile = smem + static_cast<size_t>(stage) * a.stage_bytes;
+        uint8_t *tile = smem + static_cast<size_t>(stage) * a.stage_stride;
 
         // padded taps hold zp_in in the quantised domain; the TMA zero-filled them
         const int iy0 = oy0 * S - a.pt, ix0 = xb * TW * S - a.pl;
@@ -332,6 +335,7 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     a.pt = d->pad_top, a.pl = d->pad_left, a.th = th, a.thi = thi;
     a.ybands = ybands, a.xbands = (d->ow + TW - 1) / TW, a.cchunks = (d->cp + CC - 1) / CC;
     a.stage_bytes = thi * TWI * CC;
+    a.stage_stride = (a.stage_bytes + 127) & ~127;
     a.wrow = static_cast<const uint32_t *>(wrow);
     a.out = static_cast<int8_t *>(d->out);
     a.zp_in = d->zp_in;
@@ -344,7 +348,7 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     const long long tiles = static_cast<long long>(d->n) * a.ybands * a.xbands * a.cchunks;
     const long long cap = static_cast<long long>(sm_count()) * 2;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-    const size_t smem = static_cast<size_t>(kDwStages) * a.stage_bytes + 128;
+    const size_t smem = static_cast<size_t>(kDwStages) * a.stage_stride + 128;
     int mode;
     if (d->ep.post_lut)
         mode = d->ep.act == B200_ACT_NONE ? DW_LUT : DW_GENERIC;
