@@ -125,6 +125,112 @@ __global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_kernel(const Di
     }
 }
 
+// Compile-time (C, KH, KW) variant for the stems that matter (3x3x3, 7x7x3), dilation 1: the gather
+// is fully unrolled (compile-time byte lanes, 32-bit index math, one predicated byte load per tap)
+// and the packed taps stay in registers.
+template <int C, int KH, int KW>
+__global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_sp_kernel(const DirectArgs a)
+{
+    constexpr int K = C * KH * KW;
+    constexpr int KWORDS = (K + 3) / 4;
+    constexpr bool MAGIC = K <= 128;  // |acc + ibias| < 2^22, see common.cuh
+    extern __shared__ uint32_t s_w[];  // [KWORDS][o4]
+    const int o4 = (a.o + 3) & ~3;
+    float *s_mu = reinterpret_cast<float *>(s_w + KWORDS * o4);
+    float *s_ba = s_mu + o4;
+    int *s_ib = reinterpret_cast<int *>(s_ba + o4);
+    __shared__ uint8_t s_lut[256];
+    for (int i = threadIdx.x; i < KWORDS * o4; i += blockDim.x) {
+        const int j = i / o4, o = i % o4;
+        uint32_t wv = 0;
+        if (o < a.o) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = j * 4 + e;
+                const uint32_t byte = k < K ? static_cast<uint8_t>(a.wt[o * a.ldw + k]) : 0;
+                wv |= byte << (8 * e);
+            }
+        }
+        s_w[i] = wv;
+    }
+    for (int o = threadIdx.x; o < o4; o += blockDim.x) {
+        s_mu[o] = o < a.o ? a.ep.mult[o] : 0.f;
+        s_ba[o] = o < a.o ? a.ep.badd[o] : 0.f;
+        s_ib[o] = (o < a.o ? a.ep.ibias[o] : 0) + (MAGIC ? kMagicI : 0);
+    }
+    const bool has_lut = a.ep.post_lut != nullptr;
+    if (has_lut)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = static_cast<uint8_t>(a.ep.post_lut[i]);
+    __syncthreads();
+
+    const int hw = a.h * a.w;
+    const int opix = a.oh * a.ow;
+    const int total = a.n * opix;  // < 2^31, host-checked
+    const int zp_m = a.ep.zp_out - kMagicI;
+    const uint32_t zpb = static_cast<uint32_t>(a.zp_in & 0xFF);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const int b = p / opix;
+        const int rem = p - b * opix;
+        const int oy = rem / a.ow, ox = rem - oy * a.ow;
+        const int8_t *img = a.in + static_cast<size_t>(b) * C * hw;
+        uint32_t xw[KWORDS];
+#pragma unroll
+        for (int j = 0; j < KWORDS; j++) xw[j] = 0;
+#pragma unroll
+        for (int ky = 0; ky < KH; ky++) {
+            const int iy = oy * a.sh - a.pt + ky;
+            const bool yok = iy >= 0 && iy < a.h;
+#pragma unroll
+            for (int kx = 0; kx < KW; kx++) {
+                const int ix = ox * a.sw - a.pl + kx;
+                const bool ok = yok && ix >= 0 && ix < a.w;
+                const int off = iy * a.w + ix;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int k = (ky * KW + kx) * C + c;
+                    uint32_t v = zpb;
+                    if (ok) v = static_cast<uint8_t>(img[c * hw + off]);
+                    xw[k >> 2] |= v << (8 * (k & 3));
+                }
+            }
+        }
+        int8_t *dst = a.out + static_cast<size_t>(p) * a.cp_out;
+        for (int ob = 0; ob < o4; ob += 16) {
+            uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int og = 0; og < 4; og++) {
+                const int o = ob + og * 4;
+                if (o >= o4) break;
+                const int4 ib = *reinterpret_cast<const int4 *>(&s_ib[o]);
+                int acc[4] = {ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+                for (int j = 0; j < KWORDS; j++) {
+                    const uint4 wv = *reinterpret_cast<const uint4 *>(&s_w[j * o4 + o]);
+                    acc[0] = __dp4a(static_cast<int>(xw[j]), static_cast<int>(wv.x), acc[0]);
+                    acc[1] = __dp4a(static_cast<int>(xw[j]), static_cast<int>(wv.y), acc[1]);
+                    acc[2] = __dp4a(static_cast<int>(xw[j]), static_cast<int>(wv.z), acc[2]);
+                    acc[3] = __dp4a(static_cast<int>(xw[j]), static_cast<int>(wv.w), acc[3]);
+                }
+                const float4 mu = *reinterpret_cast<const float4 *>(&s_mu[o]);
+                const float4 ba = *reinterpret_cast<const float4 *>(&s_ba[o]);
+                const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
+                int q[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float af = MAGIC ? magic_to_float(acc[e]) : static_cast<float>(acc[e]);
+                    q[e] = magic_round(fmaf(af, m4[e], b4[e]), zp_m);
+                    if (a.ep.act != B200_ACT_NONE) q[e] = max(q[e], a.ep.zp_out);
+                    if (a.ep.act == B200_ACT_RELU6) q[e] = min(q[e], a.ep.q6);
+                }
+                pk[og] = has_lut ? lut4_i8(q[0], q[1], q[2], q[3], s_lut) : pack4_sat_i8(q[0], q[1], q[2], q[3]);
+            }
+            *reinterpret_cast<uint4 *>(dst + ob) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -158,7 +264,18 @@ extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
         set_error("b200_conv2d_direct: weights + taps (%zu bytes) exceed the shared-memory budget", smem);
         return B200_ERR_UNSUPPORTED;
     }
-    conv_direct_i8_kernel<<<grid, kDirectThreads, smem, (cudaStream_t)stream>>>(a);
+    const bool unit_dil = d->dil_h == 1 && d->dil_w == 1;
+    const size_t smem_sp = static_cast<size_t>(a.kwords) * o4 * 4 + static_cast<size_t>(o4) * 12;
+    if (total >= (1ll << 31)) {
+        set_error("b200_conv2d_direct: %lld output pixels exceed the 32-bit pixel index", total);
+        return B200_ERR_UNSUPPORTED;
+    }
+    if (unit_dil && d->c == 3 && d->kh == 3 && d->kw == 3)
+        conv_direct_i8_sp_kernel<3, 3, 3><<<grid, kDirectThreads, smem_sp, (cudaStream_t)stream>>>(a);
+    else if (unit_dil && d->c == 3 && d->kh == 7 && d->kw == 7)
+        conv_direct_i8_sp_kernel<3, 7, 7><<<grid, kDirectThreads, smem_sp, (cudaStream_t)stream>>>(a);
+    else
+        conv_direct_i8_kernel<<<grid, kDirectThreads, smem, (cudaStream_t)stream>>>(a);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

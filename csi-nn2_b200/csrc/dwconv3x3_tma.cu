@@ -44,7 +44,8 @@ struct DwTmaArgs {
 
 template <int MODE>
 __device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const float (&mu)[4], const float (&ba)[4],
-                                                const EpiScalars &ep, const uint8_t *lut, int zp_m, int lut_lo)
+                                                const EpiScalars &ep, const uint8_t *lut, bool has_lut, int zp_m,
+                                                int lut_lo)
 {
     int q[4];
 #pragma unroll
@@ -67,7 +68,7 @@ __device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const float
         const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
         return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
     }
-    if (MODE == DW_GENERIC && lut != nullptr) return lut4_i8(q[0], q[1], q[2], q[3], lut);
+    if (MODE == DW_GENERIC && has_lut) return lut4_i8(q[0], q[1], q[2], q[3], lut);
     return pack4_sat_i8(q[0], q[1], q[2], q[3]);
 }
 
@@ -114,18 +115,21 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     if (a.ep.post_lut != nullptr && tid < 256) s_lut[tid] = static_cast<uint8_t>(a.ep.post_lut[tid]);
     __syncthreads();
 
-    const long long tiles = static_cast<long long>(a.n) * a.ybands * a.xbands * a.cchunks;
+    const uint32_t tiles = static_cast<uint32_t>(a.n) * a.ybands * a.xbands * a.cchunks;  // < 2^31, host-checked
 
     if (warp == kDwConsumers / 32) {
         // ===== TMA producer =====
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int cc = static_cast<int>(t % a.cchunks);
-                const int xb = static_cast<int>((t / a.cchunks) % a.xbands);
-                const int yb = static_cast<int>((t / (static_cast<long long>(a.cchunks) * a.xbands)) % a.ybands);
-                const int b = static_cast<int>(t / (static_cast<long long>(a.cchunks) * a.xbands * a.ybands));
+            for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                uint32_t rest = t;
+                const int cc = rest % a.cchunks;
+                rest /= a.cchunks;
+                const int xb = rest % a.xbands;
+                rest /= a.xbands;
+                const int yb = rest % a.ybands;
+                const int b = rest / a.ybands;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], a.stage_bytes);
                 tma_load_4d(smem + static_cast<size_t>(stage) * a.stage_stride, &tmap, &full_bar[stage], cc * CC,
@@ -142,17 +146,20 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     // ===== consumers =====
     const int cw = tid % WORDS;  // channel word inside the chunk
     const int x = tid / WORDS;   // output column inside the tile
-    const uint8_t *lut = a.ep.post_lut != nullptr ? s_lut : nullptr;
+    const bool has_lut = a.ep.post_lut != nullptr;
     const int zp_m = a.ep.zp_out - kMagicI;
     const int lut_lo = kMagicI - a.ep.zp_out - 128;
     const uint32_t padw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int cc = static_cast<int>(t % a.cchunks);
-        const int xb = static_cast<int>((t / a.cchunks) % a.xbands);
-        const int yb = static_cast<int>((t / (static_cast<long long>(a.cchunks) * a.xbands)) % a.ybands);
-        const int b = static_cast<int>(t / (static_cast<long long>(a.cchunks) * a.xbands * a.ybands));
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        uint32_t rest = t;
+        const int cc = rest % a.cchunks;
+        rest /= a.cchunks;
+        const int xb = rest % a.xbands;
+        rest /= a.xbands;
+        const int yb = rest % a.ybands;
+        const int b = rest / a.ybands;
         const int ch = cc * CC + cw * 4;          // first of this thread's four channels
         const bool ch_ok = ch < a.cp;
         const int ox = xb * TW + x;
@@ -209,7 +216,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
         auto finish = [&](int (&acc)[4], int y) {
             if (y >= 0 && y < rows_out && col_ok)
                 *reinterpret_cast<uint32_t *>(obase + y * orow) =
-                    dw_requant4<MODE>(acc, mu, ba, a.ep, lut, zp_m, lut_lo);
+                    dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo);
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[e] = init[e];
         };
@@ -346,6 +353,10 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     if (rc) return rc;
 
     const long long tiles = static_cast<long long>(d->n) * a.ybands * a.xbands * a.cchunks;
+    if (tiles >= (1ll << 31)) {
+        set_error("b200_dwconv2d: %lld tiles exceed the 32-bit tile index", tiles);
+        return B200_ERR_UNSUPPORTED;
+    }
     const long long cap = static_cast<long long>(sm_count()) * 2;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
     const size_t smem = static_cast<size_t>(kDwStages) * a.stage_stride + 128;

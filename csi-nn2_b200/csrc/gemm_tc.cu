@@ -10,13 +10,19 @@
 //                (memory-bound) layers the epilogue's instruction stream is the critical path,
 //                so it gets 4 warps per scheduler and a compile-time specialised body
 //                (activation mode, post table, magic-number int<->float) instead of runtime flags.
-// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
-// static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n-tile fastest so that
-// CTAs running side by side share the A tile through L2).
+// Work unit = a "super tile": G consecutive 128-row blocks x one n-tile, accumulated side by side
+// in one 256-column TMEM stage (G = 4 / 2 / 1 for n-tiles of <= 64 / <= 128 / <= 256 columns), so
+// the producer <-> MMA <-> epilogue hand-offs are paid once per G*128 rows.  When the whole weight
+// matrix fits (one n-tile, <= 64 KB) it is loaded ONCE per CTA and stays resident; the ring then
+// carries activations only.  Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty
+// (MMA <-> epilogue), and a static round-robin schedule (n-tile fastest so that CTAs running side
+// by side share the A tile through L2).
 //
 // Replaces shl_rvv_gemm_4x16_int8 / shl_rvv_conv1x1s1_gemm_int8 / shl_rvv_fullyconnected_int8
 // (source/thead_rvv/int8/gemm_int8.c:37, convolution_1x1_int8.c:56, fullyconnected_int8.c:94)
 // and the fp16 twins (source/thead_rvv/fp16/gemm_fp16.c); nothing of them is ported.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -25,9 +31,10 @@ constexpr int kBM = 128;        // UMMA M (cta_group::1)
 constexpr int kBKBytes = 128;   // one swizzle atom of K per stage
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
-constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
+constexpr int kResidentBBytes = 64 * 1024;
 
 // epilogue specialisations
 enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_RELU6 = 2, EPI_LUT = 3, EPI_GENERIC = 4 };
@@ -37,6 +44,9 @@ struct GemmArgs {
     int k_blocks;      // ceil(K bytes / 128)
     int bn;            // tile N, multiple of 16, <= 256
     int num_m_tiles, num_n_tiles;
+    int group;         // G: 128-row blocks per super tile
+    int num_super;     // ceil(num_m_tiles / G) * num_n_tiles
+    int b_resident;    // weights loaded once per CTA
     int stages;
     int ldo;           // elements
     void *out;
@@ -53,11 +63,10 @@ struct __align__(16) EpiParams {
 
 // four int8 outputs from four accumulators (already + ibias) -> one packed word
 template <int MODE, bool MAGIC>
-__device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float4 mu, const float4 ba,
-                                             const EpiScalars &ep, const uint8_t *lut, int zp_m,
-                                             int lut_lo)
+__device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4)[4], const float (&b4)[4],
+                                             const EpiScalars &ep, const uint8_t *lut, bool has_lut,
+                                             int zp_m, int lut_lo)
 {
-    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
     int q[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -81,7 +90,7 @@ __device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float4 mu,
         const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
         return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
     }
-    if (MODE == EPI_GENERIC && lut != nullptr) return lut4_i8(q[0], q[1], q[2], q[3], lut);
+    if (MODE == EPI_GENERIC && has_lut) return lut4_i8(q[0], q[1], q[2], q[3], lut);
     return pack4_sat_i8(q[0], q[1], q[2], q[3]);
 }
 
@@ -97,18 +106,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int stages = args.stages;
     const uint32_t a_stage_bytes = kBM * kBKBytes;
     const uint32_t b_stage_bytes = args.bn * kBKBytes;
+    // resident B: k_blocks slabs after the A ring; otherwise one B slab per ring slot
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + stages * a_stage_bytes;
-    EpiParams *epi = reinterpret_cast<EpiParams *>(smem_b + stages * b_stage_bytes);
+    const uint32_t b_slabs = args.b_resident ? args.k_blocks : stages;
+    EpiParams *epi = reinterpret_cast<EpiParams *>(smem_b + b_slabs * b_stage_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + 1);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint64_t *tmem_full = empty_bar + kMaxStages;
     uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *b_bar = tmem_empty + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(b_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+    const int G = args.group;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -121,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], kEpiWarps);
         }
+        mbar_init(b_bar, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -135,26 +148,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
+            if (args.b_resident) {
+                mbar_expect_tx(b_bar, args.k_blocks * b_stage_bytes);
+                for (int kb = 0; kb < args.k_blocks; kb++)
+                    tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, b_bar, kb * k_elems, 0);
+            }
             int stage = 0;
             uint32_t phase = 0;
-            const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / args.num_n_tiles) * kBM;
-                const int n0 = (tile % args.num_n_tiles) * args.bn;
-                for (int kb = 0; kb < args.k_blocks; kb++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
-                    tma_load_2d(smem_a + stage * a_stage_bytes, &tma_a, &full_bar[stage],
-                                kb * k_elems, m0);
-                    tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage],
-                                kb * k_elems, n0);
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
+            for (int st = blockIdx.x; st < args.num_super; st += gridDim.x) {
+                const int mt0 = (st / args.num_n_tiles) * G;
+                const int n0 = (st % args.num_n_tiles) * args.bn;
+                for (int g = 0; g < G; g++) {
+                    if (mt0 + g >= args.num_m_tiles) break;
+                    const int m0 = (mt0 + g) * kBM;
+                    for (int kb = 0; kb < args.k_blocks; kb++) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (args.b_resident) {
+                            mbar_expect_tx(&full_bar[stage], a_stage_bytes);
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
+                            tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], kb * k_elems, n0);
+                        }
+                        tma_load_2d(smem_a + stage * a_stage_bytes, &tma_a, &full_bar[stage], kb * k_elems, m0);
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
@@ -162,36 +186,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one()) {
+            if (args.b_resident) mbar_wait(b_bar, 0);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+            for (int st = blockIdx.x; st < args.num_super; st += gridDim.x, local++) {
+                const int mt0 = (st / args.num_n_tiles) * G;
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * kAccStride;
-                for (int kb = 0; kb < args.k_blocks; kb++) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes));
+                for (int g = 0; g < G; g++) {
+                    if (mt0 + g >= args.num_m_tiles) break;
+                    const uint32_t tmem_d = tmem_base + acc * kAccStride + g * args.bn;
+                    for (int kb = 0; kb < args.k_blocks; kb++) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes));
+                        const uint64_t bdesc = umma_desc_sw128(
+                            smem_u32(smem_b + (args.b_resident ? kb : stage) * b_stage_bytes));
 #pragma unroll
-                    for (int k = 0; k < kBKBytes / 32; k++) {
-                        // advance 32 bytes of K inside the swizzle atom: +2 in 16-byte units
-                        if (DT == B200_I8)
-                            tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
-                        else
-                            tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc,
-                                       (kb | k) != 0);
-                    }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
+                        for (int k = 0; k < kBKBytes / 32; k++) {
+                            // advance 32 bytes of K inside the swizzle atom: +2 in 16-byte units
+                            if (DT == B200_I8)
+                                tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
+                            else
+                                tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
+                        }
+                        tc_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
-                tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                tc_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
             }
         }
     } else {
@@ -206,14 +235,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int cw = args.bn >= 128 ? 32 : 16;
         const int zp_m = ep.zp_out - kMagicI;
         const int lut_lo = kMagicI - ep.zp_out - 128;
-        const uint8_t *lut = ep.post_lut != nullptr ? epi->lut : nullptr;
+        const bool has_lut = ep.post_lut != nullptr;
         int local = 0;
         int staged_n0 = -1;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+        for (int st = blockIdx.x; st < args.num_super; st += gridDim.x, local++) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            const int m0 = (tile / args.num_n_tiles) * kBM;
-            const int n0 = (tile % args.num_n_tiles) * args.bn;
+            const int mt0 = (st / args.num_n_tiles) * G;
+            const int n0 = (st % args.num_n_tiles) * args.bn;
             // stage this n-tile's per-channel parameters (once per CTA when N fits one tile)
             if (n0 != staged_n0) {
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -230,77 +259,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m0 + quad * 32 + lane;
-            const bool row_ok = row < args.m;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   acc * kAccStride;
-            for (int c0 = part * cw; c0 < args.bn; c0 += 4 * cw) {
-                uint32_t r[32];
-                const int ncols = min(cw, args.bn - c0);  // 32 or 16
-                if (ncols == 32) {
-                    tmem_ld_32x32(taddr + c0, r);
-                } else {
-                    uint32_t r16[16];
-                    tmem_ld_32x16(taddr + c0, r16);
+            for (int g = 0; g < G; g++) {
+                if (mt0 + g >= args.num_m_tiles) break;
+                const int row = (mt0 + g) * kBM + quad * 32 + lane;
+                const bool row_ok = row < args.m;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride +
+                                       g * args.bn;
+                for (int c0 = part * cw; c0 < args.bn; c0 += 4 * cw) {
+                    uint32_t r[32];
+                    const int ncols = min(cw, args.bn - c0);  // 32 or 16
+                    if (ncols == 32) {
+                        tmem_ld_32x32(taddr + c0, r);
+                    } else {
+                        uint32_t r16[16];
+                        tmem_ld_32x16(taddr + c0, r16);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) r[j] = r16[j];
+                        for (int j = 0; j < 16; j++) r[j] = r16[j];
 #pragma unroll
-                    for (int j = 16; j < 32; j++) r[j] = 0;
-                }
-                tmem_ld_wait();
-                if (DT == B200_I8) {
-                    int8_t *dst = static_cast<int8_t *>(args.out) + static_cast<size_t>(row) * args.ldo +
-                                  n0 + c0;
+                        for (int j = 16; j < 32; j++) r[j] = 0;
+                    }
+                    tmem_ld_wait();
+                    if (DT == B200_I8) {
+                        int8_t *dst = static_cast<int8_t *>(args.out) + static_cast<size_t>(row) * args.ldo + n0 + c0;
 #pragma unroll
-                    for (int v = 0; v < 2; v++) {
-                        if (v * 16 >= ncols) break;
-                        uint32_t packed[4];
+                        for (int v = 0; v < 2; v++) {
+                            if (v * 16 >= ncols) break;
+                            uint32_t packed[4];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; j4++) {
-                            const int c = c0 + v * 16 + j4 * 4;
-                            const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c]);
-                            const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c]);
-                            const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c]);
-                            const int a4[4] = {static_cast<int>(r[v * 16 + j4 * 4 + 0]) + ib.x,
-                                               static_cast<int>(r[v * 16 + j4 * 4 + 1]) + ib.y,
-                                               static_cast<int>(r[v * 16 + j4 * 4 + 2]) + ib.z,
-                                               static_cast<int>(r[v * 16 + j4 * 4 + 3]) + ib.w};
-                            // columns >= n of a partial vector carry unspecified values (never
-                            // read: every consumer takes the true channel count)
-                            packed[j4] = requant4<MODE, MAGIC>(a4, mu, ba, ep, lut, zp_m, lut_lo);
+                            for (int j4 = 0; j4 < 4; j4++) {
+                                const int c = c0 + v * 16 + j4 * 4;
+                                const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c]);
+                                const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c]);
+                                const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c]);
+                                const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
+                                const int a4[4] = {static_cast<int>(r[v * 16 + j4 * 4 + 0]) + ib.x,
+                                                   static_cast<int>(r[v * 16 + j4 * 4 + 1]) + ib.y,
+                                                   static_cast<int>(r[v * 16 + j4 * 4 + 2]) + ib.z,
+                                                   static_cast<int>(r[v * 16 + j4 * 4 + 3]) + ib.w};
+                                // columns >= n of a partial vector carry unspecified values (never
+                                // read: every consumer takes the true channel count)
+                                packed[j4] = requant4<MODE, MAGIC>(a4, m4, b4, ep, epi->lut, has_lut, zp_m, lut_lo);
+                            }
+                            if (row_ok && n0 + c0 + v * 16 < args.ldo)
+                                *reinterpret_cast<uint4 *>(dst + v * 16) =
+                                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
                         }
-                        if (row_ok && n0 + c0 + v * 16 < args.ldo)
-                            *reinterpret_cast<uint4 *>(dst + v * 16) =
-                                make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    }
-                } else {
-                    const int act = MODE;  // fp16: MODE is the activation
-                    uint32_t packed[16];
+                    } else {
+                        const int act = MODE;  // fp16: MODE is the activation
+                        uint32_t packed[16];
 #pragma unroll
-                    for (int j2 = 0; j2 < 16; j2++) {
-                        const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
-                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
-                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
-                        const int cb = n0 + c0 + j2 * 2;
-                        f0 = cb < args.n ? f0 : 0.f;
-                        f1 = cb + 1 < args.n ? f1 : 0.f;
-                        __half2 h = __floats2half2_rn(f0, f1);
-                        packed[j2] = *reinterpret_cast<uint32_t *>(&h);
-                    }
-                    if (row_ok) {
-                        __half *dst = static_cast<__half *>(args.out) +
-                                      static_cast<size_t>(row) * args.ldo + n0 + c0;
+                        for (int j2 = 0; j2 < 16; j2++) {
+                            const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
+                            float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
+                            float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
+                            const int cb = n0 + c0 + j2 * 2;
+                            f0 = cb < args.n ? f0 : 0.f;
+                            f1 = cb + 1 < args.n ? f1 : 0.f;
+                            __half2 h = __floats2half2_rn(f0, f1);
+                            packed[j2] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        if (row_ok) {
+                            __half *dst = static_cast<__half *>(args.out) + static_cast<size_t>(row) * args.ldo +
+                                          n0 + c0;
 #pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
-                                *reinterpret_cast<uint4 *>(dst + v * 8) =
-                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
-                                               packed[v * 4 + 3]);
+                            for (int v = 0; v < 4; v++) {
+                                if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
+                                    *reinterpret_cast<uint4 *>(dst + v * 8) =
+                                        make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
+                                                   packed[v * 4 + 3]);
+                            }
                         }
                     }
                 }
             }
-            // this warp has drained its part of the accumulator
+            // this warp has drained its part of the accumulators
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -312,10 +344,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t gemm_smem_bytes(int stages, int bn)
+static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident)
 {
-    return 1024 + static_cast<size_t>(stages) * (kBM * kBKBytes + bn * kBKBytes) + sizeof(EpiParams) +
-           (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+    const size_t a = static_cast<size_t>(stages) * kBM * kBKBytes;
+    const size_t b = static_cast<size_t>(resident ? k_blocks : stages) * bn * kBKBytes;
+    return 1024 + a + b + sizeof(EpiParams) + (2 * kMaxStages + 5) * sizeof(uint64_t) + 16;
 }
 
 static int pick_bn(int n)
@@ -327,8 +360,6 @@ static int pick_bn(int n)
     const int tiles = (n16 + 255) / 256;
     return ((n16 + tiles - 1) / tiles + 15) / 16 * 16;
 }
-
-typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
 
 template <int DT, int MODE, bool MAGIC>
 static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &ta,
@@ -376,6 +407,18 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.bn = pick_bn(d->n);
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
     args.num_n_tiles = (d->n + args.bn - 1) / args.bn;
+    // 128-row blocks per super tile: as many as fit a 256-column TMEM stage, but never so many that
+    // the machine runs short of super tiles (keep >= 4 per SM)
+    int group = kAccStride / args.bn;
+    if (group > 4) group = 4;
+    while (group > 1 && (static_cast<long long>((args.num_m_tiles + group - 1) / group) * args.num_n_tiles <
+                         4ll * sm_count()))
+        group--;
+    if (getenv("SHL_B200_GEMM_GROUP")) group = max(1, min(kAccStride / args.bn, atoi(getenv("SHL_B200_GEMM_GROUP"))));
+    args.group = group;
+    args.num_super = ((args.num_m_tiles + group - 1) / group) * args.num_n_tiles;
+    args.b_resident = args.num_n_tiles == 1 && args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
+                      !getenv("SHL_B200_GEMM_NO_RESIDENT");
     args.ldo = d->ldo;
     args.out = d->out;
     args.ep = make_epi(d->ep);
@@ -384,9 +427,9 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     // as many stages as fit: the ring also prefetches the next tiles' operands while the
     // epilogue drains, which is what keeps HBM busy on the short-K (memory-bound) layers
     int stages = kMaxStages;
-    while (stages > 2 && gemm_smem_bytes(stages, args.bn) > kSmemLimit) stages--;
+    while (stages > 2 && gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident) > kSmemLimit) stages--;
     args.stages = stages;
-    const size_t smem = gemm_smem_bytes(stages, args.bn);
+    const size_t smem = gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident);
 
     alignas(64) CUtensorMap ta, tb;
     const int box_k = kBKBytes / eb;
@@ -395,7 +438,7 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
     if (rc) return rc;
 
-    const int grid = min(args.num_m_tiles * args.num_n_tiles, sm_count());
+    const int grid = min(args.num_super, sm_count());
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t s = (cudaStream_t)stream;
