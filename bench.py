@@ -35,6 +35,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "csi-nn2_b200", "pyhost"))
 
 import numpy as np  # noqa: E402
 
@@ -126,6 +127,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
 
+    import b200_dist
     import nets
     from shl import API_C906, DT_INT8, RM_GRAPH, Harness
 
@@ -199,14 +201,10 @@ def main():
         import torch
         ptr, nbytes = C.c_void_p(), C.c_uint64()
         assert shl.shl_b200_session_weight_arena(sess, C.byref(ptr), C.byref(nbytes)) == 1
-
-        class Raw:
-            __cuda_array_interface__ = {"shape": (int(nbytes.value),), "typestr": "|u1",
-                                        "data": (int(ptr.value), False), "version": 2}
-        arena = torch.as_tensor(Raw(), device=torch.device("cuda", local_rank))
+        arena = b200_dist.device_bytes_as_tensor(ptr.value, nbytes.value, local_rank)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dist.broadcast(arena, src=0)
+        b200_dist.broadcast_arena(arena, src=0)
         torch.cuda.synchronize()
         bcast_ms = 1e3 * (time.perf_counter() - t0)
 
@@ -268,9 +266,7 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s * 1e3], device=torch.device("cuda", local_rank), dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms = b200_dist.max_over_ranks([dev_ms, e2e_s * 1e3], device=torch.device("cuda", local_rank))
     else:
         e2e_ms = e2e_s * 1e3
 

@@ -127,6 +127,36 @@ __global__ void __launch_bounds__(128) pool_f16_kernel(const PoolArgs a)
     }
 }
 
+// Global average pool, int8: one thread per 32-bit word of channels (four channels), so that a
+// 7x7x1024 map spreads over n*256 threads instead of n*64, every load is a coalesced word and the
+// h*w loads of a thread are independent (only the four f32 sums are sequential, in (y, x) order
+// as averagepool.c:100-109 prescribes).
+__global__ void __launch_bounds__(256) gap_i8_kernel(const PoolArgs a)
+{
+    const int words = a.cp / 4;
+    const int total = a.n * words;
+    const int hw = a.h * a.w;
+    const int8_t *in = static_cast<const int8_t *>(a.in);
+    int8_t *out = static_cast<int8_t *>(a.out);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int wd = i % words, b = i / words;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + static_cast<size_t>(b) * hw * a.cp) + wd;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 7
+        for (int p = 0; p < hw; p++) {
+            const uint32_t v = __ldg(src + static_cast<size_t>(p) * words);
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                acc[e] = __fadd_rn(acc[e], dequant_i8(static_cast<int8_t>(v >> (8 * e)), a.s_in, a.zp_in));
+        }
+        const float cnt = static_cast<float>(hw);
+        int q[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) q[e] = wd * 4 + e < a.c ? quant_i8_exact(__fdiv_rn(acc[e], cnt), a.s_out, a.zp_out) : 0;
+        *reinterpret_cast<uint32_t *>(out + static_cast<size_t>(b) * a.cp + wd * 4) = pack4_i8(q[0], q[1], q[2], q[3]);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -155,7 +185,11 @@ extern "C" int b200_pool2d(const b200_pool_desc *d, void *stream)
     long long g = (total + 127) / 128;
     const long long cap = static_cast<long long>(sm_count()) * 32;
     const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
-    if (d->dtype == B200_I8)
+    if (d->dtype == B200_I8 && d->is_avg && d->oh == 1 && d->ow == 1 && d->kh == d->h && d->kw == d->w &&
+        d->pad_top == 0 && d->pad_left == 0) {
+        const int tot = d->n * (d->cp / 4);
+        gap_i8_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    } else if (d->dtype == B200_I8)
         pool_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     else
         pool_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
