@@ -12,11 +12,13 @@
 //                (activation mode, post table, magic-number int<->float) instead of runtime flags.
 // Work unit = a "super tile": G consecutive 128-row blocks x one n-tile, accumulated side by side
 // in one 256-column TMEM stage (G = 4 / 2 / 1 for n-tiles of <= 64 / <= 128 / <= 256 columns), so
-// the producer <-> MMA <-> epilogue hand-offs are paid once per G*128 rows.  When the whole weight
-// matrix fits (one n-tile, <= 64 KB) it is loaded ONCE per CTA and stays resident; the ring then
-// carries activations only.  Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty
-// (MMA <-> epilogue), and a static round-robin schedule (n-tile fastest so that CTAs running side
-// by side share the A tile through L2).
+// the producer <-> MMA <-> epilogue hand-offs are paid once per G*128 rows.  A CTA owns ONE n-tile
+// (blockIdx % n_tiles) and walks the row blocks; when that n-tile's weights fit (<= 160 KB) they
+// are loaded ONCE per CTA and stay resident, so the ring carries activations only and L2 is not
+// re-read for weights per tile (at K = N = 512 that was 3x the layer's HBM traffic).  CTAs with
+// consecutive indices work on the same rows of different n-tiles, sharing the A tile through L2.
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and the
+// static schedule.
 //
 // Replaces shl_rvv_gemm_4x16_int8 / shl_rvv_conv1x1s1_gemm_int8 / shl_rvv_fullyconnected_int8
 // (source/thead_rvv/int8/gemm_int8.c:37, convolution_1x1_int8.c:56, fullyconnected_int8.c:94)
@@ -34,7 +36,7 @@ constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
-constexpr int kResidentBBytes = 64 * 1024;
+constexpr int kResidentBBytes = 160 * 1024;  // weights of one n-tile kept in smem (leaves >= 3 A stages)
 
 // epilogue specialisations
 enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_RELU6 = 2, EPI_LUT = 3, EPI_GENERIC = 4 };
@@ -45,7 +47,7 @@ struct GemmArgs {
     int bn;            // tile N, multiple of 16, <= 256
     int num_m_tiles, num_n_tiles;
     int group;         // G: 128-row blocks per super tile
-    int num_super;     // ceil(num_m_tiles / G) * num_n_tiles
+    int num_m_super;   // ceil(num_m_tiles / G)
     int b_resident;    // weights loaded once per CTA
     int stages;
     int ldo;           // elements
@@ -149,6 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
+    // schedule: this CTA's n-tile is fixed; gridDim.x is a multiple of num_n_tiles (host)
+    const int n0 = (blockIdx.x % args.num_n_tiles) * args.bn;
+    const int ms0 = blockIdx.x / args.num_n_tiles;
+    const int ms_step = gridDim.x / args.num_n_tiles;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -156,13 +162,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (args.b_resident) {
                 mbar_expect_tx(b_bar, args.k_blocks * b_stage_bytes);
                 for (int kb = 0; kb < args.k_blocks; kb++)
-                    tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, b_bar, kb * k_elems, 0);
+                    tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, b_bar, kb * k_elems, n0);
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int st = blockIdx.x; st < args.num_super; st += gridDim.x) {
-                const int mt0 = (st / args.num_n_tiles) * G;
-                const int n0 = (st % args.num_n_tiles) * args.bn;
+            for (int ms = ms0; ms < args.num_m_super; ms += ms_step) {
+                const int mt0 = ms * G;
                 for (int g = 0; g < G; g++) {
                     if (mt0 + g >= args.num_m_tiles) break;
                     const int m0 = (mt0 + g) * kBM;
@@ -190,8 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int st = blockIdx.x; st < args.num_super; st += gridDim.x, local++) {
-                const int mt0 = (st / args.num_n_tiles) * G;
+            for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
+                const int mt0 = ms * G;
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -238,11 +243,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool has_lut = ep.post_lut != nullptr;
         int local = 0;
         int staged_n0 = -1;
-        for (int st = blockIdx.x; st < args.num_super; st += gridDim.x, local++) {
+        for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            const int mt0 = (st / args.num_n_tiles) * G;
-            const int n0 = (st % args.num_n_tiles) * args.bn;
+            const int mt0 = ms * G;
             // stage this n-tile's per-channel parameters (once per CTA when N fits one tile)
             if (n0 != staged_n0) {
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -405,6 +409,11 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.n = d->n;
     args.k_blocks = (d->k * eb + kBKBytes - 1) / kBKBytes;
     args.bn = pick_bn(d->n);
+    // prefer an n-tile whose weights stay resident in shared memory: halve a 256-wide tile when
+    // that makes K * bn fit
+    if (args.k_blocks * args.bn * kBKBytes > kResidentBBytes && args.bn > 128 &&
+        args.k_blocks * 128 * kBKBytes <= kResidentBBytes)
+        args.bn = 128;
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
     args.num_n_tiles = (d->n + args.bn - 1) / args.bn;
     // 128-row blocks per super tile: as many as fit a 256-column TMEM stage, but never so many that
@@ -416,9 +425,8 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
         group--;
     if (getenv("SHL_B200_GEMM_GROUP")) group = max(1, min(kAccStride / args.bn, atoi(getenv("SHL_B200_GEMM_GROUP"))));
     args.group = group;
-    args.num_super = ((args.num_m_tiles + group - 1) / group) * args.num_n_tiles;
-    args.b_resident = args.num_n_tiles == 1 && args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
-                      !getenv("SHL_B200_GEMM_NO_RESIDENT");
+    args.num_m_super = (args.num_m_tiles + group - 1) / group;
+    args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes && !getenv("SHL_B200_GEMM_NO_RESIDENT");
     args.ldo = d->ldo;
     args.out = d->out;
     args.ep = make_epi(d->ep);
@@ -438,7 +446,11 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
     if (rc) return rc;
 
-    const int grid = min(args.num_super, sm_count());
+    // a multiple of the n-tile count so that every CTA keeps one n-tile for its whole life
+    int ctas_per_n = sm_count() / args.num_n_tiles;
+    if (ctas_per_n < 1) ctas_per_n = 1;
+    if (ctas_per_n > args.num_m_super) ctas_per_n = args.num_m_super;
+    const int grid = ctas_per_n * args.num_n_tiles;
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t s = (cudaStream_t)stream;
