@@ -207,7 +207,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
 
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + x * S * WORDS + cw;
         int8_t *obase = a.out + ((static_cast<long long>(b) * a.oh + oy0) * a.ow + ox) * a.cp + ch;
-        const long long orow = static_cast<long long>(a.ow) * a.cp;
+        const int orow = a.ow * a.cp;  // bytes between output rows (< 2^31: one image row)
 
         auto load_taps = [&](int r, uint32_t (&v)[4]) {
             const uint32_t *p = tw + r * (TWI * WORDS);
@@ -215,7 +215,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
         };
         auto finish = [&](int (&acc)[4], int y) {
             if (y >= 0 && y < rows_out && col_ok)
-                *reinterpret_cast<uint32_t *>(obase + y * orow) =
+                *reinterpret_cast<uint32_t *>(obase + static_cast<size_t>(static_cast<uint32_t>(y * orow))) =
                     dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo);
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[e] = init[e];
@@ -285,7 +285,7 @@ static int launch_cfg(int mode, int grid, size_t smem, cudaStream_t s, const CUt
         static bool attr[64] = {};                                                                   \
         if (dev >= 0 && dev < 64 && !attr[dev]) {                                                    \
             B200_CUDA_CHECK(cudaFuncSetAttribute(dw3x3_tma_kernel<S, CC, TW, M>,                     \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
             attr[dev] = true;                                                                        \
         }                                                                                            \
         dw3x3_tma_kernel<S, CC, TW, M><<<grid, kDwThreads, smem, s>>>(tm, a);                        \
@@ -327,8 +327,9 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     }
     const int CC = cfgs[best].cc, TW = cfgs[best].tw;
     const int TWI = S * (TW - 1) + 3;
-    // rows per tile: a ~28 KB halo stage
-    int thi_max = (28 * 1024) / (TWI * CC);
+    // rows per tile: ~36 KB per halo slot (3 slots, 2 CTAs per SM): tall tiles amortise the per-tile
+    // prologue (tile decode, per-channel constants, zero-point patch) over more row steps
+    int thi_max = (36 * 1024) / (TWI * CC);
     if (thi_max > 256) thi_max = 256;  // TMA box limit
     int th = (thi_max - 3) / S + 1;
     if (th < 1) th = 1;
