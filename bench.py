@@ -52,48 +52,59 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, ~every 2 ms;
+    `nvidia-smi -lms` cannot start inside a 25 ms region).  Falls back to one nvidia-smi query."""
 
     def __init__(self, device):
-        self.device, self.lines, self.proc = device, [], None
+        self.device, self.sm, self.reasons, self.max_mhz = device, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.sm:
             try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                f = [float(v) for v in out.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": [], "samples": 1, "how": "nvidia-smi after the run"}
+            except Exception:  # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": "NVML, every ~2 ms during the timed regions"}
 
 
 def cpu_reference_rate(nb1, images, repeat_input):
@@ -121,6 +132,14 @@ def main():
     ap.add_argument("--profile-out", default=None, help="write the per-step device profile (json) here")
     args = ap.parse_args()
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are pointed at stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -158,7 +177,7 @@ def main():
                                            f"{wall:.1f} s"},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ b200 arm
@@ -291,8 +310,14 @@ def main():
         top = max(per_kernel, key=lambda n: per_kernel[n]["ms"])
         k = per_kernel[top]
         achieved = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel class, from the
+            # committed `ncu --set full` capture of this same command (tools/ncu_summary.py traffic)
+            traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": k["ms"] / total, "launches_per_step": k["launches"],
                     "avg_launch_ms": k["ms"] / k["launches"], "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
                     "tensor_tops": k["ops"] / (k["ms"] * 1e-3) / 1e12}
@@ -330,7 +355,7 @@ def main():
                 "roofline": roofline, "layerwise_roofline": layerwise, "cpu_baseline": cpu,
                 "tensor_tops": 2 * nets.mobilenet_v1_macs() * images / (dev_ms * 1e-3) / 1e12,
                 "weight_broadcast_ms": bcast_ms}
-        print(json.dumps(line))
+        emit(line)
     net.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -97,6 +97,7 @@ void b200_op_bind(void *params, b200_op *op);
 b200_op *b200_op_find(void *params);
 
 /* run on device tensors; scratch is im2col space (b200_op_scratch_bytes) */
+const char *b200_op_kname(const b200_op *op, const b200_dt *in0); /* kernel that will actually run */
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out);
 int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
                 void *scratch, void *stream);

@@ -550,7 +550,8 @@ int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen)
                      g->exec != NULL);
     for (int i = 0; i < g->ns && n < buflen; i++) {
         const b200_dt *o = &g->t[g->s[i].out].dt;
-        n += snprintf(buf + n, buflen - n, "%3d %-28s %s -> [%d,%d,%d,%d]\n", i, g->s[i].op->kname, g->s[i].name,
+        n += snprintf(buf + n, buflen - n, "%3d %-28s %s -> [%d,%d,%d,%d]\n", i,
+                      b200_op_kname(g->s[i].op, &g->t[g->s[i].in0].dt), g->s[i].name,
                       o->n, o->c, o->h, o->w);
     }
     return n < buflen ? n : buflen - 1;

@@ -303,6 +303,12 @@ static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
            !getenv("SHL_B200_NO_DIRECT_CONV");
 }
 
+const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
+{
+    if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0)) return "b200_conv2d_direct";
+    return op->kname;
+}
+
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
     if (op->kind != B200_OPK_CONV || (op->direct && !in0->is_nchw)) return 0;

@@ -85,5 +85,36 @@ def launch_list(path, dst):
     print(f"wrote {dst}: {n} launches")
 
 
+CLASSES = [("gemm_tc_kernel", "b200_gemm_tcgen05"), ("dw3x3_tma_kernel", "b200_dwconv2d"), ("dwconv_", "b200_dwconv2d"),
+           ("conv_direct", "b200_conv2d_direct"), ("im2col", "b200_im2col_gemm_tcgen05"), ("gap_i8", "b200_global_avgpool"),
+           ("pool_", "b200_pool"), ("softmax", "b200_softmax")]
+
+
+def traffic(rep, dst):
+    """profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel
+    class as bench.py names them (what the `roofline.traffic` key of the bench line quotes)"""
+    import json
+    hdr, units, rows = raw_rows(rep)
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ur, uw = units[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_write.sum"]]
+    acc = {}
+    for r in rows:
+        name = r[idx["Kernel Name"]]
+        cls = next((c for key, c in CLASSES if key in name), None)
+        if cls is None:
+            continue
+        b = float(r[idx["dram__bytes_read.sum"]]) * scale[ur] + float(r[idx["dram__bytes_write.sum"]]) * scale[uw]
+        a = acc.setdefault(cls, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += b
+        a[2] += float(r[idx["gpu__time_duration.sum"]])
+    out = {k: {"launches_captured": v[0], "dram_bytes_per_launch": v[1] / v[0], "ncu_time_us_per_launch": v[2] / v[0]}
+           for k, v in acc.items()}
+    out["_source"] = f"ncu --set full --clock-control none, {rep}: one batch-256 MobileNetV1 int8 step"
+    json.dump(out, open(dst, "w"), indent=1)
+    print(f"wrote {dst}: {sorted(acc)}")
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "list": launch_list, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
