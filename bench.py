@@ -107,12 +107,23 @@ class ClockSampler:
                 "samples": len(self.sm), "how": "NVML, every ~2 ms during the timed regions"}
 
 
+WORKLOADS = {
+    # name: (builder, dtype key, metric, description)
+    "mobilenet_v1_int8": ("mobilenet_v1", "int8", "MobileNetV1 int8 inferences/sec",
+                          "MobileNetV1 int8 per-channel symmetric weights, NCHW 3x224x224"),
+    "mobilenet_v1_fp16": ("mobilenet_v1", "fp16", "MobileNetV1 fp16 inferences/sec",
+                          "MobileNetV1 fp16 (c906_mobilenetv1_f16.c layer shapes, synthetic weights), NCHW 3x224x224"),
+    "resnet50_int8": ("resnet50", "int8", "ResNet-50 int8 inferences/sec",
+                      "ResNet-50 v1.5 int8, asymmetric activations (zp_in = -7), per-channel symmetric weights, NCHW 3x224x224"),
+}
+
+
 def cpu_reference_rate(nb1, images, repeat_input):
     """images/s of the unmodified reference (GREF graph mode, batch 1 per inference: its AVX conv is
     batch-1 only, source/reference/conv_avx.h:109-135) on the host cores"""
-    from shl import DT_INT8, RM_GRAPH, Harness
+    from shl import RM_GRAPH, Harness
     ref = Harness("ref")
-    with ref.create(DT_INT8, nb1.in_shape, nb1.layers, s_in=nb1.s_in, zp_in=nb1.zp_in, run_mode=RM_GRAPH) as net:
+    with ref.create(nb1.dtype, nb1.in_shape, nb1.layers, s_in=nb1.s_in, zp_in=nb1.zp_in, run_mode=RM_GRAPH) as net:
         net(repeat_input)  # warm-up
         t0 = time.perf_counter()
         for _ in range(images):
@@ -130,6 +141,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-images", type=int, default=48, help="images of the bounded CPU-baseline sample")
     ap.add_argument("--profile-out", default=None, help="write the per-step device profile (json) here")
+    ap.add_argument("--workload", default="mobilenet_v1_int8", choices=sorted(WORKLOADS),
+                    help="headline = mobilenet_v1_int8 (BASELINE.json); the others are secondary configs")
     args = ap.parse_args()
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
 
@@ -148,12 +161,15 @@ def main():
 
     import b200_dist
     import nets
-    from shl import API_C906, DT_INT8, RM_GRAPH, Harness
+    from shl import API_C906, DT_F16, DT_INT8, RM_GRAPH, Harness
 
-    nb1 = nets.mobilenet_v1(DT_INT8, batch=1)
+    builder_name, dkey, METRIC, wdesc = WORKLOADS[args.workload]
+    builder = getattr(nets, builder_name)
+    DT = DT_INT8 if dkey == "int8" else DT_F16
+    nb1 = builder(DT, batch=1)
     x1 = nb1.input_batch()
-    config = {"workload": f"MobileNetV1 int8 per-channel symmetric weights, NCHW 3x224x224, batch {args.batch} per GPU "
-                          "(example/c906_mobilenetv1_f16.c graph shapes)",
+    config = {"workload": f"{wdesc}, batch {args.batch} per GPU (example/c906_mobilenetv1_f16.c graph shapes)"
+                          if builder_name == "mobilenet_v1" else f"{wdesc}, batch {args.batch} per GPU (torchvision shapes)",
               "global_batch": args.batch * world, "parallelism": f"batch-shard x{world}, no per-step collective",
               "l2": "activations per step (>1 GB at batch 256) exceed the 126 MB L2; no flush needed"}
 
@@ -208,9 +224,9 @@ def main():
         sys.exit("bench.py: no CUDA device visible -- the b200 backend has no CPU fallback")
 
     b200 = Harness("b200")
-    nb = nets.mobilenet_v1(DT_INT8, batch=args.batch)
+    nb = builder(DT, batch=args.batch)
     x = nb.input_batch(seed=1 + rank)
-    net = b200.create(DT_INT8, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH, api=API_C906)
+    net = b200.create(DT, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH, api=API_C906)
     sess = net.session
     stream = shl.shl_b200_session_stream(sess)
 
@@ -231,20 +247,27 @@ def main():
     hin = C.c_void_p()
     assert shim.b200_malloc_host(C.byref(hin), C.c_size_t(x.nbytes)) == 0, shim.b200_last_error()
     C.memmove(hin, x.ctypes.data, x.nbytes)
-    out_bytes = args.batch * 1000
+    out_elems = args.batch * 1000
+    out_bytes = out_elems * (1 if DT == DT_INT8 else 2)
 
     def e2e_step():
         assert b200.lib.h_net_update_input(net.handle, hin) == 0
         assert b200.lib.h_net_session_run(net.handle) == 0, b200.error()
         p = b200.lib.h_net_get_output(net.handle)
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(out_bytes,))
+        ctype = C.c_int8 if DT == DT_INT8 else C.c_uint16
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(out_elems,))
+        return arr if DT == DT_INT8 else arr.view(np.float16)
 
     # correctness gate before timing: image 0 of this rank against the oracle chain
     y = e2e_step().reshape(args.batch, 1000).copy()
     want0 = nets.oracle_forward(nb1, x[0:1]).reshape(1, 1000)
-    if not np.array_equal(y[0:1], want0):
-        sys.exit(f"bench.py: rank {rank}: GPU result differs from the oracle "
-                 f"({np.count_nonzero(y[0:1] != want0)}/1000) -- refusing to time a wrong kernel")
+    if DT == DT_INT8:
+        bad = int(np.count_nonzero(y[0:1] != want0))
+    else:
+        yf, wf = y[0:1].astype(np.float32), want0.astype(np.float32)
+        bad = int(np.count_nonzero(np.abs(yf - wf) / np.maximum(np.abs(wf), 1.0) > 2e-3))
+    if bad:
+        sys.exit(f"bench.py: rank {rank}: GPU result differs from the oracle ({bad}/1000) -- refusing to time a wrong kernel")
 
     def barrier():
         shl.shl_b200_session_sync(sess)
@@ -346,14 +369,16 @@ def main():
         value = images / (dev_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8 (s32 accumulate on tcgen05 kind::i8, f32 requantise)", "data": "synthetic", "impl": "b200",
+                "dtype": "int8 (s32 accumulate on tcgen05 kind::i8, f32 requantise)" if DT == DT_INT8
+                else "fp16 (f32 accumulate on tcgen05 kind::f16)", "data": "synthetic", "impl": "b200",
                 "config": config, "clocks": clocks,
                 "e2e": {"value": images / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / steps,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": out_bytes,
                         "api": "csinn_update_input + csinn_session_run + csinn_get_output, pinned host buffers"},
                 "gpu_launches": launches, "kernels_per_step": shl.shl_b200_session_num_kernels(sess),
                 "roofline": roofline, "layerwise_roofline": layerwise, "cpu_baseline": cpu,
-                "tensor_tops": 2 * nets.mobilenet_v1_macs() * images / (dev_ms * 1e-3) / 1e12,
+                "tensor_tops": (sum(k["ops"] for k in per_kernel.values()) * world * steps / (dev_ms * 1e-3) / 1e12)
+                if per_kernel else None,
                 "weight_broadcast_ms": bcast_ms}
         emit(line)
     net.close()

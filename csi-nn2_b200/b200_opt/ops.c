@@ -459,6 +459,23 @@ int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
         op->act = act;
         return CSINN_TRUE;
     }
+    /* a relu / relu6 node that keeps its producer's qinfo is exactly the in-domain clamp the
+     * epilogue already knows (max(q, zp), min(q, q6)): compare the tables and skip the lookup */
+    if (op->act == B200_ACT_NONE && op->kind != B200_OPK_ADD) {
+        int8_t lut[256];
+        b200_build_requant_lut(lut, act, act_in->qinfo->scale, act_in->qinfo->zero_point, act_out->qinfo->scale,
+                               act_out->qinfo->zero_point);
+        int same = 1;
+        for (int q = -128; q < 128 && same; q++) {
+            int v = q > op->zp_out ? q : op->zp_out;
+            if (act == B200_ACT_RELU6 && v > op->q6) v = op->q6;
+            same = lut[q + 128] == v;
+        }
+        if (same) {
+            op->act = act;
+            return CSINN_TRUE;
+        }
+    }
     op->d_lut = upload_lut(op->ctx, act, act_in->qinfo->scale, act_in->qinfo->zero_point,
                            act_out->qinfo->scale, act_out->qinfo->zero_point);
     return op->d_lut ? CSINN_TRUE : CSINN_FALSE;

@@ -8,6 +8,8 @@ one synthetic image with the float oracle so that every layer uses the int8 rang
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from shl import (ACT_NONE, DT_F16, DT_INT8, H_ADD, H_CONV, H_FC, H_FLATTEN, H_GAP, H_MAXPOOL, H_RELU,
@@ -112,6 +114,9 @@ class NetBuilder:
     def relu(self, src):
         yf = np.maximum(self.act[src], 0)
         s_out, zp_out = _quant_pos(float(self.act[src].std())) if self.dtype == DT_INT8 else (1.0, 0)
+        if self.dtype == DT_INT8 and os.environ.get("NETS_RELU_KEEPS_QINFO"):
+            # experiment knob: the relu node reuses its producer's qinfo (then the fused epilogue is a clamp)
+            s_out, zp_out = self.q[src]
         shape = (self.batch,) + self.shapes[src][1:]
         return self._push(Layer(H_RELU, shape, in0=src, s_out=s_out, zp_out=zp_out), yf, (s_out, zp_out))
 

@@ -146,6 +146,25 @@ def test_fuse_zp2bias_and_per_tensor_weights(b200, oracle, rng):
     assert np.array_equal(got, oracle.conv2d_i8(x, wt, None, (n, o, h, w), s_w=s1, s_b=None, **kw))
 
 
+@pytest.mark.parametrize("kind", [H_RELU, H_RELU6])
+def test_relu_keeping_its_producers_qinfo(kind, b200, oracle, rng):
+    """graph mode: a relu / relu6 node whose qinfo equals its producer's is fused as the in-domain
+    clamp (no table); must equal conv -> standalone relu of the oracle, for 1x1, 3x3 and depthwise"""
+    act = ACT_RELU if kind == H_RELU else ACT_RELU6
+    for (c, o, k, pad, dw, zp_out) in [(64, 64, 1, 0, False, -20), (32, 48, 3, 1, False, 5), (32, 32, 3, 1, True, -128)]:
+        x = rng.integers(-128, 128, size=(2, c, 12, 12), dtype=np.int8)
+        wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, depthwise=dw)
+        if kind == H_RELU6:
+            s_out = 0.11  # put 6.0 inside the int8 range so that the upper clamp matters
+        layers = [Layer(H_CONV, (2, o, 12, 12), s_out=s_out, zp_out=zp_out, w=wt, b=b, s_w=s_w, pad=(pad,) * 4,
+                        group=c if dw else 1), Layer(kind, (2, o, 12, 12), s_out=s_out, zp_out=zp_out)]
+        got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=-3, run_mode=RM_GRAPH)
+        y = oracle.conv2d_i8(x, wt, b, (2, o, 12, 12), depthwise=dw, stride=(1, 1), pad=(pad,) * 4, dilation=(1, 1),
+                             group=1, s_in=0.02, zp_in=-3, s_w=s_w, s_b=None, s_out=s_out, zp_out=zp_out)
+        want = oracle.relu_i8(y, act, s_out, zp_out, s_out, zp_out)
+        assert np.array_equal(got, want), (kind, c, o, k)
+
+
 def test_asymmetric_weights_are_refused_loudly(b200, rng):
     x = rng.integers(-128, 128, size=(1, 16, 4, 4), dtype=np.int8)
     wt, s_w, b, s_out = synth_conv_i8(rng, 16, 16, 1, 1)
