@@ -24,6 +24,7 @@
 typedef struct b200_ctx {
     int device;
     void *stream;
+    void *copy_stream; /* input prefetch (graph.c), created on first use */
     /* weight arena: bump allocator over one device allocation (graph mode) or a chain of
      * chunks (layer mode) */
     uint8_t *wbase;

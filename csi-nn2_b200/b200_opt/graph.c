@@ -39,6 +39,13 @@ typedef struct {
     size_t off;              /* offset in the activation arena */
     int is_input, is_output;
     void *d_in_nchw;  /* graph inputs that feed a non-conv op: raw NCHW copy, converted per run */
+    /* input prefetch (shl_b200_session_prefetch_input): a second raw-NCHW buffer filled on the copy
+     * stream while the previous step computes */
+    void *d_stage;
+    const void *staged_host; /* host pointer whose bytes d_stage holds (or is receiving) */
+    void *ev_staged;         /* copy stream: H2D into d_stage done */
+    void *ev_consumed;       /* compute stream: d_stage copied out, may be overwritten */
+    int uploaded;            /* the device input already holds the bytes of the current host pointer */
     void *d_out_nchw; /* graph outputs: compact NCHW copy for D2H */
     void *h_out;      /* graph outputs: host buffer handed to csinn_get_output */
 } g_tensor;
@@ -103,6 +110,9 @@ static void graph_free(b200_graph *g)
     if (g->arena) b200_free(g->arena);
     for (int i = 0; i < g->nt; i++) {
         if (g->t[i].d_in_nchw) b200_free(g->t[i].d_in_nchw);
+        if (g->t[i].d_stage) b200_free(g->t[i].d_stage);
+        if (g->t[i].ev_staged) b200_event_destroy(g->t[i].ev_staged);
+        if (g->t[i].ev_consumed) b200_event_destroy(g->t[i].ev_consumed);
         if (g->t[i].d_out_nchw) b200_free(g->t[i].d_out_nchw);
         if (g->t[i].h_out) b200_free_host(g->t[i].h_out);
     }
@@ -520,6 +530,10 @@ int shl_b200_session_run(struct csinn_session *sess)
             b200_fail("graph input '%s' has no data: call csinn_update_input first", ct->name ? ct->name : "?");
             return CSINN_FALSE;
         }
+        if (t->uploaded) {
+            t->uploaded = 0; /* csinn_update_input found the bytes prefetched and moved them in */
+            continue;
+        }
         const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
         DEV_CHECK(b200_memcpy_h2d(t->d_in_nchw ? t->d_in_nchw : t->dt.d, ct->data, raw, opt->ctx.stream));
     }
@@ -531,6 +545,75 @@ int shl_b200_session_run(struct csinn_session *sess)
         DEV_CHECK(b200_memcpy_d2h(t->h_out, t->d_out_nchw, raw, opt->ctx.stream));
     }
     DEV_CHECK(b200_stream_sync(opt->ctx.stream));
+    return CSINN_TRUE;
+}
+
+/* ---- input prefetch: overlap the H2D of the NEXT batch with the compute of the current one ------
+ * csinn_session_run is synchronous by contract, so on its own a step costs H2D + compute + D2H.
+ * A host that knows its next input calls shl_b200_session_prefetch_input(idx, next_ptr, sess)
+ * before csinn_session_run: the bytes travel on a copy stream into a staging buffer while the
+ * graph runs; the following csinn_update_input(idx, {data = next_ptr}) recognises the pointer and
+ * replaces the H2D of that step by a device-side copy.  Every batch is still copied from host
+ * memory once; nothing is skipped.  The host buffer must stay unchanged (and should be pinned)
+ * until that csinn_update_input. */
+static g_tensor *input_tensor(b200_graph *g, int index)
+{
+    int k = 0;
+    for (int i = 0; i < g->nt; i++)
+        if (g->t[i].is_input && k++ == index) return &g->t[i];
+    return NULL;
+}
+
+int shl_b200_session_prefetch_input(int index, const void *host_ptr, struct csinn_session *sess)
+{
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g || !host_ptr) {
+        b200_fail("prefetch_input before session_setup or with a null pointer");
+        return CSINN_FALSE;
+    }
+    g_tensor *t = input_tensor(opt->g, index);
+    if (!t) {
+        b200_fail("prefetch_input: no graph input %d", index);
+        return CSINN_FALSE;
+    }
+    b200_ctx *ctx = &opt->ctx;
+    b200_set_device(ctx->device);
+    const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+    if (!ctx->copy_stream) DEV_CHECK(b200_stream_create(&ctx->copy_stream));
+    if (!t->d_stage) {
+        DEV_CHECK(b200_malloc(&t->d_stage, raw));
+        DEV_CHECK(b200_event_create(&t->ev_staged));
+        DEV_CHECK(b200_event_create(&t->ev_consumed));
+    } else if (t->staged_host == NULL) {
+        /* the previous content was handed to the compute stream: wait until it has been copied out */
+        DEV_CHECK(b200_stream_wait_event(ctx->copy_stream, t->ev_consumed));
+    }
+    DEV_CHECK(b200_memcpy_h2d(t->d_stage, host_ptr, raw, ctx->copy_stream));
+    DEV_CHECK(b200_event_record(t->ev_staged, ctx->copy_stream));
+    t->staged_host = host_ptr;
+    return CSINN_TRUE;
+}
+
+/* CSINN_UPDATE_INPUT hook: the reference's bookkeeping (graph_ref/setup.c:51) + the prefetch match */
+int shl_b200_update_input(int index, struct csinn_tensor *input, struct csinn_session *sess)
+{
+    void (*gref_update)(int, struct csinn_tensor *, struct csinn_session *) = shl_gref_runtime_callback(CSINN_UPDATE_INPUT);
+    gref_update(index, input, sess);
+    b200_option *opt = b200_option_of(sess);
+    if (!opt || !opt->g) return CSINN_TRUE; /* before setup: nothing on the device yet */
+    g_tensor *t = input_tensor(opt->g, index);
+    if (!t) return CSINN_TRUE;
+    t->uploaded = 0;
+    if (t->d_stage && t->staged_host && t->staged_host == input->data) {
+        b200_ctx *ctx = &opt->ctx;
+        b200_set_device(ctx->device);
+        const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
+        DEV_CHECK(b200_stream_wait_event(ctx->stream, t->ev_staged));
+        DEV_CHECK(b200_memcpy_d2d(t->d_in_nchw ? t->d_in_nchw : t->dt.d, t->d_stage, raw, ctx->stream));
+        DEV_CHECK(b200_event_record(t->ev_consumed, ctx->stream));
+        t->staged_host = NULL;
+        t->uploaded = 1;
+    }
     return CSINN_TRUE;
 }
 

@@ -84,6 +84,7 @@ int b200_ctx_init(b200_ctx *ctx, int device)
 void b200_ctx_destroy(b200_ctx *ctx)
 {
     if (ctx->stream) b200_stream_destroy(ctx->stream);
+    if (ctx->copy_stream) b200_stream_destroy(ctx->copy_stream);
     /* arena chunks of the default context live for the process; a session's fixed arena is
      * released here */
     if (ctx->fixed_arena && ctx->wbase) b200_free(ctx->wbase);

@@ -94,6 +94,7 @@ void *shl_b200_runtime_callback(int api)
         case CSINN_SESSION_RUN:
             return shl_b200_session_run;
         case CSINN_UPDATE_INPUT:
+            return shl_b200_update_input;
         case CSINN_UPDATE_OUTPUT:
         case CSINN_SET_INPUT_NUMBER:
         case CSINN_SET_OUTPUT_NUMBER:

@@ -116,6 +116,11 @@ void *shl_b200_session_stream(struct csinn_session *sess);
 /* number of device kernels one session_run launches, and the fused step list for inspection */
 int shl_b200_session_num_kernels(struct csinn_session *sess);
 int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen);
+/* Input prefetch: start the H2D of the NEXT batch (host_ptr, pinned) on a copy stream so that it
+ * overlaps the current csinn_session_run; the following csinn_update_input with the same pointer
+ * then costs a device-side copy instead of an H2D.  Every batch still crosses PCIe once. */
+int shl_b200_session_prefetch_input(int index, const void *host_ptr, struct csinn_session *sess);
+int shl_b200_update_input(int index, struct csinn_tensor *input, struct csinn_session *sess);
 /* per-step device time (ms, CUDA events on the session stream) with the algorithmic bytes / ops of
  * each step; the device-side counterpart of shl_benchmark_layer (source/utils/debug.c:1037).
  * Returns the number of steps written (<= cap). */

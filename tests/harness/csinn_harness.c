@@ -66,6 +66,7 @@ typedef struct {
 } h_net;
 
 #ifdef HARNESS_B200
+int shl_b200_session_prefetch_input(int index, const void *host_ptr, struct csinn_session *sess);
 void shl_b200_op_release(void *params);
 int shl_b200_error_count(void);
 const char *shl_b200_last_error(void);
@@ -450,6 +451,12 @@ int h_net_update_input(void *handle, const void *input)
     csinn_update_input(0, &in_t, net->sess);
     return 0;
 }
+#ifdef HARNESS_B200
+int h_net_prefetch_input(void *handle, const void *input)
+{
+    return shl_b200_session_prefetch_input(0, input, ((h_net *)handle)->sess) == CSINN_TRUE ? 0 : -1;
+}
+#endif
 int h_net_session_run(void *handle) { return csinn_session_run(((h_net *)handle)->sess) == CSINN_TRUE ? 0 : -1; }
 const void *h_net_get_output(void *handle)
 {

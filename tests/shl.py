@@ -109,6 +109,8 @@ class Harness:
         L.h_net_session.argtypes = [C.c_void_p]
         L.h_net_update_input.argtypes = [C.c_void_p, C.c_void_p]
         L.h_net_session_run.argtypes = [C.c_void_p]
+        if which == "b200":
+            L.h_net_prefetch_input.argtypes = [C.c_void_p, C.c_void_p]
         L.h_net_get_output.restype = C.c_void_p
         L.h_net_get_output.argtypes = [C.c_void_p]
         L.h_last_error.restype = C.c_char_p
@@ -194,6 +196,27 @@ class Net:
         if rc != 0:
             raise RuntimeError(f"[{self.h.which}] run failed: {self.h.error()}")
         return out
+
+    def stream(self, batches, prefetch=True):
+        """run a sequence of host batches through csinn_update_input + csinn_session_run +
+        csinn_get_output, starting the H2D of batch k+1 (shl_b200_session_prefetch_input) before the
+        run of batch k when `prefetch`"""
+        L = self.h.lib
+        xs = [np.ascontiguousarray(b, dtype=_np_dtype(self.dtype)) for b in batches]
+        outs = []
+        for k, x in enumerate(xs):
+            assert x.shape == self.in_shape
+            assert L.h_net_update_input(self.handle, _ptr(x)) == 0
+            if prefetch and k + 1 < len(xs):
+                assert L.h_net_prefetch_input(self.handle, _ptr(xs[k + 1])) == 0, self.h.error()
+            if L.h_net_session_run(self.handle) != 0:
+                raise RuntimeError(f"[{self.h.which}] run failed: {self.h.error()}")
+            p = L.h_net_get_output(self.handle)
+            n = int(np.prod(self.out_shape))
+            ctype = C.c_int8 if _np_dtype(self.dtype) == np.int8 else C.c_uint16
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).copy()
+            outs.append(a.view(_np_dtype(self.dtype)).reshape(self.out_shape))
+        return outs
 
     def close(self):
         if self.handle:

@@ -346,6 +346,34 @@ def test_mobilenet_v1_int8_batch_properties(b200):
     assert np.array_equal(y[3:4], nets.oracle_forward(nb1, x[3:4]))
 
 
+@pytest.mark.parametrize("first_op", ["conv", "dw"])
+def test_prefetched_inputs_give_the_same_bytes(first_op, b200, rng):
+    """shl_b200_session_prefetch_input: batch k+1 travels on the copy stream while batch k computes;
+    results must equal the plain csinn_update_input + csinn_session_run sequence, for an input that
+    stays NCHW on the device (first op a dense conv) and one converted to pixel-major per run, and
+    a pointer that was prefetched but is NOT the next input must not be picked up"""
+    if first_op == "conv":
+        nb = nets.mobilenet_v1(DT_INT8, batch=4, res=64, width=0.25, classes=50)
+        shape, layers, s_in, zp_in = nb.in_shape, nb.layers, nb.s_in, nb.zp_in
+    else:
+        c = 48
+        wt, s_w, b, s_out = synth_conv_i8(rng, c, c, 3, 3, depthwise=True)
+        shape, s_in, zp_in = (4, c, 20, 20), 0.02, -3
+        layers = [Layer(H_CONV, shape, s_out=s_out, zp_out=5, w=wt, b=b, s_w=s_w, stride=(1, 1), pad=(1,) * 4, group=c)]
+    xs = [rng.integers(-128, 128, size=shape, dtype=np.int8) for _ in range(5)]
+    with b200.create(DT_INT8, shape, layers, s_in=s_in, zp_in=zp_in, run_mode=RM_GRAPH) as net:
+        plain = [net(x) for x in xs]
+        piped = net.stream(xs, prefetch=True)
+        for k in range(5):
+            assert np.array_equal(plain[k], piped[k]), f"batch {k} differs through the prefetch stage"
+        # a stale prefetch: stage xs[0], then run xs[1] -- must compute xs[1]
+        L = b200.lib
+        a, bb = np.ascontiguousarray(xs[0]), np.ascontiguousarray(xs[1])
+        assert L.h_net_prefetch_input(net.handle, a.ctypes.data) == 0
+        assert np.array_equal(net.stream([bb], prefetch=False)[0], plain[1])
+        assert np.array_equal(net.stream([a], prefetch=False)[0], plain[0])
+
+
 def test_mobilenet_v1_fp16_graph(b200):
     """BASELINE.json configs[2] shapes (c906_mobilenetv1_f16.c), fp16, at a size the oracle finishes"""
     nb = nets.mobilenet_v1(DT_F16, batch=2, res=96, width=0.5, classes=200)
