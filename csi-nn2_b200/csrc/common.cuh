@@ -38,7 +38,8 @@ int sm_count();
 int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
                         int box_w, int box_h);
 int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
-                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                   int swizzle_bytes = 128);
 
 // ---- device helpers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

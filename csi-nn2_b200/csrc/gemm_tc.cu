@@ -6,12 +6,18 @@
 // One persistent CTA per SM, 18 warps:
 //   warp 0       TMA producer (one elected lane)
 //   warp 1       tcgen05.mma issuer (one elected lane) + TMEM allocation
-//   warps 2..17  epilogue: tcgen05.ld -> requantise -> 16-byte global stores.  On the short-K
-//                (memory-bound) layers the epilogue's instruction stream is the critical path,
-//                so it gets 4 warps per scheduler and a compile-time specialised body
-//                (activation mode, post table, magic-number int<->float) instead of runtime flags.
+//   warps 2..17  epilogue: tcgen05.ld -> requantise -> swizzled shared-memory staging -> TMA store
+//                (int8; fp16 still stores 16-byte vectors directly).  On the short-K
+//                (memory-bound) layers the epilogue is the critical path -- ncu showed it bound by the
+//                LSU data pipe (82 % of peak wavefronts: a warp's 16-byte stores to 32 different rows
+//                cost ~34 wavefronts each, the per-column parameter loads 2.5 each), not by HBM --
+//                so it gets 4 warps per scheduler, a compile-time specialised body (activation
+//                mode, post table, magic-number int<->float), per-column parameters held in
+//                registers across the row blocks of a super tile, and conflict-free STS.128 into
+//                a staging tile that one thread hands to the TMA store engine.
 // Work unit = a "super tile": G consecutive 128-row blocks x one n-tile, accumulated side by side
-// in one 256-column TMEM stage (G = 4 / 2 / 1 for n-tiles of <= 64 / <= 128 / <= 256 columns), so
+// in one 256-column TMEM stage (G = 4 / 2 / 1 for n-tiles of <= 64 / <= 128 / <= 256 columns; int8
+// n-tiles are 16 / 32 / 64 / 128 wide so that G >= 2 and a staging row is one swizzle span), so
 // the producer <-> MMA <-> epilogue hand-offs are paid once per G*128 rows.  A CTA owns ONE n-tile
 // (blockIdx % n_tiles) and walks the row blocks; when that n-tile's weights fit (<= 160 KB) they
 // are loaded ONCE per CTA and stay resident, so the ring carries activations only and L2 is not
@@ -51,6 +57,7 @@ struct GemmArgs {
     int b_resident;    // weights loaded once per CTA
     int stages;
     int ldo;           // elements
+    uint32_t stage_bytes;  // int8: one output staging buffer = G * 128 rows * bn bytes (two of them)
     void *out;
     uint32_t idesc;
     EpiScalars ep;
@@ -63,11 +70,18 @@ struct __align__(16) EpiParams {
     uint8_t lut[256];
 };
 
-// four int8 outputs from four accumulators (already + ibias) -> one packed word
+__device__ __forceinline__ void epi_bar_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+}
+
+// four int8 outputs from four accumulators (already + ibias) -> one packed word.
+// EPI_LUT: lut_lo arrives minus the table's shared-memory address (lut_base), so the clamp of the
+// table index and the address addition are the same two instructions.
 template <int MODE, bool MAGIC>
 __device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4)[4], const float (&b4)[4],
                                              const EpiScalars &ep, const uint8_t *lut, bool has_lut,
-                                             int zp_m, int lut_lo)
+                                             int zp_m, int lut_lo, int lut_base)
 {
     int q[4];
 #pragma unroll
@@ -77,7 +91,7 @@ __device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4
         // t = kMagicI + round_half_even(f)   (|f| < 2^22 is guaranteed by the host)
         const int t = __float_as_int(__fadd_rn(f, kMagicF));
         if (MODE == EPI_LUT) {
-            q[e] = min(max(t - lut_lo, 0), 255);  // clamp(q, -128, 127) + 128
+            q[e] = min(max(t - lut_lo, lut_base), lut_base + 255);  // &lut[clamp(q, -128, 127) + 128]
         } else {
             q[e] = t + zp_m;
             if (MODE == EPI_RELU || MODE == EPI_RELU6) q[e] = max(q[e], ep.zp_out);
@@ -89,7 +103,11 @@ __device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4
         }
     }
     if (MODE == EPI_LUT) {
-        const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
+        uint32_t b0, b1, b2, b3;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(q[0]));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(q[1]));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(q[2]));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b3) : "r"(q[3]));
         return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
     }
     if (MODE == EPI_GENERIC && has_lut) return lut4_i8(q[0], q[1], q[2], q[3], lut);
@@ -99,7 +117,7 @@ __device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4
 template <int DT, int MODE, bool MAGIC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmArgs args)
+               const __grid_constant__ CUtensorMap tma_o, const GemmArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment; stay on the shared-memory pointer so that every
@@ -112,7 +130,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + stages * a_stage_bytes;
     const uint32_t b_slabs = args.b_resident ? args.k_blocks : stages;
-    EpiParams *epi = reinterpret_cast<EpiParams *>(smem_b + b_slabs * b_stage_bytes);
+    uint8_t *staging = smem_b + b_slabs * b_stage_bytes;  // 1024-aligned: both slab sizes are multiples of 2 KB
+    EpiParams *epi = reinterpret_cast<EpiParams *>(staging + 2 * args.stage_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + 1);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint64_t *tmem_full = empty_bar + kMaxStages;
@@ -127,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (DT == B200_I8) tma_prefetch_desc(&tma_o);
         for (int i = 0; i < stages; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -228,8 +248,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 tc_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
             }
         }
+    } else if (DT == B200_I8) {
+        // ===== int8 epilogue: TMEM -> registers -> requantise -> swizzled staging -> TMA store =====
+        const int ew = warp - 2;
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int part = ew >> 2;   // 0..3: which 16-column sub-chunks of the n-tile it owns
+        const int et = threadIdx.x - 64;
+        const EpiScalars &ep = args.ep;
+        const int bn = args.bn;     // 16 / 32 / 64 / 128
+        const int nsub = bn >> 4;
+        const int zp_m = ep.zp_out - kMagicI;
+        const int lut_base = static_cast<int>(smem_u32(epi->lut));
+        int lut_lo = kMagicI - ep.zp_out - 128 - lut_base;
+        // keep the addend in a vector register (VIADDMNMX takes one uniform operand: the bound)
+        asm("mov.b32 %0, %0;" : "+r"(lut_lo));
+        const bool has_lut = ep.post_lut != nullptr;
+        // this CTA's n-tile never changes: stage its per-channel parameters once
+        if (et < bn) {
+            const int col = n0 + et;
+            const bool ok = col < args.n;
+            epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
+            epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
+            epi->ibias[et] = ((ok && ep.ibias) ? ep.ibias[col] : 0) + (MAGIC ? kMagicI : 0);
+        }
+        epi_bar_sync();
+        // a staging row is bn bytes = one TMA swizzle span (128B / 64B / 32B / none): XOR the
+        // 16-byte chunk index with address bits [7, 7+B)
+        const uint32_t swz_mask = bn >= 128 ? 7u : (bn == 64 ? 3u : (bn == 32 ? 1u : 0u));
+        const uint32_t row_off = static_cast<uint32_t>(quad * 32 + lane) * bn;
+        const uint32_t panel_bytes = kBM * bn;
+        float mu[16], ba[16];
+        int ib[16];
+        int loaded_sub = -1;
+        int local = 0;
+        for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int mt0 = ms * G;
+            const int gmax = min(G, args.num_m_tiles - mt0);
+            uint8_t *stg = staging + (local & 1) * args.stage_bytes;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
+            for (int sub = part; sub < nsub; sub += 4) {
+                if (sub != loaded_sub) {
+                    // 16 columns x (mult, badd, ibias) -> 48 registers, reused for every row block of
+                    // the super tile (and for the CTA's whole life when the n-tile has <= 64 columns)
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const float4 m4 = *reinterpret_cast<const float4 *>(&epi->mult[sub * 16 + j4 * 4]);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&epi->badd[sub * 16 + j4 * 4]);
+                        const int4 i4 = *reinterpret_cast<const int4 *>(&epi->ibias[sub * 16 + j4 * 4]);
+                        mu[j4 * 4 + 0] = m4.x, mu[j4 * 4 + 1] = m4.y, mu[j4 * 4 + 2] = m4.z, mu[j4 * 4 + 3] = m4.w;
+                        ba[j4 * 4 + 0] = b4.x, ba[j4 * 4 + 1] = b4.y, ba[j4 * 4 + 2] = b4.z, ba[j4 * 4 + 3] = b4.w;
+                        ib[j4 * 4 + 0] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
+                    }
+                    loaded_sub = sub;
+                }
+                uint32_t off = row_off + sub * 16;
+                off ^= ((off >> 7) & swz_mask) << 4;
+#pragma unroll 1
+                for (int g = 0; g < gmax; g++) {
+                    uint32_t r[16];
+                    tmem_ld_32x16(taddr + g * bn + sub * 16, r);
+                    tmem_ld_wait();
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const float m4[4] = {mu[j4 * 4], mu[j4 * 4 + 1], mu[j4 * 4 + 2], mu[j4 * 4 + 3]};
+                        const float b4[4] = {ba[j4 * 4], ba[j4 * 4 + 1], ba[j4 * 4 + 2], ba[j4 * 4 + 3]};
+                        const int a4[4] = {static_cast<int>(r[j4 * 4 + 0]) + ib[j4 * 4 + 0],
+                                           static_cast<int>(r[j4 * 4 + 1]) + ib[j4 * 4 + 1],
+                                           static_cast<int>(r[j4 * 4 + 2]) + ib[j4 * 4 + 2],
+                                           static_cast<int>(r[j4 * 4 + 3]) + ib[j4 * 4 + 3]};
+                        // columns >= n carry requantised zeros; the TMA store clips at the row pitch
+                        packed[j4] = requant4<MODE, MAGIC>(a4, m4, b4, ep, epi->lut, has_lut, zp_m, lut_lo, lut_base);
+                    }
+                    *reinterpret_cast<uint4 *>(stg + g * panel_bytes + off) =
+                        make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+            // accumulators drained: the MMA warp may refill this TMEM stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            // hand the staged tile to the TMA store engine.  Before anybody writes the OTHER buffer
+            // (next super tile), the store issued from it one tile ago must have finished reading.
+            fence_proxy_async_smem();
+            if (et == 0) tma_store_wait_read<0>();
+            epi_bar_sync();
+            if (et == 0) {
+                for (int g = 0; g < gmax; g++)
+                    tma_store_2d(&tma_o, stg + g * panel_bytes, n0, (mt0 + g) * kBM);  // clips rows >= m
+                tma_store_commit();
+            }
+        }
+        if (et == 0) tma_store_wait<0>();
     } else {
-        // ===== epilogue =====
+        // ===== fp16 epilogue: TMEM -> registers -> bias / activation -> 16-byte global stores =====
         const int ew = warp - 2;
         const int quad = warp & 3;   // TMEM lane quadrant this warp may access
         const int part = ew >> 2;    // 0..3: which column chunks of the tile it owns
@@ -238,29 +354,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // column chunk per tcgen05.ld: 32 for wide tiles, 16 when the tile has at most 64 columns
         // (so that all four warps of a quadrant have work)
         const int cw = args.bn >= 128 ? 32 : 16;
-        const int zp_m = ep.zp_out - kMagicI;
-        const int lut_lo = kMagicI - ep.zp_out - 128;
-        const bool has_lut = ep.post_lut != nullptr;
+        const int act = MODE;  // fp16: MODE is the activation
+        // this CTA's n-tile never changes: stage its bias once
+        if (et < args.bn) {
+            const int col = n0 + et;
+            epi->badd[et] = (col < args.n && ep.badd) ? ep.badd[col] : 0.f;
+        }
+        epi_bar_sync();
         int local = 0;
-        int staged_n0 = -1;
         for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int mt0 = ms * G;
-            // stage this n-tile's per-channel parameters (once per CTA when N fits one tile)
-            if (n0 != staged_n0) {
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-                if (et < args.bn) {
-                    const int col = n0 + et;
-                    const bool ok = col < args.n;
-                    epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
-                    epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
-                    epi->ibias[et] = ((ok && ep.ibias) ? ep.ibias[col] : 0) + (MAGIC ? kMagicI : 0);
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-                staged_n0 = n0;
-            }
-
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             for (int g = 0; g < G; g++) {
@@ -283,55 +388,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         for (int j = 16; j < 32; j++) r[j] = 0;
                     }
                     tmem_ld_wait();
-                    if (DT == B200_I8) {
-                        int8_t *dst = static_cast<int8_t *>(args.out) + static_cast<size_t>(row) * args.ldo + n0 + c0;
+                    uint32_t packed[16];
 #pragma unroll
-                        for (int v = 0; v < 2; v++) {
-                            if (v * 16 >= ncols) break;
-                            uint32_t packed[4];
+                    for (int j2 = 0; j2 < 16; j2++) {
+                        const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
+                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
+                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
+                        const int cb = n0 + c0 + j2 * 2;
+                        f0 = cb < args.n ? f0 : 0.f;
+                        f1 = cb + 1 < args.n ? f1 : 0.f;
+                        __half2 h = __floats2half2_rn(f0, f1);
+                        packed[j2] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    if (row_ok) {
+                        __half *dst = static_cast<__half *>(args.out) + static_cast<size_t>(row) * args.ldo + n0 + c0;
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; j4++) {
-                                const int c = c0 + v * 16 + j4 * 4;
-                                const float4 mu = *reinterpret_cast<const float4 *>(&epi->mult[c]);
-                                const float4 ba = *reinterpret_cast<const float4 *>(&epi->badd[c]);
-                                const int4 ib = *reinterpret_cast<const int4 *>(&epi->ibias[c]);
-                                const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, b4[4] = {ba.x, ba.y, ba.z, ba.w};
-                                const int a4[4] = {static_cast<int>(r[v * 16 + j4 * 4 + 0]) + ib.x,
-                                                   static_cast<int>(r[v * 16 + j4 * 4 + 1]) + ib.y,
-                                                   static_cast<int>(r[v * 16 + j4 * 4 + 2]) + ib.z,
-                                                   static_cast<int>(r[v * 16 + j4 * 4 + 3]) + ib.w};
-                                // columns >= n of a partial vector carry unspecified values (never
-                                // read: every consumer takes the true channel count)
-                                packed[j4] = requant4<MODE, MAGIC>(a4, m4, b4, ep, epi->lut, has_lut, zp_m, lut_lo);
-                            }
-                            if (row_ok && n0 + c0 + v * 16 < args.ldo)
-                                *reinterpret_cast<uint4 *>(dst + v * 16) =
-                                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        }
-                    } else {
-                        const int act = MODE;  // fp16: MODE is the activation
-                        uint32_t packed[16];
-#pragma unroll
-                        for (int j2 = 0; j2 < 16; j2++) {
-                            const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
-                            float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
-                            float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
-                            const int cb = n0 + c0 + j2 * 2;
-                            f0 = cb < args.n ? f0 : 0.f;
-                            f1 = cb + 1 < args.n ? f1 : 0.f;
-                            __half2 h = __floats2half2_rn(f0, f1);
-                            packed[j2] = *reinterpret_cast<uint32_t *>(&h);
-                        }
-                        if (row_ok) {
-                            __half *dst = static_cast<__half *>(args.out) + static_cast<size_t>(row) * args.ldo +
-                                          n0 + c0;
-#pragma unroll
-                            for (int v = 0; v < 4; v++) {
-                                if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
-                                    *reinterpret_cast<uint4 *>(dst + v * 8) =
-                                        make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2],
-                                                   packed[v * 4 + 3]);
-                            }
+                        for (int v = 0; v < 4; v++) {
+                            if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
+                                *reinterpret_cast<uint4 *>(dst + v * 8) =
+                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2], packed[v * 4 + 3]);
                         }
                     }
                 }
@@ -348,18 +423,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident)
+static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident, size_t staging)
 {
     const size_t a = static_cast<size_t>(stages) * kBM * kBKBytes;
     const size_t b = static_cast<size_t>(resident ? k_blocks : stages) * bn * kBKBytes;
-    return 1024 + a + b + sizeof(EpiParams) + (2 * kMaxStages + 5) * sizeof(uint64_t) + 16;
+    return 1024 + a + b + 2 * staging + sizeof(EpiParams) + (2 * kMaxStages + 5) * sizeof(uint64_t) + 16;
 }
 
-static int pick_bn(int n)
+static int pick_bn(int n, int dtype)
 {
-    // one n-tile when the whole output width fits (<= 256), otherwise the multiple of 16 that
-    // splits n most evenly into the fewest tiles
     const int n16 = (n + 15) / 16 * 16;
+    if (dtype == B200_I8) {
+        // int8 tiles leave through a swizzled staging tile whose row is one TMA swizzle span:
+        // 16 / 32 / 64 / 128 columns (the weight rows past n are zero-filled by the TMA load, the
+        // columns past the row pitch clipped by the TMA store)
+        return n16 <= 16 ? 16 : (n16 <= 32 ? 32 : (n16 <= 64 ? 64 : 128));
+    }
+    // fp16: one n-tile when the whole output width fits (<= 256), otherwise the multiple of 16
+    // that splits n most evenly into the fewest tiles
     if (n16 <= 256) return n16;
     const int tiles = (n16 + 255) / 256;
     return ((n16 + tiles - 1) / tiles + 15) / 16 * 16;
@@ -367,7 +448,7 @@ static int pick_bn(int n)
 
 template <int DT, int MODE, bool MAGIC>
 static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &ta,
-                          const CUtensorMap &tb, const GemmArgs &args, int dev)
+                          const CUtensorMap &tb, const CUtensorMap &to, const GemmArgs &args, int dev)
 {
     static bool attr_set[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
@@ -376,7 +457,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
                                              (int)kSmemLimit));
         attr_set[dev] = true;
     }
-    gemm_tc_kernel<DT, MODE, MAGIC><<<grid, kThreads, smem, stream>>>(ta, tb, args);
+    gemm_tc_kernel<DT, MODE, MAGIC><<<grid, kThreads, smem, stream>>>(ta, tb, to, args);
     return B200_OK;
 }
 
@@ -408,10 +489,10 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.m = d->m;
     args.n = d->n;
     args.k_blocks = (d->k * eb + kBKBytes - 1) / kBKBytes;
-    args.bn = pick_bn(d->n);
+    args.bn = pick_bn(d->n, d->dtype);
     // prefer an n-tile whose weights stay resident in shared memory: halve a 256-wide tile when
     // that makes K * bn fit
-    if (args.k_blocks * args.bn * kBKBytes > kResidentBBytes && args.bn > 128 &&
+    if (d->dtype == B200_F16 && args.k_blocks * args.bn * kBKBytes > kResidentBBytes && args.bn > 128 &&
         args.k_blocks * 128 * kBKBytes <= kResidentBBytes)
         args.bn = 128;
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
@@ -426,7 +507,13 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     if (getenv("SHL_B200_GEMM_GROUP")) group = max(1, min(kAccStride / args.bn, atoi(getenv("SHL_B200_GEMM_GROUP"))));
     args.group = group;
     args.num_m_super = (args.num_m_tiles + group - 1) / group;
-    args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes && !getenv("SHL_B200_GEMM_NO_RESIDENT");
+    // int8: two staging buffers of one super tile each (G x 128 rows x bn bytes)
+    const size_t staging = d->dtype == B200_I8 ? static_cast<size_t>(group) * kBM * args.bn : 0;
+    args.stage_bytes = static_cast<uint32_t>(staging);
+    // weights stay resident when they fit beside the staging and at least three A stages
+    args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
+                      gemm_smem_bytes(3, args.bn, args.k_blocks, true, staging) <= kSmemLimit &&
+                      !getenv("SHL_B200_GEMM_NO_RESIDENT");
     args.ldo = d->ldo;
     args.out = d->out;
     args.ep = make_epi(d->ep);
@@ -435,16 +522,25 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     // as many stages as fit: the ring also prefetches the next tiles' operands while the
     // epilogue drains, which is what keeps HBM busy on the short-K (memory-bound) layers
     int stages = kMaxStages;
-    while (stages > 2 && gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident) > kSmemLimit) stages--;
+    while (stages > 2 && gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging) > kSmemLimit)
+        stages--;
     args.stages = stages;
-    const size_t smem = gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident);
+    const size_t smem = gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging);
 
-    alignas(64) CUtensorMap ta, tb;
+    alignas(64) CUtensorMap ta, tb, to;
     const int box_k = kBKBytes / eb;
     int rc = encode_tmap_2d(&ta, eb, d->a, d->k, d->m, static_cast<uint64_t>(d->lda) * eb, box_k, kBM);
     if (rc) return rc;
     rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
     if (rc) return rc;
+    if (d->dtype == B200_I8) {
+        // output tile: 128 rows x bn bytes, rows clipped at m, columns at the row pitch
+        rc = encode_tmap_2d(&to, 1, d->out, d->ldo, d->m, static_cast<uint64_t>(d->ldo), args.bn, kBM,
+                            args.bn >= 128 ? 128 : (args.bn >= 32 ? args.bn : 0));
+        if (rc) return rc;
+    } else {
+        to = ta;  // unused by the fp16 epilogue
+    }
 
     // a multiple of the n-tile count so that every CTA keeps one n-tile for its whole life
     int ctas_per_n = sm_count() / args.num_n_tiles;
@@ -456,9 +552,9 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     if (d->dtype == B200_F16) {
         switch (d->ep.act) {
-            case B200_ACT_NONE: rc = launch_variant<B200_F16, 0, false>(grid, smem, s, ta, tb, args, dev); break;
-            case B200_ACT_RELU: rc = launch_variant<B200_F16, 1, false>(grid, smem, s, ta, tb, args, dev); break;
-            default: rc = launch_variant<B200_F16, 2, false>(grid, smem, s, ta, tb, args, dev); break;
+            case B200_ACT_NONE: rc = launch_variant<B200_F16, 0, false>(grid, smem, s, ta, tb, to, args, dev); break;
+            case B200_ACT_RELU: rc = launch_variant<B200_F16, 1, false>(grid, smem, s, ta, tb, to, args, dev); break;
+            default: rc = launch_variant<B200_F16, 2, false>(grid, smem, s, ta, tb, to, args, dev); break;
         }
     } else {
         // |acc + ibias| <= K * 2 * 128 * 127 < 2^22 lets the epilogue convert through the magic
@@ -471,8 +567,8 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
             mode = d->ep.act == B200_ACT_NONE ? EPI_PLAIN : (d->ep.act == B200_ACT_RELU ? EPI_RELU : EPI_RELU6);
 #define B200_GEMM_CASE(MODE)                                                                      \
     case MODE:                                                                                    \
-        rc = magic ? launch_variant<B200_I8, MODE, true>(grid, smem, s, ta, tb, args, dev)        \
-                   : launch_variant<B200_I8, MODE, false>(grid, smem, s, ta, tb, args, dev);      \
+        rc = magic ? launch_variant<B200_I8, MODE, true>(grid, smem, s, ta, tb, to, args, dev)        \
+                   : launch_variant<B200_I8, MODE, false>(grid, smem, s, ta, tb, to, args, dev);      \
         break;
         switch (mode) {
             B200_GEMM_CASE(EPI_PLAIN)
@@ -480,8 +576,8 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
             B200_GEMM_CASE(EPI_RELU6)
             B200_GEMM_CASE(EPI_LUT)
             default:
-                rc = magic ? launch_variant<B200_I8, EPI_GENERIC, true>(grid, smem, s, ta, tb, args, dev)
-                           : launch_variant<B200_I8, EPI_GENERIC, false>(grid, smem, s, ta, tb, args, dev);
+                rc = magic ? launch_variant<B200_I8, EPI_GENERIC, true>(grid, smem, s, ta, tb, to, args, dev)
+                           : launch_variant<B200_I8, EPI_GENERIC, false>(grid, smem, s, ta, tb, to, args, dev);
                 break;
         }
 #undef B200_GEMM_CASE

@@ -92,7 +92,8 @@ int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w,
 }
 
 int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
-                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer)
+                   uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                   int swizzle_bytes)
 {
     encode_tiled_fn fn = encode_entry();
     if (!fn) return B200_ERR_CUDA;
@@ -103,7 +104,11 @@ int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t 
     CUtensorMapDataType dt =
         elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUresult r = fn(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                    : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                    : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                          : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed: CUresult %d (inner %llu outer %llu pitch %llu box %u x %u)",
