@@ -27,8 +27,8 @@ namespace b200 {
 
 enum { DW_PLAIN = 0, DW_RELU = 1, DW_RELU6 = 2, DW_LUT = 3, DW_GENERIC = 4 };
 constexpr int kDwStages = 3;
-constexpr int kDwConsumers = 256;
-constexpr int kDwThreads = kDwConsumers + 32;
+// consumer threads per CTA: 256 or 224 (tile widths 32/16/8 or 28/14/7 columns -- the second family
+// divides the 112 / 56 / 28 / 14 / 7 wide maps of the ImageNet networks without idle columns)
 
 struct DwTmaArgs {
     int n, c, cp, h, w, oh, ow, pt, pl;
@@ -90,12 +90,13 @@ __device__ __forceinline__ void dp4(int (&acc)[4], const uint32_t (&v)[4], const
 }
 
 template <int S, int CC, int TW, int MODE>
-__global__ void __launch_bounds__(kDwThreads, 2)
+__global__ void __launch_bounds__(CC / 4 * TW + 32, 2)
 dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
 {
     constexpr int TWI = S * (TW - 1) + 3;
     constexpr int WORDS = CC / 4;
-    static_assert(WORDS * TW == kDwConsumers, "tile shape must give 256 consumer threads");
+    constexpr int kDwConsumers = WORDS * TW;
+    static_assert(kDwConsumers % 32 == 0 && kDwConsumers <= 256, "tile shape must give whole consumer warps");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // TMA destinations must be 128-byte aligned; stay on the shared pointer (LDS / STS codegen)
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -205,58 +206,66 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
             asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
         }
 
-        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + x * S * WORDS + cw;
-        int8_t *obase = a.out + ((static_cast<long long>(b) * a.oh + oy0) * a.ow + ox) * a.cp + ch;
-        const int orow = a.ow * a.cp;  // bytes between output rows (< 2^31: one image row)
+        if (col_ok) {
+            const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + x * S * WORDS + cw;
+            // 32-bit byte offset into the output (host-checked < 2^32)
+            uint32_t ooff = ((static_cast<uint32_t>(b) * a.oh + oy0) * a.ow + ox) * a.cp + ch;
+            const uint32_t orow = static_cast<uint32_t>(a.ow) * a.cp;
 
-        auto load_taps = [&](int r, uint32_t (&v)[4]) {
-            const uint32_t *p = tw + r * (TWI * WORDS);
-            taps3(p[0], p[WORDS], p[2 * WORDS], v);
-        };
-        auto finish = [&](int (&acc)[4], int y) {
-            if (y >= 0 && y < rows_out && col_ok)
-                *reinterpret_cast<uint32_t *>(obase + static_cast<size_t>(static_cast<uint32_t>(y * orow))) =
-                    dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo);
+            auto taps = [&](int r, uint32_t (&v)[4]) {
+                const uint32_t *p = tw + r * (TWI * WORDS);
+                taps3(p[0], p[WORDS], p[2 * WORDS], v);
+            };
+            // a fresh accumulator set is produced by the ky = 0 dp4a itself (addend = ibias + magic)
+            auto first = [&](int (&acc)[4], const uint32_t (&v)[4]) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) acc[e] = init[e];
-        };
-
-        int accA[4], accB[4], accC[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) accA[e] = accB[e] = accC[e] = init[e];
-        uint32_t v[4];
-        if (S == 1) {
-            // input row r feeds output rows r (ky = 0), r - 1 (ky = 1), r - 2 (ky = 2, completes it)
-            const int rows_in = rows_out + 2;
-            for (int r = 0; r < rows_in; r += 3) {
-                load_taps(r, v);
-                dp4(accC, v, wk[0]), dp4(accB, v, wk[1]), dp4(accA, v, wk[2]);
-                finish(accA, r - 2);
-                if (r + 1 >= rows_in) break;
-                load_taps(r + 1, v);
-                dp4(accA, v, wk[0]), dp4(accC, v, wk[1]), dp4(accB, v, wk[2]);
-                finish(accB, r - 1);
-                if (r + 2 >= rows_in) break;
-                load_taps(r + 2, v);
-                dp4(accB, v, wk[0]), dp4(accA, v, wk[1]), dp4(accC, v, wk[2]);
-                finish(accC, r);
-            }
-        } else {
-            // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
-            load_taps(0, v);
-            dp4(accA, v, wk[0]);
-            for (int y = 0; y < rows_out; y += 2) {
-                load_taps(2 * y + 1, v);
-                dp4(accA, v, wk[1]);
-                load_taps(2 * y + 2, v);
-                dp4(accA, v, wk[2]), dp4(accB, v, wk[0]);
-                finish(accA, y);
-                if (y + 1 >= rows_out) break;
-                load_taps(2 * y + 3, v);
-                dp4(accB, v, wk[1]);
-                load_taps(2 * y + 4, v);
-                dp4(accB, v, wk[2]), dp4(accA, v, wk[0]);
-                finish(accB, y + 1);
+                for (int e = 0; e < 4; e++) acc[e] = __dp4a(static_cast<int>(v[e]), static_cast<int>(wk[0][e]), init[e]);
+            };
+            auto store = [&](const int (&acc)[4]) {
+                *reinterpret_cast<uint32_t *>(a.out + ooff) = dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo);
+                ooff += orow;
+            };
+            int accA[4], accB[4], accC[4];
+            uint32_t v[4];
+            if (S == 1) {
+                // input row r feeds output rows r (ky 0), r - 1 (ky 1), r - 2 (ky 2, completes it).
+                // rows_out is uniform over the CTA: the exits below do not diverge.
+                taps(0, v);
+                first(accA, v);
+                taps(1, v);
+                dp4(accA, v, wk[1]), first(accB, v);
+                for (int y = 0;; y += 3) {
+                    taps(y + 2, v);
+                    dp4(accA, v, wk[2]), dp4(accB, v, wk[1]), first(accC, v);
+                    store(accA);
+                    if (y + 1 >= rows_out) break;
+                    taps(y + 3, v);
+                    dp4(accB, v, wk[2]), dp4(accC, v, wk[1]), first(accA, v);
+                    store(accB);
+                    if (y + 2 >= rows_out) break;
+                    taps(y + 4, v);
+                    dp4(accC, v, wk[2]), dp4(accA, v, wk[1]), first(accB, v);
+                    store(accC);
+                    if (y + 3 >= rows_out) break;
+                }
+            } else {
+                // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
+                taps(0, v);
+                first(accA, v);
+                for (int y = 0;; y += 2) {
+                    taps(2 * y + 1, v);
+                    dp4(accA, v, wk[1]);
+                    taps(2 * y + 2, v);
+                    dp4(accA, v, wk[2]), first(accB, v);
+                    store(accA);
+                    if (y + 1 >= rows_out) break;
+                    taps(2 * y + 3, v);
+                    dp4(accB, v, wk[1]);
+                    taps(2 * y + 4, v);
+                    dp4(accB, v, wk[2]), first(accA, v);
+                    store(accB);
+                    if (y + 2 >= rows_out) break;
+                }
             }
         }
 
@@ -288,7 +297,7 @@ static int launch_cfg(int mode, int grid, size_t smem, cudaStream_t s, const CUt
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
             attr[dev] = true;                                                                        \
         }                                                                                            \
-        dw3x3_tma_kernel<S, CC, TW, M><<<grid, kDwThreads, smem, s>>>(tm, a);                        \
+        dw3x3_tma_kernel<S, CC, TW, M><<<grid, CC / 4 * TW + 32, smem, s>>>(tm, a);                  \
         break;                                                                                       \
     }
     switch (mode) {
@@ -312,11 +321,11 @@ using namespace b200;
 int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream)
 {
     const int S = d->stride_h;
-    // tile shape: (CC, TW) with CC/4 * TW = 256 threads; prefer full column use and a thin halo
-    static const DwCfg cfgs[3] = {{32, 32}, {64, 16}, {128, 8}};
+    // tile shape: (CC, TW) with CC/4 * TW = 256 or 224 threads; prefer full column use and a thin halo
+    static const DwCfg cfgs[6] = {{32, 32}, {64, 16}, {128, 8}, {32, 28}, {64, 14}, {128, 7}};
     int best = 0;
     double best_score = -1;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 6; i++) {
         const int cc = cfgs[i].cc, tw = cfgs[i].tw;
         const int xb = (d->ow + tw - 1) / tw, cb = (d->cp + cc - 1) / cc;
         const int twi = S * (tw - 1) + 3;
@@ -354,8 +363,8 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     if (rc) return rc;
 
     const long long tiles = static_cast<long long>(d->n) * a.ybands * a.xbands * a.cchunks;
-    if (tiles >= (1ll << 31)) {
-        set_error("b200_dwconv2d: %lld tiles exceed the 32-bit tile index", tiles);
+    if (tiles >= (1ll << 31) || static_cast<long long>(d->n) * d->oh * d->ow * d->cp >= (1ll << 32)) {
+        set_error("b200_dwconv2d: %lld tiles / output bytes exceed the 32-bit indices of the 3x3 kernel", tiles);
         return B200_ERR_UNSUPPORTED;
     }
     const long long cap = static_cast<long long>(sm_count()) * 2;
@@ -369,15 +378,21 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t s = (cudaStream_t)stream;
-    if (S == 1) {
-        if (best == 0) rc = launch_cfg<1, 32, 32>(mode, grid, smem, s, tm, a, dev);
-        else if (best == 1) rc = launch_cfg<1, 64, 16>(mode, grid, smem, s, tm, a, dev);
-        else rc = launch_cfg<1, 128, 8>(mode, grid, smem, s, tm, a, dev);
-    } else {
-        if (best == 0) rc = launch_cfg<2, 32, 32>(mode, grid, smem, s, tm, a, dev);
-        else if (best == 1) rc = launch_cfg<2, 64, 16>(mode, grid, smem, s, tm, a, dev);
-        else rc = launch_cfg<2, 128, 8>(mode, grid, smem, s, tm, a, dev);
+#define B200_DW_CFG(I, CCv, TWv)                                                        \
+    case I:                                                                             \
+        rc = S == 1 ? launch_cfg<1, CCv, TWv>(mode, grid, smem, s, tm, a, dev)          \
+                    : launch_cfg<2, CCv, TWv>(mode, grid, smem, s, tm, a, dev);         \
+        break;
+    switch (best) {
+        B200_DW_CFG(0, 32, 32)
+        B200_DW_CFG(1, 64, 16)
+        B200_DW_CFG(2, 128, 8)
+        B200_DW_CFG(3, 32, 28)
+        B200_DW_CFG(4, 64, 14)
+        default:
+            B200_DW_CFG(5, 128, 7)
     }
+#undef B200_DW_CFG
     if (rc) return rc;
     B200_LAUNCH_CHECK();
     return B200_OK;
