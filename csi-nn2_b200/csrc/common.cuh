@@ -231,6 +231,21 @@ __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+// 16 registers per thread -> 32 lanes x 16 consecutive 32-bit columns (thread = lane): used to seed
+// an accumulator with its per-column integer bias before the MMAs accumulate on top of it
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait()
+{
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
 
 // UMMA shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, rows of 128 bytes:
 // 8-row x 128-byte swizzle atoms stacked every 1024 bytes (SBO); LBO unused for swizzled K-major.
@@ -323,6 +338,53 @@ __device__ __forceinline__ float magic_to_float(int biased_acc)
 __device__ __forceinline__ int magic_round(float f, int zp_minus_magic)
 {
     return __float_as_int(__fadd_rn(f, kMagicF)) + zp_minus_magic;
+}
+
+// Packed f32x2 arithmetic (FADD2 / FFMA2 on sm_100): one issue slot for two lanes' worth of
+// epilogue math.  IEEE round-to-nearest per element, so results equal the scalar sequence.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_bits(uint32_t lo, uint32_t hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack_bits(uint64_t v, int &lo, int &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// two accumulators -> kMagicI + round_half_even(fma(float(acc), mult, badd)) each, as int bits.
+// MAGIC: the accumulators carry + kMagicI already (they were seeded with it), so float(acc) is
+// one packed FADD; otherwise two I2F.
+template <bool MAGIC>
+__device__ __forceinline__ void requant_pair(uint32_t a0, uint32_t a1, uint64_t mult2, uint64_t badd2, int &t0,
+                                             int &t1)
+{
+    uint64_t x;
+    if (MAGIC)
+        x = f2_add(f2_pack_bits(a0, a1), f2_pack(-kMagicF, -kMagicF));
+    else
+        x = f2_pack(static_cast<float>(static_cast<int>(a0)), static_cast<float>(static_cast<int>(a1)));
+    x = f2_fma(x, mult2, badd2);
+    x = f2_add(x, f2_pack(kMagicF, kMagicF));
+    f2_unpack_bits(x, t0, t1);
 }
 
 __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d)

@@ -43,19 +43,20 @@ struct DwTmaArgs {
 };
 
 template <int MODE>
-__device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const float (&mu)[4], const float (&ba)[4],
+__device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const uint64_t (&mu2)[2], const uint64_t (&ba2)[2],
                                                 const EpiScalars &ep, const uint8_t *lut, bool has_lut, int zp_m,
                                                 int lut_lo)
 {
-    int q[4];
+    int t[4], q[4];
+    // packed f32x2: magic -> float, fma, round (3 issue slots per two outputs)
+    requant_pair<true>(acc[0], acc[1], mu2[0], ba2[0], t[0], t[1]);
+    requant_pair<true>(acc[2], acc[3], mu2[1], ba2[1], t[2], t[3]);
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        const float f = fmaf(magic_to_float(acc[e]), mu[e], ba[e]);
-        const int t = __float_as_int(__fadd_rn(f, kMagicF));
         if (MODE == DW_LUT) {
-            q[e] = min(max(t - lut_lo, 0), 255);
+            q[e] = min(max(t[e] - lut_lo, 0), 255);
         } else {
-            q[e] = t + zp_m;
+            q[e] = t[e] + zp_m;
             if (MODE == DW_RELU || MODE == DW_RELU6) q[e] = max(q[e], ep.zp_out);
             if (MODE == DW_RELU6) q[e] = min(q[e], ep.q6);
             if (MODE == DW_GENERIC) {
@@ -90,7 +91,7 @@ __device__ __forceinline__ void dp4(int (&acc)[4], const uint32_t (&v)[4], const
 }
 
 template <int S, int CC, int TW, int MODE>
-__global__ void __launch_bounds__(CC / 4 * TW + 32, 2)
+__global__ void __launch_bounds__(CC / 4 * TW + 32, 3)
 dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
 {
     constexpr int TWI = S * (TW - 1) + 3;
@@ -153,6 +154,10 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     const uint32_t padw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t wk[3][4];
+    uint64_t mu[2], ba[2];
+    int init[4];
+    int cur_cc = -1;
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         uint32_t rest = t;
         const int cc = rest % a.cchunks;
@@ -168,11 +173,11 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
         const int rows_out = min(a.th, a.oh - oy0);
         const bool col_ok = ox < a.ow && ch_ok;
 
-        // per-thread constants of this tile's channel chunk (L1 / L2 hits)
-        uint32_t wk[3][4];
-        float mu[4], ba[4];
-        int init[4];
-        {
+        // per-thread constants of this tile's channel chunk: reloaded only when the chunk changes
+        // (gridDim.x is a multiple of cchunks whenever the grid is capped, so a CTA normally keeps
+        // one chunk for its whole life and these L2 round trips leave the per-tile critical path)
+        if (cc != cur_cc) {
+            cur_cc = cc;
             const int chs = ch_ok ? ch : 0;
 #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
@@ -182,8 +187,8 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
             const float4 m4 = __ldg(reinterpret_cast<const float4 *>(a.ep.mult + chs));
             const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.ep.badd + chs));
             const int4 i4 = __ldg(reinterpret_cast<const int4 *>(a.ep.ibias + chs));
-            mu[0] = m4.x, mu[1] = m4.y, mu[2] = m4.z, mu[3] = m4.w;
-            ba[0] = b4.x, ba[1] = b4.y, ba[2] = b4.z, ba[3] = b4.w;
+            mu[0] = f2_pack(m4.x, m4.y), mu[1] = f2_pack(m4.z, m4.w);
+            ba[0] = f2_pack(b4.x, b4.y), ba[1] = f2_pack(b4.z, b4.w);
             init[0] = i4.x + kMagicI, init[1] = i4.y + kMagicI, init[2] = i4.z + kMagicI, init[3] = i4.w + kMagicI;
         }
 
@@ -338,7 +343,9 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     const int TWI = S * (TW - 1) + 3;
     // rows per tile: ~36 KB per halo slot (3 slots, 2 CTAs per SM): tall tiles amortise the per-tile
     // prologue (tile decode, per-channel constants, zero-point patch) over more row steps
-    int thi_max = (36 * 1024) / (TWI * CC);
+    static const int slot_kb = getenv("SHL_B200_DW_SLOT_KB") ? atoi(getenv("SHL_B200_DW_SLOT_KB")) : 36;
+    static const int ctas_per_sm = getenv("SHL_B200_DW_CTAS") ? atoi(getenv("SHL_B200_DW_CTAS")) : 2;
+    int thi_max = (slot_kb * 1024) / (TWI * CC);
     if (thi_max > 256) thi_max = 256;  // TMA box limit
     int th = (thi_max - 3) / S + 1;
     if (th < 1) th = 1;
@@ -367,7 +374,10 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
         set_error("b200_dwconv2d: %lld tiles / output bytes exceed the 32-bit indices of the 3x3 kernel", tiles);
         return B200_ERR_UNSUPPORTED;
     }
-    const long long cap = static_cast<long long>(sm_count()) * 2;
+    // a capped grid is a multiple of the channel-chunk count: a CTA then sees one chunk only and
+    // loads its per-channel constants once
+    long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
+    if (cap > a.cchunks) cap -= cap % a.cchunks;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
     const size_t smem = static_cast<size_t>(kDwStages) * a.stage_stride + 128;
     int mode;

@@ -38,7 +38,7 @@ namespace b200 {
 constexpr int kBM = 128;        // UMMA M (cta_group::1)
 constexpr int kBKBytes = 128;   // one swizzle atom of K per stage
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kThreads = (3 + kEpiWarps) * 32;  // + TMA producer, MMA issuer, TMA-store warp
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
@@ -75,25 +75,20 @@ __device__ __forceinline__ void epi_bar_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 }
 
-// four int8 outputs from four accumulators (already + ibias) -> one packed word.
+// four int8 outputs from four rounded values t = kMagicI + round_half_even(f) -> one packed word.
 // EPI_LUT: lut_lo arrives minus the table's shared-memory address (lut_base), so the clamp of the
 // table index and the address addition are the same two instructions.
-template <int MODE, bool MAGIC>
-__device__ __forceinline__ uint32_t requant4(const int (&a)[4], const float (&m4)[4], const float (&b4)[4],
-                                             const EpiScalars &ep, const uint8_t *lut, bool has_lut,
-                                             int zp_m, int lut_lo, int lut_base)
+template <int MODE>
+__device__ __forceinline__ uint32_t finish4(const int (&t)[4], const EpiScalars &ep, const uint8_t *lut,
+                                            bool has_lut, int zp_m, int lut_lo, int lut_base)
 {
     int q[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        const float af = MAGIC ? magic_to_float(a[e]) : static_cast<float>(a[e]);
-        const float f = fmaf(af, m4[e], b4[e]);
-        // t = kMagicI + round_half_even(f)   (|f| < 2^22 is guaranteed by the host)
-        const int t = __float_as_int(__fadd_rn(f, kMagicF));
         if (MODE == EPI_LUT) {
-            q[e] = min(max(t - lut_lo, lut_base), lut_base + 255);  // &lut[clamp(q, -128, 127) + 128]
+            q[e] = min(max(t[e] - lut_lo, lut_base), lut_base + 255);  // &lut[clamp(q, -128, 127) + 128]
         } else {
-            q[e] = t + zp_m;
+            q[e] = t[e] + zp_m;
             if (MODE == EPI_RELU || MODE == EPI_RELU6) q[e] = max(q[e], ep.zp_out);
             if (MODE == EPI_RELU6) q[e] = min(q[e], ep.q6);
             if (MODE == EPI_GENERIC) {
@@ -137,7 +132,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t *tmem_full = empty_bar + kMaxStages;
     uint64_t *tmem_empty = tmem_full + 2;
     uint64_t *b_bar = tmem_empty + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(b_bar + 1);
+    uint64_t *stg_full = b_bar + 1;    // epilogue warps -> store warp: staging buffer written
+    uint64_t *stg_empty = stg_full + 2;  // store warp -> epilogue warps: the TMA store has read it
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(stg_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -154,6 +151,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = 0; i < 2; i++) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], kEpiWarps);
+            mbar_init(&stg_full[i], kEpiWarps);
+            mbar_init(&stg_empty[i], 1);
         }
         mbar_init(b_bar, 1);
         mbar_fence_init();
@@ -162,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
-    if (warp >= 2 && args.ep.post_lut != nullptr) {
+    if (warp >= 2 && warp < 2 + kEpiWarps && args.ep.post_lut != nullptr) {
         const int t = threadIdx.x - 64;
         if (t < 256) epi->lut[t] = static_cast<uint8_t>(args.ep.post_lut[t]);
     }
@@ -219,7 +218,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int mt0 = ms * G;
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                // int8: the epilogue warps seed every accumulator with ibias (+ magic) before its first
+                // use and again after each drain, so completion #n of tmem_empty means "seeded n times"
+                mbar_wait(&tmem_empty[acc], DT == B200_I8 ? acc_phase : (acc_phase ^ 1));
                 tc_fence_after();
                 for (int g = 0; g < G; g++) {
                     if (mt0 + g >= args.num_m_tiles) break;
@@ -234,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         for (int k = 0; k < kBKBytes / 32; k++) {
                             // advance 32 bytes of K inside the swizzle atom: +2 in 16-byte units
                             if (DT == B200_I8)
-                                tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
+                                tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, 1u);
                             else
                                 tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, (kb | k) != 0);
                         }
@@ -247,6 +248,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 tc_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
             }
+        }
+    } else if (warp == 2 + kEpiWarps) {
+        // ===== TMA-store warp (int8): hands finished staging tiles to the store engine, so that the
+        // epilogue warps never meet at a CTA-wide barrier -- a fast warp runs up to two super tiles
+        // ahead of a slow one =====
+        if (DT == B200_I8 && elect_one()) {
+            int local = 0;
+            for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
+                const int buf = local & 1;
+                const int mt0 = ms * G;
+                const int gmax = min(G, args.num_m_tiles - mt0);
+                const uint8_t *stg = staging + buf * args.stage_bytes;
+                mbar_wait(&stg_full[buf], (local >> 1) & 1);
+                for (int g = 0; g < gmax; g++)
+                    tma_store_2d(&tma_o, stg + g * (kBM * args.bn), n0, (mt0 + g) * kBM);  // clips rows >= m
+                tma_store_commit();
+                tma_store_wait_read<0>();
+                mbar_arrive(&stg_empty[buf]);
+            }
+            tma_store_wait<0>();
         }
     } else if (DT == B200_I8) {
         // ===== int8 epilogue: TMEM -> registers -> requantise -> swizzled staging -> TMA store =====
@@ -277,9 +298,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t swz_mask = bn >= 128 ? 7u : (bn == 64 ? 3u : (bn == 32 ? 1u : 0u));
         const uint32_t row_off = static_cast<uint32_t>(quad * 32 + lane) * bn;
         const uint32_t panel_bytes = kBM * bn;
-        float mu[16], ba[16];
-        int ib[16];
+        const uint32_t tquad = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        uint64_t mu2[8], ba2[8];  // (mult, badd) of 16 columns as f32x2 pairs
+        uint32_t ib[16];          // ibias (+ kMagicI): the value an accumulator column starts from
         int loaded_sub = -1;
+        auto load_sub = [&](int sub) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+                const float4 m4 = *reinterpret_cast<const float4 *>(&epi->mult[sub * 16 + j4 * 4]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&epi->badd[sub * 16 + j4 * 4]);
+                const int4 i4 = *reinterpret_cast<const int4 *>(&epi->ibias[sub * 16 + j4 * 4]);
+                mu2[j4 * 2] = f2_pack(m4.x, m4.y), mu2[j4 * 2 + 1] = f2_pack(m4.z, m4.w);
+                ba2[j4 * 2] = f2_pack(b4.x, b4.y), ba2[j4 * 2 + 1] = f2_pack(b4.z, b4.w);
+                ib[j4 * 4 + 0] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
+            }
+            loaded_sub = sub;
+        };
+        // seed both accumulator stages: the MMAs always accumulate, which takes the "+ ibias" (and
+        // the magic-number bias of the int -> float conversion) out of the per-output instruction count
+        for (int sub = part; sub < nsub; sub += 4) {
+            load_sub(sub);
+            for (int a2 = 0; a2 < 2; a2++)
+                for (int g = 0; g < G; g++) tmem_st_32x16(tquad + a2 * kAccStride + g * bn + sub * 16, ib);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&tmem_empty[0]);
+            mbar_arrive(&tmem_empty[1]);
+        }
         int local = 0;
         for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
             const int acc = local & 1;
@@ -287,24 +335,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int mt0 = ms * G;
             const int gmax = min(G, args.num_m_tiles - mt0);
             uint8_t *stg = staging + (local & 1) * args.stage_bytes;
+            // the store issued from this staging buffer two tiles ago must have finished reading it
+            mbar_wait(&stg_empty[local & 1], acc_phase ^ 1);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
+            const uint32_t taddr = tquad + acc * kAccStride;
             for (int sub = part; sub < nsub; sub += 4) {
-                if (sub != loaded_sub) {
-                    // 16 columns x (mult, badd, ibias) -> 48 registers, reused for every row block of
-                    // the super tile (and for the CTA's whole life when the n-tile has <= 64 columns)
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++) {
-                        const float4 m4 = *reinterpret_cast<const float4 *>(&epi->mult[sub * 16 + j4 * 4]);
-                        const float4 b4 = *reinterpret_cast<const float4 *>(&epi->badd[sub * 16 + j4 * 4]);
-                        const int4 i4 = *reinterpret_cast<const int4 *>(&epi->ibias[sub * 16 + j4 * 4]);
-                        mu[j4 * 4 + 0] = m4.x, mu[j4 * 4 + 1] = m4.y, mu[j4 * 4 + 2] = m4.z, mu[j4 * 4 + 3] = m4.w;
-                        ba[j4 * 4 + 0] = b4.x, ba[j4 * 4 + 1] = b4.y, ba[j4 * 4 + 2] = b4.z, ba[j4 * 4 + 3] = b4.w;
-                        ib[j4 * 4 + 0] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
-                    }
-                    loaded_sub = sub;
-                }
+                // 16 columns x (mult, badd, ibias) -> 48 registers, reused for every row block of
+                // the super tile (and for the CTA's whole life when the n-tile has <= 64 columns)
+                if (sub != loaded_sub) load_sub(sub);
                 uint32_t off = row_off + sub * 16;
                 off ^= ((off >> 7) & swz_mask) << 4;
 #pragma unroll 1
@@ -312,38 +351,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint32_t r[16];
                     tmem_ld_32x16(taddr + g * bn + sub * 16, r);
                     tmem_ld_wait();
+                    tmem_st_32x16(taddr + g * bn + sub * 16, ib);  // re-seed for the tile after next
                     uint32_t packed[4];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; j4++) {
-                        const float m4[4] = {mu[j4 * 4], mu[j4 * 4 + 1], mu[j4 * 4 + 2], mu[j4 * 4 + 3]};
-                        const float b4[4] = {ba[j4 * 4], ba[j4 * 4 + 1], ba[j4 * 4 + 2], ba[j4 * 4 + 3]};
-                        const int a4[4] = {static_cast<int>(r[j4 * 4 + 0]) + ib[j4 * 4 + 0],
-                                           static_cast<int>(r[j4 * 4 + 1]) + ib[j4 * 4 + 1],
-                                           static_cast<int>(r[j4 * 4 + 2]) + ib[j4 * 4 + 2],
-                                           static_cast<int>(r[j4 * 4 + 3]) + ib[j4 * 4 + 3]};
+                        int t[4];
+                        requant_pair<MAGIC>(r[j4 * 4 + 0], r[j4 * 4 + 1], mu2[j4 * 2], ba2[j4 * 2], t[0], t[1]);
+                        requant_pair<MAGIC>(r[j4 * 4 + 2], r[j4 * 4 + 3], mu2[j4 * 2 + 1], ba2[j4 * 2 + 1], t[2], t[3]);
                         // columns >= n carry requantised zeros; the TMA store clips at the row pitch
-                        packed[j4] = requant4<MODE, MAGIC>(a4, m4, b4, ep, epi->lut, has_lut, zp_m, lut_lo, lut_base);
+                        packed[j4] = finish4<MODE>(t, ep, epi->lut, has_lut, zp_m, lut_lo, lut_base);
                     }
                     *reinterpret_cast<uint4 *>(stg + g * panel_bytes + off) =
                         make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
             }
-            // accumulators drained: the MMA warp may refill this TMEM stage
+            tmem_st_wait();
+            // accumulators drained and re-seeded: the MMA warp may refill this TMEM stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            // hand the staged tile to the TMA store engine.  Before anybody writes the OTHER buffer
-            // (next super tile), the store issued from it one tile ago must have finished reading.
+            // hand this warp's part of the staged tile to the store warp (generic-proxy writes
+            // ordered before the async-proxy read by the fence; the arrive releases them)
             fence_proxy_async_smem();
-            if (et == 0) tma_store_wait_read<0>();
-            epi_bar_sync();
-            if (et == 0) {
-                for (int g = 0; g < gmax; g++)
-                    tma_store_2d(&tma_o, stg + g * panel_bytes, n0, (mt0 + g) * kBM);  // clips rows >= m
-                tma_store_commit();
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_full[local & 1]);
         }
-        if (et == 0) tma_store_wait<0>();
     } else {
         // ===== fp16 epilogue: TMEM -> registers -> bias / activation -> 16-byte global stores =====
         const int ew = warp - 2;
@@ -427,7 +459,7 @@ static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident, s
 {
     const size_t a = static_cast<size_t>(stages) * kBM * kBKBytes;
     const size_t b = static_cast<size_t>(resident ? k_blocks : stages) * bn * kBKBytes;
-    return 1024 + a + b + 2 * staging + sizeof(EpiParams) + (2 * kMaxStages + 5) * sizeof(uint64_t) + 16;
+    return 1024 + a + b + 2 * staging + sizeof(EpiParams) + (2 * kMaxStages + 9) * sizeof(uint64_t) + 16;
 }
 
 static int pick_bn(int n, int dtype)

@@ -142,12 +142,21 @@ __global__ void __launch_bounds__(256) gap_i8_kernel(const PoolArgs a)
         const int wd = i % words, b = i / words;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(in + static_cast<size_t>(b) * hw * a.cp) + wd;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 7
-        for (int p = 0; p < hw; p++) {
-            const uint32_t v = __ldg(src + static_cast<size_t>(p) * words);
+        // loads in batches of 16 independent words (latency paid once per batch, not per pixel);
+        // the sums stay sequential in (y, x) order
+        for (int p0 = 0; p0 < hw; p0 += 16) {
+            uint32_t v[16];
 #pragma unroll
-            for (int e = 0; e < 4; e++)
-                acc[e] = __fadd_rn(acc[e], dequant_i8(static_cast<int8_t>(v >> (8 * e)), a.s_in, a.zp_in));
+            for (int j = 0; j < 16; j++)
+                v[j] = p0 + j < hw ? __ldg(src + static_cast<size_t>(p0 + j) * words) : 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (p0 + j < hw) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        acc[e] = __fadd_rn(acc[e], dequant_i8(static_cast<int8_t>(v[j] >> (8 * e)), a.s_in, a.zp_in));
+                }
+            }
         }
         const float cnt = static_cast<float>(hw);
         int q[4];
@@ -188,7 +197,7 @@ extern "C" int b200_pool2d(const b200_pool_desc *d, void *stream)
     if (d->dtype == B200_I8 && d->is_avg && d->oh == 1 && d->ow == 1 && d->kh == d->h && d->kw == d->w &&
         d->pad_top == 0 && d->pad_left == 0) {
         const int tot = d->n * (d->cp / 4);
-        gap_i8_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+        gap_i8_kernel<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     } else if (d->dtype == B200_I8)
         pool_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     else
