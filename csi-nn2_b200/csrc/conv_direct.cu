@@ -10,6 +10,8 @@
 // k order = (ky, kx, c), the order b200_opt/quant.c packs conv weights in.  Epilogue = the
 // contract of include/b200nn.h.  Replaces, for this shape, the im2col loop + 4x16 GEMM of
 // shl_rvv_conv_im2col_gemm_int8 (source/thead_rvv/int8/convolution_gemm_int8.c:106-170).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -235,6 +237,8 @@ __global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_sp_kernel(const
 
 using namespace b200;
 
+int b200_conv_stem_tc_launch(const b200_conv_direct_desc *d, void *stream);  // conv_stem_tc.cu
+
 extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
 {
     if (!d || !d->in || !d->wt || !d->out || !d->ep.mult || !d->ep.badd || !d->ep.ibias) {
@@ -246,6 +250,11 @@ extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
         d->stride_h < 1 || d->stride_w < 1 || d->dil_h < 1 || d->dil_w < 1 || d->ldw < K) {
         set_error("b200_conv2d_direct: unsupported shape (C*kh*kw=%d must be <= 160, O=%d <= 256)", K, d->o);
         return B200_ERR_UNSUPPORTED;
+    }
+    // the 3-channel stems run as an implicit GEMM on the tensor core (conv_stem_tc.cu)
+    if (!getenv("SHL_B200_NO_STEM_TC")) {
+        const int rc = b200_conv_stem_tc_launch(d, stream);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
     DirectArgs a;
     a.n = d->n, a.c = d->c, a.h = d->h, a.w = d->w, a.o = d->o, a.oh = d->oh, a.ow = d->ow, a.cp_out = d->cp_out;

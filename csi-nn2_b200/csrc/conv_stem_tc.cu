@@ -1,0 +1,417 @@
+// conv_stem_tc.cu -- a network's FIRST conv layer (3 input channels, 3x3 or 7x7, NCHW input) as an
+// implicit GEMM on tcgen05: the im2col matrix is never written to HBM.  A tile is a segment of up
+// to 128 output pixels of ONE output row; worker warps copy the kh input rows x 3 channels it needs
+// into shared memory with aligned 32-bit loads (issued one tile ahead, so their latency hides
+// behind the previous tile's epilogue; padding is written as zp_in here, once per word, instead of
+// being tested per tap), each thread then picks its pixel's K = C*kh*kw bytes out of that staging
+// buffer into a 128B-swizzled A tile (one row per pixel, K padded to a multiple of 32), one thread
+// issues tcgen05.mma kind::i8 against the resident weights, and the same workers requantise the
+// accumulators (contract of include/b200nn.h) and store pixel-major rows.
+//
+// Why: on CUDA cores this layer costs K/4 dp4a per output plus the epilogue -- 38 instructions per
+// output for 3x3x3 -> 32 channels, 136 us at batch 256, six times its HBM floor.  On the tensor
+// core the per-output cost is the epilogue alone; the gather is paid once per pixel, not per channel.
+//
+// CTA = 3 worker groups of 4 warps + 1 MMA warp, one CTA per SM, persistent.  A group owns two A
+// tiles and two TMEM accumulators and software-pipelines itself: stage + gather tile i -> signal the
+// MMA warp -> epilogue of tile i-1 (whose MMA ran meanwhile), with tile i+1's loads in flight.  The three groups run staggered, so the
+// gather of one overlaps the epilogue of another; no CTA-wide barrier inside the loop.
+// Accumulators are seeded with ibias (+ the magic constant) by tcgen05.st, like the GEMM's.
+//
+// Replaces, for this shape, shl_rvv_conv_im2col_gemm_int8
+// (source/thead_rvv/int8/convolution_gemm_int8.c:106-170); semantics shl_ref_conv2d_quant
+// (source/reference/convolution.c:370).
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kStemGroups = 3;
+constexpr int kStemThreads = (kStemGroups * 4 + 1) * 32;
+
+struct StemArgs {
+    int n, h, w, o, oh, ow, cp_out;
+    int sh, sw, pt, pl;
+    int ldw;            // weight row pitch in bytes
+    const int8_t *in;   // NCHW
+    const int8_t *wt;   // [O][ldw], k = (ky, kx, c)
+    int8_t *out;        // [n*oh*ow][cp_out]
+    int zp_in;
+    uint32_t idesc;
+    EpiScalars ep;
+};
+
+__device__ __forceinline__ void group_bar_sync(int g)
+{
+    asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+}
+
+// 32 lanes x 16 columns seed store / load share the GEMM's helpers (common.cuh)
+
+template <int C, int KH, int KW, int SW, int NCH, int MODE>
+__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_tc_kernel(const StemArgs a)
+{
+    constexpr int ROWS = KH * C;                          // staged input rows per tile, (ky, c) order
+    constexpr int WW = (128 * SW + KW - 1 + 3 + 3) / 4;   // words per staged row (segment + halo + alignment slack)
+    constexpr int WROW = WW * 4;
+    constexpr int JW = (WW + 31) / 32;                    // words per lane per row
+    constexpr int JR = (ROWS + 3) / 4;                    // rows per warp of a group
+    constexpr uint32_t STG = ROWS * WROW;                 // staging bytes per group
+    constexpr int K = C * KH * KW;
+    constexpr int KP = (K + 31) / 32 * 32;      // K padded to whole MMA k-steps
+    constexpr int KSTEPS = KP / 32;
+    constexpr int ATOMS = (KP + 127) / 128;     // 128-byte swizzle atoms per row
+    constexpr int KWORDS = KP / 4;
+    constexpr int N = NCH * 16;
+    constexpr bool MAGIC = K <= 128;
+    constexpr uint32_t A_TILE = ATOMS * 128 * 128;   // bytes
+    constexpr uint32_t B_TILE = ATOMS * N * 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *smem_a = smem;                                   // [group][2][A_TILE]
+    uint8_t *smem_b = smem_a + kStemGroups * 2 * A_TILE;       // [ATOMS][N rows][128 B]
+    uint8_t *smem_s = smem_b + B_TILE;                         // [group][ROWS][WROW] staged input rows
+    float *s_mu = reinterpret_cast<float *>(smem_s + kStemGroups * ((STG + 15) & ~15u));
+    float *s_ba = s_mu + N;
+    int *s_ib = reinterpret_cast<int *>(s_ba + N);
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_ib + N);
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(s_lut + 256);   // [group][2]
+    uint64_t *mma_done = a_full + kStemGroups * 2;                  // [group][2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(mma_done + kStemGroups * 2);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool has_lut = a.ep.post_lut != nullptr;
+
+    // ---- one-time setup: weights into the swizzled B tile, per-channel parameters, barriers, TMEM
+    for (int i = tid; i < ATOMS * N * 8; i += kStemThreads) {
+        const int chunk = i & 7, row = (i >> 3) % N, atom = i / (8 * N);
+        const int k0 = atom * 128 + chunk * 16;
+        uint32_t wv[4] = {0, 0, 0, 0};
+        if (row < a.o) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int k = k0 + e;
+                if (k < K) wv[e >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(a.wt[row * a.ldw + k])) << (8 * (e & 3));
+            }
+        }
+        *reinterpret_cast<uint4 *>(smem_b + atom * (N * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+            make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    for (int o = tid; o < N; o += kStemThreads) {
+        s_mu[o] = o < a.o ? a.ep.mult[o] : 0.f;
+        s_ba[o] = o < a.o ? a.ep.badd[o] : 0.f;
+        s_ib[o] = (o < a.o ? a.ep.ibias[o] : 0) + (MAGIC ? kMagicI : 0);
+    }
+    if (has_lut)
+        for (int i = tid; i < 256; i += kStemThreads) s_lut[i] = static_cast<uint8_t>(a.ep.post_lut[i]);
+    if (tid == 0) {
+        for (int i = 0; i < kStemGroups * 2; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&mma_done[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == kStemGroups * 4) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();  // the B tile was written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int nseg = (a.ow + 127) / 128;
+    const int tiles = a.n * a.oh * nseg;                // < 2^31, host-checked
+    // tile (i, g) of this CTA: consecutive tiles go to consecutive CTAs
+    auto tile_of = [&](int i, int g) { return (i * kStemGroups + g) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x); };
+
+    if (warp == kStemGroups * 4) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            for (int i = 0;; i++) {
+                bool any = false;
+                for (int g = 0; g < kStemGroups; g++) {
+                    if (tile_of(i, g) >= tiles) continue;
+                    any = true;
+                    const int s = i & 1;
+                    mbar_wait(&a_full[g * 2 + s], (i >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (g * 2 + s) * N;
+                    const uint32_t a_addr = smem_u32(smem_a + (g * 2 + s) * A_TILE);
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++) {
+                        const uint64_t adesc = umma_desc_sw128(a_addr + (ks >> 2) * (128 * 128)) + 2 * (ks & 3);
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b) + (ks >> 2) * (N * 128)) + 2 * (ks & 3);
+                        tc_mma_i8(tmem_d, adesc, bdesc, a.idesc, 1u);  // accumulators are pre-seeded
+                    }
+                    tc_commit(&mma_done[g * 2 + s]);
+                }
+                if (!any) break;
+            }
+        }
+    } else {
+        // ===== worker groups: gather + epilogue =====
+        const int g = warp >> 2;
+        const int r = tid & 127;                      // row of the tile = TMEM lane
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const EpiScalars &ep = a.ep;
+        const int zp_m = ep.zp_out - kMagicI;
+        const int lut_base = static_cast<int>(smem_u32(s_lut));
+        int lut_lo = kMagicI - ep.zp_out - 128 - lut_base;
+        asm("mov.b32 %0, %0;" : "+r"(lut_lo));
+        const int hw = a.h * a.w;
+        const uint32_t zpw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
+        const int wq = warp & 3;
+        uint8_t *stg = smem_s + g * ((STG + 15) & ~15u);
+
+        // seed both accumulators of this group
+        for (int ch = 0; ch < NCH; ch++) {
+            uint32_t ib[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+                const int4 i4 = *reinterpret_cast<const int4 *>(&s_ib[ch * 16 + j4 * 4]);
+                ib[j4 * 4] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
+            }
+            tmem_st_32x16(tlane + (g * 2 + 0) * N + ch * 16, ib);
+            tmem_st_32x16(tlane + (g * 2 + 1) * N + ch * 16, ib);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+
+        // tile -> (image, output row, first output column); decoded ONCE per tile, when its loads are
+        // issued, and carried through the gather (one iteration later) and the epilogue (two later)
+        struct TilePos { int b, oy, ox0; };
+        auto decode = [&](int t) {
+            TilePos tp;
+            const int seg = nseg == 1 ? 0 : t % nseg;
+            const int row = nseg == 1 ? t : t / nseg;
+            tp.b = row / a.oh;
+            tp.oy = row - tp.b * a.oh;
+            tp.ox0 = seg * 128;
+            return tp;
+        };
+        // loop-invariant part of this thread's load addresses: its rows (ky, c) and word columns
+        int rowoff[JR], kyr[JR];
+#pragma unroll
+        for (int jr = 0; jr < JR; jr++) {
+            const int row = min(wq + 4 * jr, ROWS - 1);
+            kyr[jr] = row / C;
+            rowoff[jr] = (row - kyr[jr] * C) * hw + kyr[jr] * a.w + 4 * lane;
+        }
+        // aligned words of the tile's input rows -> registers (padding and out-of-image words = zp_in)
+        uint32_t pre[JR][JW];
+        auto prefetch = [&](const TilePos &tp) {
+            const int iy0 = tp.oy * a.sh - a.pt;
+            const int ix_al = (tp.ox0 * SW - a.pl) & ~3;  // floor to a multiple of 4 (also for -1..-3)
+            const int8_t *base = a.in + (static_cast<long long>(tp.b) * C * hw + static_cast<long long>(iy0) * a.w + ix_al);
+            bool cok[JW];
+#pragma unroll
+            for (int jw = 0; jw < JW; jw++)   // w % 4 == 0: a word is inside or outside as a whole
+                cok[jw] = static_cast<unsigned>(ix_al + 4 * (lane + 32 * jw)) < static_cast<unsigned>(a.w);
+#pragma unroll
+            for (int jr = 0; jr < JR; jr++) {
+                const bool rok = wq + 4 * jr < ROWS && static_cast<unsigned>(iy0 + kyr[jr]) < static_cast<unsigned>(a.h);
+#pragma unroll
+                for (int jw = 0; jw < JW; jw++) {
+                    uint32_t v = zpw;
+                    if (rok && cok[jw]) v = __ldg(reinterpret_cast<const uint32_t *>(base + rowoff[jr] + 128 * jw));
+                    pre[jr][jw] = v;
+                }
+            }
+        };
+
+        auto epilogue = [&](int i, const TilePos &tp) {
+            const int s = i & 1;
+            const int ox = tp.ox0 + r;
+            const int p = (tp.b * a.oh + tp.oy) * a.ow + ox;
+            const bool pix_ok = ox < a.ow;
+            mbar_wait(&mma_done[g * 2 + s], (i >> 1) & 1);
+            tc_fence_after();
+            int8_t *dst = a.out + static_cast<size_t>(p) * a.cp_out;
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t acc[16], ib[16];
+                const uint32_t taddr = tlane + (g * 2 + s) * N + ch * 16;
+                tmem_ld_32x16(taddr, acc);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const int4 i4 = *reinterpret_cast<const int4 *>(&s_ib[ch * 16 + j4 * 4]);
+                    ib[j4 * 4] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
+                }
+                tmem_ld_wait();
+                tmem_st_32x16(taddr, ib);  // re-seed for tile i + 2
+                uint32_t packed[4];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 m4 = *reinterpret_cast<const float4 *>(&s_mu[ch * 16 + j4 * 4]);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(&s_ba[ch * 16 + j4 * 4]);
+                    int t[4];
+                    requant_pair<MAGIC>(acc[j4 * 4 + 0], acc[j4 * 4 + 1], f2_pack(m4.x, m4.y), f2_pack(b4.x, b4.y), t[0], t[1]);
+                    requant_pair<MAGIC>(acc[j4 * 4 + 2], acc[j4 * 4 + 3], f2_pack(m4.z, m4.w), f2_pack(b4.z, b4.w), t[2], t[3]);
+                    packed[j4] = finish4<MODE>(t, ep, s_lut, has_lut, zp_m, lut_lo, lut_base);
+                }
+                if (pix_ok && ch * 16 < a.cp_out) *reinterpret_cast<uint4 *>(dst + ch * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+        };
+
+        TilePos tp_prev = {0, 0, 0}, tp_cur = {0, 0, 0}, tp_next = {0, 0, 0};
+        if (tile_of(0, g) < tiles) {
+            tp_next = decode(tile_of(0, g));
+            prefetch(tp_next);
+        }
+        for (int i = 0;; i++) {
+            const bool has = tile_of(i, g) < tiles;
+            tp_prev = tp_cur;
+            tp_cur = tp_next;
+            if (has) {
+                // ---- staged rows: registers -> shared memory (the previous tile's readers passed the
+                // second barrier of their iteration)
+#pragma unroll
+                for (int jr = 0; jr < JR; jr++) {
+                    const int row = wq + 4 * jr;
+#pragma unroll
+                    for (int jw = 0; jw < JW; jw++) {
+                        const int col = lane + 32 * jw;
+                        if (row < ROWS && col < WW) *reinterpret_cast<uint32_t *>(stg + row * WROW + col * 4) = pre[jr][jw];
+                    }
+                }
+            }
+            group_bar_sync(g);
+            if (has) {
+                // next tile's loads fly during this tile's gather and the previous tile's epilogue
+                if (tile_of(i + 1, g) < tiles) {
+                    tp_next = decode(tile_of(i + 1, g));
+                    prefetch(tp_next);
+                }
+                // ---- gather this thread's pixel: K bytes, (ky, kx, c) order, out of the staged rows
+                const int shift = (tp_cur.ox0 * SW - a.pl) & 3;
+                const uint8_t *src = stg + r * SW + shift;
+                uint32_t xw[KWORDS];
+#pragma unroll
+                for (int j = 0; j < KWORDS; j++) xw[j] = 0;
+#pragma unroll
+                for (int ky = 0; ky < KH; ky++) {
+#pragma unroll
+                    for (int kx = 0; kx < KW; kx++) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const int k = (ky * KW + kx) * C + c;
+                            const uint32_t v = src[(ky * C + c) * WROW + kx];
+                            xw[k >> 2] |= v << (8 * (k & 3));
+                        }
+                    }
+                }
+                uint8_t *arow = smem_a + (g * 2 + (i & 1)) * A_TILE + r * 128;
+#pragma unroll
+                for (int j = 0; j < KWORDS / 4; j++) {
+                    const int atom = j >> 3, chunk = j & 7;
+                    *reinterpret_cast<uint4 *>(arow + atom * (128 * 128) + ((chunk ^ (r & 7)) << 4)) =
+                        make_uint4(xw[j * 4], xw[j * 4 + 1], xw[j * 4 + 2], xw[j * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+            }
+            // every thread of the group has written its row (and finished re-seeding, one
+            // iteration ago, the accumulator this tile will use)
+            group_bar_sync(g);
+            if (has && r == 0) mbar_arrive(&a_full[g * 2 + (i & 1)]);
+            if (i > 0) epilogue(i - 1, tp_prev);
+            if (!has) break;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kStemGroups * 4) tmem_dealloc(tmem_base, 512);
+}
+
+template <int C, int KH, int KW, int SW, int NCH>
+static int stem_launch(int mode, int grid, cudaStream_t s, const StemArgs &a, int dev)
+{
+    constexpr int KP = (C * KH * KW + 31) / 32 * 32;
+    constexpr int ATOMS = (KP + 127) / 128;
+    constexpr int N = NCH * 16;
+    constexpr int STG = (KH * C * ((128 * SW + KW - 1 + 3 + 3) / 4) * 4 + 15) & ~15;
+    const size_t smem = 1024 + static_cast<size_t>(kStemGroups) * 2 * ATOMS * 128 * 128 + ATOMS * N * 128 +
+                        kStemGroups * STG + N * 12 + 256 + kStemGroups * 4 * 8 + 16;
+#define B200_STEM_CASE(M)                                                                                   \
+    case M: {                                                                                               \
+        static bool attr[64] = {};                                                                          \
+        if (dev >= 0 && dev < 64 && !attr[dev]) {                                                           \
+            B200_CUDA_CHECK(cudaFuncSetAttribute(conv_stem_tc_kernel<C, KH, KW, SW, NCH, M>,                    \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            attr[dev] = true;                                                                               \
+        }                                                                                                   \
+        conv_stem_tc_kernel<C, KH, KW, SW, NCH, M><<<grid, kStemThreads, smem, s>>>(a);                         \
+        break;                                                                                              \
+    }
+    switch (mode) {
+        B200_STEM_CASE(EPI_PLAIN)
+        B200_STEM_CASE(EPI_RELU)
+        B200_STEM_CASE(EPI_RELU6)
+        B200_STEM_CASE(EPI_LUT)
+        default:
+            B200_STEM_CASE(EPI_GENERIC)
+    }
+#undef B200_STEM_CASE
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// called by b200_conv2d_direct (conv_direct.cu); returns B200_ERR_UNSUPPORTED when the shape is not
+// one of the tensor-core stems (the caller then runs the dp4a kernel)
+int b200_conv_stem_tc_launch(const b200_conv_direct_desc *d, void *stream)
+{
+    const bool s3 = d->c == 3 && d->kh == 3 && d->kw == 3;
+    const bool s7 = d->c == 3 && d->kh == 7 && d->kw == 7;
+    const int nch = (d->o + 15) / 16;
+    // aligned 32-bit row loads: every image row must start on a 4-byte boundary
+    if (!(s3 || s7) || d->dil_h != 1 || d->dil_w != 1 || nch > 4 || d->cp_out < nch * 16 || d->cp_out % 16 ||
+        (reinterpret_cast<uintptr_t>(d->out) & 15) || d->stride_h != d->stride_w || d->stride_w > 2 ||
+        (s7 && d->stride_w != 2) || d->w % 4 || (reinterpret_cast<uintptr_t>(d->in) & 3) || d->pad_left > 64)
+        return B200_ERR_UNSUPPORTED;
+    const long long total = static_cast<long long>(d->n) * d->oh * d->ow;
+    if (total >= (1ll << 31) - 128 || static_cast<long long>(d->n) * d->c * d->h * d->w >= (1ll << 31))
+        return B200_ERR_UNSUPPORTED;
+    StemArgs a;
+    a.n = d->n, a.h = d->h, a.w = d->w, a.o = d->o, a.oh = d->oh, a.ow = d->ow, a.cp_out = d->cp_out;
+    a.sh = d->stride_h, a.sw = d->stride_w, a.pt = d->pad_top, a.pl = d->pad_left, a.ldw = d->ldw;
+    a.in = static_cast<const int8_t *>(d->in), a.wt = static_cast<const int8_t *>(d->wt);
+    a.out = static_cast<int8_t *>(d->out), a.zp_in = d->zp_in, a.ep = make_epi(d->ep);
+    // column chunks the kernel is instantiated for: 3x3 -> 1 / 2 / 4, 7x7 -> 2 / 4
+    const int nch_k = s3 ? (nch <= 2 ? nch : 4) : (nch <= 2 ? 2 : 4);
+    a.idesc = umma_idesc(2 /*S32*/, 1 /*S8*/, 128, nch_k * 16);
+    const long long tiles_ll = static_cast<long long>(d->n) * d->oh * ((d->ow + 127) / 128);
+    if (tiles_ll >= (1ll << 31) / 8) return B200_ERR_UNSUPPORTED;
+    const int tiles = static_cast<int>(tiles_ll);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    int mode;
+    if (d->ep.post_lut)
+        mode = d->ep.act == B200_ACT_NONE ? EPI_LUT : EPI_GENERIC;
+    else
+        mode = d->ep.act == B200_ACT_NONE ? EPI_PLAIN : (d->ep.act == B200_ACT_RELU ? EPI_RELU : EPI_RELU6);
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (s3 && d->stride_w == 2)
+        rc = nch <= 1 ? stem_launch<3, 3, 3, 2, 1>(mode, grid, s, a, dev)
+                      : (nch == 2 ? stem_launch<3, 3, 3, 2, 2>(mode, grid, s, a, dev)
+                                  : stem_launch<3, 3, 3, 2, 4>(mode, grid, s, a, dev));
+    else if (s3)
+        rc = nch <= 1 ? stem_launch<3, 3, 3, 1, 1>(mode, grid, s, a, dev)
+                      : (nch == 2 ? stem_launch<3, 3, 3, 1, 2>(mode, grid, s, a, dev)
+                                  : stem_launch<3, 3, 3, 1, 4>(mode, grid, s, a, dev));
+    else
+        rc = nch <= 2 ? stem_launch<3, 7, 7, 2, 2>(mode, grid, s, a, dev)
+                      : stem_launch<3, 7, 7, 2, 4>(mode, grid, s, a, dev);
+    if (rc) return rc;
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

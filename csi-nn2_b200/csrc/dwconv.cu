@@ -228,7 +228,11 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
     }
     if (d->dtype == B200_I8 && d->wt_row3 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
         !getenv("SHL_B200_DW_GENERIC") &&
-        d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2))
+        d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2) &&
+        // the TMA kernel folds zero-point padding into per-class accumulator seeds: at most one
+        // padded row / column on each side of any output's 3x3 window
+        d->pad_top <= 1 && d->pad_left <= 1 && (d->oh - 1) * d->stride_h - d->pad_top + 2 <= d->h &&
+        (d->ow - 1) * d->stride_w - d->pad_left + 2 <= d->w)
         return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);
     DwArgs a;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;

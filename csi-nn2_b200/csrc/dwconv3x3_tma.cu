@@ -25,7 +25,7 @@
 
 namespace b200 {
 
-enum { DW_PLAIN = 0, DW_RELU = 1, DW_RELU6 = 2, DW_LUT = 3, DW_GENERIC = 4 };
+enum { DW_PLAIN = EPI_PLAIN, DW_RELU = EPI_RELU, DW_RELU6 = EPI_RELU6, DW_LUT = EPI_LUT, DW_GENERIC = EPI_GENERIC };
 constexpr int kDwStages = 3;
 // consumer threads per CTA: 256 or 224 (tile widths 32/16/8 or 28/14/7 columns -- the second family
 // divides the 112 / 56 / 28 / 14 / 7 wide maps of the ImageNet networks without idle columns)
@@ -45,32 +45,13 @@ struct DwTmaArgs {
 template <int MODE>
 __device__ __forceinline__ uint32_t dw_requant4(const int (&acc)[4], const uint64_t (&mu2)[2], const uint64_t (&ba2)[2],
                                                 const EpiScalars &ep, const uint8_t *lut, bool has_lut, int zp_m,
-                                                int lut_lo)
+                                                int lut_lo, int lut_base)
 {
-    int t[4], q[4];
+    int t[4];
     // packed f32x2: magic -> float, fma, round (3 issue slots per two outputs)
     requant_pair<true>(acc[0], acc[1], mu2[0], ba2[0], t[0], t[1]);
     requant_pair<true>(acc[2], acc[3], mu2[1], ba2[1], t[2], t[3]);
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        if (MODE == DW_LUT) {
-            q[e] = min(max(t[e] - lut_lo, 0), 255);
-        } else {
-            q[e] = t[e] + zp_m;
-            if (MODE == DW_RELU || MODE == DW_RELU6) q[e] = max(q[e], ep.zp_out);
-            if (MODE == DW_RELU6) q[e] = min(q[e], ep.q6);
-            if (MODE == DW_GENERIC) {
-                if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
-                if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
-            }
-        }
-    }
-    if (MODE == DW_LUT) {
-        const uint32_t b0 = lut[q[0]], b1 = lut[q[1]], b2 = lut[q[2]], b3 = lut[q[3]];
-        return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-    }
-    if (MODE == DW_GENERIC && has_lut) return lut4_i8(q[0], q[1], q[2], q[3], lut);
-    return pack4_sat_i8(q[0], q[1], q[2], q[3]);
+    return finish4<MODE>(t, ep, lut, has_lut, zp_m, lut_lo, lut_base);  // DW_* == EPI_* (common.cuh)
 }
 
 // tap words of four channels from three horizontally adjacent input words
@@ -103,6 +84,12 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     __shared__ uint64_t full_bar[kDwStages], empty_bar[kDwStages];
     __shared__ uint8_t s_lut[256];
+    // accumulator seeds [row class][column class][CC]: ibias + kMagicI + zp_in * (sum of the weights
+    // of the taps that fall into the padding for that class).  The TMA zero-fills padded taps where
+    // the contract wants zp_in, so the difference -- zp_in * w summed over the padded taps -- is added
+    // through the seed instead of patching the tile in shared memory (no CTA barrier, no extra pass).
+    // class bits: row 1 = top row padded (ky 0), 2 = bottom (ky 2); column 1 = left (kx 0), 2 = right (kx 2)
+    __shared__ __align__(16) int s_seed[16 * CC];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -150,14 +137,17 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     const int x = tid / WORDS;   // output column inside the tile
     const bool has_lut = a.ep.post_lut != nullptr;
     const int zp_m = a.ep.zp_out - kMagicI;
-    const int lut_lo = kMagicI - a.ep.zp_out - 128;
-    const uint32_t padw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
+    // table index clamp and shared-memory address in the same two instructions (see finish4)
+    const int lut_base = static_cast<int>(smem_u32(s_lut));
+    int lut_lo = kMagicI - a.ep.zp_out - 128 - lut_base;
+    asm("mov.b32 %0, %0;" : "+r"(lut_lo));
     int stage = 0;
     uint32_t phase = 0;
     uint32_t wk[3][4];
     uint64_t mu[2], ba[2];
-    int init[4];
     int cur_cc = -1;
+    const bool top_pad = a.pt > 0;                                   // output row 0 reads a padded row
+    const bool bot_pad = (a.oh - 1) * S - a.pt + 2 >= a.h;           // output row oh-1 does
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         uint32_t rest = t;
         const int cc = rest % a.cchunks;
@@ -186,30 +176,35 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
             }
             const float4 m4 = __ldg(reinterpret_cast<const float4 *>(a.ep.mult + chs));
             const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.ep.badd + chs));
-            const int4 i4 = __ldg(reinterpret_cast<const int4 *>(a.ep.ibias + chs));
             mu[0] = f2_pack(m4.x, m4.y), mu[1] = f2_pack(m4.z, m4.w);
             ba[0] = f2_pack(b4.x, b4.y), ba[1] = f2_pack(b4.z, b4.w);
-            init[0] = i4.x + kMagicI, init[1] = i4.y + kMagicI, init[2] = i4.z + kMagicI, init[3] = i4.w + kMagicI;
+            // rebuild the seed table for this chunk (all consumers: nobody may still read the old one)
+            asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
+            for (int i = tid; i < 16 * CC; i += kDwConsumers) {
+                const int c = i % CC, cls = i / CC;
+                const int cg = cc * CC + c;
+                int v = 0;
+                if (cg < a.cp) {
+                    int padsum = 0;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++) {
+                        const uint32_t wv = __ldg(a.wrow + ky * a.cp + cg);
+                        const bool rowpad = (ky == 0 && (cls & 4)) || (ky == 2 && (cls & 8));
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            const bool colpad = (kx == 0 && (cls & 1)) || (kx == 2 && (cls & 2));
+                            if (rowpad || colpad) padsum += static_cast<int8_t>(wv >> (8 * kx));
+                        }
+                    }
+                    v = __ldg(a.ep.ibias + cg) + kMagicI + a.zp_in * padsum;
+                }
+                s_seed[i] = v;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
         }
 
         mbar_wait(&full_bar[stage], phase);
         uint8_t *tile = smem + static_cast<size_t>(stage) * a.stage_stride;
-
-        // padded taps hold zp_in in the quantised domain; the TMA zero-filled them
-        const int iy0 = oy0 * S - a.pt, ix0 = xb * TW * S - a.pl;
-        const bool border = iy0 < 0 || ix0 < 0 || iy0 + a.thi > a.h || ix0 + TWI > a.w;
-        if (a.zp_in != 0 && border) {
-            for (int cell = tid; cell < a.thi * TWI; cell += kDwConsumers) {
-                const int r = cell / TWI, cx = cell % TWI;
-                const int iy = iy0 + r, ix = ix0 + cx;
-                if (iy < 0 || iy >= a.h || ix < 0 || ix >= a.w) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(tile + static_cast<size_t>(cell) * CC);
-#pragma unroll
-                    for (int q = 0; q < CC / 16; q++) dst[q] = make_uint4(padw, padw, padw, padw);
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
-        }
 
         if (col_ok) {
             const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + x * S * WORDS + cw;
@@ -221,13 +216,30 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
                 const uint32_t *p = tw + r * (TWI * WORDS);
                 taps3(p[0], p[WORDS], p[2 * WORDS], v);
             };
-            // a fresh accumulator set is produced by the ky = 0 dp4a itself (addend = ibias + magic)
-            auto first = [&](int (&acc)[4], const uint32_t (&v)[4]) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) acc[e] = __dp4a(static_cast<int>(v[e]), static_cast<int>(wk[0][e]), init[e]);
+            // a fresh accumulator set is produced by the ky = 0 dp4a itself: the addend is the seed
+            // of the output row it starts (row `yo` of the tile), fetched with one 128-bit shared load
+            const int colc = ((ox * S - a.pl < 0) ? 1 : 0) | ((ox * S - a.pl + 2 >= a.w) ? 2 : 0);
+            // shared-memory addresses of this thread's seeds: interior rows, and the tile row (if any)
+            // that is the image's last row with a padded ky = 2; only tile row 0 can have ky = 0 padded
+            const uint32_t seed_mid = smem_u32(s_seed + colc * CC + cw * 4);
+            const uint32_t seed_bot = seed_mid + 8 * CC * 4;
+            const int y_bot = bot_pad ? a.oh - 1 - oy0 : -1;       // tile row that is the last image row
+            const uint32_t seed_row0 = seed_mid + (((top_pad && oy0 == 0) ? 4 : 0) | (y_bot == 0 ? 8 : 0)) * CC * 4;
+            auto first_at = [&](int (&acc)[4], const uint32_t (&v)[4], uint32_t seed_addr) {
+                int s0, s1, s2, s3;
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3) : "r"(seed_addr));
+                acc[0] = __dp4a(static_cast<int>(v[0]), static_cast<int>(wk[0][0]), s0);
+                acc[1] = __dp4a(static_cast<int>(v[1]), static_cast<int>(wk[0][1]), s1);
+                acc[2] = __dp4a(static_cast<int>(v[2]), static_cast<int>(wk[0][2]), s2);
+                acc[3] = __dp4a(static_cast<int>(v[3]), static_cast<int>(wk[0][3]), s3);
+            };
+            // a fresh accumulator set is produced by the ky = 0 dp4a itself: the addend is the seed
+            // of the output row it starts (tile row yo >= 1), one 128-bit shared load
+            auto first = [&](int (&acc)[4], const uint32_t (&v)[4], int yo) {
+                first_at(acc, v, yo == y_bot ? seed_bot : seed_mid);
             };
             auto store = [&](const int (&acc)[4]) {
-                *reinterpret_cast<uint32_t *>(a.out + ooff) = dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo);
+                *reinterpret_cast<uint32_t *>(a.out + ooff) = dw_requant4<MODE>(acc, mu, ba, a.ep, s_lut, has_lut, zp_m, lut_lo, lut_base);
                 ooff += orow;
             };
             int accA[4], accB[4], accC[4];
@@ -236,47 +248,45 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
                 // input row r feeds output rows r (ky 0), r - 1 (ky 1), r - 2 (ky 2, completes it).
                 // rows_out is uniform over the CTA: the exits below do not diverge.
                 taps(0, v);
-                first(accA, v);
+                first_at(accA, v, seed_row0);
                 taps(1, v);
-                dp4(accA, v, wk[1]), first(accB, v);
+                dp4(accA, v, wk[1]), first(accB, v, 1);
                 for (int y = 0;; y += 3) {
                     taps(y + 2, v);
-                    dp4(accA, v, wk[2]), dp4(accB, v, wk[1]), first(accC, v);
+                    dp4(accA, v, wk[2]), dp4(accB, v, wk[1]), first(accC, v, y + 2);
                     store(accA);
                     if (y + 1 >= rows_out) break;
                     taps(y + 3, v);
-                    dp4(accB, v, wk[2]), dp4(accC, v, wk[1]), first(accA, v);
+                    dp4(accB, v, wk[2]), dp4(accC, v, wk[1]), first(accA, v, y + 3);
                     store(accB);
                     if (y + 2 >= rows_out) break;
                     taps(y + 4, v);
-                    dp4(accC, v, wk[2]), dp4(accA, v, wk[1]), first(accB, v);
+                    dp4(accC, v, wk[2]), dp4(accA, v, wk[1]), first(accB, v, y + 4);
                     store(accC);
                     if (y + 3 >= rows_out) break;
                 }
             } else {
                 // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
                 taps(0, v);
-                first(accA, v);
+                first_at(accA, v, seed_row0);
                 for (int y = 0;; y += 2) {
                     taps(2 * y + 1, v);
                     dp4(accA, v, wk[1]);
                     taps(2 * y + 2, v);
-                    dp4(accA, v, wk[2]), first(accB, v);
+                    dp4(accA, v, wk[2]), first(accB, v, y + 1);
                     store(accA);
                     if (y + 1 >= rows_out) break;
                     taps(2 * y + 3, v);
                     dp4(accB, v, wk[1]);
                     taps(2 * y + 4, v);
-                    dp4(accB, v, wk[2]), first(accA, v);
+                    dp4(accB, v, wk[2]), first(accA, v, y + 2);
                     store(accB);
                     if (y + 2 >= rows_out) break;
                 }
             }
         }
 
-        // hand the slot back: generic-proxy accesses (the zero-point patch) must be ordered before
-        // the next async-proxy (TMA) write into it
-        fence_proxy_async_smem();
+        // hand the slot back (it was only read)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == kDwStages) {
@@ -341,9 +351,9 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     }
     const int CC = cfgs[best].cc, TW = cfgs[best].tw;
     const int TWI = S * (TW - 1) + 3;
-    // rows per tile: ~36 KB per halo slot (3 slots, 2 CTAs per SM): tall tiles amortise the per-tile
+    // rows per tile: ~33 KB per halo slot (3 slots + the seed table, 2 CTAs per SM): tall tiles amortise the per-tile
     // prologue (tile decode, per-channel constants, zero-point patch) over more row steps
-    static const int slot_kb = getenv("SHL_B200_DW_SLOT_KB") ? atoi(getenv("SHL_B200_DW_SLOT_KB")) : 36;
+    static const int slot_kb = getenv("SHL_B200_DW_SLOT_KB") ? atoi(getenv("SHL_B200_DW_SLOT_KB")) : 33;
     static const int ctas_per_sm = getenv("SHL_B200_DW_CTAS") ? atoi(getenv("SHL_B200_DW_CTAS")) : 2;
     int thi_max = (slot_kb * 1024) / (TWI * CC);
     if (thi_max > 256) thi_max = 256;  // TMA box limit

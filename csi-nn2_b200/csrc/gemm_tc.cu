@@ -44,9 +44,6 @@ constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
 constexpr int kResidentBBytes = 160 * 1024;  // weights of one n-tile kept in smem (leaves >= 3 A stages)
 
-// epilogue specialisations
-enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_RELU6 = 2, EPI_LUT = 3, EPI_GENERIC = 4 };
-
 struct GemmArgs {
     int m, n;
     int k_blocks;      // ceil(K bytes / 128)
@@ -73,40 +70,6 @@ struct __align__(16) EpiParams {
 __device__ __forceinline__ void epi_bar_sync()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-}
-
-// four int8 outputs from four rounded values t = kMagicI + round_half_even(f) -> one packed word.
-// EPI_LUT: lut_lo arrives minus the table's shared-memory address (lut_base), so the clamp of the
-// table index and the address addition are the same two instructions.
-template <int MODE>
-__device__ __forceinline__ uint32_t finish4(const int (&t)[4], const EpiScalars &ep, const uint8_t *lut,
-                                            bool has_lut, int zp_m, int lut_lo, int lut_base)
-{
-    int q[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        if (MODE == EPI_LUT) {
-            q[e] = min(max(t[e] - lut_lo, lut_base), lut_base + 255);  // &lut[clamp(q, -128, 127) + 128]
-        } else {
-            q[e] = t[e] + zp_m;
-            if (MODE == EPI_RELU || MODE == EPI_RELU6) q[e] = max(q[e], ep.zp_out);
-            if (MODE == EPI_RELU6) q[e] = min(q[e], ep.q6);
-            if (MODE == EPI_GENERIC) {
-                if (ep.act != B200_ACT_NONE) q[e] = max(q[e], ep.zp_out);
-                if (ep.act == B200_ACT_RELU6) q[e] = min(q[e], ep.q6);
-            }
-        }
-    }
-    if (MODE == EPI_LUT) {
-        uint32_t b0, b1, b2, b3;
-        asm("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(q[0]));
-        asm("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(q[1]));
-        asm("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(q[2]));
-        asm("ld.shared.u8 %0, [%1];" : "=r"(b3) : "r"(q[3]));
-        return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-    }
-    if (MODE == EPI_GENERIC && has_lut) return lut4_i8(q[0], q[1], q[2], q[3], lut);
-    return pack4_sat_i8(q[0], q[1], q[2], q[3]);
 }
 
 template <int DT, int MODE, bool MAGIC>

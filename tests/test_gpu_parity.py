@@ -91,27 +91,32 @@ def test_conv_int8_against_the_reference_library(b200, ref, rng):
 
 
 FIRST_LAYER = [(2, 3, 32, 32, 32, 3, 2, 1, 5), (1, 3, 40, 40, 64, 7, 2, 3, 0), (1, 4, 17, 19, 24, 3, 1, 1, -9),
-               (1, 1, 16, 16, 8, 5, 1, 2, 3), (3, 3, 224, 224, 32, 3, 2, 1, 0)]
+               (1, 1, 16, 16, 8, 5, 1, 2, 3), (3, 3, 224, 224, 32, 3, 2, 1, 0),
+               (1, 3, 33, 35, 48, 3, 2, 1, -7), (5, 3, 30, 30, 16, 3, 1, 1, 11), (2, 3, 61, 47, 24, 7, 2, 3, -128)]
 
 
-@pytest.mark.parametrize("direct", [True, False], ids=["direct", "im2col"])
+@pytest.mark.parametrize("direct", ["stem_tc", "dp4a", "im2col"])
 @pytest.mark.parametrize("case", FIRST_LAYER, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_zp%d" % c)
 def test_first_layer_conv_from_nchw(case, direct, b200, oracle, rng):
     """graph mode: the network input stays NCHW on the device and the first conv reads it directly,
-    through the dp4a kernel (csrc/conv_direct.cu) or, forced, through the NCHW im2col gather + GEMM;
-    a relu node with its own qinfo rides in the epilogue either way"""
+    through the tensor-core stem kernel (csrc/conv_stem_tc.cu: 3-channel 3x3 / 7x7), the dp4a kernel
+    (csrc/conv_direct.cu: every other small-K shape, or forced) or, forced, through the NCHW im2col
+    gather + GEMM; a relu node with its own qinfo rides in the epilogue either way"""
     n, c, h, w, o, k, stride, pad, zp_in = case
     x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
     wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k)
     oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
     layers = [Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=0, w=wt, b=b, s_w=s_w, stride=(stride, stride),
                     pad=(pad,) * 4), Layer(H_RELU, (n, o, oh, ow), s_out=s_out / 2, zp_out=-128)]
-    if not direct:
+    if direct == "im2col":
         os.environ["SHL_B200_NO_DIRECT_CONV"] = "1"
+    if direct == "dp4a":
+        os.environ["SHL_B200_NO_STEM_TC"] = "1"
     try:
         got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=zp_in, run_mode=RM_GRAPH)
     finally:
         os.environ.pop("SHL_B200_NO_DIRECT_CONV", None)
+        os.environ.pop("SHL_B200_NO_STEM_TC", None)
     want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), stride=(stride, stride), pad=(pad,) * 4, dilation=(1, 1),
                             group=1, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out, zp_out=0,
                             post=(ACT_RELU, s_out / 2, -128))
