@@ -25,8 +25,11 @@
 
 namespace b200 {
 
-constexpr int kStemGroups = 3;
-constexpr int kStemThreads = (kStemGroups * 4 + 1) * 32;
+// worker groups per CTA: 5 when the tiles are small (K <= 128, N <= 32: 20 worker warps keep the
+// schedulers busy through the shared-memory and TMEM latencies of gather and epilogue), else 3
+// (TMEM: groups x 2 x N columns <= 512; shared memory: groups x 2 A tiles)
+__host__ __device__ constexpr int stem_groups(int k, int nch) { return (k <= 128 && nch <= 2) ? 5 : 3; }
+__host__ __device__ constexpr int stem_threads(int k, int nch) { return (stem_groups(k, nch) * 4 + 1) * 32; }
 
 struct StemArgs {
     int n, h, w, o, oh, ow, cp_out;
@@ -37,6 +40,7 @@ struct StemArgs {
     int8_t *out;        // [n*oh*ow][cp_out]
     int zp_in;
     uint32_t idesc;
+    uint32_t oh_inv;    // ceil(2^32 / oh): tile row -> image by multiply-high, corrected by one compare
     EpiScalars ep;
 };
 
@@ -48,8 +52,10 @@ __device__ __forceinline__ void group_bar_sync(int g)
 // 32 lanes x 16 columns seed store / load share the GEMM's helpers (common.cuh)
 
 template <int C, int KH, int KW, int SW, int NCH, int MODE>
-__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_tc_kernel(const StemArgs a)
+__global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_tc_kernel(const StemArgs a)
 {
+    constexpr int kStemGroups = stem_groups(C * KH * KW, NCH);
+    constexpr int kStemThreads = stem_threads(C * KH * KW, NCH);
     constexpr int ROWS = KH * C;                          // staged input rows per tile, (ky, c) order
     constexpr int WW = (128 * SW + KW - 1 + 3 + 3) / 4;   // words per staged row (segment + halo + alignment slack)
     constexpr int WROW = WW * 4;
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_tc_kernel(const Ste
             TilePos tp;
             const int seg = nseg == 1 ? 0 : t % nseg;
             const int row = nseg == 1 ? t : t / nseg;
-            tp.b = row / a.oh;
+            tp.b = static_cast<int>(__umulhi(static_cast<uint32_t>(row), a.oh_inv));
+            if (tp.b * a.oh > row) tp.b--;
+            if ((tp.b + 1) * a.oh <= row) tp.b++;
             tp.oy = row - tp.b * a.oh;
             tp.ox0 = seg * 128;
             return tp;
@@ -335,6 +343,8 @@ static int stem_launch(int mode, int grid, cudaStream_t s, const StemArgs &a, in
     constexpr int ATOMS = (KP + 127) / 128;
     constexpr int N = NCH * 16;
     constexpr int STG = (KH * C * ((128 * SW + KW - 1 + 3 + 3) / 4) * 4 + 15) & ~15;
+    constexpr int kStemGroups = stem_groups(C * KH * KW, NCH);
+    constexpr int kStemThreads = stem_threads(C * KH * KW, NCH);
     const size_t smem = 1024 + static_cast<size_t>(kStemGroups) * 2 * ATOMS * 128 * 128 + ATOMS * N * 128 +
                         kStemGroups * STG + N * 12 + 256 + kStemGroups * 4 * 8 + 16;
 #define B200_STEM_CASE(M)                                                                                   \
@@ -387,6 +397,7 @@ int b200_conv_stem_tc_launch(const b200_conv_direct_desc *d, void *stream)
     // column chunks the kernel is instantiated for: 3x3 -> 1 / 2 / 4, 7x7 -> 2 / 4
     const int nch_k = s3 ? (nch <= 2 ? nch : 4) : (nch <= 2 ? 2 : 4);
     a.idesc = umma_idesc(2 /*S32*/, 1 /*S8*/, 128, nch_k * 16);
+    a.oh_inv = d->oh == 1 ? 0xFFFFFFFFu : static_cast<uint32_t>(((1ull << 32) + d->oh - 1) / d->oh);
     const long long tiles_ll = static_cast<long long>(d->n) * d->oh * ((d->ow + 127) / 128);
     if (tiles_ll >= (1ll << 31) / 8) return B200_ERR_UNSUPPORTED;
     const int tiles = static_cast<int>(tiles_ll);
