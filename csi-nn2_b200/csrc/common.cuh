@@ -34,6 +34,31 @@ void count_launch(int n = 1);
     } while (0)
 
 int sm_count();
+bool pdl_enabled();  // runtime.cu: programmatic dependent launch when SHL_B200_PDL is set (opt-in, see there)
+
+// Every kernel of the library is launched through this: with the programmatic-stream-serialization
+// attribute (SHL_B200_PDL=1) a kernel may be scheduled while its predecessor in the stream (or CUDA graph) is still
+// draining, run its prologue (barrier init, TMEM allocation, weight / table staging -- constants
+// written at session setup) and then block in pdl_wait() until the predecessor has completed and
+// its writes are visible.  Kernels call pdl_launch_dependents() first thing, so the chain never
+// serialises on launch latency.  All accesses to activations (reads and writes: the arena reuses
+// buffers) come after pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // 2-D tiled tensor map, SWIZZLE_128B, zero fill out of bounds (runtime.cu)
 int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
                         int box_w, int box_h);
@@ -42,6 +67,15 @@ int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t 
                    int swizzle_bytes = 128);
 
 // ---- device helpers -------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -32,6 +32,8 @@ constexpr int kDirectThreads = 128;
 
 __global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_kernel(const DirectArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     extern __shared__ uint32_t s_w[];  // [kwords][o4] words, o4 = O rounded up to 4
     const int o4 = (a.o + 3) & ~3;
     float *s_mu = reinterpret_cast<float *>(s_w + a.kwords * o4);
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_kernel(const Di
 template <int C, int KH, int KW>
 __global__ void __launch_bounds__(kDirectThreads) conv_direct_i8_sp_kernel(const DirectArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     constexpr int K = C * KH * KW;
     constexpr int KWORDS = (K + 3) / 4;
     constexpr bool MAGIC = K <= 128;  // |acc + ibias| < 2^22, see common.cuh
@@ -280,11 +284,11 @@ extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
         return B200_ERR_UNSUPPORTED;
     }
     if (unit_dil && d->c == 3 && d->kh == 3 && d->kw == 3)
-        conv_direct_i8_sp_kernel<3, 3, 3><<<grid, kDirectThreads, smem_sp, (cudaStream_t)stream>>>(a);
+        launch_kernel(conv_direct_i8_sp_kernel<3, 3, 3>, dim3(grid), dim3(kDirectThreads), smem_sp, (cudaStream_t)stream, a);
     else if (unit_dil && d->c == 3 && d->kh == 7 && d->kw == 7)
-        conv_direct_i8_sp_kernel<3, 7, 7><<<grid, kDirectThreads, smem_sp, (cudaStream_t)stream>>>(a);
+        launch_kernel(conv_direct_i8_sp_kernel<3, 7, 7>, dim3(grid), dim3(kDirectThreads), smem_sp, (cudaStream_t)stream, a);
     else
-        conv_direct_i8_kernel<<<grid, kDirectThreads, smem, (cudaStream_t)stream>>>(a);
+        launch_kernel(conv_direct_i8_kernel, dim3(grid), dim3(kDirectThreads), smem, (cudaStream_t)stream, a);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const bool has_lut = a.ep.post_lut != nullptr;
+    pdl_launch_dependents();  // see launch_kernel (common.cuh): the setup below reads constants only
 
     // ---- one-time setup: weights into the swizzled B tile, per-channel parameters, barriers, TMEM
     for (int i = tid; i < ATOMS * N * 8; i += kStemThreads) {
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
             tc_fence_before();
         };
 
+        pdl_wait();  // image and output buffer belong to the predecessor until here
         TilePos tp_prev = {0, 0, 0}, tp_cur = {0, 0, 0}, tp_next = {0, 0, 0};
         if (tile_of(0, g) < tiles) {
             tp_next = decode(tile_of(0, g));
@@ -355,7 +357,8 @@ static int stem_launch(int mode, int grid, cudaStream_t s, const StemArgs &a, in
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
             attr[dev] = true;                                                                               \
         }                                                                                                   \
-        conv_stem_tc_kernel<C, KH, KW, SW, NCH, M><<<grid, kStemThreads, smem, s>>>(a);                         \
+        B200_CUDA_CHECK(launch_kernel(conv_stem_tc_kernel<C, KH, KW, SW, NCH, M>, dim3(grid), dim3(kStemThreads),  \
+                                      smem, s, a));                                                          \
         break;                                                                                              \
     }
     switch (mode) {

@@ -30,6 +30,8 @@ struct DwArgs {
 
 __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     __shared__ int8_t s_lut[256];
     if (a.ep.post_lut != nullptr)
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.ep.post_lut[i];
@@ -128,6 +130,8 @@ __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
 
 __global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     const int chunks = a.cp / 8;
     const int xgroups = (a.ow + kTW - 1) / kTW;
     const long long total = static_cast<long long>(a.n) * a.oh * xgroups * chunks;
@@ -247,9 +251,9 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
     const long long cap = static_cast<long long>(sm_count()) * 32;
     const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
     if (d->dtype == B200_I8)
-        dwconv_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+        launch_kernel(dwconv_i8_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     else
-        dwconv_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+        launch_kernel(dwconv_f16_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

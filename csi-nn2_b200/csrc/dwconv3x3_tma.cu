@@ -93,6 +93,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();  // see launch_kernel (common.cuh)
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         for (int i = 0; i < kDwStages; i++) {
@@ -109,6 +110,7 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     if (warp == kDwConsumers / 32) {
         // ===== TMA producer =====
         if (elect_one()) {
+            pdl_wait();  // the input is the predecessor's output
             int stage = 0;
             uint32_t phase = 0;
             for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -203,6 +205,9 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
             asm volatile("bar.sync 1, %0;" ::"n"(kDwConsumers) : "memory");
         }
 
+        // the output buffer may alias a tensor the predecessor still reads (returns at once after
+        // the first tile; the chunk setup above -- constants only -- overlaps the predecessor's tail)
+        pdl_wait();
         mbar_wait(&full_bar[stage], phase);
         uint8_t *tile = smem + static_cast<size_t>(stage) * a.stage_stride;
 
@@ -312,7 +317,7 @@ static int launch_cfg(int mode, int grid, size_t smem, cudaStream_t s, const CUt
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); \
             attr[dev] = true;                                                                        \
         }                                                                                            \
-        dw3x3_tma_kernel<S, CC, TW, M><<<grid, CC / 4 * TW + 32, smem, s>>>(tm, a);                  \
+        B200_CUDA_CHECK(launch_kernel(dw3x3_tma_kernel<S, CC, TW, M>, dim3(grid), dim3(CC / 4 * TW + 32), smem, s, tm, a)); \
         break;                                                                                       \
     }
     switch (mode) {

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) lut_i8_kernel(const uint4 *__restrict__ i
                                                      uint4 *__restrict__ out, long long nvec,
                                                      const int8_t *__restrict__ lut)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     __shared__ uint8_t s_lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = static_cast<uint8_t>(lut[i]);
     __syncthreads();
@@ -39,6 +41,8 @@ __global__ void __launch_bounds__(256) relu_f16_kernel(const uint4 *__restrict__
                                                        uint4 *__restrict__ out, long long nvec,
                                                        int act)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     const __half2 zero = __float2half2_rn(0.f), six = __float2half2_rn(6.f);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -64,6 +68,8 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
                                                      uint4 *__restrict__ out, long long nvec,
                                                      const AddArgs p)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     __shared__ uint8_t s_lut[256];
     if (p.post_lut != nullptr)
         for (int i = threadIdx.x; i < 256; i += blockDim.x)
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(256) add_f16_kernel(const uint4 *__restrict__ 
                                                       uint4 *__restrict__ out, long long nvec,
                                                       int act)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const uint4 va = __ldg(a + i), vb = __ldg(b + i);
@@ -134,7 +142,7 @@ extern "C" int b200_lut_i8(const void *in, void *out, size_t count, const int8_t
         return B200_ERR_ARG;
     }
     const long long nvec = static_cast<long long>(count / 16);
-    lut_i8_kernel<<<ew_grid(nvec), 256, 0, (cudaStream_t)stream>>>(
+    launch_kernel(lut_i8_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
         static_cast<const uint4 *>(in), static_cast<uint4 *>(out), nvec, lut_dev);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -147,7 +155,7 @@ extern "C" int b200_relu_f16(const void *in, void *out, size_t count, int act, v
         return B200_ERR_ARG;
     }
     const long long nvec = static_cast<long long>(count / 8);
-    relu_f16_kernel<<<ew_grid(nvec), 256, 0, (cudaStream_t)stream>>>(
+    launch_kernel(relu_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
         static_cast<const uint4 *>(in), static_cast<uint4 *>(out), nvec, act);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -166,11 +174,11 @@ extern "C" int b200_add(int dtype, const void *a, const void *b, void *out, size
     const long long nvec = static_cast<long long>(count / vec);
     if (dtype == B200_I8) {
         AddArgs p{s_a, s_b, s_out, zp_a, zp_b, zp_out, act, post_lut};
-        add_i8_kernel<<<ew_grid(nvec), 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(add_i8_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
             nvec, p);
     } else {
-        add_f16_kernel<<<ew_grid(nvec), 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(add_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
             nvec, act);
     }

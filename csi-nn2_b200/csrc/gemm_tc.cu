@@ -102,6 +102,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int G = args.group;
+    // let the next kernel of the stream start its own prologue as soon as SMs free up; everything
+    // before the griddepcontrol waits below touches only constants (weights, tables) and on-chip state
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -146,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = 0; kb < args.k_blocks; kb++)
                     tma_load_2d(smem_b + kb * b_stage_bytes, &tma_b, b_bar, kb * k_elems, n0);
             }
+            pdl_wait();  // the activations are the predecessor's output
             int stage = 0;
             uint32_t phase = 0;
             for (int ms = ms0; ms < args.num_m_super; ms += ms_step) {
@@ -217,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // epilogue warps never meet at a CTA-wide barrier -- a fast warp runs up to two super tiles
         // ahead of a slow one =====
         if (DT == B200_I8 && elect_one()) {
+            pdl_wait();  // the output buffer may alias a tensor the predecessor still reads
             int local = 0;
             for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
                 const int buf = local & 1;
@@ -356,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             epi->badd[et] = (col < args.n && ep.badd) ? ep.badd[col] : 0.f;
         }
         epi_bar_sync();
+        pdl_wait();  // fp16 rows are stored straight to global memory
         int local = 0;
         for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
             const int acc = local & 1;
@@ -452,7 +458,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
                                              (int)kSmemLimit));
         attr_set[dev] = true;
     }
-    gemm_tc_kernel<DT, MODE, MAGIC><<<grid, kThreads, smem, stream>>>(ta, tb, to, args);
+    B200_CUDA_CHECK(launch_kernel(gemm_tc_kernel<DT, MODE, MAGIC>, dim3(grid), dim3(kThreads), smem, stream, ta, tb, to, args));
     return B200_OK;
 }
 

@@ -15,6 +15,8 @@ template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T *__restrict__ src, T *__restrict__ dst, int n, int c,
                                     int hw, int cp, T pad)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     constexpr int V = 16 / sizeof(T);
     const int chunks = cp / V;
     const long long total = static_cast<long long>(n) * chunks * hw;
@@ -38,6 +40,8 @@ template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, T *__restrict__ dst, int n, int c,
                                     int hw, int cp)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     constexpr int V = 16 / sizeof(T);
     const int chunks = cp / V;
     const long long total = static_cast<long long>(n) * chunks * hw;
@@ -69,6 +73,8 @@ struct Im2colArgs {
 template <typename T>
 __global__ void im2col_kernel(const Im2colArgs a, T pad)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     constexpr int V = 16 / sizeof(T);
     const int vecs = a.ldk / V;
     const int kvalid = a.kh * a.kw * a.cg;
@@ -151,11 +157,11 @@ extern "C" int b200_nchw_to_nhwc(const void *src, void *dst, int n, int c, int h
     const long long total = static_cast<long long>(n) * h * w * (cp * elem_bytes / 16);
     const int grid = grid_for(total, 256);
     if (elem_bytes == 1)
-        nchw_to_nhwc_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(nchw_to_nhwc_kernel<int8_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const int8_t *>(src), static_cast<int8_t *>(dst), n, c, h * w, cp,
             static_cast<int8_t>(pad));
     else
-        nchw_to_nhwc_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(nchw_to_nhwc_kernel<uint16_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), n, c, h * w, cp,
             static_cast<uint16_t>(pad));
     B200_LAUNCH_CHECK();
@@ -174,10 +180,10 @@ extern "C" int b200_nhwc_to_nchw(const void *src, void *dst, int n, int c, int h
     const long long total = static_cast<long long>(n) * h * w * (cp * elem_bytes / 16);
     const int grid = grid_for(total, 256);
     if (elem_bytes == 1)
-        nhwc_to_nchw_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(nhwc_to_nchw_kernel<int8_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const int8_t *>(src), static_cast<int8_t *>(dst), n, c, h * w, cp);
     else
-        nhwc_to_nchw_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        launch_kernel(nhwc_to_nchw_kernel<uint16_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), n, c, h * w, cp);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -207,9 +213,9 @@ extern "C" int b200_im2col(const b200_im2col_desc *d, void *stream)
     const long long total = static_cast<long long>(d->n) * d->oh * d->ow * (d->ldk * eb / 16);
     const int grid = grid_for(total, 256);
     if (eb == 1)
-        im2col_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(a, static_cast<int8_t>(d->pad_value));
+        launch_kernel(im2col_kernel<int8_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, static_cast<int8_t>(d->pad_value));
     else
-        im2col_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(a, static_cast<uint16_t>(0));
+        launch_kernel(im2col_kernel<uint16_t>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, static_cast<uint16_t>(0));
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -22,6 +22,8 @@ struct PoolArgs {
 
 __global__ void __launch_bounds__(128) pool_i8_kernel(const PoolArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     const int chunks = a.cp / 16;
     const long long total = static_cast<long long>(a.n) * a.oh * a.ow * chunks;
     const int8_t *in = static_cast<const int8_t *>(a.in);
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(128) pool_i8_kernel(const PoolArgs a)
 
 __global__ void __launch_bounds__(128) pool_f16_kernel(const PoolArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     const int chunks = a.cp / 8;
     const long long total = static_cast<long long>(a.n) * a.oh * a.ow * chunks;
     const __half *in = static_cast<const __half *>(a.in);
@@ -133,6 +137,8 @@ __global__ void __launch_bounds__(128) pool_f16_kernel(const PoolArgs a)
 // as averagepool.c:100-109 prescribes).
 __global__ void __launch_bounds__(256) gap_i8_kernel(const PoolArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     const int words = a.cp / 4;
     const int total = a.n * words;
     const int hw = a.h * a.w;
@@ -197,11 +203,11 @@ extern "C" int b200_pool2d(const b200_pool_desc *d, void *stream)
     if (d->dtype == B200_I8 && d->is_avg && d->oh == 1 && d->ow == 1 && d->kh == d->h && d->kw == d->w &&
         d->pad_top == 0 && d->pad_left == 0) {
         const int tot = d->n * (d->cp / 4);
-        gap_i8_kernel<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+        launch_kernel(gap_i8_kernel, dim3((tot + 127) / 128), dim3(128), 0, (cudaStream_t)stream, a);
     } else if (d->dtype == B200_I8)
-        pool_i8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+        launch_kernel(pool_i8_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     else
-        pool_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+        launch_kernel(pool_f16_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

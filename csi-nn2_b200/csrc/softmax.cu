@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) softmax_kernel(const void *__restrict__ i
                                                       int cp_out, float s_in, int zp_in,
                                                       float s_out, int zp_out)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     extern __shared__ double s_mem[];
     double *s_e = s_mem;                                   // [c]
     float *s_x = reinterpret_cast<float *>(s_e + c);       // [c]
@@ -82,10 +84,10 @@ extern "C" int b200_softmax(int dtype, const void *in, void *out, int rows, int 
         return B200_ERR_UNSUPPORTED;
     }
     if (dtype == B200_I8)
-        softmax_kernel<B200_I8><<<rows, 256, smem, (cudaStream_t)stream>>>(
+        launch_kernel(softmax_kernel<B200_I8>, dim3(rows), dim3(256), smem, (cudaStream_t)stream, 
             in, out, c, cp_in, cp_out, s_in, zp_in, s_out, zp_out);
     else
-        softmax_kernel<B200_F16><<<rows, 256, smem, (cudaStream_t)stream>>>(
+        launch_kernel(softmax_kernel<B200_F16>, dim3(rows), dim3(256), smem, (cudaStream_t)stream, 
             in, out, c, cp_in, cp_out, s_in, zp_in, s_out, zp_out);
     B200_LAUNCH_CHECK();
     return B200_OK;

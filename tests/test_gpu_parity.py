@@ -44,6 +44,10 @@ CONV_CASES = [
     (1, 1024, 7, 7, 128, 1, 1, 0, 1, False, -128, H_CONV),   # 8 k-blocks, extreme zero point
     (2, 1024, 1, 1, 1000, 1, 1, 0, 1, False, 0, H_CONV),     # MobileNetV1 classifier: 4 n-tiles
     (2, 128, 56, 56, 128, 1, 1, 0, 1, False, 0, H_CONV),     # many tiles per CTA (double-buffered TMEM)
+    (2, 512, 14, 14, 512, 1, 1, 0, 1, False, -128, H_CONV),  # 256-column n-tiles, resident weights, 4 k-blocks
+    (1, 128, 28, 28, 256, 1, 1, 0, 1, False, 0, H_CONV),     # one 256-column n-tile: activations read once
+    (3, 96, 9, 11, 200, 1, 1, 0, 1, False, 7, H_CONV),       # ragged 256-column tile (N = 200), ragged M and K
+    (1, 256, 20, 20, 400, 1, 1, 0, 1, False, 0, H_CONV_RELU),  # two n-tiles, the second ragged
     (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 0, H_CONV_RELU),
     (1, 64, 14, 14, 64, 1, 1, 0, 1, False, 3, H_CONV_RELU6),
     (1, 32, 14, 14, 48, 3, 1, 1, 1, False, -7, H_CONV),      # im2col path, asymmetric pad value
