@@ -307,7 +307,7 @@ static int run_steps(b200_graph *g, void *stream)
     /* graph outputs: compact NCHW copies, ready for D2H */
     for (int i = 0; i < g->nt; i++) {
         g_tensor *t = &g->t[i];
-        if (!t->is_output) continue;
+        if (!t->is_output || !t->d_out_nchw) continue;
         DEV_CHECK(b200_nhwc_to_nchw(t->dt.d, t->d_out_nchw, t->dt.n, t->dt.c, t->dt.h, t->dt.w, t->dt.cp,
                                     t->dt.eb, stream));
     }
@@ -446,7 +446,8 @@ int shl_b200_session_setup(struct csinn_session *sess)
         }
         if (t->is_output) {
             const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
-            DEV_CHECK(b200_malloc(&t->d_out_nchw, raw));
+            /* a 1x1 map is already NCHW up to the row pitch: read back by a strided copy, no kernel */
+            if (t->dt.h * t->dt.w != 1) DEV_CHECK(b200_malloc(&t->d_out_nchw, raw));
             DEV_CHECK(b200_malloc_host(&t->h_out, raw));
             struct csinn_tensor *ct = t->node->data;
             ct->data = t->h_out; /* what csinn_get_output hands back (graph_ref/setup.c:37-42) */
@@ -542,7 +543,11 @@ int shl_b200_session_run(struct csinn_session *sess)
         g_tensor *t = &g->t[i];
         if (!t->is_output) continue;
         const size_t raw = (size_t)t->dt.n * t->dt.c * t->dt.h * t->dt.w * t->dt.eb;
-        DEV_CHECK(b200_memcpy_d2h(t->h_out, t->d_out_nchw, raw, opt->ctx.stream));
+        if (t->d_out_nchw)
+            DEV_CHECK(b200_memcpy_d2h(t->h_out, t->d_out_nchw, raw, opt->ctx.stream));
+        else
+            DEV_CHECK(b200_memcpy_d2h_rows(t->h_out, t->dt.d, (size_t)t->dt.c * t->dt.eb, (size_t)t->dt.cp * t->dt.eb,
+                                           (size_t)t->dt.n, opt->ctx.stream));
     }
     DEV_CHECK(b200_stream_sync(opt->ctx.stream));
     return CSINN_TRUE;

@@ -203,6 +203,12 @@ int b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
     B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return B200_OK;
 }
+int b200_memcpy_d2h_rows(void *dst, const void *src, size_t row_bytes, size_t src_pitch, size_t rows, void *stream)
+{
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost,
+                                      (cudaStream_t)stream));
+    return B200_OK;
+}
 int b200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream)
 {
     B200_CUDA_CHECK(

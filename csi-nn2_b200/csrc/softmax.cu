@@ -2,10 +2,12 @@
 // H = W = 1), restating source/reference/softmax.c:20-66 step by step: f32 max, exp evaluated in
 // double on the f32 difference, an f32 accumulator that receives the double terms ONE BY ONE in
 // channel order (that order is what fixes the result bits, so one thread does it from values the
-// whole block computed in parallel), then double division narrowed to f32 and requantised.
+// whole block computed in parallel, through the integer restatement in softmax_sum.h), then
+// double division narrowed to f32 and requantised.
 #include <float.h>
 
 #include "common.cuh"
+#include "softmax_sum.h"
 
 namespace b200 {
 
@@ -47,12 +49,33 @@ __global__ void __launch_bounds__(256) softmax_kernel(const void *__restrict__ i
     for (int j = tid; j < c; j += blockDim.x)
         s_e[j] = exp(static_cast<double>(__fsub_rn(s_x[j], mx)));
     __syncthreads();
+    // the term-by-term float accumulation of the reference in its integer form (softmax_sum.h; same
+    // bits): per binade of the running sum every thread turns its terms into integer increments,
+    // then one thread adds them up -- a 4-cycle add per term where the literal float <- double step
+    // costs ~50 (this chain is what the kernel's run time consists of)
+    uint32_t *s_d = reinterpret_cast<uint32_t *>(s_x);  // the x values are dead from here on
+    __shared__ int s_j;
     if (tid == 0) {
-        float acc = 0.f;
-        for (int j = 0; j < c; j++) acc = static_cast<float>(static_cast<double>(acc) + s_e[j]);
-        s_acc = acc;
+        s_acc = 0.f;
+        s_j = 0;
     }
     __syncthreads();
+    for (;;) {
+        const float acc_now = s_acc;
+        const int j0 = s_j;
+        if (j0 >= c) break;
+        const uint32_t ex = (__float_as_uint(acc_now) >> 23) & 0xFF;
+        const bool normal = ex != 0 && ex < 0xFE;
+        if (normal)
+            for (int j = j0 + tid; j < c; j += blockDim.x) s_d[j] = b200_softmax_term(s_e[j], static_cast<int>(ex) - 127);
+        __syncthreads();  // also: everybody has read s_acc / s_j
+        if (tid == 0) {
+            float a = acc_now;
+            s_j = b200_softmax_chain(normal ? s_d : nullptr, s_e, j0, c, &a);
+            s_acc = a;
+        }
+        __syncthreads();
+    }
     const double acc = static_cast<double>(s_acc);
     for (int j = tid; j < cp_out; j += blockDim.x) {
         const float v = j < c ? static_cast<float>(s_e[j] / acc) : 0.f;

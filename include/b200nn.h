@@ -85,6 +85,10 @@ int b200_malloc_host(void **hptr, size_t bytes); /* pinned */
 int b200_free_host(void *hptr);
 int b200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+/* `rows` rows of row_bytes, src_pitch apart on the device, packed densely on the host: a pixel-major
+ * [n][1][1][cp] tensor IS the NCHW tensor [n][c] up to the row padding, so such a graph output is
+ * read back with the copy engine alone (no compaction kernel) */
+int b200_memcpy_d2h_rows(void *dst, const void *src, size_t row_bytes, size_t src_pitch, size_t rows, void *stream);
 int b200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int b200_memset(void *dst, int value, size_t bytes, void *stream);
 int b200_stream_create(void **stream);

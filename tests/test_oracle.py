@@ -13,6 +13,8 @@ LSB where the real value sits within f32 noise of a rounding tie.  The bound ass
 satisfy against each other (test_reference_builds_disagree_like_the_oracle).  Elementwise and
 pooling ops are restated float-op by float-op and must match bit for bit.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -239,3 +241,16 @@ def test_network_oracle_chain_equals_reference_graph(ref, ref_noavx):
     got = ref.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
     d = np.abs(got.astype(int) - want.astype(int))
     assert d.max() <= 1 and np.count_nonzero(d) <= 2, (d.max(), np.count_nonzero(d))
+
+
+def test_softmax_denominator_code_matches_the_literal_loop():
+    """csi-nn2_b200/csrc/softmax_sum.h (the denominator code of the CUDA softmax kernel, plain C)
+    compiled for the CPU: the short-chain double accumulation equals the reference's literal
+    `float += double` loop (source/reference/softmax.c:53-55) bit for bit -- softmax-like terms, long
+    tails, many binade crossings, exact rounding ties, zeros and subnormal-range sums"""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness", "lib", "libsoftmax_sum_check.so"))
+    lib.softmax_sum_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]
+    for mode in range(5):
+        for n in (1, 7, 8, 9, 1000, 1001, 4096):
+            assert lib.softmax_sum_check(400, n, mode, 99 + 31 * mode + n) == 0, (mode, n)
