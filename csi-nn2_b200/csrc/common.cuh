@@ -44,20 +44,37 @@ bool pdl_enabled();  // runtime.cu: programmatic dependent launch when SHL_B200_
 // serialises on launch latency.  All accesses to activations (reads and writes: the arena reuses
 // buffers) come after pdl_wait().
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 Args &&...args)
+inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         int cluster_x, Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster_x > 1) {  // thread-block cluster along x: CTAs 2j, 2j+1 share TMA multicast loads
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        n++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args &&...args)
+{
+    return launch_kernel_cluster(kern, grid, block, smem, stream, 1, static_cast<Args &&>(args)...);
 }
 // 2-D tiled tensor map, SWIZZLE_128B, zero fill out of bounds (runtime.cu)
 int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
@@ -142,6 +159,27 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster
+// whose bit is set in cta_mask: one L2 read feeds several SMs
+__device__ __forceinline__ void tma_load_2d_multicast(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0,
+                                                      int c1, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
                                             int c0, int c1, int c2, int c3)
 {
@@ -209,6 +247,15 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile(
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
             smem_u32(bar))
+        : "memory");
+}
+// the same arrive on the mbarrier at this shared-memory offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
         : "memory");
 }
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,

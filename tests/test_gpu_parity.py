@@ -94,6 +94,26 @@ def test_conv_int8_against_the_reference_library(b200, ref, rng):
         ref_band(got, want)
 
 
+@pytest.mark.parametrize("case", [(2, 512, 14, 14, 512, -128), (1, 128, 28, 28, 256, 0), (3, 96, 9, 11, 200, 7),
+                                  (1, 256, 20, 20, 400, 0), (2, 1024, 1, 1, 1000, 0)],
+                         ids=lambda c: "n%d_c%d_%dx%d_o%d_zp%d" % c)
+def test_pointwise_conv_with_cluster_multicast(case, b200, oracle, rng):
+    """SHL_B200_GEMM_CLUSTER=1: CTA pairs (thread-block clusters of two) fetch each activation stage once
+    and multicast it to both CTAs (csrc/gemm_tc.cu); results are the same bytes as the unpaired kernel"""
+    n, c, h, w, o, zp_in = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 1, 1)
+    layer = Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w)
+    os.environ["SHL_B200_GEMM_CLUSTER"] = "1"
+    try:
+        got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=zp_in)
+    finally:
+        os.environ.pop("SHL_B200_GEMM_CLUSTER", None)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, h, w), stride=(1, 1), pad=(0,) * 4, dilation=(1, 1), group=1, s_in=0.02,
+                            zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out, zp_out=3)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} outputs differ from the oracle"
+
+
 FIRST_LAYER = [(2, 3, 32, 32, 32, 3, 2, 1, 5), (1, 3, 40, 40, 64, 7, 2, 3, 0), (1, 4, 17, 19, 24, 3, 1, 1, -9),
                (1, 1, 16, 16, 8, 5, 1, 2, 3), (3, 3, 224, 224, 32, 3, 2, 1, 0),
                (1, 3, 33, 35, 48, 3, 2, 1, -7), (5, 3, 30, 30, 16, 3, 1, 1, 11), (2, 3, 61, 47, 24, 7, 2, 3, -128)]
