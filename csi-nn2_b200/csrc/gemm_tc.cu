@@ -29,6 +29,7 @@
 // Replaces shl_rvv_gemm_4x16_int8 / shl_rvv_conv1x1s1_gemm_int8 / shl_rvv_fullyconnected_int8
 // (source/thead_rvv/int8/gemm_int8.c:37, convolution_1x1_int8.c:56, fullyconnected_int8.c:94)
 // and the fp16 twins (source/thead_rvv/fp16/gemm_fp16.c); nothing of them is ported.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -52,6 +53,7 @@ struct GemmArgs {
     int group;         // G: 128-row blocks per super tile
     int num_m_super;   // ceil(num_m_tiles / G)
     int b_resident;    // weights loaded once per CTA
+    long long *trace;  // developer diagnostic (SHL_B200_GEMM_TRACE): per-CTA clock64 stamps, else null
     int cluster;       // 2: CTA pairs (same rows, neighbouring n-tiles) fetch each activation stage once -- each CTA
                        // loads 64 of its 128 rows and multicasts them to both; 1: no cluster
     int stages;
@@ -105,6 +107,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int G = args.group;
     const uint32_t cta_rank = args.cluster > 1 ? cluster_ctarank() : 0;
+    // trace layout per CTA: [0] start, [1] after prologue, [2] weights resident, [3] end,
+    // [8 + 2i] MMA of super tile i issued, [9 + 2i] epilogue of super tile i done (warp 2)
+    long long *tr = args.trace ? args.trace + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
     // let the next kernel of the stream start its own prologue as soon as SMs free up; everything
     // before the griddepcontrol waits below touches only constants (weights, tables) and on-chip state
     pdl_launch_dependents();
@@ -139,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // the peer's barriers must exist before a multicast load or commit of ours can land on them
     if (args.cluster > 1) cluster_sync_all();
     tc_fence_after();
+    if (tr && threadIdx.x == 0) tr[1] = clock64();
     const uint32_t tmem_base = *tmem_ptr;
     const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
     // schedule: this CTA's n-tile is fixed; gridDim.x is a multiple of num_n_tiles (host)
@@ -193,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // ===== MMA issuer =====
         if (elect_one()) {
             if (args.b_resident) mbar_wait(b_bar, 0);
+            if (tr) tr[2] = clock64();
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -233,6 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
                 tc_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
+                if (tr && local < 28) tr[8 + 2 * local] = clock64();
             }
         }
     } else if (warp == 2 + kEpiWarps) {
@@ -357,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (tr && et == 0 && local < 28) tr[9 + 2 * local] = clock64();
             // hand this warp's part of the staged tile to the store warp (generic-proxy writes
             // ordered before the async-proxy read by the fence; the arrive releases them)
             fence_proxy_async_smem();
@@ -442,6 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     // neither CTA of a pair may exit while the other can still multicast into its shared memory
     if (args.cluster > 1) cluster_sync_all();
+    if (tr && threadIdx.x == 0) tr[3] = clock64();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -480,6 +491,13 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
         attr_set[dev] = true;
     }
     GemmArgs la = args;
+    static long long *trace_dev = nullptr;
+    const bool tracing = getenv("SHL_B200_GEMM_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_dev) B200_CUDA_CHECK(cudaMalloc(&trace_dev, 256 * 64 * sizeof(long long)));
+        B200_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, 256 * 64 * sizeof(long long), stream));
+        la.trace = grid <= 256 ? trace_dev : nullptr;
+    }
     if (la.cluster > 1) {
         // a persistent grid must be co-resident: pair up only if the device can hold grid / 2 clusters at once
         static int max_clusters[64] = {};
@@ -503,6 +521,20 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
     }
     B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC>, dim3(grid), dim3(kThreads), smem, stream,
                                           la.cluster, ta, tb, to, la));
+    if (tracing && la.trace) {  // diagnostic only: synchronous, prints a few CTAs' timelines (cycles from CTA start)
+        static long long host[256 * 64];
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        B200_CUDA_CHECK(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "gemm trace m=%d n=%d k_blocks=%d bn=%d G=%d stages=%d grid=%d\n", la.m, la.n, la.k_blocks, la.bn,
+                la.group, la.stages, grid);
+        for (int c = 0; c < grid; c += grid / 4 > 0 ? grid / 4 : 1) {
+            const long long *t = host + c * 64, t0 = t[0];
+            fprintf(stderr, " cta %3d: prologue %lld  B-resident %lld  end %lld |", c, t[1] - t0, t[2] - t0, t[3] - t0);
+            for (int i = 0; i < 28 && t[8 + 2 * i]; i++)
+                fprintf(stderr, " mma%d %lld epi%d %lld", i, t[8 + 2 * i] - t0, i, t[9 + 2 * i] ? t[9 + 2 * i] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
     return B200_OK;
 }
 
@@ -559,6 +591,7 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
                       gemm_smem_bytes(3, args.bn, args.k_blocks, true, staging) <= kSmemLimit &&
                       !getenv("SHL_B200_GEMM_NO_RESIDENT");
+    args.trace = nullptr;
     args.ldo = d->ldo;
     args.out = d->out;
     args.ep = make_epi(d->ep);
