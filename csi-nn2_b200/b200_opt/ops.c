@@ -304,9 +304,19 @@ static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
            !getenv("SHL_B200_NO_DIRECT_CONV");
 }
 
+/* the 3-channel 3x3 / 7x7 stems run as an implicit GEMM on the tensor core (csrc/conv_stem_tc.cu);
+ * same conditions as b200_conv_stem_tc_launch (the shim decides, this only names the kernel) */
+static int conv_stem_on_tc(const b200_op *op, const b200_dt *in0)
+{
+    return in0->c == 3 && op->kh == op->kw && (op->kh == 3 || op->kh == 7) && op->dh == 1 && op->dw == 1 &&
+           op->sh == op->sw && op->sw <= 2 && (op->kh == 3 || op->sw == 2) && op->o <= 64 && in0->w % 4 == 0 &&
+           !getenv("SHL_B200_NO_STEM_TC");
+}
+
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
 {
-    if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0)) return "b200_conv2d_direct";
+    if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0))
+        return conv_stem_on_tc(op, in0) ? "b200_conv2d_stem_tcgen05" : "b200_conv2d_direct";
     return op->kname;
 }
 

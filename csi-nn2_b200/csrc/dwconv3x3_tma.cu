@@ -98,7 +98,7 @@ struct TileWalk {
 };
 
 template <int S, int CC, int TW, int MODE>
-__global__ void __launch_bounds__(CC / 4 * TW + 32, 3)
+__global__ void __launch_bounds__(CC / 4 * TW + 32, 2)
 dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
 {
     constexpr int TWI = S * (TW - 1) + 3;
