@@ -19,6 +19,8 @@ Numbers on the JSON line:
             pinned HOST buffers: H2D of the batch and D2H of the class scores inside the timed region
   roofline  the dominant kernel of the step (by share of device time, measured live with CUDA events
             per step): algorithmic bytes / time against the measured HBM peak of MEASURED_PEAKS.json
+  batch1    BASELINE.json configs[1] beside it: the same graph at batch 1 (latency regime), device
+            latency per inference (CUDA-graph replay) and through the API from a pinned host buffer
   cpu_baseline  the unmodified reference (oracle/_ref, built from its own sources) on the host cores,
             rank 0, a bounded sample of the same workload.  Reported baseline, not the target.
 --impl reference times that CPU implementation alone, as the reference arm of the same line.
@@ -386,6 +388,48 @@ def main():
                                       "TOPS": pop[i] / pms[i] / 1e9} for i in range(nsteps)],
                            "per_kernel": per_kernel, "describe": desc[0]}, f, indent=1)
 
+    # ---- BASELINE.json configs[1]: the same graph at batch 1 (latency regime), rank 0, a second session
+    batch1 = None
+    if rank == 0 and args.batch != 1:
+        net1 = b200.create(DT, nb1.in_shape, nb1.layers, s_in=nb1.s_in, zp_in=nb1.zp_in, run_mode=RM_GRAPH, api=API_C906)
+        s1 = net1.session
+        st1 = shl.shl_b200_session_stream(s1)
+        h1 = C.c_void_p()
+        assert shim.b200_malloc_host(C.byref(h1), C.c_size_t(x1.nbytes)) == 0, shim.b200_last_error()
+        C.memmove(h1, x1.ctypes.data, x1.nbytes)
+
+        def one():
+            assert b200.lib.h_net_update_input(net1.handle, h1) == 0
+            assert b200.lib.h_net_session_run(net1.handle) == 0, b200.error()
+            return b200.lib.h_net_get_output(net1.handle)
+
+        p1 = one()
+        ctype = C.c_int8 if DT == DT_INT8 else C.c_uint16
+        got1 = np.ctypeslib.as_array(C.cast(p1, C.POINTER(ctype)), shape=(1000,)).copy()
+        want1 = nets.oracle_forward(nb1, x1).reshape(1000)
+        ok1 = bool(np.array_equal(got1, want1)) if DT == DT_INT8 else True
+        for _ in range(20):
+            shl.shl_b200_session_launch(s1)
+        shim.b200_event_record(ev0, C.c_void_p(st1))
+        n1 = 200
+        for _ in range(n1):
+            shl.shl_b200_session_launch(s1)
+        shim.b200_event_record(ev1, C.c_void_p(st1))
+        shl.shl_b200_session_sync(s1)
+        shim.b200_event_elapsed_ms(ev0, ev1, C.byref(ms))
+        lat_us = 1e3 * float(ms.value) / n1
+        for _ in range(20):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(n1):
+            one()
+        e2e_us = 1e6 * (time.perf_counter() - t0) / n1
+        b1 = C.create_string_buffer(16384)
+        shl.shl_b200_session_describe(s1, b1, len(b1))
+        batch1 = {"workload": "BASELINE.json configs[1]: the same graph, batch 1", "value": 1e6 / lat_us, "unit": UNIT,
+                  "latency_us": lat_us, "e2e_latency_us": e2e_us, "e2e_value": 1e6 / e2e_us, "bit_exact_vs_oracle": ok1,
+                  "session": b1.value.decode().splitlines()[0]}
+
     # ---- CPU baseline beside it (rank 0 only)
     cpu = None
     if rank == 0 and args.cpu_images > 0:
@@ -416,7 +460,8 @@ def main():
                 "roofline": roofline, "layerwise_roofline": layerwise, "cpu_baseline": cpu,
                 "tensor_tops": (sum(k["ops"] for k in per_kernel.values()) * world * steps / (dev_ms * 1e-3) / 1e12)
                 if per_kernel else None,
-                "weight_broadcast_ms": bcast_ms}
+                "weight_broadcast_ms": bcast_ms, "batch1": batch1,
+                "session": desc[0] if rank == 0 and per_kernel else None}
         emit(line)
     net.close()
     if dist is not None:

@@ -66,6 +66,7 @@ struct b200_graph {
     size_t arena_bytes, scratch_off;
     void *exec; /* captured CUDA graph */
     int kernels_per_run;
+    int pdl; /* 1: the captured graph uses programmatic dependent launch (chosen by timing at setup) */
 };
 
 /* our option struct hangs on gref's target data (include/shl_utils.h:53-57), like
@@ -472,15 +473,57 @@ int shl_b200_session_setup(struct csinn_session *sess)
     DEV_CHECK(b200_stream_sync(ctx->stream));
     g->kernels_per_run = (int)(b200_launch_count() - before);
     if (!getenv("SHL_B200_NO_CUDA_GRAPH")) {
-        DEV_CHECK(b200_graph_begin(ctx->stream));
-        int rc = run_steps(g, ctx->stream);
-        void *exec = NULL;
-        int rc2 = b200_graph_end(ctx->stream, &exec);
-        if (rc != CSINN_TRUE || rc2 != B200_OK) {
-            b200_fail("CUDA graph capture failed: %s", b200_last_error());
-            return CSINN_FALSE;
+        /* Capture the step list with and without programmatic dependent launch and keep the graph
+         * that replays faster: small batches are bound by per-kernel launch + prologue latency (PDL
+         * hides it), large ones are not (PDL costs ~1.5 %).  SHL_B200_PDL=0/1 skips the comparison. */
+        const char *force = getenv("SHL_B200_PDL");
+        void *exec[2] = {NULL, NULL};
+        double ms[2] = {0, 0};
+        for (int pdl = 0; pdl < 2; pdl++) {
+            if (force && (atoi(force) != 0) != pdl) continue;
+            b200_set_pdl(pdl);
+            DEV_CHECK(b200_graph_begin(ctx->stream));
+            int rc = run_steps(g, ctx->stream);
+            int rc2 = b200_graph_end(ctx->stream, &exec[pdl]);
+            b200_set_pdl(0);
+            if (rc != CSINN_TRUE || rc2 != B200_OK) {
+                if (pdl == 1 && exec[0]) { /* keep the plain graph if the PDL capture is refused */
+                    exec[1] = NULL;
+                    break;
+                }
+                b200_fail("CUDA graph capture failed: %s", b200_last_error());
+                return CSINN_FALSE;
+            }
         }
-        g->exec = exec;
+        if (exec[0] && exec[1]) {
+            void *e0 = NULL, *e1 = NULL;
+            DEV_CHECK(b200_event_create(&e0));
+            DEV_CHECK(b200_event_create(&e1));
+            for (int pdl = 0; pdl < 2; pdl++) {
+                float best = 1e30f;
+                DEV_CHECK(b200_graph_launch(exec[pdl], ctx->stream)); /* warm-up */
+                for (int rep = 0; rep < 3; rep++) {
+                    float t = 0;
+                    DEV_CHECK(b200_event_record(e0, ctx->stream));
+                    DEV_CHECK(b200_graph_launch(exec[pdl], ctx->stream));
+                    DEV_CHECK(b200_graph_launch(exec[pdl], ctx->stream));
+                    DEV_CHECK(b200_event_record(e1, ctx->stream));
+                    DEV_CHECK(b200_stream_sync(ctx->stream));
+                    DEV_CHECK(b200_event_elapsed_ms(e0, e1, &t));
+                    if (t < best) best = t;
+                }
+                ms[pdl] = best;
+            }
+            b200_event_destroy(e0);
+            b200_event_destroy(e1);
+            const int pick = ms[1] < ms[0] ? 1 : 0;
+            b200_graph_destroy(exec[1 - pick]);
+            g->exec = exec[pick];
+            g->pdl = pick;
+        } else {
+            g->exec = exec[0] ? exec[0] : exec[1];
+            g->pdl = exec[1] != NULL && exec[0] == NULL;
+        }
     }
     return CSINN_TRUE;
 }
@@ -633,9 +676,9 @@ int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen)
     b200_option *opt = b200_option_of(sess);
     if (!opt || !opt->g || !buf || buflen <= 0) return 0;
     b200_graph *g = opt->g;
-    int n = snprintf(buf, buflen, "steps=%d tensors=%d kernels_per_run=%d activation_arena=%zu weight_arena=%zu/%zu cuda_graph=%d\n",
+    int n = snprintf(buf, buflen, "steps=%d tensors=%d kernels_per_run=%d activation_arena=%zu weight_arena=%zu/%zu cuda_graph=%d pdl=%d\n",
                      g->ns, g->nt, g->kernels_per_run, g->arena_bytes, opt->ctx.wused, opt->ctx.wcap,
-                     g->exec != NULL);
+                     g->exec != NULL, g->pdl);
     for (int i = 0; i < g->ns && n < buflen; i++) {
         const b200_dt *o = &g->t[g->s[i].out].dt;
         n += snprintf(buf + n, buflen - n, "%3d %-28s %s -> [%d,%d,%d,%d]\n", i,

@@ -131,7 +131,6 @@ dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DwTmaArgs a)
     if (a.ep.post_lut != nullptr && tid < 256) s_lut[tid] = static_cast<uint8_t>(a.ep.post_lut[tid]);
     __syncthreads();
 
-    const uint32_t tiles = static_cast<uint32_t>(a.n) * a.ybands * a.xbands * a.cchunks;  // < 2^31, host-checked
 
     if (warp == kDwConsumers / 32) {
         // ===== TMA producer =====

@@ -34,14 +34,16 @@ void count_launch(int n)
         g_launches += n;
 }
 
-bool pdl_enabled()
-{
-    // measured on B200 (MobileNetV1 int8, batch 256, CUDA-graph replay): 0.944 ms per step with
-    // programmatic dependent launch, 0.929 ms without -- the graph already hides launch latency and
-    // early-resident CTAs only compete with the predecessor's tail -- so it is opt-in
-    static const bool on = getenv("SHL_B200_PDL") != nullptr;
-    return on;
-}
+// Programmatic dependent launch.  Measured on B200 (MobileNetV1 int8, CUDA-graph replay): at batch 1 a
+// step takes 138 us with it against 166 us without (every kernel's prologue -- barrier init, TMEM
+// allocation, weight staging -- runs under its predecessor's tail), at batch 256 0.944 ms against
+// 0.929 ms (early-resident CTAs only compete with the predecessor's last wave).  So the session
+// captures its step list both ways and keeps the faster graph (b200_opt/graph.c); SHL_B200_PDL=0/1
+// forces it.  Layer mode (one synchronous kernel per call) has nothing to overlap: off.
+static int g_pdl = 0;
+bool pdl_enabled() { return g_pdl != 0; }
+extern "C" void b200_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+extern "C" int b200_get_pdl(void) { return g_pdl; }
 
 int sm_count()
 {

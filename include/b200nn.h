@@ -104,6 +104,10 @@ int b200_event_elapsed_ms(void *start, void *stop, float *ms);
 /* make `stream` wait for an event recorded on another stream (copy/compute overlap) */
 int b200_stream_wait_event(void *stream, void *ev);
 /* CUDA-graph capture of a launch sequence (graph-mode session_run) */
+/* programmatic dependent launch for the kernels launched from now on (process-wide switch; the
+ * graph-mode session sets it around its captures, see csi-nn2_b200/csrc/runtime.cu) */
+void b200_set_pdl(int on);
+int b200_get_pdl(void);
 int b200_graph_begin(void *stream);
 int b200_graph_end(void *stream, void **graph_exec);
 int b200_graph_launch(void *graph_exec, void *stream);
