@@ -249,6 +249,8 @@ int b200_pool2d(const b200_pool_desc *d, void *stream);
 
 /* softmax over the channel axis of [rows][cp] (axis=1 of an NCHW tensor with H=W=1);
  * source/reference/softmax.c:20-66 (double exp, f32 accumulate in channel order). */
+/* test hook: the softmax denominator code alone (rows x c doubles -> rows floats), see csrc/softmax.cu */
+int b200_test_softmax_denominator(const void *e_dev, int rows, int c, void *out_dev, void *stream);
 int b200_softmax(int dtype, const void *in, void *out, int rows, int c, int cp_in, int cp_out,
                  float s_in, int zp_in, float s_out, int zp_out, void *stream);
 

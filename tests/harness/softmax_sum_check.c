@@ -33,6 +33,48 @@ static float sum_integer_form(const double *e, int n, uint32_t *d)
     return acc;
 }
 
+/* the scan form of the CUDA kernel (csrc/softmax.cu), sequentially: per binade, all remaining terms'
+ * increments, the first term at which the running integer sum leaves the binade (or that must be
+ * literal), everything before it consumed at once, that one term by the literal step */
+static float sum_scan_form(const double *e, int n_all, uint32_t *d)
+{
+    float acc = 0.f;
+    int j0 = 0;
+    while (j0 < n_all) {
+        const int n = j0 + 64 < n_all ? j0 + 64 : n_all; /* the kernel scans windows of 64 terms */
+        uint32_t bits;
+        memcpy(&bits, &acc, sizeof bits);
+        const uint32_t ex = (bits >> 23) & 0xFF;
+        if (ex == 0 || ex >= 0xFE) {
+            acc = b200_softmax_sum_literal(e + j0, 1, acc);
+            j0++;
+            continue;
+        }
+        const uint32_t a = (bits & 0x7FFFFFu) | 0x800000u;
+        const uint64_t room = (1ull << 24) - a;
+        uint64_t run = 0;
+        int p = n;
+        for (int j = j0; j < n; j++) {
+            d[j] = b200_softmax_term(e[j], (int)ex - 127);
+            const uint64_t nxt = run + ((d[j] & B200_SOFTMAX_LITERAL) ? (1ull << 40) : d[j]);
+            if (nxt >= room) {
+                p = j;
+                break;
+            }
+            run = nxt;
+        }
+        const uint32_t nb = (ex << 23) | ((a + (uint32_t)run) & 0x7FFFFFu);
+        memcpy(&acc, &nb, sizeof acc);
+        if (p >= n) {
+            j0 = n;
+            continue;
+        }
+        acc = b200_softmax_sum_literal(e + p, 1, acc);
+        j0 = p + 1;
+    }
+    return acc;
+}
+
 /* cases: how many sequences; n: terms per sequence; mode selects the distribution of the terms */
 int softmax_sum_check(int cases, int n, int mode, uint64_t seed)
 {
@@ -55,7 +97,10 @@ int softmax_sum_check(int cases, int n, int mode, uint64_t seed)
         const float want = b200_softmax_sum_literal(e, n, 0.f);
         const float got = b200_softmax_sum(e, n);
         const float got_i = sum_integer_form(e, n, d);
-        if (memcmp(&want, &got, sizeof want) != 0 || memcmp(&want, &got_i, sizeof want) != 0) bad++;
+        const float got_s = sum_scan_form(e, n, d);
+        if (memcmp(&want, &got, sizeof want) != 0 || memcmp(&want, &got_i, sizeof want) != 0 ||
+            memcmp(&want, &got_s, sizeof want) != 0)
+            bad++;
     }
     free(e);
     free(d);

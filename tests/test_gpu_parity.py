@@ -463,3 +463,47 @@ def test_dwconv_sweep_shapes(b200, oracle, rng):
         want = oracle.conv2d_i8(x, wt, b, x.shape, depthwise=True, stride=(1, 1), pad=(1,) * 4, dilation=(1, 1),
                                 group=1, s_in=0.02, zp_in=-7, s_w=s_w, s_b=None, s_out=s_out, zp_out=-4)
         assert np.array_equal(got, want), c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["softmax_like", "few_maxima", "wide_range", "ties", "tiny"])
+def test_softmax_denominator_on_the_device_equals_the_literal_loop(mode):
+    """the softmax kernel's denominator (parallel integer scan per binade of the running sum,
+    csrc/softmax.cu + softmax_sum.h) against the reference's literal `float acc += double` loop
+    (source/reference/softmax.c:53-55) evaluated in numpy: the float sums must have the same bits --
+    the int8 / fp16 outputs of the op are too coarse to show a wrong last bit of the denominator"""
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = C.CDLL(os.path.join(root, "csi-nn2_b200", "lib", "libb200nn.so"))
+    shim.b200_last_error.restype = C.c_char_p
+    rng = np.random.default_rng({"softmax_like": 1, "few_maxima": 2, "wide_range": 3, "ties": 4, "tiny": 5}[mode])
+    rows = 48
+    for c in (1, 7, 255, 256, 257, 1000, 2048):
+        u = rng.random((rows, c))
+        if mode == "softmax_like":
+            e = np.exp(-20.0 * u)
+        elif mode == "few_maxima":
+            e = np.where(rng.random((rows, c)) < 0.02, 1.0, np.exp(-40.0 * u))
+        elif mode == "wide_range":
+            e = np.ldexp(u, -(60.0 * rng.random((rows, c))).astype(np.int32))
+        elif mode == "ties":
+            e = np.ldexp((1 + (7 * u).astype(np.int64)).astype(np.float64), -24 - (3 * rng.random((rows, c))).astype(np.int32))
+        else:
+            e = np.where(rng.random((rows, c)) < 0.5, 0.0, np.ldexp(u, -140))
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        want = np.zeros(rows, np.float32)
+        for r in range(rows):
+            acc = np.float32(0)
+            for v in e[r]:
+                acc = np.float32(np.float64(acc) + v)
+            want[r] = acc
+        d_e, d_o = C.c_void_p(), C.c_void_p()
+        assert shim.b200_malloc(C.byref(d_e), C.c_size_t(e.nbytes)) == 0, shim.b200_last_error()
+        assert shim.b200_malloc(C.byref(d_o), C.c_size_t(4 * rows)) == 0, shim.b200_last_error()
+        got = np.zeros(rows, np.float32)
+        assert shim.b200_memcpy_h2d(d_e, e.ctypes.data_as(C.c_void_p), C.c_size_t(e.nbytes), None) == 0
+        assert shim.b200_test_softmax_denominator(d_e, rows, c, d_o, None) == 0, shim.b200_last_error()
+        assert shim.b200_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_o, C.c_size_t(4 * rows), None) == 0
+        assert shim.b200_stream_sync(None) == 0, shim.b200_last_error()
+        shim.b200_free(d_e), shim.b200_free(d_o)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, c, int(np.count_nonzero(got != want)))
