@@ -207,6 +207,150 @@ __global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
     }
 }
 
+
+// fp16 depthwise 3x3, stride 1 / 2, dilation 1: one thread owns FOUR channels of TWO adjacent
+// output columns and slides down a band of output rows.  Every input row is loaded once per thread
+// (4 / 5 pixels x 8 bytes), converted to f32 once, and feeds the three output rows it belongs to
+// through rotating accumulator sets (f32 accumulation like the reference, packed f32x2 FMAs), so
+// vertical taps are reused from registers and horizontal ones from the same loads -- the generic
+// kernel above reloads every tap.  Weights tap-major [9][cp] halves; bias seeds the accumulators.
+template <int S>
+__global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int band_rows, int ybands)
+{
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
+    constexpr int NX = S + 3;  // input columns per row for two output columns
+    const int quads = a.cp / 4;
+    const int xpairs = (a.ow + 1) / 2;
+    const long long total = static_cast<long long>(a.n) * ybands * xpairs * quads;
+    const __half *in = static_cast<const __half *>(a.in);
+    const __half *wt = static_cast<const __half *>(a.wt);
+    __half *out = static_cast<__half *>(a.out);
+
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cq = static_cast<int>(i % quads);
+        long long rest = i / quads;
+        const int xp = static_cast<int>(rest % xpairs);
+        rest /= xpairs;
+        const int yb = static_cast<int>(rest % ybands);
+        const int b = static_cast<int>(rest / ybands);
+        const int c0 = cq * 4;
+        const int ox0 = xp * 2;
+        const int oy0 = yb * band_rows;
+        const int rows = min(band_rows, a.oh - oy0);
+
+        // weights of the 9 taps and the bias of these four channels, as f32x2 pairs
+        uint64_t w[3][3][2], seed[2];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(wt + static_cast<size_t>(t) * a.cp + c0));
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+            w[t / 3][t % 3][0] = f2_pack(lo.x, lo.y), w[t / 3][t % 3][1] = f2_pack(hi.x, hi.y);
+        }
+        {
+            const float b0 = a.ep.badd ? __ldg(a.ep.badd + c0) : 0.f, b1 = a.ep.badd ? __ldg(a.ep.badd + c0 + 1) : 0.f;
+            const float b2 = a.ep.badd ? __ldg(a.ep.badd + c0 + 2) : 0.f, b3 = a.ep.badd ? __ldg(a.ep.badd + c0 + 3) : 0.f;
+            seed[0] = f2_pack(b0, b1), seed[1] = f2_pack(b2, b3);
+        }
+        const int ix0 = ox0 * S - a.pl;
+        const __half *img = in + (static_cast<size_t>(b) * a.h * a.w) * a.cp + c0;
+
+        // one input row: NX pixels x 4 channels -> f32x2 pairs (zero outside the image: fp16 padding is 0)
+        auto load_row = [&](int iy, uint64_t (&x)[NX][2]) {
+            const bool yok = iy >= 0 && iy < a.h;
+#pragma unroll
+            for (int p = 0; p < NX; p++) {
+                const int ix = ix0 + p;
+                uint2 raw = make_uint2(0u, 0u);
+                if (yok && ix >= 0 && ix < a.w)
+                    raw = __ldg(reinterpret_cast<const uint2 *>(img + (static_cast<size_t>(iy) * a.w + ix) * a.cp));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                x[p][0] = f2_pack(lo.x, lo.y), x[p][1] = f2_pack(hi.x, hi.y);
+            }
+        };
+        // acc[col][pair] += row (x) kernel row ky
+        auto fma_row = [&](uint64_t (&acc)[2][2], const uint64_t (&x)[NX][2], int ky) {
+#pragma unroll
+            for (int col = 0; col < 2; col++)
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) acc[col][h] = f2_fma(x[col * S + kx][h], w[ky][kx][h], acc[col][h]);
+        };
+        auto start = [&](uint64_t (&acc)[2][2], const uint64_t (&x)[NX][2]) {
+#pragma unroll
+            for (int col = 0; col < 2; col++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) acc[col][h] = seed[h];
+            fma_row(acc, x, 0);
+        };
+        int oy = oy0;
+        auto store = [&](const uint64_t (&acc)[2][2]) {
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+                if (ox0 + col < a.ow) {
+                    int b0, b1, b2, b3;
+                    f2_unpack_bits(acc[col][0], b0, b1);
+                    f2_unpack_bits(acc[col][1], b2, b3);
+                    float f0 = act_f(__int_as_float(b0), a.ep.act), f1 = act_f(__int_as_float(b1), a.ep.act);
+                    float f2 = act_f(__int_as_float(b2), a.ep.act), f3 = act_f(__int_as_float(b3), a.ep.act);
+                    f0 = c0 + 0 < a.c ? f0 : 0.f, f1 = c0 + 1 < a.c ? f1 : 0.f;
+                    f2 = c0 + 2 < a.c ? f2 : 0.f, f3 = c0 + 3 < a.c ? f3 : 0.f;
+                    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+                    *reinterpret_cast<uint2 *>(out + ((static_cast<size_t>(b) * a.oh + oy) * a.ow + ox0 + col) * a.cp + c0) =
+                        make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+                }
+            }
+            oy++;
+        };
+
+        uint64_t x[NX][2], accA[2][2], accB[2][2], accC[2][2];
+        const int iy0 = oy0 * S - a.pt;
+        if (S == 1) {
+            // input row r (image row iy0 + r) feeds output rows r (ky 0), r - 1 (ky 1), r - 2 (ky 2, completes it)
+            load_row(iy0, x);
+            start(accA, x);
+            load_row(iy0 + 1, x);
+            fma_row(accA, x, 1), start(accB, x);
+            for (int y = 0;; y += 3) {
+                load_row(iy0 + y + 2, x);
+                fma_row(accA, x, 2), fma_row(accB, x, 1), start(accC, x);
+                store(accA);
+                if (y + 1 >= rows) break;
+                load_row(iy0 + y + 3, x);
+                fma_row(accB, x, 2), fma_row(accC, x, 1), start(accA, x);
+                store(accB);
+                if (y + 2 >= rows) break;
+                load_row(iy0 + y + 4, x);
+                fma_row(accC, x, 2), fma_row(accA, x, 1), start(accB, x);
+                store(accC);
+                if (y + 3 >= rows) break;
+            }
+        } else {
+            // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
+            load_row(iy0, x);
+            start(accA, x);
+            for (int y = 0;; y += 2) {
+                load_row(iy0 + 2 * y + 1, x);
+                fma_row(accA, x, 1);
+                load_row(iy0 + 2 * y + 2, x);
+                fma_row(accA, x, 2), start(accB, x);
+                store(accA);
+                if (y + 1 >= rows) break;
+                load_row(iy0 + 2 * y + 3, x);
+                fma_row(accB, x, 1);
+                load_row(iy0 + 2 * y + 4, x);
+                fma_row(accB, x, 2), start(accA, x);
+                store(accB);
+                if (y + 2 >= rows) break;
+            }
+        }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -241,6 +385,29 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
     DwArgs a;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
     a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;
+    if (d->dtype == B200_F16 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
+        d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2) && !getenv("SHL_B200_DW_GENERIC")) {
+        // register-sliding fp16 3x3: bands of output rows per thread, enough threads for ~8 waves
+        a.pt = d->pad_top, a.pl = d->pad_left, a.dh = 1, a.dw = 1;
+        a.in = d->in, a.wt = d->wt, a.out = d->out, a.zp_in = 0;
+        a.ep = make_epi(d->ep);
+        const long long cols = static_cast<long long>(d->n) * ((d->ow + 1) / 2) * (d->cp / 4);
+        int ybands = 1;
+        while (ybands < d->oh && cols * ybands < static_cast<long long>(sm_count()) * 128 * 16 && d->oh / (ybands * 2) >= 4)
+            ybands *= 2;
+        const int band_rows = (d->oh + ybands - 1) / ybands;
+        ybands = (d->oh + band_rows - 1) / band_rows;
+        const long long total = cols * ybands;
+        long long g = (total + 127) / 128;
+        const long long cap = static_cast<long long>(sm_count()) * 32;
+        const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+        if (d->stride_h == 1)
+            launch_kernel(dwconv3x3_f16_kernel<1>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a, band_rows, ybands);
+        else
+            launch_kernel(dwconv3x3_f16_kernel<2>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a, band_rows, ybands);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+    }
     a.pt = d->pad_top, a.pl = d->pad_left, a.dh = d->dil_h, a.dw = d->dil_w;
     a.in = d->in, a.wt = d->wt, a.out = d->out, a.zp_in = d->zp_in;
     a.ep = make_epi(d->ep);

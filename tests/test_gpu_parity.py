@@ -298,7 +298,10 @@ def test_golden_vectors_of_the_reference(golden, b200):
 
 
 F16_CASES = [(1, 64, 8, 16, 64, 1, 1, 0, False), (1, 512, 9, 9, 200, 1, 1, 0, False), (1, 3, 32, 32, 32, 3, 2, 1, False),
-             (2, 48, 14, 14, 56, 3, 1, 1, False), (1, 32, 14, 14, 32, 3, 1, 1, True), (1, 128, 15, 15, 128, 3, 2, 1, True)]
+             (2, 48, 14, 14, 56, 3, 1, 1, False), (1, 32, 14, 14, 32, 3, 1, 1, True), (1, 128, 15, 15, 128, 3, 2, 1, True),
+             # register-sliding fp16 depthwise 3x3: odd widths, several row bands, ragged channels, no padding
+             (3, 24, 57, 31, 24, 3, 1, 1, True), (2, 40, 112, 112, 40, 3, 2, 1, True), (1, 1024, 7, 7, 1024, 3, 1, 1, True),
+             (2, 16, 9, 10, 16, 3, 1, 0, True), (1, 72, 33, 18, 72, 3, 2, 0, True), (1, 8, 1, 1, 8, 3, 1, 1, True)]
 
 
 @pytest.mark.parametrize("case", F16_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_dw%d" % c)
