@@ -300,7 +300,8 @@ static void fill_epilogue(const b200_op *op, b200_epilogue *ep)
  * direct dp4a kernel (csrc/conv_direct.cu) */
 static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
 {
-    return in0->is_nchw && op->dtype == B200_I8 && op->group == 1 && op->kdim <= 160 && op->o <= 256 &&
+    return in0->is_nchw && op->group == 1 && op->kdim <= 160 &&
+           ((op->dtype == B200_I8 && op->o <= 256) || (op->dtype == B200_F16 && op->o <= 64)) &&
            !getenv("SHL_B200_NO_DIRECT_CONV");
 }
 
@@ -316,7 +317,7 @@ static int conv_stem_on_tc(const b200_op *op, const b200_dt *in0)
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
 {
     if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0))
-        return conv_stem_on_tc(op, in0) ? "b200_conv2d_stem_tcgen05" : "b200_conv2d_direct";
+        return (op->dtype == B200_I8 && conv_stem_on_tc(op, in0)) ? "b200_conv2d_stem_tcgen05" : "b200_conv2d_direct";
     return op->kname;
 }
 
@@ -338,9 +339,12 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
         c.o = op->o, c.oh = out->h, c.ow = out->w, c.cp_out = out->cp;
         c.kh = op->kh, c.kw = op->kw, c.stride_h = op->sh, c.stride_w = op->sw;
         c.pad_top = op->pt, c.pad_left = op->pl, c.dil_h = op->dh, c.dil_w = op->dw;
-        c.ldw = op->ldk, c.in = in->d, c.wt = op->d_w, c.out = out->d, c.zp_in = op->zp_in;
+        c.ldw = op->ldk * op->eb, c.in = in->d, c.wt = op->d_w, c.out = out->d, c.zp_in = op->zp_in;
         fill_epilogue(op, &c.ep);
-        DEV_CHECK(b200_conv2d_direct(&c, stream));
+        if (op->dtype == B200_F16)
+            DEV_CHECK(b200_conv2d_direct_f16(&c, stream));
+        else
+            DEV_CHECK(b200_conv2d_direct(&c, stream));
         return CSINN_TRUE;
     }
     b200_gemm_desc g;

@@ -196,6 +196,8 @@ typedef struct {
     b200_epilogue ep;
 } b200_conv_direct_desc;
 int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream);
+/* fp16 twin (same descriptor; f32 accumulation; C*kh*kw <= 160, O <= 64) */
+int b200_conv2d_direct_f16(const b200_conv_direct_desc *d, void *stream);
 
 /* ---- depthwise conv2d (HBM-bound stencil) ------------------------------------ */
 /* Replaces shl_rvv_dwconv3x3s1_int8 / s2 (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31 )
