@@ -315,7 +315,84 @@ static int run_steps(b200_graph *g, void *stream)
     return CSINN_TRUE;
 }
 
+/* The HHB on-disk format (rank 3 of SURVEY.md 8f): what shl_gref_session_setup writes for
+ * sess->model.save_mode == CSINN_SAVE_AND_RUN / CSINN_SAVE_ONLY (source/graph_ref/setup.c:733-855),
+ * without sub-graphs -- header, section table at 4096, graph structure at 8192, session info after
+ * it -- through the reference's own serialisers (source/nn2/format.c, compiled as they are).  The
+ * b200 backend never rewrites host weights, so the file holds the model as the user built it. */
+static int save_binary_model(struct csinn_session *sess, struct shl_ref_graph *graph)
+{
+    const char *path = sess->model.bm_path ? sess->model.bm_path : "shl.hhb.bm";
+    FILE *b = fopen(path, "wb");
+    if (!b) {
+        b200_fail("binary model: cannot open '%s' for writing", path);
+        return CSINN_FALSE;
+    }
+    shl_dump_bm_header(b);
+    struct shl_binary_model_section_info *sinfo = shl_mem_alloc(sizeof(*sinfo));
+    long off = 8192;
+    fseek(b, off, SEEK_SET);
+    const int gsize = shl_dump_bm_graph_struct_section(b, graph);
+    sinfo->sections[0].graph_offset = off / 4096;
+    sinfo->sections[0].graph_size = gsize;
+    off = (off + gsize + 4095) / 4096 * 4096;
+    fseek(b, off, SEEK_SET);
+    const int isize = shl_dump_bm_graph_info_section(b, sess);
+    sinfo->sections[0].info_offset = off / 4096;
+    sinfo->sections[0].info_size = isize;
+    sinfo->section_num = 2;
+    fseek(b, 4096, SEEK_SET);
+    shl_dump_bm_section_info(b, sinfo);
+    fclose(b);
+    shl_mem_free(sinfo);
+    return CSINN_TRUE;
+}
+
+static int build_from_graph(struct csinn_session *sess);
+
 int shl_b200_session_setup(struct csinn_session *sess)
+{
+    if (build_from_graph(sess) != CSINN_TRUE) return CSINN_FALSE;
+    if (sess->model.save_mode == CSINN_SAVE_AND_RUN || sess->model.save_mode == CSINN_SAVE_ONLY)
+        return save_binary_model(sess, shl_gref_get_graph(sess));
+    return CSINN_TRUE;
+}
+
+/* csinn_load_binary_model (source/nn2/setup.c:546) for a session restored by
+ * csinn_import_binary_model (source/nn2/format.c:1304): rebuild the graph from the blob (cf.
+ * shl_gref_load_binary_model, source/graph_ref/setup.c:929, and shl_c920_load_binary_model,
+ * source/c920_opt/setup.c:300), hand its nodes to this session and set it up like a recorded one.
+ * Models saved for any of the api ids this backend registers under (RVV, C906, C908, C920, C920V2)
+ * load here; the blob must stay alive and writable (the loader fixes its offsets up in place). */
+int shl_b200_load_binary_model(struct csinn_session *sess)
+{
+    char *bm_base = sess->model.bm_addr;
+    if (!bm_base || !sess->td) {
+        b200_fail("load_binary_model: no model address / session not initialised");
+        return CSINN_FALSE;
+    }
+    struct shl_binary_model_section_info *sinfo = (struct shl_binary_model_section_info *)(bm_base + 4096);
+    if (sinfo->section_num != 2) {
+        b200_fail("load_binary_model: %d sections -- models with sub-graphs (NPU partitions) are not supported",
+                  sinfo->section_num);
+        return CSINN_FALSE;
+    }
+    struct shl_ref_graph *graph = shl_mem_alloc(sizeof(*graph));
+    shl_bm_graph_struct_load(graph, (struct shl_ref_graph *)(bm_base + sinfo->sections[0].graph_offset * 4096));
+    struct shl_gref_target_data *td = sess->td;
+    td->graph = graph;
+    for (int i = 0; i < graph->layer_index; i++) {
+        struct shl_node *n = graph->layer[i];
+        if (n->type < 0 || n->type >= CSINN_OP_SIZE || !n->data) {
+            b200_fail("load_binary_model: layer %d has node type %d", i, n->type);
+            return CSINN_FALSE;
+        }
+        ((struct csinn_params_base *)n->data)->sess = sess;
+    }
+    return build_from_graph(sess);
+}
+
+static int build_from_graph(struct csinn_session *sess)
 {
     b200_option *opt = b200_option_of(sess);
     struct shl_ref_graph *graph = shl_gref_get_graph(sess);

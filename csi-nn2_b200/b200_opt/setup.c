@@ -95,6 +95,8 @@ void *shl_b200_runtime_callback(int api)
             return shl_b200_session_run;
         case CSINN_UPDATE_INPUT:
             return shl_b200_update_input;
+        case CSINN_LOAD_BG:
+            return shl_b200_load_binary_model;
         case CSINN_UPDATE_OUTPUT:
         case CSINN_SET_INPUT_NUMBER:
         case CSINN_SET_OUTPUT_NUMBER:

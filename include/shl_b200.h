@@ -104,6 +104,11 @@ void shl_b200_session_init(struct csinn_session *sess);
 void shl_b200_session_deinit(struct csinn_session *sess);
 int shl_b200_session_setup(struct csinn_session *sess);
 int shl_b200_session_run(struct csinn_session *sess);
+/* CSINN_LOAD_BG: the HHB binary model format (csinn_import_binary_model / csinn_load_binary_model,
+ * source/nn2/format.c:1304, source/nn2/setup.c:546; cf. shl_gref_load_binary_model,
+ * source/graph_ref/setup.c:929).  session_setup writes the same format when
+ * sess->model.save_mode asks for it (source/graph_ref/setup.c:733-855). */
+int shl_b200_load_binary_model(struct csinn_session *sess);
 
 /* ---- b200-specific session controls (additions; everything above is the reference's API) - */
 /* device ordinal for sessions created afterwards (default: $LOCAL_RANK, else 0) */

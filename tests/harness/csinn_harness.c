@@ -282,6 +282,11 @@ static int layer_call(h_net *net, int i)
 
 void h_net_destroy(void *handle);
 
+/* the next graph-mode h_net_create saves the model in the HHB binary format at session_setup
+ * (sess->model.save_mode = CSINN_SAVE_AND_RUN, as a model.c generated with `--save` would) */
+static char g_save_path[512];
+void h_set_save_path(const char *path) { snprintf(g_save_path, sizeof(g_save_path), "%s", path ? path : ""); }
+
 void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int in_rank, float s_in,
                    int zp_in, const h_layer *layers, int n)
 {
@@ -377,6 +382,11 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
             }
         }
         csinn_set_output(0, net->t[n], sess);
+        if (g_save_path[0]) {
+            sess->model.save_mode = CSINN_SAVE_AND_RUN;
+            sess->model.bm_path = strdup(g_save_path);
+            g_save_path[0] = 0;
+        }
         int rc = csinn_session_setup(sess);
         net->setup_done = 1;
         /* the reference's own session_setup hooks return void (graph_ref/setup.c:688), so only a
@@ -394,6 +404,29 @@ long long h_net_output_bytes(void *handle)
 {
     h_net *net = handle;
     return tsize(net->t[net->n]) * elem_bytes(net->dtype);
+}
+
+/* a session restored from the HHB binary format, as an HHB-generated main would do it:
+ * csinn_import_binary_model(blob) and then update_input / session_run / get_output.  The blob is
+ * copied (the loader fixes offsets up in place and the session keeps pointing into it). */
+void *h_net_import(const void *blob, long long size)
+{
+    g_err[0] = 0;
+    char *copy = malloc((size_t)size);
+    memcpy(copy, blob, (size_t)size);
+    const int errs0 = BACKEND_ERRORS();
+    struct csinn_session *sess = csinn_import_binary_model(copy);
+    if (!sess || BACKEND_ERRORS() != errs0) {
+        set_err("csinn_import_binary_model failed");
+        return NULL;
+    }
+    h_net *net = calloc(1, sizeof(*net));
+    net->api = sess->base_api, net->dtype = sess->base_dtype, net->run_mode = sess->base_run_mode, net->n = 0;
+    net->sess = sess;
+    net->t = calloc(1, sizeof(void *));
+    net->t[0] = sess->output[0]; /* h_net_output_bytes: dims of the graph output */
+    net->setup_done = 1;
+    return net;
 }
 
 void *h_net_session(void *handle) { return ((h_net *)handle)->sess; }

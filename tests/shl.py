@@ -114,6 +114,9 @@ class Harness:
         L.h_net_get_output.restype = C.c_void_p
         L.h_net_get_output.argtypes = [C.c_void_p]
         L.h_last_error.restype = C.c_char_p
+        L.h_set_save_path.argtypes = [C.c_char_p]
+        L.h_net_import.restype = C.c_void_p
+        L.h_net_import.argtypes = [C.c_void_p, C.c_longlong]
         assert L.h_layer_sizeof() == C.sizeof(HLayer), "h_layer layout mismatch"
         self.default_api = API_RVV if which == "b200" else API_REF
 
@@ -132,12 +135,47 @@ class Harness:
                run_mode=RM_LAYER, api: Optional[int] = None) -> "Net":
         return Net(self, dtype, in_shape, layers, s_in, zp_in, run_mode, self.default_api if api is None else api)
 
+    def save_next(self, path: str) -> None:
+        """the next graph-mode network writes itself in the HHB binary model format at session_setup
+        (sess->model.save_mode = CSINN_SAVE_AND_RUN, sess->model.bm_path = path)"""
+        self.lib.h_set_save_path(path.encode())
+
+    def import_model(self, blob: bytes, dtype: int, in_shape: Sequence[int], out_shape: Sequence[int]) -> "ImportedNet":
+        """csinn_import_binary_model on a copy of `blob` (the file written through save_next)"""
+        return ImportedNet(self, blob, dtype, in_shape, out_shape)
+
     def run(self, dtype, in_shape, layers, x, **kw) -> np.ndarray:
         net = self.create(dtype, in_shape, layers, **kw)
         try:
             return net(x)
         finally:
             net.close()
+
+
+class ImportedNet:
+    """a session restored from the binary model format; run like a graph-mode Net"""
+
+    def __init__(self, h: Harness, blob: bytes, dtype, in_shape, out_shape):
+        self.h, self.dtype = h, dtype
+        self.in_shape, self.out_shape = tuple(int(d) for d in in_shape), tuple(int(d) for d in out_shape)
+        buf = C.create_string_buffer(blob, len(blob))
+        self.handle = h.lib.h_net_import(buf, len(blob))
+        if not self.handle:
+            raise RuntimeError(f"[{h.which}] model import failed: {h.error()}")
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=_np_dtype(self.dtype))
+        assert x.shape == self.in_shape, (x.shape, self.in_shape)
+        out = np.empty(self.out_shape, dtype=_np_dtype(self.dtype))
+        assert out.nbytes == self.h.lib.h_net_output_bytes(self.handle), (out.nbytes, self.h.lib.h_net_output_bytes(self.handle))
+        if self.h.lib.h_net_run(self.handle, _ptr(x), _ptr(out)) != 0:
+            raise RuntimeError(f"[{self.h.which}] run failed: {self.h.error()}")
+        return out
+
+    def close(self):
+        if self.handle:
+            self.h.lib.h_net_destroy(self.handle)
+            self.handle = None
 
 
 class Net:

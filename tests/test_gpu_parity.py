@@ -536,3 +536,33 @@ def test_softmax_denominator_on_the_device_equals_the_literal_loop(mode):
         assert shim.b200_stream_sync(None) == 0, shim.b200_last_error()
         shim.b200_free(d_e), shim.b200_free(d_o)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, c, int(np.count_nonzero(got != want)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [DT_INT8, DT_F16], ids=["int8", "fp16"])
+def test_binary_model_saved_and_restored_on_b200(dtype, b200, tmp_path):
+    """HHB binary model format: a graph-mode MobileNetV1 (narrow, 64x64) built
+    through the API under the C920 id with save_mode = CSINN_SAVE_AND_RUN writes itself at
+    session_setup (b200_opt/graph.c, the reference's own serialisers); csinn_import_binary_model +
+    csinn_load_binary_model (CSINN_LOAD_BG -> shl_b200_load_binary_model) restore it into a fresh
+    session whose outputs are the same bytes; the restored int8 model also equals the oracle chain"""
+    nb = nets.mobilenet_v1(dtype, batch=2, res=64, width=0.25, classes=40)
+    x = nb.input_batch()
+    path = str(tmp_path / "b200_model.bm")
+    b200.save_next(path)
+    net = b200.create(dtype, nb.in_shape, nb.layers, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH, api=API_C920)
+    try:
+        want = net(x)
+    finally:
+        net.close()
+    blob = open(path, "rb").read()
+    assert len(blob) > 8192
+    restored = b200.import_model(blob, dtype, nb.in_shape, want.shape)
+    try:
+        got = restored(x)
+        again = restored(x)
+    finally:
+        restored.close()
+    assert np.array_equal(got, want) and np.array_equal(again, want)
+    if dtype == DT_INT8:
+        assert np.array_equal(got.reshape(2, -1), nets.oracle_forward(nb, x).reshape(2, -1))

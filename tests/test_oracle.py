@@ -254,3 +254,23 @@ def test_softmax_denominator_code_matches_the_literal_loop():
     for mode in range(5):
         for n in (1, 7, 8, 9, 1000, 1001, 4096):
             assert lib.softmax_sum_check(400, n, mode, 99 + 31 * mode + n) == 0, (mode, n)
+
+
+def test_binary_model_round_trip_through_the_reference(ref, rng, tmp_path):
+    """the HHB binary model format through the reference's own library (source/graph_ref/setup.c:733,
+    :929): a graph-mode network saved at session_setup and restored by csinn_import_binary_model gives
+    the same outputs -- pins the harness path the b200 save / load tests use"""
+    from shl import H_RELU, RM_GRAPH
+    n, c, h, w, o = 1, 8, 6, 6, 12
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 3, 3)
+    layers = [Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=2, w=wt, b=b, s_w=s_w, pad=(1,) * 4),
+              Layer(H_RELU, (n, o, h, w), s_out=s_out / 2, zp_out=-128)]
+    path = str(tmp_path / "ref_model.bm")
+    ref.save_next(path)
+    want = ref.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=-3, run_mode=RM_GRAPH)
+    blob = open(path, "rb").read()
+    assert len(blob) > 8192
+    net = ref.import_model(blob, DT_INT8, x.shape, (n, o, h, w))
+    got = net(x)
+    assert np.array_equal(got, want)
