@@ -82,6 +82,7 @@ typedef struct b200_op {
     int32_t *d_ibias;
     int8_t *d_lut; /* post table or the ACT table */
     int zp_in, zp_out, act, q6;
+    float act_p0, act_p1; /* parameters of a unary op (leaky slope; clip min, max) */
     /* the output qinfo the epilogue quantises to (needed when a relu is fused later) */
     float s_out;
     /* eltwise / pool / softmax */
@@ -104,7 +105,7 @@ int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_
                 void *scratch, void *stream);
 /* fuse a following relu / relu6 node (with its own qinfo) into this op's epilogue */
 int b200_op_can_fuse_act(const b200_op *op);
-int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
+int b200_op_fuse_act(b200_op *op, int act, float p0, float p1, const struct csinn_tensor *act_in,
                      const struct csinn_tensor *act_out);
 
 /* quant.c */

@@ -175,7 +175,31 @@ static int tensor_add(b200_graph *g, struct shl_node *n)
     return g->nt++;
 }
 
-static int is_act_node(const struct shl_node *n) { return n->type == CSINN_OP_RELU || n->type == CSINN_OP_RELU6; }
+/* unary nodes that can ride in their producer's epilogue (int8: as the post table; fp16: relu / relu6 only) */
+static int is_act_node(const struct shl_node *n)
+{
+    return n->type == CSINN_OP_RELU || n->type == CSINN_OP_RELU6 || n->type == CSINN_OP_LEAKY_RELU ||
+           n->type == CSINN_OP_SIGMOID || n->type == CSINN_OP_CLIP;
+}
+static int act_of_node(const struct shl_node *n, float *p0, float *p1)
+{
+    *p0 = *p1 = 0.f;
+    switch (n->type) {
+        case CSINN_OP_RELU:
+            return B200_ACT_RELU;
+        case CSINN_OP_RELU6:
+            return B200_ACT_RELU6;
+        case CSINN_OP_LEAKY_RELU:
+            *p0 = ((struct csinn_relu_params *)n->data)->n;
+            return B200_ACT_LEAKY_RELU;
+        case CSINN_OP_SIGMOID:
+            return B200_ACT_SIGMOID;
+        default:
+            *p0 = ((struct csinn_clip_params *)n->data)->min_value;
+            *p1 = ((struct csinn_clip_params *)n->data)->max_value;
+            return B200_ACT_CLIP;
+    }
+}
 
 /* number of layer nodes that read tensor node `tn` */
 static int consumers(struct shl_ref_graph *graph, struct shl_node *tn, struct shl_node **only)
@@ -453,8 +477,9 @@ static int build_from_graph(struct csinn_session *sess)
         if (b200_op_can_fuse_act(op) && !is_graph_output(graph, out_tn)) {
             struct shl_node *next = NULL;
             if (consumers(graph, out_tn, &next) == 1 && next && is_act_node(next) && next->in[0] == out_tn) {
-                const int act = next->type == CSINN_OP_RELU ? B200_ACT_RELU : B200_ACT_RELU6;
-                if (b200_op_fuse_act(op, act, next->in[0]->data, next->out[0]->data) == CSINN_TRUE) {
+                float p0, p1;
+                const int act = act_of_node(next, &p0, &p1);
+                if (b200_op_fuse_act(op, act, p0, p1, next->in[0]->data, next->out[0]->data) == CSINN_TRUE) {
                     for (int k = i + 1; k < graph->layer_index; k++)
                         if (graph->layer[k] == next) skip[k] = 1;
                     out_tn = next->out[0];

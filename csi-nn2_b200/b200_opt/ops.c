@@ -412,8 +412,10 @@ int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_
         case B200_OPK_ACT:
             if (op->dtype == B200_I8)
                 DEV_CHECK(b200_lut_i8(in0->d, out->d, b200_dt_bytes(out), op->d_lut, stream));
-            else
+            else if (op->act == B200_ACT_RELU || op->act == B200_ACT_RELU6)
                 DEV_CHECK(b200_relu_f16(in0->d, out->d, b200_dt_bytes(out) / 2, op->act, stream));
+            else
+                DEV_CHECK(b200_unary_f16(in0->d, out->d, b200_dt_bytes(out) / 2, op->act, op->act_p0, op->act_p1, stream));
             return CSINN_TRUE;
         case B200_OPK_ADD:
             DEV_CHECK(b200_add(op->dtype, in0->d, in1->d, out->d, b200_dt_bytes(out) / op->eb,
@@ -458,25 +460,26 @@ int b200_op_can_fuse_act(const b200_op *op)
            op->d_lut == NULL;
 }
 
-static int8_t *upload_lut(b200_ctx *ctx, int act, float s_in, int zp_in, float s_out, int zp_out)
+static int8_t *upload_lut(b200_ctx *ctx, int act, float p0, float p1, float s_in, int zp_in, float s_out, int zp_out)
 {
     int8_t lut[256];
-    b200_build_requant_lut(lut, act, s_in, zp_in, s_out, zp_out);
+    b200_build_unary_lut(lut, act, p0, p1, s_in, zp_in, s_out, zp_out);
     return b200_warena_put(ctx, lut, 256);
 }
 
-int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
+int b200_op_fuse_act(b200_op *op, int act, float p0, float p1, const struct csinn_tensor *act_in,
                      const struct csinn_tensor *act_out)
 {
     if (op->dtype == B200_F16) {
-        /* relu on top of an already fused relu6 etc. is not produced by the planner */
-        if (op->act != B200_ACT_NONE) return CSINN_FALSE;
+        /* relu on top of an already fused relu6 etc. is not produced by the planner; the fp16
+         * epilogues know relu / relu6 only (leaky relu, sigmoid, clip stay separate steps) */
+        if (op->act != B200_ACT_NONE || (act != B200_ACT_RELU && act != B200_ACT_RELU6)) return CSINN_FALSE;
         op->act = act;
         return CSINN_TRUE;
     }
     /* a relu / relu6 node that keeps its producer's qinfo is exactly the in-domain clamp the
      * epilogue already knows (max(q, zp), min(q, q6)): compare the tables and skip the lookup */
-    if (op->act == B200_ACT_NONE && op->kind != B200_OPK_ADD) {
+    if (op->act == B200_ACT_NONE && op->kind != B200_OPK_ADD && (act == B200_ACT_RELU || act == B200_ACT_RELU6)) {
         int8_t lut[256];
         b200_build_requant_lut(lut, act, act_in->qinfo->scale, act_in->qinfo->zero_point, act_out->qinfo->scale,
                                act_out->qinfo->zero_point);
@@ -491,7 +494,7 @@ int b200_op_fuse_act(b200_op *op, int act, const struct csinn_tensor *act_in,
             return CSINN_TRUE;
         }
     }
-    op->d_lut = upload_lut(op->ctx, act, act_in->qinfo->scale, act_in->qinfo->zero_point,
+    op->d_lut = upload_lut(op->ctx, act, p0, p1, act_in->qinfo->scale, act_in->qinfo->zero_point,
                            act_out->qinfo->scale, act_out->qinfo->zero_point);
     return op->d_lut ? CSINN_TRUE : CSINN_FALSE;
 }
@@ -736,19 +739,22 @@ int shl_b200_fullyconnected(struct csinn_tensor *input, struct csinn_tensor *out
 }
 
 /* ---- relu / relu6 -------------------------------------------------------------------------------- */
-static int act_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params, int act)
+static const char *const kActNames[] = {"b200_identity", "b200_relu", "b200_relu6", "b200_leaky_relu", "b200_sigmoid",
+                                        "b200_clip"};
+
+static int act_init_p(struct csinn_tensor *input, struct csinn_tensor *output, void *params, int act, float p0, float p1)
 {
     struct csinn_params_base *base = params;
-    b200_op *op = op_new(base, B200_OPK_ACT, input->dtype, act == B200_ACT_RELU ? "b200_relu" : "b200_relu6");
+    b200_op *op = op_new(base, B200_OPK_ACT, input->dtype, kActNames[act]);
     if (!op) return CSINN_FALSE;
-    op->act = act;
+    op->act = act, op->act_p0 = p0, op->act_p1 = p1;
     if (op->dtype == B200_I8) {
         if (!input->qinfo || !output->qinfo) {
             b200_fail("relu: int8 tensors without qinfo");
             free(op);
             return CSINN_FALSE;
         }
-        op->d_lut = upload_lut(op->ctx, act, input->qinfo->scale, input->qinfo->zero_point,
+        op->d_lut = upload_lut(op->ctx, act, p0, p1, input->qinfo->scale, input->qinfo->zero_point,
                                output->qinfo->scale, output->qinfo->zero_point);
         if (!op->d_lut) {
             free(op);
@@ -759,6 +765,28 @@ static int act_init(struct csinn_tensor *input, struct csinn_tensor *output, voi
     base->cb->exec = (int (*)())shl_b200_relu;
     return CSINN_TRUE;
 }
+static int act_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params, int act)
+{
+    return act_init_p(input, output, params, act, 0.f, 0.f);
+}
+/* leaky relu / sigmoid / clip: replace shl_rvv_leaky_relu_int8, shl_rvv_sigmoid_*, shl_rvv_clip_int8
+ * (source/thead_rvv/setup.c:154-508 registrations); semantics source/reference/leaky_relu.c:33,
+ * sigmoid.c:33, clip.c:32-38 through shl_ref_siso_callback_base */
+static int leaky_relu_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_relu_params *params)
+{
+    return act_init_p(input, output, params, B200_ACT_LEAKY_RELU, params->n, 0.f);
+}
+static int sigmoid_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_sigmoid_params *params)
+{
+    return act_init_p(input, output, params, B200_ACT_SIGMOID, 0.f, 0.f);
+}
+static int clip_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_clip_params *params)
+{
+    return act_init_p(input, output, params, B200_ACT_CLIP, params->min_value, params->max_value);
+}
+void *shl_b200_leaky_relu_init_fn(void) { return (void *)leaky_relu_init; }
+void *shl_b200_sigmoid_init_fn(void) { return (void *)sigmoid_init; }
+void *shl_b200_clip_init_fn(void) { return (void *)clip_init; }
 int shl_b200_relu_init(struct csinn_tensor *input, struct csinn_tensor *output,
                        struct csinn_relu_params *params)
 {

@@ -71,6 +71,9 @@ static void build_table(void)
         reg_op(dt, CSINN_OP_FULLYCONNECTED, shl_b200_fullyconnected_init, shl_b200_fullyconnected, shl_gref_fullyconnected, shl_b200_perf);
         reg_op(dt, CSINN_OP_RELU, shl_b200_relu_init, shl_b200_relu, shl_gref_relu, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_RELU6, shl_b200_relu6_init_fn(), shl_b200_relu, shl_gref_relu6, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_LEAKY_RELU, shl_b200_leaky_relu_init_fn(), shl_b200_relu, shl_gref_leaky_relu, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_SIGMOID, shl_b200_sigmoid_init_fn(), shl_b200_relu, shl_gref_sigmoid, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_CLIP, shl_b200_clip_init_fn(), shl_b200_relu, shl_gref_clip, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_ADD, shl_b200_add_init, shl_b200_add, shl_gref_add, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_MAXPOOL2D, shl_b200_pool2d_init, shl_b200_pool2d, shl_gref_maxpool2d, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_AVGPOOL2D, shl_b200_avgpool_init_fn(), shl_b200_pool2d, shl_gref_avgpool2d, shl_b200_perf_siso);

@@ -57,6 +57,36 @@ __global__ void __launch_bounds__(256) relu_f16_kernel(const uint4 *__restrict__
     }
 }
 
+// the unary ops without a packed-half form: f32 arithmetic on the converted value (what the
+// reference's fp16 path does: convert, f32 op, convert back -- utils.c:609)
+__global__ void __launch_bounds__(256) unary_f16_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                        long long nvec, int act, float p0, float p1)
+{
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        uint4 v = __ldg(in + i);
+        __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float2 f = __half22float2(h[q]);
+            float *x = &f.x;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float r = x[e];
+                if (act == B200_ACT_LEAKY_RELU) r = r > 0.f ? r : r * p0;
+                else if (act == B200_ACT_SIGMOID) r = static_cast<float>(1.0 / (1.0 + exp(-static_cast<double>(r))));
+                else if (act == B200_ACT_CLIP) r = r < p0 ? p0 : (r > p1 ? p1 : r);
+                else r = act_f(r, act);
+                x[e] = r;
+            }
+            h[q] = __floats2half2_rn(f.x, f.y);
+        }
+        out[i] = v;
+    }
+}
+
 struct AddArgs {
     float s_a, s_b, s_out;
     int zp_a, zp_b, zp_out, act;
@@ -157,6 +187,19 @@ extern "C" int b200_relu_f16(const void *in, void *out, size_t count, int act, v
     const long long nvec = static_cast<long long>(count / 8);
     launch_kernel(relu_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
         static_cast<const uint4 *>(in), static_cast<uint4 *>(out), nvec, act);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_unary_f16(const void *in, void *out, size_t count, int act, float p0, float p1, void *stream)
+{
+    if (!in || !out || count == 0 || count % 8 || !aligned16(in) || !aligned16(out)) {
+        set_error("b200_unary_f16: bad arguments (count=%zu must be a non-zero multiple of 8)", count);
+        return B200_ERR_ARG;
+    }
+    const long long nvec = static_cast<long long>(count / 8);
+    launch_kernel(unary_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream,
+                  static_cast<const uint4 *>(in), static_cast<uint4 *>(out), nvec, act, p0, p1);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

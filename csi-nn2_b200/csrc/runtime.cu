@@ -342,18 +342,41 @@ int b200_flush_l2(void *stream)
 // Host-side table for the `post` stage of the epilogue and for standalone relu / relu6
 // nodes: the reference's float sequence (source/reference/utils.c:609, relu.c:20,
 // relu6.c:20, source/nn2/utils.c:550) evaluated once per possible int8 input.
-void b200_build_requant_lut(int8_t lut[256], int act, float s_in, int zp_in, float s_out,
-                            int zp_out)
+void b200_build_unary_lut(int8_t lut[256], int act, float p0, float p1, float s_in, int zp_in, float s_out, int zp_out)
 {
     for (int q = -128; q < 128; q++) {
         volatile float d = (float)q - (float)zp_in;
         volatile float r = d * s_in;
-        if (act != B200_ACT_NONE) r = r > 0 ? r : 0;
-        if (act == B200_ACT_RELU6) r = (float)fmin(r, 6);
+        switch (act) {
+            case B200_ACT_RELU:
+                r = r > 0 ? r : 0;
+                break;
+            case B200_ACT_RELU6:
+                r = r > 0 ? r : 0;
+                r = (float)fmin(r, 6);
+                break;
+            case B200_ACT_LEAKY_RELU: /* val > 0 ? val : val * n */
+                r = r > 0 ? r : r * p0;
+                break;
+            case B200_ACT_SIGMOID: /* 1.0f / (1.0f + exp(-val)): exp and the division in double, stored to float */
+                r = (float)(1.0f / (1.0f + exp(-(double)r)));
+                break;
+            case B200_ACT_CLIP:
+                r = r < p0 ? p0 : (r > p1 ? p1 : r);
+                break;
+            default:
+                break;
+        }
         volatile float t = r / s_out;
         float v = (float)(nearbyint((double)t) + (double)zp_out);
         lut[q + 128] = v > 127 ? 127 : (v < -128 ? -128 : (int8_t)v);
     }
+}
+
+void b200_build_requant_lut(int8_t lut[256], int act, float s_in, int zp_in, float s_out,
+                            int zp_out)
+{
+    b200_build_unary_lut(lut, act, 0.f, 0.f, s_in, zp_in, s_out, zp_out);
 }
 
 }  // extern "C"

@@ -59,7 +59,16 @@ typedef enum {
 } b200_status;
 
 typedef enum { B200_I8 = 0, B200_F16 = 1 } b200_dtype;
-typedef enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_RELU6 = 2 } b200_act;
+typedef enum {
+    B200_ACT_NONE = 0,
+    B200_ACT_RELU = 1,
+    B200_ACT_RELU6 = 2,
+    /* unary ops that exist only as tables (int8) or in the fp16 elementwise kernel -- never as an
+     * in-epilogue clamp: source/reference/leaky_relu.c:33, sigmoid.c:33, clip.c:32-38 */
+    B200_ACT_LEAKY_RELU = 3, /* p0 = negative slope */
+    B200_ACT_SIGMOID = 4,
+    B200_ACT_CLIP = 5        /* p0 = min, p1 = max */
+} b200_act;
 
 /* Requantisation / epilogue parameters shared by conv, depthwise, fc.
  * For B200_F16 only `badd` (bias as float, may be NULL) and `act` are used. */
@@ -125,6 +134,9 @@ static inline int b200_round_channels(int c, int elem_bytes)
 }
 
 /* host helper: the 256-entry requantisation table described above (index = q + 128) */
+/* the reference's dequant -> f32 unary op -> requant (shl_ref_siso_callback_base, source/reference/utils.c:609)
+ * as a function of the int8 input, evaluated on the host with the same float / libm sequence */
+void b200_build_unary_lut(int8_t lut[256], int act, float p0, float p1, float s_in, int zp_in, float s_out, int zp_out);
 void b200_build_requant_lut(int8_t lut[256], int act, float s_in, int zp_in, float s_out,
                             int zp_out);
 
@@ -224,6 +236,8 @@ int b200_dwconv2d(const b200_dwconv_desc *d, void *stream);
  * qinfo (source/reference/relu.c:39, relu6.c:42); count % 16 == 0 on pixel-major tensors. */
 int b200_lut_i8(const void *in, void *out, size_t count, const int8_t *lut_dev, void *stream);
 /* fp16 relu / relu6 */
+/* fp16 unary ops of b200_act (f32 arithmetic on the converted value, like the reference's fp16 path) */
+int b200_unary_f16(const void *in, void *out, size_t count, int act, float p0, float p1, void *stream);
 int b200_relu_f16(const void *in, void *out, size_t count, int act, void *stream);
 /* elementwise add, same shapes, per-tensor qinfo (source/reference/add.c:36 through
  * diso_callback_base utils.c:622): r = (qa-zpa)*sa + (qb-zpb)*sb ; q = quant(r) ; optional

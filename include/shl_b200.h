@@ -72,6 +72,10 @@ int shl_b200_fullyconnected(struct csinn_tensor *input, struct csinn_tensor *out
                             struct csinn_fc_params *params);
 int shl_b200_relu_init(struct csinn_tensor *input, struct csinn_tensor *output,
                        struct csinn_relu_params *params);
+/* leaky relu / sigmoid / clip share shl_b200_relu as exec; their init callbacks */
+void *shl_b200_leaky_relu_init_fn(void);
+void *shl_b200_sigmoid_init_fn(void);
+void *shl_b200_clip_init_fn(void);
 int shl_b200_relu(struct csinn_tensor *input, struct csinn_tensor *output,
                   struct csinn_relu_params *params);
 int shl_b200_add_init(struct csinn_tensor *input0, struct csinn_tensor *input1,

@@ -263,6 +263,33 @@ void oracle_relu_i8(const int8_t *in, int8_t *out, int64_t count, int act, float
         out[i] = (int8_t)post_stage(in[i], s_in, zp_in, act, s_out, zp_out);
 }
 
+/* leaky relu / sigmoid / clip through shl_ref_siso_callback_base (source/reference/utils.c:609):
+ * dequantise, the f32 loop of leaky_relu.c:31-34 / sigmoid.c:31-34 / clip.c:31-40, requantise */
+void oracle_unary_i8(const int8_t *in, int8_t *out, int64_t count, int op, float p0, float p1, float s_in,
+                     int zp_in, float s_out, int zp_out)
+{
+    for (int64_t i = 0; i < count; i++) {
+        float val = dequant_i8(in[i], s_in, zp_in);
+        float r;
+        switch (op) {
+            case ORACLE_UNARY_LEAKY_RELU:
+                r = val > 0 ? val : val * p0;
+                break;
+            case ORACLE_UNARY_SIGMOID:
+                r = 1.0f / (1.0f + exp(-val));
+                break;
+            default: /* ORACLE_UNARY_CLIP */
+                if (val < p0)
+                    r = p0;
+                else if (val > p1)
+                    r = p1;
+                else
+                    r = val;
+        }
+        out[i] = quant_i8(r, s_out, zp_out);
+    }
+}
+
 void oracle_add_i8(const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,
                    int zp_a, float s_b, int zp_b, float s_out, int zp_out)
 {

@@ -36,6 +36,9 @@ enum {
     H_SOFTMAX,
     H_FLATTEN,
     H_RESHAPE,
+    H_LEAKY_RELU, /* csinn_leaky_relu, slope in p0 */
+    H_SIGMOID,
+    H_CLIP,       /* csinn_clip, [p0, p1] */
 };
 
 typedef struct {
@@ -53,6 +56,7 @@ typedef struct {
     int32_t w_channels;
     const float *s_b;
     int32_t count_include_pad, ceil_mode, axis;
+    float p0, p1; /* unary-op parameters */
 } h_layer;
 
 typedef struct {
@@ -196,6 +200,26 @@ static int layer_init(h_net *net, int i)
             net->params[i] = p;
             return L->kind == H_RELU ? csinn_relu_init(in, out, p) : csinn_relu6_init(in, out, p);
         }
+        case H_LEAKY_RELU: {
+            struct csinn_relu_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->n = L->p0;
+            net->params[i] = p;
+            return csinn_leaky_relu_init(in, out, p);
+        }
+        case H_SIGMOID: {
+            struct csinn_sigmoid_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            net->params[i] = p;
+            return csinn_sigmoid_init(in, out, p);
+        }
+        case H_CLIP: {
+            struct csinn_clip_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->min_value = L->p0, p->max_value = L->p1;
+            net->params[i] = p;
+            return csinn_clip_init(in, out, p);
+        }
         case H_ADD: {
             struct csinn_diso_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -262,6 +286,12 @@ static int layer_call(h_net *net, int i)
             return csinn_relu(in, out, p);
         case H_RELU6:
             return csinn_relu6(in, out, p);
+        case H_LEAKY_RELU:
+            return csinn_leaky_relu(in, out, p);
+        case H_SIGMOID:
+            return csinn_sigmoid(in, out, p);
+        case H_CLIP:
+            return csinn_clip(in, out, p);
         case H_ADD:
             return csinn_add(in, net->t[L->in1], out, p);
         case H_MAXPOOL:

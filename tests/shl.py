@@ -28,9 +28,10 @@ API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
 RM_LAYER, RM_GRAPH = 0, 1
 
 (H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
- H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE) = range(14)
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP) = range(17)
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+UNARY_LEAKY_RELU, UNARY_SIGMOID, UNARY_CLIP = 3, 4, 5
 
 
 class HLayer(C.Structure):
@@ -44,6 +45,7 @@ class HLayer(C.Structure):
         ("w", C.c_void_p), ("b", C.c_void_p), ("s_w", C.c_void_p), ("zp_w", C.c_void_p),
         ("w_channels", C.c_int32), ("s_b", C.c_void_p),
         ("count_include_pad", C.c_int32), ("ceil_mode", C.c_int32), ("axis", C.c_int32),
+        ("p0", C.c_float), ("p1", C.c_float),
     ]
 
 
@@ -70,6 +72,8 @@ class Layer:
     count_include_pad: int = 0
     ceil_mode: int = 0
     axis: int = 1
+    p0: float = 0.0          # unary-op parameters: leaky slope; clip min, max
+    p1: float = 0.0
     _keep: list = field(default_factory=list, repr=False)
 
 
@@ -213,6 +217,7 @@ class Net:
             a.dh, a.dw = int(l.dilation[0]), int(l.dilation[1])
             a.group, a.fuse_zp2bias = int(l.group), int(l.fuse_zp2bias)
             a.count_include_pad, a.ceil_mode, a.axis = int(l.count_include_pad), int(l.ceil_mode), int(l.axis)
+            a.p0, a.p1 = float(l.p0), float(l.p1)
         dims = (C.c_int32 * len(self.in_shape))(*self.in_shape)
         self._arr = arr
         self.handle = h.lib.h_net_create(api, dtype, run_mode, dims, len(self.in_shape), float(s_in), int(zp_in),
@@ -360,6 +365,13 @@ class Oracle:
         out = np.empty_like(x)
         self.lib.oracle_relu_i8(_ptr(x), _ptr(out), C.c_int64(x.size), act, C.c_float(s_in), zp_in,
                                 C.c_float(s_out), zp_out)
+        return out
+
+    def unary_i8(self, x, op, p0, p1, s_in, zp_in, s_out, zp_out):
+        x = np.ascontiguousarray(x, np.int8)
+        out = np.empty_like(x)
+        self.lib.oracle_unary_i8(_ptr(x), _ptr(out), C.c_int64(x.size), op, C.c_float(p0), C.c_float(p1),
+                                 C.c_float(s_in), zp_in, C.c_float(s_out), zp_out)
         return out
 
     def add_i8(self, a, b, s_a, zp_a, s_b, zp_b, s_out, zp_out):

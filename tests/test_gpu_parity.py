@@ -566,3 +566,62 @@ def test_binary_model_saved_and_restored_on_b200(dtype, b200, tmp_path):
     assert np.array_equal(got, want) and np.array_equal(again, want)
     if dtype == DT_INT8:
         assert np.array_equal(got.reshape(2, -1), nets.oracle_forward(nb, x).reshape(2, -1))
+
+
+UNARY = [("leaky", 14, 3, 0.1, 0.0), ("sigmoid", 15, 4, 0.0, 0.0), ("clip", 16, 5, -0.5, 1.25)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+@pytest.mark.parametrize("name,kind,op,p0,p1", UNARY, ids=[u[0] for u in UNARY])
+def test_unary_ops_int8_bit_exact(name, kind, op, p0, p1, mode, b200, oracle, rng):
+    """leaky relu / sigmoid / clip, int8: standalone (a 256-entry table of the reference's float
+    sequence) and, in graph mode, riding in the producing convolution's epilogue"""
+    x = rng.integers(-128, 128, size=(2, 24, 9, 11), dtype=np.int8)
+    got = b200.run(DT_INT8, x.shape, [Layer(kind, x.shape, s_out=0.043, zp_out=-20, p0=p0, p1=p1)], x, s_in=0.05,
+                   zp_in=9, run_mode=mode)
+    assert np.array_equal(got, oracle.unary_i8(x, op, p0, p1, 0.05, 9, 0.043, -20))
+    # conv -> unary (fused in graph mode, two kernels in layer mode): same bytes as oracle conv then oracle unary
+    n, c, h, w, o = 2, 32, 10, 10, 48
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 1, 1)
+    layers = [Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=4, w=wt, b=b, s_w=s_w),
+              Layer(kind, (n, o, h, w), s_out=s_out / 3, zp_out=-100, p0=p0, p1=p1)]
+    got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=-5, run_mode=mode)
+    mid = oracle.conv2d_i8(x, wt, b, (n, o, h, w), stride=(1, 1), pad=(0,) * 4, dilation=(1, 1), group=1, s_in=0.02,
+                           zp_in=-5, s_w=s_w, s_b=None, s_out=s_out, zp_out=4)
+    assert np.array_equal(got, oracle.unary_i8(mid, op, p0, p1, s_out, 4, s_out / 3, -100))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kind,op,p0,p1", UNARY, ids=[u[0] for u in UNARY])
+def test_unary_ops_fp16_within_tolerance(name, kind, op, p0, p1, b200, rng):
+    x = (3.0 * rng.standard_normal((2, 24, 9, 11))).astype(np.float16)
+    got = b200.run(DT_F16, x.shape, [Layer(kind, x.shape, p0=p0, p1=p1)], x).astype(np.float32)
+    xf = x.astype(np.float32)
+    want = {3: np.where(xf > 0, xf, xf * np.float32(p0)), 4: 1.0 / (1.0 + np.exp(-xf.astype(np.float64))),
+            5: np.clip(xf, p0, p1)}[op].astype(np.float32)
+    f16_close(got.astype(np.float16), want)
+
+
+@pytest.mark.gpu
+def test_graph_mode_fuses_unary_nodes_into_their_producer(b200, rng):
+    """graph.c: conv -> relu / leaky relu / sigmoid / clip with the unary node as the only consumer
+    becomes ONE step (int8: the node is the epilogue's post table); the session reports its steps"""
+    import ctypes as C
+    shl = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csi-nn2_b200", "lib",
+                              "libshl_b200.so"))
+    shl.shl_b200_session_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    n, c, h, w, o = 1, 32, 8, 8, 32
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 1, 1)
+    for kind, p0, p1 in [(H_RELU, 0, 0), (14, 0.1, 0), (15, 0, 0), (16, -0.5, 1.0)]:
+        layers = [Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=4, w=wt, b=b, s_w=s_w),
+                  Layer(kind, (n, o, h, w), s_out=s_out / 3, zp_out=-100, p0=p0, p1=p1)]
+        net = b200.create(DT_INT8, (n, c, h, w), layers, s_in=0.02, zp_in=-5, run_mode=RM_GRAPH)
+        try:
+            buf = C.create_string_buffer(4096)
+            shl.shl_b200_session_describe(net.session, buf, len(buf))
+            head = buf.value.decode().splitlines()[0]
+            assert "steps=1 " in head, head
+        finally:
+            net.close()

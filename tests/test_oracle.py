@@ -274,3 +274,17 @@ def test_binary_model_round_trip_through_the_reference(ref, rng, tmp_path):
     net = ref.import_model(blob, DT_INT8, x.shape, (n, o, h, w))
     got = net(x)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind,op,p0,p1", [(14, 3, 0.1, 0.0), (14, 3, 0.015625, 0.0), (15, 4, 0.0, 0.0), (16, 5, -1.0, 2.5),
+                                           (16, 5, 0.0, 6.0)], ids=["leaky0.1", "leaky2^-6", "sigmoid", "clip-1_2.5", "clip0_6"])
+def test_unary_ops_oracle_equals_the_reference(kind, op, p0, p1, ref, oracle, rng):
+    """leaky relu / sigmoid / clip (source/reference/leaky_relu.c:33, sigmoid.c:33, clip.c:32-38
+    through shl_ref_siso_callback_base): the oracle's float sequence against the reference library,
+    every int8 input value, bit for bit"""
+    x = np.arange(-128, 128, dtype=np.int8).reshape(1, 16, 4, 4)
+    for s_in, zp_in, s_out, zp_out in [(0.05, 9, 0.043, -20), (0.11, -128, 1.0 / 256, -128), (0.02, 0, 0.02, 0)]:
+        layer = Layer(kind, x.shape, s_out=s_out, zp_out=zp_out, p0=p0, p1=p1)
+        want = ref.run(DT_INT8, x.shape, [layer], x, s_in=s_in, zp_in=zp_in)
+        got = oracle.unary_i8(x, op, p0, p1, s_in, zp_in, s_out, zp_out)
+        assert np.array_equal(got, want), (s_in, zp_in, s_out, zp_out, int(np.count_nonzero(got != want)))
