@@ -83,6 +83,7 @@ typedef struct b200_op {
     int8_t *d_lut; /* post table or the ACT table */
     int zp_in, zp_out, act, q6;
     float act_p0, act_p1; /* parameters of a unary op (leaky slope; clip min, max) */
+    int binop;            /* B200_OPK_ADD: b200_binop (add / sub / mul) */
     /* the output qinfo the epilogue quantises to (needed when a relu is fused later) */
     float s_out;
     /* eltwise / pool / softmax */

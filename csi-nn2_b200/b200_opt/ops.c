@@ -418,7 +418,7 @@ int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_
                 DEV_CHECK(b200_unary_f16(in0->d, out->d, b200_dt_bytes(out) / 2, op->act, op->act_p0, op->act_p1, stream));
             return CSINN_TRUE;
         case B200_OPK_ADD:
-            DEV_CHECK(b200_add(op->dtype, in0->d, in1->d, out->d, b200_dt_bytes(out) / op->eb,
+            DEV_CHECK(b200_binary(op->binop, op->dtype, in0->d, in1->d, out->d, b200_dt_bytes(out) / op->eb,
                                op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out, op->zp_out,
                                op->d_lut, op->act, stream));
             return CSINN_TRUE;
@@ -805,8 +805,29 @@ int shl_b200_relu(struct csinn_tensor *input, struct csinn_tensor *output,
 }
 
 /* ---- add -------------------------------------------------------------------------------------------- */
+static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
+                       struct csinn_diso_params *params, int binop);
 int shl_b200_add_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
                       struct csinn_tensor *output, struct csinn_diso_params *params)
+{
+    return binary_init(input0, input1, output, params, B200_BINOP_ADD);
+}
+/* sub / mul: replace shl_rvv_sub_int8 / shl_rvv_mul_int8 (source/thead_rvv/setup.c registrations) for
+ * same-shape operands; exec is shl_b200_add */
+static int sub_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
+                    struct csinn_diso_params *params)
+{
+    return binary_init(input0, input1, output, params, B200_BINOP_SUB);
+}
+static int mul_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
+                    struct csinn_diso_params *params)
+{
+    return binary_init(input0, input1, output, params, B200_BINOP_MUL);
+}
+void *shl_b200_sub_init_fn(void) { return (void *)sub_init; }
+void *shl_b200_mul_init_fn(void) { return (void *)mul_init; }
+static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
+                       struct csinn_diso_params *params, int binop)
 {
     if (input0->dim_count != input1->dim_count) {
         b200_fail("add: broadcasting is not supported (ranks %d vs %d)", input0->dim_count, input1->dim_count);
@@ -821,8 +842,10 @@ int shl_b200_add_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
         b200_fail("add: constant second operand is not supported");
         return CSINN_FALSE;
     }
-    b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, "b200_add");
+    static const char *const names[] = {"b200_add", "b200_sub", "b200_mul"};
+    b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, names[binop]);
     if (!op) return CSINN_FALSE;
+    op->binop = binop;
     if (op->dtype == B200_I8) {
         if (!input0->qinfo || !input1->qinfo || !output->qinfo) {
             b200_fail("add: int8 tensors without qinfo");

@@ -91,7 +91,12 @@ struct AddArgs {
     float s_a, s_b, s_out;
     int zp_a, zp_b, zp_out, act;
     const int8_t *post_lut;
+    int binop;  // b200_binop: add / sub / mul (source/reference/add.c, sub.c, mul.c: one f32 op between the dequantised values)
 };
+__device__ __forceinline__ float binop_f(float a, float b, int binop)
+{
+    return binop == B200_BINOP_SUB ? __fsub_rn(a, b) : (binop == B200_BINOP_MUL ? __fmul_rn(a, b) : __fadd_rn(a, b));
+}
 
 __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a,
                                                      const uint4 *__restrict__ b,
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
             for (int e = 0; e < 4; e++) {
                 const int qa = static_cast<int8_t>(wa[q] >> (8 * e));
                 const int qb = static_cast<int8_t>(wb[q] >> (8 * e));
-                const float f = __fadd_rn(dequant_i8(qa, p.s_a, p.zp_a), dequant_i8(qb, p.s_b, p.zp_b));
+                const float f = binop_f(dequant_i8(qa, p.s_a, p.zp_a), dequant_i8(qb, p.s_b, p.zp_b), p.binop);
                 int qo = quant_i8_exact(f, p.s_out, p.zp_out);
                 if (p.post_lut != nullptr) qo = static_cast<int8_t>(s_lut[qo + 128]);
                 o |= (static_cast<uint32_t>(qo) & 0xFF) << (8 * e);
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
 __global__ void __launch_bounds__(256) add_f16_kernel(const uint4 *__restrict__ a,
                                                       const uint4 *__restrict__ b,
                                                       uint4 *__restrict__ out, long long nvec,
-                                                      int act)
+                                                      int act, int binop)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(256) add_f16_kernel(const uint4 *__restrict__ 
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
-            ho[q] = __floats2half2_rn(act_f(fa.x + fb.x, act), act_f(fa.y + fb.y, act));
+            ho[q] = __floats2half2_rn(act_f(binop_f(fa.x, fb.x, binop), act), act_f(binop_f(fa.y, fb.y, binop), act));
         }
         out[i] = vo;
     }
@@ -208,6 +213,17 @@ extern "C" int b200_add(int dtype, const void *a, const void *b, void *out, size
                         int zp_a, float s_b, int zp_b, float s_out, int zp_out,
                         const int8_t *post_lut, int act, void *stream)
 {
+    return b200_binary(B200_BINOP_ADD, dtype, a, b, out, count, s_a, zp_a, s_b, zp_b, s_out, zp_out, post_lut, act, stream);
+}
+
+extern "C" int b200_binary(int binop, int dtype, const void *a, const void *b, void *out, size_t count, float s_a,
+                           int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                           const int8_t *post_lut, int act, void *stream)
+{
+    if (binop < B200_BINOP_ADD || binop > B200_BINOP_MUL) {
+        set_error("b200_binary: unknown op %d", binop);
+        return B200_ERR_ARG;
+    }
     const int vec = dtype == B200_I8 ? 16 : 8;
     if ((dtype != B200_I8 && dtype != B200_F16) || !a || !b || !out || count == 0 || count % vec ||
         !aligned16(a) || !aligned16(b) || !aligned16(out)) {
@@ -216,14 +232,14 @@ extern "C" int b200_add(int dtype, const void *a, const void *b, void *out, size
     }
     const long long nvec = static_cast<long long>(count / vec);
     if (dtype == B200_I8) {
-        AddArgs p{s_a, s_b, s_out, zp_a, zp_b, zp_out, act, post_lut};
+        AddArgs p{s_a, s_b, s_out, zp_a, zp_b, zp_out, act, post_lut, binop};
         launch_kernel(add_i8_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
             nvec, p);
     } else {
         launch_kernel(add_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
-            nvec, act);
+            nvec, act, binop);
     }
     B200_LAUNCH_CHECK();
     return B200_OK;

@@ -73,6 +73,8 @@ int shl_b200_fullyconnected(struct csinn_tensor *input, struct csinn_tensor *out
 int shl_b200_relu_init(struct csinn_tensor *input, struct csinn_tensor *output,
                        struct csinn_relu_params *params);
 /* leaky relu / sigmoid / clip share shl_b200_relu as exec; their init callbacks */
+void *shl_b200_sub_init_fn(void); /* sub / mul share shl_b200_add as exec */
+void *shl_b200_mul_init_fn(void);
 void *shl_b200_leaky_relu_init_fn(void);
 void *shl_b200_sigmoid_init_fn(void);
 void *shl_b200_clip_init_fn(void);

@@ -299,6 +299,17 @@ void oracle_add_i8(const int8_t *a, const int8_t *b, int8_t *out, int64_t count,
     }
 }
 
+/* sub / mul: sub.c:21-33, mul.c:21-33 (one f32 op between the dequantised operands) */
+void oracle_binary_i8(int op, const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,
+                      int zp_a, float s_b, int zp_b, float s_out, int zp_out)
+{
+    for (int64_t i = 0; i < count; i++) {
+        float x = dequant_i8(a[i], s_a, zp_a), y = dequant_i8(b[i], s_b, zp_b);
+        float r = op == 1 ? x - y : (op == 2 ? x * y : x + y);
+        out[i] = quant_i8(r, s_out, zp_out);
+    }
+}
+
 void oracle_avgpool_i8(const oracle_pool_params *p, const int8_t *in, int8_t *out)
 {
 #pragma omp parallel for collapse(2) schedule(static)

@@ -103,6 +103,10 @@ void oracle_unary_i8(const int8_t *in, int8_t *out, int64_t count, int op, float
 void oracle_add_i8(const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,
                    int zp_a, float s_b, int zp_b, float s_out, int zp_out);
 
+/* op: 0 add, 1 sub, 2 mul */
+void oracle_binary_i8(int op, const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,
+                      int zp_a, float s_b, int zp_b, float s_out, int zp_out);
+
 typedef struct {
     int32_t n, c, h, w, oh, ow, kh, kw, stride_h, stride_w, pad_top, pad_left;
     int32_t count_include_pad;

@@ -39,6 +39,8 @@ enum {
     H_LEAKY_RELU, /* csinn_leaky_relu, slope in p0 */
     H_SIGMOID,
     H_CLIP,       /* csinn_clip, [p0, p1] */
+    H_SUB,
+    H_MUL,
 };
 
 typedef struct {
@@ -220,10 +222,14 @@ static int layer_init(h_net *net, int i)
             net->params[i] = p;
             return csinn_clip_init(in, out, p);
         }
-        case H_ADD: {
+        case H_ADD:
+        case H_SUB:
+        case H_MUL: {
             struct csinn_diso_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
             net->params[i] = p;
+            if (L->kind == H_SUB) return csinn_sub_init(in, net->t[L->in1], out, p);
+            if (L->kind == H_MUL) return csinn_mul_init(in, net->t[L->in1], out, p);
             return csinn_add_init(in, net->t[L->in1], out, p);
         }
         case H_MAXPOOL:
@@ -292,6 +298,10 @@ static int layer_call(h_net *net, int i)
             return csinn_sigmoid(in, out, p);
         case H_CLIP:
             return csinn_clip(in, out, p);
+        case H_SUB:
+            return csinn_sub(in, net->t[L->in1], out, p);
+        case H_MUL:
+            return csinn_mul(in, net->t[L->in1], out, p);
         case H_ADD:
             return csinn_add(in, net->t[L->in1], out, p);
         case H_MAXPOOL:

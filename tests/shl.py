@@ -28,7 +28,7 @@ API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
 RM_LAYER, RM_GRAPH = 0, 1
 
 (H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
- H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP) = range(17)
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL) = range(19)
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 UNARY_LEAKY_RELU, UNARY_SIGMOID, UNARY_CLIP = 3, 4, 5
@@ -372,6 +372,14 @@ class Oracle:
         out = np.empty_like(x)
         self.lib.oracle_unary_i8(_ptr(x), _ptr(out), C.c_int64(x.size), op, C.c_float(p0), C.c_float(p1),
                                  C.c_float(s_in), zp_in, C.c_float(s_out), zp_out)
+        return out
+
+    def binary_i8(self, op, a, b, s_a, zp_a, s_b, zp_b, s_out, zp_out):
+        """op: 0 add, 1 sub, 2 mul"""
+        a, b = np.ascontiguousarray(a, np.int8), np.ascontiguousarray(b, np.int8)
+        out = np.empty_like(a)
+        self.lib.oracle_binary_i8(op, _ptr(a), _ptr(b), _ptr(out), C.c_int64(a.size), C.c_float(s_a), zp_a,
+                                  C.c_float(s_b), zp_b, C.c_float(s_out), zp_out)
         return out
 
     def add_i8(self, a, b, s_a, zp_a, s_b, zp_b, s_out, zp_out):

@@ -625,3 +625,28 @@ def test_graph_mode_fuses_unary_nodes_into_their_producer(b200, rng):
             assert "steps=1 " in head, head
         finally:
             net.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30)], ids=["sub", "mul"])
+def test_sub_mul_int8_bit_exact(kind, op, s_out, zp_out, b200, oracle, rng):
+    shape = (2, 24, 9, 11)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128), Layer(kind, shape, in0=0, in1=1, s_out=s_out, zp_out=zp_out)]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    want = oracle.binary_i8(op, x, r, 0.04, 3, 0.021, -128, s_out, zp_out)
+    for mode in (RM_LAYER, RM_GRAPH):
+        got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=mode)
+        assert np.array_equal(got, want), mode
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [17, 18], ids=["sub", "mul"])
+def test_sub_mul_fp16_within_tolerance(kind, b200, rng):
+    shape = (2, 24, 9, 11)
+    x = rng.standard_normal(shape).astype(np.float16)
+    layers = [Layer(H_RELU, shape), Layer(kind, shape, in0=0, in1=1)]
+    got = b200.run(DT_F16, shape, layers, x, run_mode=RM_GRAPH)
+    xf = x.astype(np.float32)
+    r = np.maximum(xf, 0)
+    f16_close(got, xf - r if kind == 17 else xf * r)

@@ -288,3 +288,15 @@ def test_unary_ops_oracle_equals_the_reference(kind, op, p0, p1, ref, oracle, rn
         want = ref.run(DT_INT8, x.shape, [layer], x, s_in=s_in, zp_in=zp_in)
         got = oracle.unary_i8(x, op, p0, p1, s_in, zp_in, s_out, zp_out)
         assert np.array_equal(got, want), (s_in, zp_in, s_out, zp_out, int(np.count_nonzero(got != want)))
+
+
+@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30)], ids=["sub", "mul"])
+def test_sub_mul_oracle_equals_the_reference(kind, op, s_out, zp_out, ref, oracle, rng):
+    """csinn_sub / csinn_mul between same-shape tensors (source/reference/sub.c:36, mul.c:36): oracle vs
+    the reference library, bit for bit"""
+    shape = (2, 24, 9, 11)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128), Layer(kind, shape, in0=0, in1=1, s_out=s_out, zp_out=zp_out)]
+    got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    assert np.array_equal(got, oracle.binary_i8(op, x, r, 0.04, 3, 0.021, -128, s_out, zp_out))
