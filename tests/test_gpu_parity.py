@@ -650,3 +650,21 @@ def test_sub_mul_fp16_within_tolerance(kind, b200, rng):
     xf = x.astype(np.float32)
     r = np.maximum(xf, 0)
     f16_close(got, xf - r if kind == 17 else xf * r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,op", [(H_ADD, 0), (17, 1), (18, 2)], ids=["add", "sub", "mul"])
+def test_binary_ops_on_rounding_ties_and_saturation(kind, op, b200, oracle, rng):
+    """the int8 binary kernel decides rint() of the IEEE quotient from r * RN(1 / s_out) and takes the
+    real division only near half-integers (csrc/eltwise.cu): scales chosen so that the quotient IS a
+    half-integer (or within an ulp of one) for about half of all input pairs, plus scales that saturate"""
+    shape = (4, 32, 24, 24)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    for s_a, zp_a, s_r, zp_r, s_out, zp_out in [(0.02, 0, 0.02, -128, 0.04, 0), (0.03, 3, 0.015, -128, 0.06, -7),
+                                                (0.5, -1, 0.25, -128, 0.125, 5), (0.001, 0, 0.003, -128, 0.5, 0),
+                                                (1.0, 0, 1.0, -128, 1.0 / 3.0, 0)]:
+        layers = [Layer(H_RELU, shape, s_out=s_r, zp_out=zp_r), Layer(kind, shape, in0=0, in1=1, s_out=s_out, zp_out=zp_out)]
+        r = oracle.relu_i8(x, ACT_RELU, s_a, zp_a, s_r, zp_r)
+        want = oracle.binary_i8(op, x, r, s_a, zp_a, s_r, zp_r, s_out, zp_out)
+        got = b200.run(DT_INT8, shape, layers, x, s_in=s_a, zp_in=zp_a, run_mode=RM_GRAPH)
+        assert np.array_equal(got, want), (s_a, s_r, s_out, int(np.count_nonzero(got != want)))
