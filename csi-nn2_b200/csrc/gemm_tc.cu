@@ -573,6 +573,11 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
         args.k_blocks * 128 * kBKBytes <= kResidentBBytes)
         args.bn = 128;
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
+    // few rows (classifier layers, small batches): narrower int8 n-tiles so that more SMs get a tile
+    // -- the kernel is latency-bound there and every CTA streams only its own slice of the weights
+    if (d->dtype == B200_I8 && !getenv("SHL_B200_GEMM_NO_NARROW"))
+        while (args.bn > 32 && static_cast<long long>(args.num_m_tiles) * ((d->n + args.bn - 1) / args.bn) * 2 <= sm_count())
+            args.bn /= 2;
     args.num_n_tiles = (d->n + args.bn - 1) / args.bn;
     // 128-row blocks per super tile: as many as fit a 256-column TMEM stage, but never so many that
     // the machine runs short of super tiles (keep >= 4 per SM)
