@@ -379,8 +379,17 @@ int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void 
     int th = (thi_max - 3) / S + 1;
     if (th < 1) th = 1;
     if (th > d->oh) th = d->oh;
-    const int ybands = (d->oh + th - 1) / th;
+    int ybands = (d->oh + th - 1) / th;
     th = (d->oh + ybands - 1) / ybands;
+    // small batches: shorter tiles until every SM has one (the halo rows cost less than idle SMs)
+    {
+        const long long per_band = static_cast<long long>(d->n) * ((d->ow + TW - 1) / TW) * ((d->cp + CC - 1) / CC);
+        while (per_band * ybands < sm_count() && th > 4) {
+            th = (th + 1) / 2;
+            ybands = (d->oh + th - 1) / th;
+            th = (d->oh + ybands - 1) / ybands;
+        }
+    }
     const int thi = S * (th - 1) + 3;
 
     DwTmaArgs a;
