@@ -118,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
-        if (DT == B200_I8) tma_prefetch_desc(&tma_o);
+        tma_prefetch_desc(&tma_o);
         for (int i = 0; i < stages; i++) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], args.cluster);  // a slot is free when every CTA of the pair has consumed it
@@ -390,7 +390,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             epi->badd[et] = (col < args.n && ep.badd) ? ep.badd[col] : 0.f;
         }
         epi_bar_sync();
-        pdl_wait();  // fp16 rows are stored straight to global memory
+        pdl_wait();  // the output buffer may alias a tensor the predecessor still reads
+        uint8_t *wstg = staging + static_cast<size_t>(ew) * 4096;  // this warp's two 2 KB slabs (512-byte aligned)
+        uint32_t item = 0;
         int local = 0;
         for (int ms = ms0; ms < args.num_m_super; ms += ms_step, local++) {
             const int acc = local & 1;
@@ -430,15 +432,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         __half2 h = __floats2half2_rn(f0, f1);
                         packed[j2] = *reinterpret_cast<uint32_t *>(&h);
                     }
-                    if (row_ok) {
-                        __half *dst = static_cast<__half *>(args.out) + static_cast<size_t>(row) * args.ldo + n0 + c0;
+                    // Leave through this warp's own staging slab (32 rows x ncols halves, 64B / 32B swizzle so
+                    // that a warp's 16-byte writes to 32 different rows spread over all banks) and its own
+                    // TMA store: rows of a tile are ldo halves apart in memory, so direct 16-byte stores
+                    // cost the LSU ~34 wavefronts per instruction (what bounded the int8 epilogue before its
+                    // staging).  Two slabs per warp: the store issued two items ago has read its slab.
+                    uint8_t *slab = wstg + (item & 1) * 2048;
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    const uint32_t rowb = static_cast<uint32_t>(lane) * (ncols * 2);
 #pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            if (v * 8 < ncols && n0 + c0 + v * 8 < args.ldo)
-                                *reinterpret_cast<uint4 *>(dst + v * 8) =
-                                    make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2], packed[v * 4 + 3]);
+                    for (int v = 0; v < 4; v++) {
+                        if (v * 8 < ncols) {
+                            const uint32_t chunk = ncols == 32 ? (v ^ ((lane >> 1) & 3)) : (v ^ ((lane >> 2) & 1));
+                            *reinterpret_cast<uint4 *>(slab + rowb + chunk * 16) =
+                                make_uint4(packed[v * 4], packed[v * 4 + 1], packed[v * 4 + 2], packed[v * 4 + 3]);
                         }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tma_o, slab, n0 + c0, (mt0 + g) * kBM + quad * 32);  // clips rows >= m, columns >= ldo
+                        tma_store_commit();
+                    }
+                    item++;
+                    (void)row_ok;
                 }
             }
             // this warp has drained its part of the accumulators
@@ -446,6 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -472,11 +491,13 @@ static int pick_bn(int n, int dtype)
         // columns past the row pitch clipped by the TMA store)
         return n16 <= 16 ? 16 : (n16 <= 32 ? 32 : (n16 <= 64 ? 64 : 128));
     }
-    // fp16: one n-tile when the whole output width fits (<= 256), otherwise the multiple of 16
-    // that splits n most evenly into the fewest tiles
-    if (n16 <= 256) return n16;
+    // fp16: one n-tile when the whole output width fits (<= 256), otherwise the width that splits n
+    // most evenly into the fewest tiles. Tiles of 128 columns and more leave in 32-column slabs (the
+    // epilogue's TMA store box), so they are a multiple of 32 wide -- weight rows past n are
+    // zero-filled by the load, columns past the row pitch clipped by the store
+    if (n16 <= 256) return n16 >= 128 ? (n16 + 31) / 32 * 32 : n16;
     const int tiles = (n16 + 255) / 256;
-    return ((n16 + tiles - 1) / tiles + 15) / 16 * 16;
+    return ((n16 + tiles - 1) / tiles + 31) / 32 * 32;
 }
 
 template <int DT, int MODE, bool MAGIC>
@@ -590,7 +611,9 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.group = group;
     args.num_m_super = (args.num_m_tiles + group - 1) / group;
     // int8: two staging buffers of one super tile each (G x 128 rows x bn bytes)
-    const size_t staging = d->dtype == B200_I8 ? static_cast<size_t>(group) * kBM * args.bn : 0;
+    // fp16: every epilogue warp owns two 2 KB slabs (kEpiWarps x 4 KB = 2 x 32 KB)
+    const size_t staging = d->dtype == B200_I8 ? static_cast<size_t>(group) * kBM * args.bn
+                                               : static_cast<size_t>(kEpiWarps) * 2048;
     args.stage_bytes = static_cast<uint32_t>(staging);
     // weights stay resident when they fit beside the staging and at least three A stages
     args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
@@ -622,7 +645,10 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
                             args.bn >= 128 ? 128 : (args.bn >= 32 ? args.bn : 0));
         if (rc) return rc;
     } else {
-        to = ta;  // unused by the fp16 epilogue
+        // fp16 output slab of one warp: 32 rows x (32 or 16) halves, 64B / 32B swizzle
+        const int cw = args.bn >= 128 ? 32 : 16;
+        rc = encode_tmap_2d(&to, 2, d->out, d->ldo, d->m, static_cast<uint64_t>(d->ldo) * 2, cw, 32, cw * 2);
+        if (rc) return rc;
     }
 
     // a multiple of the n-tile count so that every CTA keeps one n-tile for its whole life
