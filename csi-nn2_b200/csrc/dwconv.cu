@@ -257,19 +257,30 @@ __global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int 
         const int ix0 = ox0 * S - a.pl;
         const __half *img = in + (static_cast<size_t>(b) * a.h * a.w) * a.cp + c0;
 
-        // one input row: NX pixels x 4 channels -> f32x2 pairs (zero outside the image: fp16 padding is 0)
-        auto load_row = [&](int iy, uint64_t (&x)[NX][2]) {
-            const bool yok = iy >= 0 && iy < a.h;
+        // one input row: NX pixels x 4 channels (zero outside the image: fp16 padding is 0).  The raw
+        // halves of row r + 1 are requested before row r is used, so every thread keeps two rows of
+        // loads in flight -- the kernel is latency-bound on these, not on the FMAs.
+        const int iy_last = (oy0 + rows - 1) * S - a.pt + 2;
+        uint2 raw[NX];
+        auto fetch = [&](int iy) {
+            const bool yok = iy >= 0 && iy < a.h && iy <= iy_last;
 #pragma unroll
             for (int p = 0; p < NX; p++) {
                 const int ix = ix0 + p;
-                uint2 raw = make_uint2(0u, 0u);
+                raw[p] = make_uint2(0u, 0u);
                 if (yok && ix >= 0 && ix < a.w)
-                    raw = __ldg(reinterpret_cast<const uint2 *>(img + (static_cast<size_t>(iy) * a.w + ix) * a.cp));
-                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                    raw[p] = __ldg(reinterpret_cast<const uint2 *>(img + (static_cast<size_t>(iy) * a.w + ix) * a.cp));
+            }
+        };
+        // converts the fetched row to f32x2 pairs and requests the next one
+        auto load_row = [&](int iy, uint64_t (&x)[NX][2]) {
+#pragma unroll
+            for (int p = 0; p < NX; p++) {
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw[p].x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw[p].y));
                 x[p][0] = f2_pack(lo.x, lo.y), x[p][1] = f2_pack(hi.x, hi.y);
             }
+            fetch(iy + 1);
         };
         // acc[col][pair] += row (x) kernel row ky
         auto fma_row = [&](uint64_t (&acc)[2][2], const uint64_t (&x)[NX][2], int ky) {
@@ -309,6 +320,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int 
 
         uint64_t x[NX][2], accA[2][2], accB[2][2], accC[2][2];
         const int iy0 = oy0 * S - a.pt;
+        fetch(iy0);
         if (S == 1) {
             // input row r (image row iy0 + r) feeds output rows r (ky 0), r - 1 (ky 1), r - 2 (ky 2, completes it)
             load_row(iy0, x);
