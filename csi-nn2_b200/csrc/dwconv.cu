@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int 
     const __half *in = static_cast<const __half *>(a.in);
     const __half *wt = static_cast<const __half *>(a.wt);
     __half *out = static_cast<__half *>(a.out);
+    const long long in_row = static_cast<long long>(a.w) * a.cp, out_row = static_cast<long long>(a.ow) * a.cp;  // halves
+    const bool clamp_lo = a.ep.act != B200_ACT_NONE, clamp_hi = a.ep.act == B200_ACT_RELU6;
+    const __half2 zero2 = __floats2half2_rn(0.f, 0.f), six2 = __floats2half2_rn(6.f, 6.f);
 
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -254,33 +257,40 @@ __global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int 
             const float b2 = a.ep.badd ? __ldg(a.ep.badd + c0 + 2) : 0.f, b3 = a.ep.badd ? __ldg(a.ep.badd + c0 + 3) : 0.f;
             seed[0] = f2_pack(b0, b1), seed[1] = f2_pack(b2, b3);
         }
+        // Addressing is hoisted out of the row loop (it used to cost three times the FMAs): one input
+        // pointer stepping a row at a time, column validity as a bit mask, rows tested against one bound.
         const int ix0 = ox0 * S - a.pl;
-        const __half *img = in + (static_cast<size_t>(b) * a.h * a.w) * a.cp + c0;
+        int xmask = 0;
+#pragma unroll
+        for (int p = 0; p < NX; p++) xmask |= (ix0 + p >= 0 && ix0 + p < a.w) ? 1 << p : 0;
+        const int iy0 = oy0 * S - a.pt;
+        const int iy_max = min(a.h - 1, (oy0 + rows - 1) * S - a.pt + 2);
+        // row iy0, column ix0 of this image (dereferenced only where both are inside it)
+        const __half *rp = in + (static_cast<long long>(b) * a.h + iy0) * in_row + static_cast<long long>(ix0) * a.cp + c0;
+        int iy = iy0;
 
         // one input row: NX pixels x 4 channels (zero outside the image: fp16 padding is 0).  The raw
         // halves of row r + 1 are requested before row r is used, so every thread keeps two rows of
-        // loads in flight -- the kernel is latency-bound on these, not on the FMAs.
-        const int iy_last = (oy0 + rows - 1) * S - a.pt + 2;
+        // loads in flight.
         uint2 raw[NX];
-        auto fetch = [&](int iy) {
-            const bool yok = iy >= 0 && iy < a.h && iy <= iy_last;
+        auto fetch = [&]() {
+            const bool yok = iy >= 0 && iy <= iy_max;
 #pragma unroll
             for (int p = 0; p < NX; p++) {
-                const int ix = ix0 + p;
                 raw[p] = make_uint2(0u, 0u);
-                if (yok && ix >= 0 && ix < a.w)
-                    raw[p] = __ldg(reinterpret_cast<const uint2 *>(img + (static_cast<size_t>(iy) * a.w + ix) * a.cp));
+                if (yok && ((xmask >> p) & 1)) raw[p] = __ldg(reinterpret_cast<const uint2 *>(rp + p * a.cp));
             }
+            rp += in_row, iy++;
         };
         // converts the fetched row to f32x2 pairs and requests the next one
-        auto load_row = [&](int iy, uint64_t (&x)[NX][2]) {
+        auto load_row = [&](uint64_t (&x)[NX][2]) {
 #pragma unroll
             for (int p = 0; p < NX; p++) {
                 const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw[p].x));
                 const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw[p].y));
                 x[p][0] = f2_pack(lo.x, lo.y), x[p][1] = f2_pack(hi.x, hi.y);
             }
-            fetch(iy + 1);
+            fetch();
         };
         // acc[col][pair] += row (x) kernel row ky
         auto fma_row = [&](uint64_t (&acc)[2][2], const uint64_t (&x)[NX][2], int ky) {
@@ -298,63 +308,65 @@ __global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int 
                 for (int h = 0; h < 2; h++) acc[col][h] = seed[h];
             fma_row(acc, x, 0);
         };
-        int oy = oy0;
+        // padded channels are written as zeros; relu / relu6 clamp the rounded halves (0 and 6 are exact)
+        const uint32_t m01 = (c0 < a.c ? 0xFFFFu : 0u) | (c0 + 1 < a.c ? 0xFFFF0000u : 0u);
+        const uint32_t m23 = (c0 + 2 < a.c ? 0xFFFFu : 0u) | (c0 + 3 < a.c ? 0xFFFF0000u : 0u);
+        const bool col1 = ox0 + 1 < a.ow;
+        __half *op = out + ((static_cast<long long>(b) * a.oh + oy0) * a.ow + ox0) * a.cp + c0;
         auto store = [&](const uint64_t (&acc)[2][2]) {
 #pragma unroll
             for (int col = 0; col < 2; col++) {
-                if (ox0 + col < a.ow) {
+                if (col == 0 || col1) {
                     int b0, b1, b2, b3;
                     f2_unpack_bits(acc[col][0], b0, b1);
                     f2_unpack_bits(acc[col][1], b2, b3);
-                    float f0 = act_f(__int_as_float(b0), a.ep.act), f1 = act_f(__int_as_float(b1), a.ep.act);
-                    float f2 = act_f(__int_as_float(b2), a.ep.act), f3 = act_f(__int_as_float(b3), a.ep.act);
-                    f0 = c0 + 0 < a.c ? f0 : 0.f, f1 = c0 + 1 < a.c ? f1 : 0.f;
-                    f2 = c0 + 2 < a.c ? f2 : 0.f, f3 = c0 + 3 < a.c ? f3 : 0.f;
-                    const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
-                    *reinterpret_cast<uint2 *>(out + ((static_cast<size_t>(b) * a.oh + oy) * a.ow + ox0 + col) * a.cp + c0) =
-                        make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+                    __half2 h01 = __floats2half2_rn(__int_as_float(b0), __int_as_float(b1));
+                    __half2 h23 = __floats2half2_rn(__int_as_float(b2), __int_as_float(b3));
+                    if (clamp_lo) h01 = __hmax2(h01, zero2), h23 = __hmax2(h23, zero2);
+                    if (clamp_hi) h01 = __hmin2(h01, six2), h23 = __hmin2(h23, six2);
+                    *reinterpret_cast<uint2 *>(op + col * a.cp) =
+                        make_uint2(*reinterpret_cast<const uint32_t *>(&h01) & m01, *reinterpret_cast<const uint32_t *>(&h23) & m23);
                 }
             }
-            oy++;
+            op += out_row;
         };
 
         uint64_t x[NX][2], accA[2][2], accB[2][2], accC[2][2];
-        const int iy0 = oy0 * S - a.pt;
-        fetch(iy0);
+        fetch();
         if (S == 1) {
             // input row r (image row iy0 + r) feeds output rows r (ky 0), r - 1 (ky 1), r - 2 (ky 2, completes it)
-            load_row(iy0, x);
+            load_row(x);
             start(accA, x);
-            load_row(iy0 + 1, x);
+            load_row(x);
             fma_row(accA, x, 1), start(accB, x);
             for (int y = 0;; y += 3) {
-                load_row(iy0 + y + 2, x);
+                load_row(x);
                 fma_row(accA, x, 2), fma_row(accB, x, 1), start(accC, x);
                 store(accA);
                 if (y + 1 >= rows) break;
-                load_row(iy0 + y + 3, x);
+                load_row(x);
                 fma_row(accB, x, 2), fma_row(accC, x, 1), start(accA, x);
                 store(accB);
                 if (y + 2 >= rows) break;
-                load_row(iy0 + y + 4, x);
+                load_row(x);
                 fma_row(accC, x, 2), fma_row(accA, x, 1), start(accB, x);
                 store(accC);
                 if (y + 3 >= rows) break;
             }
         } else {
             // output row y reads input rows 2y (ky 0), 2y + 1 (ky 1), 2y + 2 (ky 2 = ky 0 of row y + 1)
-            load_row(iy0, x);
+            load_row(x);
             start(accA, x);
             for (int y = 0;; y += 2) {
-                load_row(iy0 + 2 * y + 1, x);
+                load_row(x);
                 fma_row(accA, x, 1);
-                load_row(iy0 + 2 * y + 2, x);
+                load_row(x);
                 fma_row(accA, x, 2), start(accB, x);
                 store(accA);
                 if (y + 1 >= rows) break;
-                load_row(iy0 + 2 * y + 3, x);
+                load_row(x);
                 fma_row(accB, x, 1);
-                load_row(iy0 + 2 * y + 4, x);
+                load_row(x);
                 fma_row(accB, x, 2), start(accA, x);
                 store(accB);
                 if (y + 2 >= rows) break;
