@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) dwconv_f16_kernel(const DwArgs a)
 // vertical taps are reused from registers and horizontal ones from the same loads -- the generic
 // kernel above reloads every tap.  Weights tap-major [9][cp] halves; bias seeds the accumulators.
 template <int S>
-__global__ void __launch_bounds__(128) dwconv3x3_f16_kernel(const DwArgs a, int band_rows, int ybands)
+__global__ void __launch_bounds__(128, 5) dwconv3x3_f16_kernel(const DwArgs a, int band_rows, int ybands)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
