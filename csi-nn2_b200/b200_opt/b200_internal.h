@@ -63,8 +63,10 @@ enum b200_op_kind {
     B200_OPK_POOL,
     B200_OPK_SOFTMAX,
     B200_OPK_COPY,    /* reshape / flatten whose memory order is unchanged */
+    B200_OPK_CONCAT,  /* one step per input: its slice of the output (b200_op_run's `part`) */
 };
 
+#define B200_CONCAT_MAX 32
 typedef struct b200_op {
     int kind;
     int dtype; /* b200_dtype */
@@ -84,6 +86,10 @@ typedef struct b200_op {
     int zp_in, zp_out, act, q6;
     float act_p0, act_p1; /* parameters of a unary op (leaky slope; clip min, max) */
     int binop;            /* B200_OPK_ADD: b200_binop (add / sub / mul) */
+    /* B200_OPK_CONCAT: device axis (0..3 = n, c, h, w), per-input offset along it and requant table */
+    int cat_n, cat_axis;
+    int cat_off[B200_CONCAT_MAX];
+    int8_t *cat_lut[B200_CONCAT_MAX];
     /* the output qinfo the epilogue quantises to (needed when a relu is fused later) */
     float s_out;
     /* eltwise / pool / softmax */
@@ -102,7 +108,8 @@ b200_op *b200_op_find(void *params);
 /* run on device tensors; scratch is im2col space (b200_op_scratch_bytes) */
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0); /* kernel that will actually run */
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out);
-int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
+/* `part`: which input of a concat `in0` is (0 for every other kind) */
+int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
                 void *scratch, void *stream);
 /* fuse a following relu / relu6 node (with its own qinfo) into this op's epilogue */
 int b200_op_can_fuse_act(const b200_op *op);

@@ -53,6 +53,7 @@ typedef struct {
 typedef struct {
     b200_op *op;
     int in0, in1, out;
+    int part; /* concat: which input in0 is */
     size_t scratch;
     char name[96];
 } g_step;
@@ -258,7 +259,7 @@ static size_t weight_bound(struct shl_ref_graph *graph)
             size_t e = csinn_tensor_size(ct);
             total += e * 8 + (size_t)(ct->dim_count ? ct->dim[0] : 1) * 64 * 4 + 8192;
         }
-        total += 4096;
+        total += 4096 + (size_t)l->in_num * 256; /* concat: one requant table per input */
     }
     return total;
 }
@@ -323,7 +324,7 @@ static int run_steps(b200_graph *g, void *stream)
     for (int i = 0; i < g->ns; i++) {
         g_step *s = &g->s[i];
         const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
-        if (b200_op_run(s->op, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
+        if (b200_op_run(s->op, s->part, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
             CSINN_TRUE) {
             shl_debug_error("b200: step %d (%s) failed: %s\n", i, s->name, shl_b200_last_error());
             return CSINN_FALSE;
@@ -452,7 +453,10 @@ static int build_from_graph(struct csinn_session *sess)
 
     b200_graph *g = calloc(1, sizeof(*g));
     g->t = calloc((size_t)graph->layer_index * 2 + graph->input_num + graph->output_num + 4, sizeof(g_tensor));
-    g->s = calloc((size_t)graph->layer_index + 1, sizeof(g_step));
+    size_t max_steps = 1;
+    for (int i = 0; i < graph->layer_index; i++)
+        max_steps += graph->layer[i]->in_num > 1 ? (size_t)graph->layer[i]->in_num : 1;
+    g->s = calloc(max_steps, sizeof(g_step));
     opt->g = g;
 
     for (int i = 0; i < graph->input_num; i++) {
@@ -486,6 +490,31 @@ static int build_from_graph(struct csinn_session *sess)
                     strncat(g->s[g->ns].name, "+act", sizeof(g->s[g->ns].name) - strlen(g->s[g->ns].name) - 1);
                 }
             }
+        }
+        if (op->kind == B200_OPK_CONCAT) {
+            /* one step per input, each writing its slice of the shared output tensor */
+            const int out_idx = tensor_add(g, out_tn);
+            int bad = out_idx < 0 || n->in_num != op->cat_n;
+            for (int j = 0; !bad && j < n->in_num; j++) {
+                g_step *s = &g->s[g->ns];
+                if (j) snprintf(s->name, sizeof(s->name), "%s", g->s[g->ns - 1].name);
+                s->op = op, s->part = j, s->in1 = -1, s->out = out_idx;
+                s->in0 = tensor_add(g, n->in[j]);
+                if (s->in0 < 0 || (g->t[s->in0].first_def < 0 && !g->t[s->in0].is_input)) {
+                    bad = 1;
+                    break;
+                }
+                g->t[s->in0].last_use = g->ns;
+                if (g->t[out_idx].first_def < 0) g->t[out_idx].first_def = g->ns;
+                g->t[out_idx].last_use = g->ns;
+                g->ns++;
+            }
+            if (bad) {
+                b200_fail("layer %d '%s': concat input that no earlier layer produced", i, n->name ? n->name : "?");
+                free(skip);
+                return CSINN_FALSE;
+            }
+            continue;
         }
         g_step *s = &g->s[g->ns];
         s->op = op;
@@ -815,7 +844,7 @@ int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, 
             g_step *s = &g->s[i];
             b200_event_record(ev[i], stream);
             const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
-            if (b200_op_run(s->op, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
+            if (b200_op_run(s->op, s->part, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
                 CSINN_TRUE)
                 return 0;
         }

@@ -381,10 +381,25 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
     return CSINN_TRUE;
 }
 
-int b200_op_run(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
+int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
                 void *scratch, void *stream)
 {
     switch (op->kind) {
+        case B200_OPK_CONCAT: {
+            if (part < 0 || part >= op->cat_n) {
+                b200_fail("concat: input %d of %d", part, op->cat_n);
+                return CSINN_FALSE;
+            }
+            b200_concat_desc c;
+            memset(&c, 0, sizeof(c));
+            c.dtype = op->dtype;
+            c.n = in0->n, c.c = in0->c, c.h = in0->h, c.w = in0->w, c.cp_in = in0->cp;
+            c.on = out->n, c.oc = out->c, c.oh = out->h, c.ow = out->w, c.cp_out = out->cp;
+            c.axis = op->cat_axis, c.offset = op->cat_off[part];
+            c.in = in0->d, c.out = out->d, c.lut = op->cat_lut[part];
+            DEV_CHECK(b200_concat_slice(&c, stream));
+            return CSINN_TRUE;
+        }
         case B200_OPK_CONV:
             return run_conv(op, in0, out, scratch, stream);
         case B200_OPK_FC: {
@@ -559,7 +574,7 @@ static int layer_exec(void *params, struct csinn_tensor *in0, struct csinn_tenso
     void *scratch = NULL;
     const size_t sb = b200_op_scratch_bytes(op, &d0, &dout);
     if (sb && !(scratch = stage(op, 6, sb))) return CSINN_FALSE;
-    if (b200_op_run(op, &d0, in1 ? &d1 : NULL, &dout, scratch, stream) != CSINN_TRUE) return CSINN_FALSE;
+    if (b200_op_run(op, 0, &d0, in1 ? &d1 : NULL, &dout, scratch, stream) != CSINN_TRUE) return CSINN_FALSE;
     DEV_CHECK(b200_nhwc_to_nchw(dout.d, d_raw, dout.n, dout.c, dout.h, dout.w, dout.cp, dout.eb, stream));
     DEV_CHECK(b200_memcpy_d2h(output->data, d_raw, raw, stream));
     DEV_CHECK(b200_stream_sync(stream));
@@ -974,6 +989,100 @@ int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *outpu
 int shl_b200_reshape(struct csinn_tensor *input, struct csinn_tensor *output, void *params)
 {
     return layer_exec(params, input, NULL, output);
+}
+
+/* ---- concat --------------------------------------------------------------------------------------------- */
+/* replaces shl_rvv_concat_int8 / _fp16 (source/thead_rvv/setup.c registrations); semantics
+ * source/reference/concat.c:52-80: each input dequantised with its own qinfo, the output quantised
+ * with its own -> one 256-entry table per input.  Any axis of a rank 1..4 tensor. */
+int shl_b200_concat_init(struct csinn_tensor **input, struct csinn_tensor *output,
+                         struct csinn_concat_params *params)
+{
+    const int k = params->inputs_count;
+    if (k < 1 || k > B200_CONCAT_MAX) {
+        b200_fail("concat: %d inputs (1..%d supported)", k, B200_CONCAT_MAX);
+        return CSINN_FALSE;
+    }
+    int axis = params->axis;
+    if (axis < 0) axis += output->dim_count;
+    if (axis < 0 || axis >= output->dim_count) {
+        b200_fail("concat: axis %d of a rank-%d tensor", params->axis, output->dim_count);
+        return CSINN_FALSE;
+    }
+    /* API axis -> device axis of b200_dt_from_tensor's (n, c, h, w) view */
+    static const int dev_axis[5][4] = {{0}, {1}, {0, 1}, {0, 1, 3}, {0, 1, 2, 3}};
+    b200_dt dout;
+    if (!b200_dt_from_tensor(&dout, output)) {
+        b200_fail("concat: unsupported output tensor (dtype %d, rank %d)", output->dtype, output->dim_count);
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(&params->base, B200_OPK_CONCAT, output->dtype, "b200_concat_slice");
+    if (!op) return CSINN_FALSE;
+    op->cat_n = k, op->cat_axis = dev_axis[output->dim_count][axis];
+    int along = 0;
+    for (int i = 0; i < k; i++) {
+        const struct csinn_tensor *t = input[i];
+        int ok = t && t->dtype == output->dtype && t->dim_count == output->dim_count && !t->is_const;
+        for (int d = 0; ok && d < output->dim_count; d++)
+            if (d != axis && t->dim[d] != output->dim[d]) ok = 0;
+        if (ok && op->dtype == B200_I8 && (!t->qinfo || !output->qinfo)) ok = 0;
+        if (!ok) {
+            b200_fail("concat: input %d does not match the output (dtype, rank, the other dimensions, qinfo) or is "
+                      "a constant", i);
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->cat_off[i] = along;
+        along += t->dim[axis];
+        if (op->dtype == B200_I8) {
+            int8_t lut[256];
+            b200_build_requant_lut(lut, B200_ACT_NONE, t->qinfo->scale, t->qinfo->zero_point, output->qinfo->scale,
+                                   output->qinfo->zero_point);
+            op->cat_lut[i] = b200_warena_put(op->ctx, lut, 256);
+            if (!op->cat_lut[i]) {
+                free(op);
+                return CSINN_FALSE;
+            }
+        }
+    }
+    if (along != output->dim[axis]) {
+        b200_fail("concat: inputs add up to %d along axis %d, the output has %d", along, axis, output->dim[axis]);
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_concat;
+    return CSINN_TRUE;
+}
+
+int shl_b200_concat(struct csinn_tensor **input, struct csinn_tensor *output, struct csinn_concat_params *params)
+{
+    b200_op *op = b200_op_find(params);
+    if (!op || op->kind != B200_OPK_CONCAT) {
+        b200_fail("concat exec before init: no b200 operator bound to these params");
+        return CSINN_FALSE;
+    }
+    b200_set_device(op->ctx->device);
+    void *stream = op->ctx->stream;
+    b200_dt dout;
+    if (!b200_dt_from_tensor(&dout, output) || !output->data) {
+        b200_fail("unsupported or unallocated output tensor");
+        return CSINN_FALSE;
+    }
+    const size_t raw = (size_t)dout.n * dout.c * dout.h * dout.w * dout.eb;
+    dout.d = stage(op, 4, b200_dt_bytes(&dout));
+    void *d_raw = stage(op, 5, raw);
+    if (!dout.d || !d_raw) return CSINN_FALSE;
+    for (int i = 0; i < op->cat_n; i++) {
+        /* the staging slots are reused input after input: everything is ordered on one stream */
+        b200_dt din;
+        if (upload_nchw(op, 0, input[i], &din, stream) != CSINN_TRUE) return CSINN_FALSE;
+        if (b200_op_run(op, i, &din, NULL, &dout, NULL, stream) != CSINN_TRUE) return CSINN_FALSE;
+    }
+    DEV_CHECK(b200_nhwc_to_nchw(dout.d, d_raw, dout.n, dout.c, dout.h, dout.w, dout.cp, dout.eb, stream));
+    DEV_CHECK(b200_memcpy_d2h(output->data, d_raw, raw, stream));
+    DEV_CHECK(b200_stream_sync(stream));
+    return CSINN_TRUE;
 }
 
 /* ---- perf callbacks: kernel name for the trace profiler ------------------------------------------------ */

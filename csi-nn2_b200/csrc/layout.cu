@@ -294,3 +294,162 @@ extern "C" int b200_im2col(const b200_im2col_desc *d, void *stream)
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+// ---- concat: one input of a concatenation copied into its slice of the output --------------------
+// source/reference/concat.c:20-72: every input is dequantised with its own qinfo, the pieces are
+// laid side by side along `axis`, the whole output is quantised with the output qinfo.  For int8
+// that is a 256-entry table per input (requant(dequant(q))); fp16 -> f32 -> fp16 is the identity.
+// One launch moves one input; V bytes per thread (16 when the channel counts allow it).  On the
+// channel axis the last input also zeroes the output's padding lanes.
+namespace b200 {
+
+struct ConcatArgs {
+    const uint8_t *in;
+    uint8_t *out;
+    const int8_t *lut;  // NULL: plain copy
+    int n, h, w;        // input pixels
+    int oh, ow;         // output rows / columns per image
+    int n_off, h_off, w_off;
+    int in_pitch, out_pitch;  // bytes per pixel
+    int row_bytes;            // bytes copied per pixel (input channels)
+    int out_byte_off;         // byte offset of the slice inside an output pixel
+    int zero_bytes;           // bytes zeroed after the slice (padding lanes)
+    int spatial;              // 1: a pixel offset has to be applied
+};
+
+template <typename VT>
+__device__ __forceinline__ VT lut_apply(VT v, const uint8_t *s_lut);
+template <>
+__device__ __forceinline__ uint8_t lut_apply<uint8_t>(uint8_t v, const uint8_t *s_lut)
+{
+    return s_lut[v ^ 0x80];
+}
+template <>
+__device__ __forceinline__ uint32_t lut_apply<uint32_t>(uint32_t v, const uint8_t *s_lut)
+{
+    uint32_t o = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) o |= static_cast<uint32_t>(s_lut[((v >> (8 * e)) & 0xFF) ^ 0x80]) << (8 * e);
+    return o;
+}
+template <>
+__device__ __forceinline__ uint4 lut_apply<uint4>(uint4 v, const uint8_t *s_lut)
+{
+    return make_uint4(lut_apply<uint32_t>(v.x, s_lut), lut_apply<uint32_t>(v.y, s_lut),
+                      lut_apply<uint32_t>(v.z, s_lut), lut_apply<uint32_t>(v.w, s_lut));
+}
+template <typename VT>
+__device__ __forceinline__ VT vec_zero();
+template <>
+__device__ __forceinline__ uint8_t vec_zero<uint8_t>() { return 0; }
+template <>
+__device__ __forceinline__ uint16_t vec_zero<uint16_t>() { return 0; }
+template <>
+__device__ __forceinline__ uint32_t vec_zero<uint32_t>() { return 0; }
+template <>
+__device__ __forceinline__ uint4 vec_zero<uint4>() { return make_uint4(0, 0, 0, 0); }
+
+template <typename VT, bool LUT>
+__global__ void __launch_bounds__(256) concat_slice_kernel(ConcatArgs a)
+{
+    pdl_launch_dependents();
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
+    __shared__ uint8_t s_lut[256];
+    if constexpr (LUT) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = static_cast<uint8_t>(a.lut[i]);
+        __syncthreads();
+    }
+    constexpr int V = sizeof(VT);
+    const int copy_units = a.row_bytes / V;
+    const int units = copy_units + a.zero_bytes / V;
+    const long long total = static_cast<long long>(a.n) * a.h * a.w * units;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i / units;
+        const int u = static_cast<int>(i - p * units);
+        long long po = p;
+        if (a.spatial) {
+            const int x = static_cast<int>(p % a.w);
+            const long long r = p / a.w;
+            const int y = static_cast<int>(r % a.h);
+            const int b = static_cast<int>(r / a.h);
+            po = (static_cast<long long>(b + a.n_off) * a.oh + (y + a.h_off)) * a.ow + (x + a.w_off);
+        }
+        VT v;
+        if (u < copy_units) {
+            v = *reinterpret_cast<const VT *>(a.in + p * a.in_pitch + static_cast<long long>(u) * V);
+            if constexpr (LUT) v = lut_apply<VT>(v, s_lut);
+        } else {
+            v = vec_zero<VT>();
+        }
+        *reinterpret_cast<VT *>(a.out + po * a.out_pitch + a.out_byte_off + static_cast<long long>(u) * V) = v;
+    }
+}
+
+template <typename VT>
+static void launch_concat(const ConcatArgs &a, int grid, cudaStream_t stream)
+{
+    if constexpr (sizeof(VT) != 2) {
+        if (a.lut) {
+            launch_kernel(concat_slice_kernel<VT, true>, dim3(grid), dim3(256), 0, stream, a);
+            return;
+        }
+    }
+    {
+        launch_kernel(concat_slice_kernel<VT, false>, dim3(grid), dim3(256), 0, stream, a);
+    }
+}
+
+}  // namespace b200
+
+extern "C" int b200_concat_slice(const b200_concat_desc *d, void *stream)
+{
+    using namespace b200;
+    const int eb = !d ? 0 : (d->dtype == B200_I8 ? 1 : (d->dtype == B200_F16 ? 2 : 0));
+    if (!d || !eb || !d->in || !d->out || d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c <= 0 || d->axis < 0 ||
+        d->axis > 3 || d->offset < 0 || d->cp_in < d->c || (d->cp_in * eb) % 16 || (d->cp_out * eb) % 16 ||
+        (d->dtype != B200_I8 && d->lut)) {
+        set_error("b200_concat_slice: bad descriptor");
+        return B200_ERR_ARG;
+    }
+    const int span[4] = {d->n, d->c, d->h, d->w}, room[4] = {d->on, d->oc, d->oh, d->ow};
+    for (int ax = 0; ax < 4; ax++) {
+        const int off = ax == d->axis ? d->offset : 0;
+        if (off + span[ax] > room[ax] || (ax != d->axis && span[ax] != room[ax])) {
+            set_error("b200_concat_slice: slice does not fit the output (axis %d: %d + %d > %d)", ax, off, span[ax],
+                      room[ax]);
+            return B200_ERR_ARG;
+        }
+    }
+    if (d->cp_out < d->oc) {
+        set_error("b200_concat_slice: output channel pitch %d below its channel count %d", d->cp_out, d->oc);
+        return B200_ERR_ARG;
+    }
+    ConcatArgs a;
+    a.in = static_cast<const uint8_t *>(d->in), a.out = static_cast<uint8_t *>(d->out), a.lut = d->lut;
+    a.n = d->n, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
+    a.n_off = d->axis == 0 ? d->offset : 0, a.h_off = d->axis == 2 ? d->offset : 0, a.w_off = d->axis == 3 ? d->offset : 0;
+    a.spatial = d->axis != 1;
+    a.in_pitch = d->cp_in * eb, a.out_pitch = d->cp_out * eb;
+    a.row_bytes = d->c * eb;
+    a.out_byte_off = d->axis == 1 ? d->offset * eb : 0;
+    // padding lanes: after the last channel slice, or after every pixel's channels on the other axes
+    const int written_to = a.out_byte_off + a.row_bytes;
+    const int is_tail = d->axis != 1 || d->offset + d->c == d->oc;
+    a.zero_bytes = is_tail ? a.out_pitch - written_to : 0;
+    int v = 16;
+    while (v > eb && (a.row_bytes % v || a.out_byte_off % v || a.zero_bytes % v)) v = v == 16 ? 4 : eb;
+    const long long total = static_cast<long long>(d->n) * d->h * d->w * ((a.row_bytes + a.zero_bytes) / v);
+    const int grid = grid_for(total, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v == 16)
+        launch_concat<uint4>(a, grid, s);
+    else if (v == 4)
+        launch_concat<uint32_t>(a, grid, s);
+    else if (v == 2)
+        launch_concat<uint16_t>(a, grid, s);
+    else
+        launch_concat<uint8_t>(a, grid, s);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -251,6 +251,23 @@ int b200_add(int dtype, const void *a, const void *b, void *out, size_t count, f
              float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
              void *stream);
 
+/* concat (source/reference/concat.c:20-72; replaces shl_rvv_concat_int8 / _fp16 of
+ * source/thead_rvv/setup.c): ONE input copied into its slice of the pixel-major output.  axis counts
+ * in (n, c, h, w) = 0..3, `offset` = sum of the earlier inputs' extents along it.  int8: `lut`
+ * (device, 256 bytes, index q + 128) is requant_out(dequant_in(q)) for this input; NULL = plain
+ * copy (fp16, where f16 -> f32 -> f16 is the identity).  The output's padding lanes are zeroed by
+ * the slice that ends at the last channel. */
+typedef struct {
+    int32_t dtype;
+    int32_t n, c, h, w, cp_in;      /* this input */
+    int32_t on, oc, oh, ow, cp_out; /* the whole output */
+    int32_t axis, offset;
+    const void *in;
+    void *out;
+    const int8_t *lut;
+} b200_concat_desc;
+int b200_concat_slice(const b200_concat_desc *d, void *stream);
+
 /* maxpool / avgpool on pixel-major tensors; reference: source/reference/maxpool.c:64,
  * averagepool.c:71 (sequential f32 sum in (y,x) order, divided by the valid-tap count unless
  * count_include_pad). global average pool = kh=h, kw=w (global_averagepool.c:21). */

@@ -92,6 +92,11 @@ int shl_b200_softmax_init(struct csinn_tensor *input, struct csinn_tensor *outpu
                           struct csinn_softmax_params *params);
 int shl_b200_softmax(struct csinn_tensor *input, struct csinn_tensor *output,
                      struct csinn_softmax_params *params);
+/* concat along any axis of rank 1..4 tensors (replaces shl_rvv_concat_int8 / shl_rvv_concat_fp16,
+ * source/thead_rvv/setup.c; semantics source/reference/concat.c:52) */
+int shl_b200_concat_init(struct csinn_tensor **input, struct csinn_tensor *output,
+                         struct csinn_concat_params *params);
+int shl_b200_concat(struct csinn_tensor **input, struct csinn_tensor *output, struct csinn_concat_params *params);
 int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params);
 int shl_b200_reshape(struct csinn_tensor *input, struct csinn_tensor *output, void *params);
 /* perf callbacks: kernel name for the trace profiler (cf. source/thead_rvv/performance.c:442);

@@ -310,6 +310,19 @@ void oracle_binary_i8(int op, const int8_t *a, const int8_t *b, int8_t *out, int
     }
 }
 
+/* concat: source/reference/concat.c:20-48 (outer x [input i: dim_i[axis] * inner] copies) between the
+ * per-input dequantisation and the output quantisation of shl_ref_concat_quant :52-80 */
+void oracle_concat_i8(int k, const int8_t *const *in, const int64_t *axis_dim, const float *s_in,
+                      const int32_t *zp_in, int64_t outer, int64_t inner, float s_out, int zp_out, int8_t *out)
+{
+    for (int64_t o = 0; o < outer; o++)
+        for (int i = 0; i < k; i++) {
+            const int64_t run = axis_dim[i] * inner;
+            const int8_t *src = in[i] + o * run;
+            for (int64_t j = 0; j < run; j++) *out++ = quant_i8(dequant_i8(src[j], s_in[i], zp_in[i]), s_out, zp_out);
+        }
+}
+
 void oracle_avgpool_i8(const oracle_pool_params *p, const int8_t *in, int8_t *out)
 {
 #pragma omp parallel for collapse(2) schedule(static)

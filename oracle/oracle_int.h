@@ -104,6 +104,8 @@ void oracle_add_i8(const int8_t *a, const int8_t *b, int8_t *out, int64_t count,
                    int zp_a, float s_b, int zp_b, float s_out, int zp_out);
 
 /* op: 0 add, 1 sub, 2 mul */
+void oracle_concat_i8(int k, const int8_t *const *in, const int64_t *axis_dim, const float *s_in,
+                      const int32_t *zp_in, int64_t outer, int64_t inner, float s_out, int zp_out, int8_t *out);
 void oracle_binary_i8(int op, const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,
                       int zp_a, float s_b, int zp_b, float s_out, int zp_out);
 

@@ -41,6 +41,7 @@ enum {
     H_CLIP,       /* csinn_clip, [p0, p1] */
     H_SUB,
     H_MUL,
+    H_CONCAT, /* csinn_concat of (in0, in1) along `axis`; p0 == 3: of (in0, in1, in0) */
 };
 
 typedef struct {
@@ -232,6 +233,14 @@ static int layer_init(h_net *net, int i)
             if (L->kind == H_MUL) return csinn_mul_init(in, net->t[L->in1], out, p);
             return csinn_add_init(in, net->t[L->in1], out, p);
         }
+        case H_CONCAT: {
+            struct csinn_concat_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->inputs_count = L->p0 == 3.f ? 3 : 2, p->axis = L->axis;
+            net->params[i] = p;
+            struct csinn_tensor *ins[3] = {in, net->t[L->in1], in};
+            return csinn_concat_init(ins, out, p);
+        }
         case H_MAXPOOL:
         case H_AVGPOOL:
         case H_GAP: {
@@ -304,6 +313,10 @@ static int layer_call(h_net *net, int i)
             return csinn_mul(in, net->t[L->in1], out, p);
         case H_ADD:
             return csinn_add(in, net->t[L->in1], out, p);
+        case H_CONCAT: {
+            struct csinn_tensor *ins[3] = {in, net->t[L->in1], in};
+            return csinn_concat(ins, out, p);
+        }
         case H_MAXPOOL:
             return csinn_maxpool2d(in, out, p);
         case H_AVGPOOL:

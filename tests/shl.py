@@ -28,7 +28,7 @@ API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
 RM_LAYER, RM_GRAPH = 0, 1
 
 (H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
- H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL) = range(19)
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL, H_CONCAT) = range(20)
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 UNARY_LEAKY_RELU, UNARY_SIGMOID, UNARY_CLIP = 3, 4, 5
@@ -380,6 +380,23 @@ class Oracle:
         out = np.empty_like(a)
         self.lib.oracle_binary_i8(op, _ptr(a), _ptr(b), _ptr(out), C.c_int64(a.size), C.c_float(s_a), zp_a,
                                   C.c_float(s_b), zp_b, C.c_float(s_out), zp_out)
+        return out
+
+    def concat_i8(self, xs, qs, axis, s_out, zp_out):
+        """xs: int8 arrays equal in every dimension but `axis`; qs: their (scale, zero_point)"""
+        xs = [np.ascontiguousarray(x, np.int8) for x in xs]
+        shape = list(xs[0].shape)
+        shape[axis] = sum(x.shape[axis] for x in xs)
+        out = np.empty(shape, np.int8)
+        k = len(xs)
+        ptrs = (C.c_void_p * k)(*[x.ctypes.data for x in xs])
+        dims = (C.c_int64 * k)(*[x.shape[axis] for x in xs])
+        sc = (C.c_float * k)(*[q[0] for q in qs])
+        zp = (C.c_int32 * k)(*[q[1] for q in qs])
+        outer = int(np.prod(shape[:axis], dtype=np.int64))
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        self.lib.oracle_concat_i8(k, ptrs, dims, sc, zp, C.c_int64(outer), C.c_int64(inner), C.c_float(s_out), zp_out,
+                                  _ptr(out))
         return out
 
     def add_i8(self, a, b, s_a, zp_a, s_b, zp_b, s_out, zp_out):

@@ -668,3 +668,51 @@ def test_binary_ops_on_rounding_ties_and_saturation(kind, op, b200, oracle, rng)
         want = oracle.binary_i8(op, x, r, s_a, zp_a, s_r, zp_r, s_out, zp_out)
         got = b200.run(DT_INT8, shape, layers, x, s_in=s_a, zp_in=zp_a, run_mode=RM_GRAPH)
         assert np.array_equal(got, want), (s_a, s_r, s_out, int(np.count_nonzero(got != want)))
+
+
+from test_oracle import CONCAT_CASES, concat_case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,axis,three", CONCAT_CASES)
+def test_concat_int8_bit_exact(shape, axis, three, b200, oracle, rng):
+    x, layers, want = concat_case(shape, axis, three, oracle, rng)
+    for mode in (RM_LAYER, RM_GRAPH):
+        got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=mode)
+        assert np.array_equal(got, want), mode
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,axis,three", CONCAT_CASES)
+def test_concat_fp16_is_a_copy(shape, axis, three, b200, rng):
+    from shl import H_CONCAT
+    x = rng.standard_normal(shape).astype(np.float16)
+    out_shape = list(shape)
+    out_shape[axis] *= 3 if three else 2
+    layers = [Layer(H_RELU, shape), Layer(H_CONCAT, tuple(out_shape), in0=0, in1=1, axis=axis, p0=3.0 if three else 0.0)]
+    r = np.maximum(x, np.float16(0))
+    want = np.concatenate([x, r, x] if three else [x, r], axis=axis)
+    for mode in (RM_LAYER, RM_GRAPH):
+        got = b200.run(DT_F16, shape, layers, x, run_mode=mode)
+        assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), mode
+
+
+@pytest.mark.gpu
+def test_concat_feeds_a_convolution_in_graph_mode(b200, oracle, rng):
+    """an inception-style join: the channel padding lanes of the concatenated tensor are read by the next GEMM"""
+    from shl import H_CONCAT
+    shape = (2, 13, 6, 6)
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    o, c = 24, 26
+    w = rng.integers(-127, 128, size=(o, c, 1, 1), dtype=np.int8)
+    s_w = (1e-3 * (1 + np.arange(o) / o)).astype(np.float32)
+    b = rng.integers(-1000, 1000, size=o, dtype=np.int32)
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128),
+              Layer(H_CONCAT, (2, c, 6, 6), in0=0, in1=1, s_out=0.033, zp_out=5, axis=1),
+              Layer(H_CONV, (2, o, 6, 6), w=w, b=b, s_w=s_w, s_out=0.05, zp_out=-3)]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    cat = oracle.concat_i8([x, r], [(0.04, 3), (0.021, -128)], 1, 0.033, 5)
+    want = oracle.conv2d_i8(cat, w, b, (2, o, 6, 6), stride=(1, 1), pad=(0,) * 4, dilation=(1, 1), group=1, s_in=0.033,
+                            zp_in=5, s_w=s_w, s_b=None, s_out=0.05, zp_out=-3)
+    got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=RM_GRAPH)
+    assert np.array_equal(got, want)

@@ -300,3 +300,36 @@ def test_sub_mul_oracle_equals_the_reference(kind, op, s_out, zp_out, ref, oracl
     got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
     r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
     assert np.array_equal(got, oracle.binary_i8(op, x, r, 0.04, 3, 0.021, -128, s_out, zp_out))
+
+
+CONCAT_CASES = [
+    # shape of the network input, axis, three inputs?  (the second operand is relu(input) with its own qinfo)
+    ((2, 32, 9, 11), 1, False),
+    ((2, 13, 5, 7), 1, True),
+    ((2, 24, 6, 5), 2, False),
+    ((3, 7, 4, 9), 3, True),
+    ((2, 16, 3, 3), 0, False),
+]
+
+
+def concat_case(shape, axis, three, oracle, rng):
+    """network: t1 = relu(x) requantised; out = concat(x, t1[, x]) along axis"""
+    from shl import H_CONCAT
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    out_shape = list(shape)
+    out_shape[axis] *= 3 if three else 2
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128),
+              Layer(H_CONCAT, tuple(out_shape), in0=0, in1=1, s_out=0.033, zp_out=5, axis=axis, p0=3.0 if three else 0.0)]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    xs, qs = [x, r], [(0.04, 3), (0.021, -128)]
+    if three:
+        xs, qs = xs + [x], qs + [(0.04, 3)]
+    return x, layers, oracle.concat_i8(xs, qs, axis, 0.033, 5)
+
+
+@pytest.mark.parametrize("shape,axis,three", CONCAT_CASES)
+def test_concat_oracle_equals_the_reference(shape, axis, three, ref, oracle, rng):
+    """csinn_concat (source/reference/concat.c:52): oracle vs the reference library, bit for bit"""
+    x, layers, want = concat_case(shape, axis, three, oracle, rng)
+    got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
+    assert np.array_equal(got, want)
