@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(128, 5) dwconv3x3_f16_kernel(const DwArgs a, i
 using namespace b200;
 
 int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream);  // dwconv3x3_tma.cu
+int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_umma.cu
 
 extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
 {
@@ -404,8 +405,13 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         // the TMA kernel folds zero-point padding into per-class accumulator seeds: at most one
         // padded row / column on each side of any output's 3x3 window
         d->pad_top <= 1 && d->pad_left <= 1 && (d->oh - 1) * d->stride_h - d->pad_top + 2 <= d->h &&
-        (d->ow - 1) * d->stride_w - d->pad_left + 2 <= d->w)
+        (d->ow - 1) * d->stride_w - d->pad_left + 2 <= d->w) {
+        // stride 1 with "same" padding: the taps are accumulated on the tensor cores
+        int handled = 0;
+        const int rc = b200_dwconv3x3_umma_launch(d, d->wt_row3, stream, &handled);
+        if (rc || handled) return rc;
         return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);
+    }
     DwArgs a;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
     a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;

@@ -87,11 +87,17 @@ static encode_tiled_fn encode_entry()
 int encode_tmap_nhwc_u8(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
                         int box_w, int box_h)
 {
+    return encode_tmap_nhwc_u8_nb(map, base, n, h, w, cp, box_c, box_w, box_h, 1);
+}
+
+int encode_tmap_nhwc_u8_nb(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c,
+                           int box_w, int box_h, int box_n)
+{
     encode_tiled_fn fn = encode_entry();
     if (!fn) return B200_ERR_CUDA;
     cuuint64_t gdim[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t gstride[3] = {(cuuint64_t)cp, (cuuint64_t)cp * w, (cuuint64_t)cp * w * h};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
