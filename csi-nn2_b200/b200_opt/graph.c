@@ -180,7 +180,8 @@ static int tensor_add(b200_graph *g, struct shl_node *n)
 static int is_act_node(const struct shl_node *n)
 {
     return n->type == CSINN_OP_RELU || n->type == CSINN_OP_RELU6 || n->type == CSINN_OP_LEAKY_RELU ||
-           n->type == CSINN_OP_SIGMOID || n->type == CSINN_OP_CLIP;
+           n->type == CSINN_OP_SIGMOID || n->type == CSINN_OP_CLIP || n->type == CSINN_OP_SILU ||
+           n->type == CSINN_OP_ERF;
 }
 static int act_of_node(const struct shl_node *n, float *p0, float *p1)
 {
@@ -195,6 +196,10 @@ static int act_of_node(const struct shl_node *n, float *p0, float *p1)
             return B200_ACT_LEAKY_RELU;
         case CSINN_OP_SIGMOID:
             return B200_ACT_SIGMOID;
+        case CSINN_OP_SILU:
+            return B200_ACT_SILU;
+        case CSINN_OP_ERF:
+            return B200_ACT_ERF;
         default:
             *p0 = ((struct csinn_clip_params *)n->data)->min_value;
             *p1 = ((struct csinn_clip_params *)n->data)->max_value;

@@ -755,7 +755,7 @@ int shl_b200_fullyconnected(struct csinn_tensor *input, struct csinn_tensor *out
 
 /* ---- relu / relu6 -------------------------------------------------------------------------------- */
 static const char *const kActNames[] = {"b200_identity", "b200_relu", "b200_relu6", "b200_leaky_relu", "b200_sigmoid",
-                                        "b200_clip"};
+                                        "b200_clip", "b200_silu", "b200_erf"};
 
 static int act_init_p(struct csinn_tensor *input, struct csinn_tensor *output, void *params, int act, float p0, float p1)
 {
@@ -799,6 +799,18 @@ static int clip_init(struct csinn_tensor *input, struct csinn_tensor *output, st
 {
     return act_init_p(input, output, params, B200_ACT_CLIP, params->min_value, params->max_value);
 }
+/* silu / erf: replace the shl_gref_silu / shl_gref_erf registrations of source/thead_rvv/setup.c (which run
+ * source/reference/silu.c:37, erf.c:37) */
+static int silu_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_sigmoid_params *params)
+{
+    return act_init_p(input, output, params, B200_ACT_SILU, 0.f, 0.f);
+}
+static int erf_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_siso_params *params)
+{
+    return act_init_p(input, output, params, B200_ACT_ERF, 0.f, 0.f);
+}
+void *shl_b200_silu_init_fn(void) { return (void *)silu_init; }
+void *shl_b200_erf_init_fn(void) { return (void *)erf_init; }
 void *shl_b200_leaky_relu_init_fn(void) { return (void *)leaky_relu_init; }
 void *shl_b200_sigmoid_init_fn(void) { return (void *)sigmoid_init; }
 void *shl_b200_clip_init_fn(void) { return (void *)clip_init; }

@@ -73,6 +73,8 @@ static void build_table(void)
         reg_op(dt, CSINN_OP_RELU6, shl_b200_relu6_init_fn(), shl_b200_relu, shl_gref_relu6, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_LEAKY_RELU, shl_b200_leaky_relu_init_fn(), shl_b200_relu, shl_gref_leaky_relu, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_SIGMOID, shl_b200_sigmoid_init_fn(), shl_b200_relu, shl_gref_sigmoid, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_SILU, shl_b200_silu_init_fn(), shl_b200_relu, shl_gref_silu, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_ERF, shl_b200_erf_init_fn(), shl_b200_relu, shl_gref_erf, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_CLIP, shl_b200_clip_init_fn(), shl_b200_relu, shl_gref_clip, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_ADD, shl_b200_add_init, shl_b200_add, shl_gref_add, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_SUB, shl_b200_sub_init_fn(), shl_b200_add, shl_gref_sub, shl_b200_perf_diso);

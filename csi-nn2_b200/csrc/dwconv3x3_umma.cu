@@ -45,6 +45,7 @@ struct DwUmmaArgs {
     uint32_t inv_twi, inv_thi;  // floor(2^32 / d) + 1: exact quotients for the small flat indices
     uint32_t idesc;
     int swap_lbo_sbo;  // diagnostic: exchange the two descriptor strides
+    int diag;          // diagnostic (wrong results): 1 = no TMA after the ring's first fill, 2 = no MMAs, 4 = no epilogue math / stores
     const uint32_t *wrow;  // [3 (ky)][cp] words (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0)
     int8_t *out;
     int zp_in;
@@ -151,6 +152,11 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
             for (int t = t0; t < a.ntiles; t += tstep) {
                 const int yb = t % a.ybands, img0 = (t / a.ybands) * a.nb;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                if ((a.diag & 1) && phase) {
+                    mbar_arrive(&full_bar[stage]);
+                    if (++stage == kUStages) stage = 0, phase ^= 1;
+                    continue;
+                }
                 mbar_expect_tx(&full_bar[stage], 2 * a.plane_bytes);
                 uint8_t *dst = smem + static_cast<size_t>(stage) * 2 * a.plane_stride;
                 tma_load_4d(dst, &tmap, &full_bar[stage], cc * 32, -1, yb * a.th - 1, img0);
@@ -171,7 +177,7 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t tile = smem_u32(smem + static_cast<size_t>(stage) * 2 * a.plane_stride);
-                for (int mb = 0; mb < nmb; mb++) {
+                for (int mb = 0; mb < ((a.diag & 2) ? 0 : nmb); mb++) {
 #pragma unroll
                     for (int pl = 0; pl < 2; pl++) {
                         const uint32_t d = tmem_base + buf * kUBufCols + (mb * 2 + pl) * 16;
@@ -231,7 +237,7 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
             const int nmb = blocks_of(yb);
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            for (int mb = 0; mb < nmb; mb++) {
+            for (int mb = 0; mb < ((a.diag & 4) ? 0 : nmb); mb++) {
                 uint32_t acc[16];
                 tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kUBufCols + (mb * 2 + g) * 16, acc);
                 const uint32_t p = mb * 128 + q * 32 + lane;
@@ -281,7 +287,7 @@ int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void
 {
     *handled = 0;
     const char *e_on = getenv("SHL_B200_DW_UMMA"), *e_swap = getenv("SHL_B200_DW_UMMA_SWAP");
-    const int enabled = e_on ? atoi(e_on) : 1, swap = e_swap ? atoi(e_swap) : 0;
+    const int enabled = e_on ? atoi(e_on) : 0, swap = e_swap ? atoi(e_swap) : 0;
     if (!enabled) return B200_OK;
     if (d->stride_h != 1 || d->stride_w != 1 || d->pad_top != 1 || d->pad_left != 1 || d->oh != d->h || d->ow != d->w)
         return B200_OK;
@@ -326,6 +332,7 @@ int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void
     a.inv_thi = static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(thi)) + 1;
     a.idesc = umma_idesc(2 /*S32*/, 1 /*S8*/, 128, 16);
     a.swap_lbo_sbo = swap;
+    a.diag = getenv("SHL_B200_DW_UMMA_DIAG") ? atoi(getenv("SHL_B200_DW_UMMA_DIAG")) : 0;
     a.wrow = static_cast<const uint32_t *>(wrow);
     a.out = static_cast<int8_t *>(d->out);
     a.zp_in = d->zp_in;

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256) unary_f16_kernel(const uint4 *__restrict_
                 if (act == B200_ACT_LEAKY_RELU) r = r > 0.f ? r : r * p0;
                 else if (act == B200_ACT_SIGMOID) r = static_cast<float>(1.0 / (1.0 + exp(-static_cast<double>(r))));
                 else if (act == B200_ACT_CLIP) r = r < p0 ? p0 : (r > p1 ? p1 : r);
+                else if (act == B200_ACT_SILU) r = static_cast<float>(static_cast<double>(r) / (1.0 + exp(-static_cast<double>(r))));
+                else if (act == B200_ACT_ERF) r = static_cast<float>(erf(static_cast<double>(r)));
                 else r = act_f(r, act);
                 x[e] = r;
             }

@@ -370,6 +370,12 @@ void b200_build_unary_lut(int8_t lut[256], int act, float p0, float p1, float s_
             case B200_ACT_CLIP:
                 r = r < p0 ? p0 : (r > p1 ? p1 : r);
                 break;
+            case B200_ACT_SILU: /* val / (1.0f + exp(-val)): double arithmetic, stored to float */
+                r = (float)((double)r / (1.0f + exp(-(double)r)));
+                break;
+            case B200_ACT_ERF:
+                r = (float)erf((double)r);
+                break;
             default:
                 break;
         }

@@ -67,7 +67,9 @@ typedef enum {
      * in-epilogue clamp: source/reference/leaky_relu.c:33, sigmoid.c:33, clip.c:32-38 */
     B200_ACT_LEAKY_RELU = 3, /* p0 = negative slope */
     B200_ACT_SIGMOID = 4,
-    B200_ACT_CLIP = 5        /* p0 = min, p1 = max */
+    B200_ACT_CLIP = 5,       /* p0 = min, p1 = max */
+    B200_ACT_SILU = 6,       /* val / (1.0f + exp(-val)), source/reference/silu.c:31 */
+    B200_ACT_ERF = 7         /* erf(val), source/reference/erf.c:31 */
 } b200_act;
 
 /* Requantisation / epilogue parameters shared by conv, depthwise, fc.

@@ -78,6 +78,8 @@ void *shl_b200_mul_init_fn(void);
 void *shl_b200_leaky_relu_init_fn(void);
 void *shl_b200_sigmoid_init_fn(void);
 void *shl_b200_clip_init_fn(void);
+void *shl_b200_silu_init_fn(void); /* csinn_silu: val / (1 + exp(-val)), source/reference/silu.c:21 */
+void *shl_b200_erf_init_fn(void);  /* csinn_erf, source/reference/erf.c:21 */
 int shl_b200_relu(struct csinn_tensor *input, struct csinn_tensor *output,
                   struct csinn_relu_params *params);
 int shl_b200_add_init(struct csinn_tensor *input0, struct csinn_tensor *input1,

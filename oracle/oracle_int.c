@@ -278,6 +278,12 @@ void oracle_unary_i8(const int8_t *in, int8_t *out, int64_t count, int op, float
             case ORACLE_UNARY_SIGMOID:
                 r = 1.0f / (1.0f + exp(-val));
                 break;
+            case ORACLE_UNARY_SILU: /* silu.c:31 */
+                r = val / (1.0f + exp(-val));
+                break;
+            case ORACLE_UNARY_ERF: /* erf.c:31 */
+                r = erf(val);
+                break;
             default: /* ORACLE_UNARY_CLIP */
                 if (val < p0)
                     r = p0;

@@ -97,7 +97,7 @@ int oracle_fc_f32(const oracle_conv_params *p, const float *in, const float *wt,
 /* elementwise, bit-exact float sequence (relu.c:39, relu6.c, add.c:36) */
 void oracle_relu_i8(const int8_t *in, int8_t *out, int64_t count, int act, float s_in, int zp_in,
                     float s_out, int zp_out);
-enum { ORACLE_UNARY_LEAKY_RELU = 3, ORACLE_UNARY_SIGMOID = 4, ORACLE_UNARY_CLIP = 5 };
+enum { ORACLE_UNARY_LEAKY_RELU = 3, ORACLE_UNARY_SIGMOID = 4, ORACLE_UNARY_CLIP = 5, ORACLE_UNARY_SILU = 6, ORACLE_UNARY_ERF = 7 };
 void oracle_unary_i8(const int8_t *in, int8_t *out, int64_t count, int op, float p0, float p1, float s_in,
                      int zp_in, float s_out, int zp_out);
 void oracle_add_i8(const int8_t *a, const int8_t *b, int8_t *out, int64_t count, float s_a,

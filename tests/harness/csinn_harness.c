@@ -42,6 +42,8 @@ enum {
     H_SUB,
     H_MUL,
     H_CONCAT, /* csinn_concat of (in0, in1) along `axis`; p0 == 3: of (in0, in1, in0) */
+    H_SILU,
+    H_ERF,
 };
 
 typedef struct {
@@ -216,6 +218,18 @@ static int layer_init(h_net *net, int i)
             net->params[i] = p;
             return csinn_sigmoid_init(in, out, p);
         }
+        case H_SILU: {
+            struct csinn_sigmoid_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            net->params[i] = p;
+            return csinn_silu_init(in, out, p);
+        }
+        case H_ERF: {
+            struct csinn_siso_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            net->params[i] = p;
+            return csinn_erf_init(in, out, p);
+        }
         case H_CLIP: {
             struct csinn_clip_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -307,6 +321,10 @@ static int layer_call(h_net *net, int i)
             return csinn_sigmoid(in, out, p);
         case H_CLIP:
             return csinn_clip(in, out, p);
+        case H_SILU:
+            return csinn_silu(in, out, p);
+        case H_ERF:
+            return csinn_erf(in, out, p);
         case H_SUB:
             return csinn_sub(in, net->t[L->in1], out, p);
         case H_MUL:

@@ -461,8 +461,8 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     the halo, unpadded borders and a fused relu table"""
     if rows == "generic":
         os.environ["SHL_B200_DW_GENERIC"] = "1"
-    if rows == "tma":
-        os.environ["SHL_B200_DW_UMMA"] = "0"
+    if rows == "umma":
+        os.environ["SHL_B200_DW_UMMA"] = "1"
     try:
         for (n, c, h, w, stride, pad, zp_in) in [(2, 32, 13, 29, 1, 1, -7), (7, 48, 7, 7, 1, 1, 5), (5, 16, 3, 2, 1, 1, -3),
                                                  (1, 40, 1, 1, 1, 1, 9), (1, 16, 40, 200, 1, 1, -9), (1, 64, 56, 56, 1, 1, 0),
@@ -573,7 +573,8 @@ def test_binary_model_saved_and_restored_on_b200(dtype, b200, tmp_path):
         assert np.array_equal(got.reshape(2, -1), nets.oracle_forward(nb, x).reshape(2, -1))
 
 
-UNARY = [("leaky", 14, 3, 0.1, 0.0), ("sigmoid", 15, 4, 0.0, 0.0), ("clip", 16, 5, -0.5, 1.25)]
+UNARY = [("leaky", 14, 3, 0.1, 0.0), ("sigmoid", 15, 4, 0.0, 0.0), ("clip", 16, 5, -0.5, 1.25), ("silu", 20, 6, 0.0, 0.0),
+         ("erf", 21, 7, 0.0, 0.0)]
 
 
 @pytest.mark.gpu
@@ -605,7 +606,8 @@ def test_unary_ops_fp16_within_tolerance(name, kind, op, p0, p1, b200, rng):
     got = b200.run(DT_F16, x.shape, [Layer(kind, x.shape, p0=p0, p1=p1)], x).astype(np.float32)
     xf = x.astype(np.float32)
     want = {3: np.where(xf > 0, xf, xf * np.float32(p0)), 4: 1.0 / (1.0 + np.exp(-xf.astype(np.float64))),
-            5: np.clip(xf, p0, p1)}[op].astype(np.float32)
+            5: np.clip(xf, p0, p1), 6: xf.astype(np.float64) / (1.0 + np.exp(-xf.astype(np.float64))),
+            7: np.vectorize(__import__("math").erf)(xf.astype(np.float64))}[op].astype(np.float32)
     f16_close(got.astype(np.float16), want)
 
 
@@ -619,7 +621,7 @@ def test_graph_mode_fuses_unary_nodes_into_their_producer(b200, rng):
     shl.shl_b200_session_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     n, c, h, w, o = 1, 32, 8, 8, 32
     wt, s_w, b, s_out = synth_conv_i8(rng, c, o, 1, 1)
-    for kind, p0, p1 in [(H_RELU, 0, 0), (14, 0.1, 0), (15, 0, 0), (16, -0.5, 1.0)]:
+    for kind, p0, p1 in [(H_RELU, 0, 0), (14, 0.1, 0), (15, 0, 0), (16, -0.5, 1.0), (20, 0, 0), (21, 0, 0)]:
         layers = [Layer(H_CONV, (n, o, h, w), s_out=s_out, zp_out=4, w=wt, b=b, s_w=s_w),
                   Layer(kind, (n, o, h, w), s_out=s_out / 3, zp_out=-100, p0=p0, p1=p1)]
         net = b200.create(DT_INT8, (n, c, h, w), layers, s_in=0.02, zp_in=-5, run_mode=RM_GRAPH)

@@ -277,9 +277,10 @@ def test_binary_model_round_trip_through_the_reference(ref, rng, tmp_path):
 
 
 @pytest.mark.parametrize("kind,op,p0,p1", [(14, 3, 0.1, 0.0), (14, 3, 0.015625, 0.0), (15, 4, 0.0, 0.0), (16, 5, -1.0, 2.5),
-                                           (16, 5, 0.0, 6.0)], ids=["leaky0.1", "leaky2^-6", "sigmoid", "clip-1_2.5", "clip0_6"])
+                                           (16, 5, 0.0, 6.0), (20, 6, 0.0, 0.0), (21, 7, 0.0, 0.0)],
+                         ids=["leaky0.1", "leaky2^-6", "sigmoid", "clip-1_2.5", "clip0_6", "silu", "erf"])
 def test_unary_ops_oracle_equals_the_reference(kind, op, p0, p1, ref, oracle, rng):
-    """leaky relu / sigmoid / clip (source/reference/leaky_relu.c:33, sigmoid.c:33, clip.c:32-38
+    """leaky relu / sigmoid / clip / silu / erf (source/reference/leaky_relu.c:33, sigmoid.c:33, clip.c:32-38, silu.c:31, erf.c:31
     through shl_ref_siso_callback_base): the oracle's float sequence against the reference library,
     every int8 input value, bit for bit"""
     x = np.arange(-128, 128, dtype=np.int8).reshape(1, 16, 4, 4)
