@@ -902,7 +902,7 @@ static int pool_init_common(struct csinn_tensor *input, struct csinn_tensor *out
         return CSINN_UNSUPPORT_LAYOUT;
     }
     b200_op *op = op_new(&params->base, B200_OPK_POOL, input->dtype,
-                         global ? "b200_global_avgpool" : (avg ? "b200_avgpool" : "b200_maxpool"));
+                         global ? (avg ? "b200_global_avgpool" : "b200_global_maxpool") : (avg ? "b200_avgpool" : "b200_maxpool"));
     if (!op) return CSINN_FALSE;
     op->pool_avg = avg, op->pool_global = global;
     op->kh = params->filter_height, op->kw = params->filter_width;
@@ -942,6 +942,14 @@ static int global_avgpool_init(struct csinn_tensor *input, struct csinn_tensor *
 {
     return pool_init_common(input, output, params, 1, 1);
 }
+/* replaces shl_rvv_global_maxpool2d_init_int8 / _fp16 (source/thead_rvv/setup.c); semantics
+ * source/reference/global_maxpool.c:21: max pooling over the whole map, stride 1, no padding */
+static int global_maxpool_init(struct csinn_tensor *input, struct csinn_tensor *output,
+                               struct csinn_pool_params *params)
+{
+    return pool_init_common(input, output, params, 0, 1);
+}
+void *shl_b200_global_maxpool_init_fn(void) { return (void *)global_maxpool_init; }
 void *shl_b200_avgpool_init_fn(void) { return (void *)avgpool_init; }
 void *shl_b200_global_avgpool_init_fn(void) { return (void *)global_avgpool_init; }
 int shl_b200_pool2d(struct csinn_tensor *input, struct csinn_tensor *output,

@@ -83,6 +83,7 @@ static void build_table(void)
         reg_op(dt, CSINN_OP_MAXPOOL2D, shl_b200_pool2d_init, shl_b200_pool2d, shl_gref_maxpool2d, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_AVGPOOL2D, shl_b200_avgpool_init_fn(), shl_b200_pool2d, shl_gref_avgpool2d, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_GLOBAL_AVGPOOL2D, shl_b200_global_avgpool_init_fn(), shl_b200_pool2d, shl_gref_global_avgpool2d, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_GLOBAL_MAXPOOL2D, shl_b200_global_maxpool_init_fn(), shl_b200_pool2d, shl_gref_global_maxpool2d, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_SOFTMAX, shl_b200_softmax_init, shl_b200_softmax, shl_gref_softmax, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_RESHAPE, shl_b200_reshape_init, shl_b200_reshape, shl_gref_reshape, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_FLATTEN, shl_b200_reshape_init, shl_b200_reshape, shl_gref_flatten, shl_b200_perf_siso);

@@ -170,32 +170,41 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            // descriptors are constants up to the A start address: the upper word (SBO, version) and the
+            // LBO field of each tap pair once, per MMA one add into the 14-bit address field
+            uint64_t a_tmpl[5], b_desc[2][5];
+            uint32_t a_off[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int ta = 2 * j, tb = 2 * j + 1;  // taps of this K = 32 step: flat offsets (ky * twi + kx) pixels
+                const int offa = (ta / 3) * a.twi + ta % 3;
+                const int offb = j < 4 ? (tb / 3) * a.twi + tb % 3 : offa + 1;
+                const uint32_t lbo = static_cast<uint32_t>(offb - offa) * 16;
+                a_tmpl[j] = a.swap_lbo_sbo ? umma_desc_nosw(0, 128, lbo) : umma_desc_nosw(0, lbo, 128);
+                a_off[j] = static_cast<uint32_t>(offa);
+#pragma unroll
+                for (int pl = 0; pl < 2; pl++)
+                    b_desc[pl][j] = a.swap_lbo_sbo ? umma_desc_nosw(smem_u32(s_b) + (pl * 5 + j) * 512, 128, 256)
+                                                   : umma_desc_nosw(smem_u32(s_b) + (pl * 5 + j) * 512, 256, 128);
+            }
+            const uint32_t plane16 = static_cast<uint32_t>(a.plane_stride) >> 4;
             for (int t = t0; t < a.ntiles; t += tstep, it++) {
                 const int buf = it & 1;
                 const int nmb = blocks_of(t % a.ybands);
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tile = smem_u32(smem + static_cast<size_t>(stage) * 2 * a.plane_stride);
+                // start addresses in 16-byte units (= pixels); the whole ring lies below 256 KB
+                const uint32_t tile16 = (smem_u32(smem) + static_cast<uint32_t>(stage) * 2 * a.plane_stride) >> 4;
+                uint32_t d = tmem_base + buf * kUBufCols;
                 for (int mb = 0; mb < ((a.diag & 2) ? 0 : nmb); mb++) {
 #pragma unroll
                     for (int pl = 0; pl < 2; pl++) {
-                        const uint32_t d = tmem_base + buf * kUBufCols + (mb * 2 + pl) * 16;
-                        const uint32_t abase = tile + pl * a.plane_stride + mb * 128 * 16;
+                        const uint32_t abase = tile16 + pl * plane16 + mb * 128;
 #pragma unroll
-                        for (int j = 0; j < 5; j++) {
-                            // taps 2j and 2j+1: flat offsets (ky * twi + kx) pixels
-                            const int ta = 2 * j, tb = 2 * j + 1;
-                            const int offa = (ta / 3) * a.twi + ta % 3;
-                            const int offb = j < 4 ? (tb / 3) * a.twi + tb % 3 : offa + 1;
-                            const uint32_t lbo = static_cast<uint32_t>(offb - offa) * 16;
-                            const uint64_t adesc = a.swap_lbo_sbo ? umma_desc_nosw(abase + offa * 16, 128, lbo)
-                                                                  : umma_desc_nosw(abase + offa * 16, lbo, 128);
-                            const uint64_t bdesc = a.swap_lbo_sbo
-                                                       ? umma_desc_nosw(smem_u32(s_b) + (pl * 5 + j) * 512, 128, 256)
-                                                       : umma_desc_nosw(smem_u32(s_b) + (pl * 5 + j) * 512, 256, 128);
-                            tc_mma_i8(d, adesc, bdesc, a.idesc, j > 0 ? 1u : 0u);
-                        }
+                        for (int j = 0; j < 5; j++)
+                            tc_mma_i8(d, a_tmpl[j] + (abase + a_off[j]), b_desc[pl][j], a.idesc, j > 0 ? 1u : 0u);
+                        d += 16;
                     }
                 }
                 tc_commit(&empty_bar[stage]);  // the slot is free once these MMAs have read it
@@ -227,6 +236,22 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
             }
         }
         const uint32_t seed0 = smem_u32(s_seed + g * 16);
+        // the pixel a thread owns in 128-pixel block mb does not depend on the tile: decode once.
+        // pix[mb] = image in the tile (8 bits) | tile row (8) | column class (2) | column valid (1); ooff[mb] = its
+        // byte offset inside the tile's output (host-checked < 2^32)
+        uint32_t pix[kUMaxMB], ooff[kUMaxMB];
+#pragma unroll
+        for (int mb = 0; mb < kUMaxMB; mb++) {
+            const uint32_t p = mb * 128 + q * 32 + lane;
+            const uint32_t r = __umulhi(p, a.inv_twi);
+            const uint32_t xx = p - r * a.twi;
+            const uint32_t nbi = __umulhi(r, a.inv_thi);
+            const uint32_t yy = r - nbi * a.thi;
+            const uint32_t colc = (xx == 0 ? 1u : 0u) | (xx == static_cast<uint32_t>(a.w - 1) ? 2u : 0u);
+            const bool okc = ch_ok && xx < static_cast<uint32_t>(a.w) && nbi < static_cast<uint32_t>(a.nb) && yy < static_cast<uint32_t>(a.th);
+            pix[mb] = (nbi << 24) | (yy << 16) | (colc << 1) | (okc ? 1u : 0u);
+            ooff[mb] = ((nbi * a.h + yy) * a.w + xx) * a.cp + chs;
+        }
         pdl_wait();  // the output buffer may alias a tensor the predecessor still reads
         int it = 0;
         for (int t = t0; t < a.ntiles; t += tstep, it++) {
@@ -235,19 +260,18 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
             const int y0 = yb * a.th;
             const int rows_out = min(a.th, a.h - y0);
             const int nmb = blocks_of(yb);
+            int8_t *obase = a.out + (static_cast<size_t>(img0) * a.h + y0) * a.w * a.cp;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            for (int mb = 0; mb < ((a.diag & 4) ? 0 : nmb); mb++) {
+#pragma unroll
+            for (int mb = 0; mb < kUMaxMB; mb++) {
+                if (mb >= ((a.diag & 4) ? 0 : nmb)) break;
                 uint32_t acc[16];
                 tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kUBufCols + (mb * 2 + g) * 16, acc);
-                const uint32_t p = mb * 128 + q * 32 + lane;
-                const uint32_t r = __umulhi(p, a.inv_twi);
-                const int xx = static_cast<int>(p - r * a.twi);
-                const uint32_t nbi = __umulhi(r, a.inv_thi);
-                const int yy = static_cast<int>(r - nbi * a.thi);
-                const int img = img0 + static_cast<int>(nbi), y = y0 + yy;
-                const bool ok = ch_ok && xx < a.w && yy < rows_out && static_cast<int>(nbi) < a.nb && img < a.n;
-                const int cls = (xx == 0 ? 1 : 0) | (xx == a.w - 1 ? 2 : 0) | (y == 0 ? 4 : 0) | (y == a.h - 1 ? 8 : 0);
+                const int yy = (pix[mb] >> 16) & 0xFF, nbi = pix[mb] >> 24;
+                const int y = y0 + yy;
+                const bool ok = (pix[mb] & 1) && yy < rows_out && img0 + nbi < a.n;
+                const int cls = ((pix[mb] >> 1) & 3) | (y == 0 ? 4 : 0) | (y == a.h - 1 ? 8 : 0);
                 const uint32_t sa = seed0 + cls * (32 * 4);
                 tmem_ld_wait();
                 uint32_t o[4];
@@ -260,10 +284,7 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
                     requant_pair<true>(acc[4 * v + 2] + s2, acc[4 * v + 3] + s3, mu[2 * v + 1], ba[2 * v + 1], tt[2], tt[3]);
                     o[v] = finish4<MODE>(tt, a.ep, s_lut, has_lut, zp_m, lut_lo, lut_base);
                 }
-                if (ok) {
-                    const size_t off = ((static_cast<size_t>(img) * a.h + y) * a.w + xx) * a.cp + chs;
-                    *reinterpret_cast<uint4 *>(a.out + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
+                if (ok) *reinterpret_cast<uint4 *>(obase + ooff[mb]) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             tc_fence_before();
             __syncwarp();
@@ -319,6 +340,7 @@ int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void
     const int thi = th + 2;
     const long long ntiles = static_cast<long long>((d->n + nb - 1) / nb) * ybands;
     if (ntiles * cchunks >= (1ll << 31)) return B200_OK;
+    if (static_cast<long long>(nb) * d->h * d->w * d->cp >= (1ll << 32) || nb > 255 || th > 255) return B200_OK;
 
     DwUmmaArgs a;
     a.n = d->n, a.cp = d->cp, a.h = d->h, a.w = d->w;

@@ -44,6 +44,7 @@ enum {
     H_CONCAT, /* csinn_concat of (in0, in1) along `axis`; p0 == 3: of (in0, in1, in0) */
     H_SILU,
     H_ERF,
+    H_GMP, /* csinn_global_maxpool2d */
 };
 
 typedef struct {
@@ -257,6 +258,7 @@ static int layer_init(h_net *net, int i)
         }
         case H_MAXPOOL:
         case H_AVGPOOL:
+        case H_GMP:
         case H_GAP: {
             struct csinn_pool_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -267,6 +269,7 @@ static int layer_init(h_net *net, int i)
             net->params[i] = p;
             if (L->kind == H_MAXPOOL) return csinn_maxpool2d_init(in, out, p);
             if (L->kind == H_AVGPOOL) return csinn_avgpool2d_init(in, out, p);
+            if (L->kind == H_GMP) return csinn_global_maxpool2d_init(in, out, p);
             return csinn_global_avgpool2d_init(in, out, p);
         }
         case H_SOFTMAX: {
@@ -341,6 +344,8 @@ static int layer_call(h_net *net, int i)
             return csinn_avgpool2d(in, out, p);
         case H_GAP:
             return csinn_global_avgpool2d(in, out, p);
+        case H_GMP:
+            return csinn_global_maxpool2d(in, out, p);
         case H_SOFTMAX:
             return csinn_softmax(in, out, p);
         case H_FLATTEN:

@@ -723,3 +723,20 @@ def test_concat_feeds_a_convolution_in_graph_mode(b200, oracle, rng):
                             zp_in=5, s_w=s_w, s_b=None, s_out=0.05, zp_out=-3)
     got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=RM_GRAPH)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_global_maxpool_int8_bit_exact_and_fp16(b200, oracle, rng):
+    from shl import H_GMP
+    for shape in [(2, 24, 7, 7), (1, 5, 13, 3), (3, 1024, 7, 7)]:
+        out_shape = (shape[0], shape[1], 1, 1)
+        x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+        want = oracle.pool_i8(x, out_shape, avg=False, kernel=shape[2:], stride=(1, 1), pad=(0, 0), count_include_pad=0,
+                              s_in=0.04, zp_in=3, s_out=0.03, zp_out=-9)
+        for mode in (RM_LAYER, RM_GRAPH):
+            got = b200.run(DT_INT8, shape, [Layer(H_GMP, out_shape, s_out=0.03, zp_out=-9)], x, s_in=0.04, zp_in=3,
+                           run_mode=mode)
+            assert np.array_equal(got, want), (shape, mode)
+        xh = rng.standard_normal(shape).astype(np.float16)
+        got = b200.run(DT_F16, shape, [Layer(H_GMP, out_shape)], xh, run_mode=RM_GRAPH)
+        assert np.array_equal(got.reshape(shape[0], shape[1]), xh.max(axis=(2, 3)))

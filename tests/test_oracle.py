@@ -334,3 +334,16 @@ def test_concat_oracle_equals_the_reference(shape, axis, three, ref, oracle, rng
     x, layers, want = concat_case(shape, axis, three, oracle, rng)
     got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
     assert np.array_equal(got, want)
+
+
+def test_global_maxpool_oracle_equals_the_reference(ref, oracle, rng):
+    """csinn_global_maxpool2d (source/reference/global_maxpool.c:21): max pooling over the whole map"""
+    from shl import H_GMP
+    for shape in [(2, 24, 7, 7), (1, 5, 13, 3)]:
+        x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+        out_shape = (shape[0], shape[1], 1, 1)
+        layer = Layer(H_GMP, out_shape, s_out=0.03, zp_out=-9)
+        got = ref.run(DT_INT8, shape, [layer], x, s_in=0.04, zp_in=3)
+        want = oracle.pool_i8(x, out_shape, avg=False, kernel=shape[2:], stride=(1, 1), pad=(0, 0), count_include_pad=0,
+                              s_in=0.04, zp_in=3, s_out=0.03, zp_out=-9)
+        assert np.array_equal(got, want)
