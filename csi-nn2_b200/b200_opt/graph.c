@@ -525,9 +525,10 @@ static int build_from_graph(struct csinn_session *sess)
         s->op = op;
         s->in0 = tensor_add(g, n->in[0]);
         s->in1 = -1;
-        if (op->kind == B200_OPK_ADD) s->in1 = tensor_add(g, n->in[1]);
+        const int two_inputs = op->kind == B200_OPK_ADD && !op->d_const; /* a constant operand lives in the weight arena */
+        if (two_inputs) s->in1 = tensor_add(g, n->in[1]);
         s->out = tensor_add(g, out_tn);
-        if (s->in0 < 0 || s->out < 0 || (op->kind == B200_OPK_ADD && s->in1 < 0)) {
+        if (s->in0 < 0 || s->out < 0 || (two_inputs && s->in1 < 0)) {
             free(skip);
             return CSINN_FALSE;
         }

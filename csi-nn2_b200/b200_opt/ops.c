@@ -433,9 +433,18 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
                 DEV_CHECK(b200_unary_f16(in0->d, out->d, b200_dt_bytes(out) / 2, op->act, op->act_p0, op->act_p1, stream));
             return CSINN_TRUE;
         case B200_OPK_ADD:
-            DEV_CHECK(b200_binary(op->binop, op->dtype, in0->d, in1->d, out->d, b200_dt_bytes(out) / op->eb,
-                               op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out, op->zp_out,
-                               op->d_lut, op->act, stream));
+            if (!op->d_const && !in1) {
+                b200_fail("%s: second operand missing", op->kname);
+                return CSINN_FALSE;
+            }
+            if (op->d_const && in0->cp != op->const_count) {
+                b200_fail("%s: constant operand packed for %d channels, the activation has %d", op->kname, op->const_count, in0->cp);
+                return CSINN_FALSE;
+            }
+            DEV_CHECK(b200_binary_bcast(op->binop, op->dtype, in0->d, op->d_const ? op->d_const : in1->d,
+                                        op->d_const ? (size_t)op->const_count : 0, out->d, b200_dt_bytes(out) / op->eb,
+                                        op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out, op->zp_out, op->d_lut,
+                                        op->act, stream));
             return CSINN_TRUE;
         case B200_OPK_POOL: {
             b200_pool_desc p;
@@ -856,23 +865,63 @@ void *shl_b200_mul_init_fn(void) { return (void *)mul_init; }
 static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
                        struct csinn_diso_params *params, int binop)
 {
-    if (input0->dim_count != input1->dim_count) {
-        b200_fail("add: broadcasting is not supported (ranks %d vs %d)", input0->dim_count, input1->dim_count);
+    /* a constant second operand may be one element or one value per channel ([C], [C,1,1], [1,C,1,1]):
+     * the broadcasting of shl_ref_add_f32 (source/reference/add.c:21); anything else must match in0 */
+    int per_channel = 0, scalar = 0;
+    b200_dt d0;
+    if (input0->is_const || !b200_dt_from_tensor(&d0, input0)) {
+        b200_fail("add: first operand must be a non-constant int8 / fp16 tensor of rank 1..4");
         return CSINN_FALSE;
     }
-    for (int i = 0; i < input0->dim_count; i++)
-        if (input0->dim[i] != input1->dim[i]) {
-            b200_fail("add: broadcasting is not supported (dim %d: %d vs %d)", i, input0->dim[i], input1->dim[i]);
+    if (input1->is_const) {
+        int64_t elems = 1;
+        int big = 0, big_dim = -1;
+        for (int i = 0; i < input1->dim_count; i++) {
+            elems *= input1->dim[i];
+            if (input1->dim[i] != 1) big++, big_dim = i;
+        }
+        const int from_end = input1->dim_count - 1 - big_dim; /* [.., C, 1, 1] against NCHW: the channel axis */
+        const int ch_from_end = input0->dim_count - 1 - (input0->dim_count >= 2 ? 1 : 0);
+        scalar = elems == 1;
+        per_channel = !scalar && big == 1 && elems == d0.c && from_end == ch_from_end;
+        if (!input1->data || input1->dtype != input0->dtype || (!scalar && !per_channel)) {
+            b200_fail("add: constant second operand must be one element or one value per channel of the same dtype");
             return CSINN_FALSE;
         }
-    if (input1->is_const) {
-        b200_fail("add: constant second operand is not supported");
-        return CSINN_FALSE;
+    } else {
+        if (input0->dim_count != input1->dim_count) {
+            b200_fail("add: broadcasting between activations is not supported (ranks %d vs %d)", input0->dim_count,
+                      input1->dim_count);
+            return CSINN_FALSE;
+        }
+        for (int i = 0; i < input0->dim_count; i++)
+            if (input0->dim[i] != input1->dim[i]) {
+                b200_fail("add: broadcasting between activations is not supported (dim %d: %d vs %d)", i, input0->dim[i],
+                          input1->dim[i]);
+                return CSINN_FALSE;
+            }
     }
     static const char *const names[] = {"b200_add", "b200_sub", "b200_mul"};
     b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, names[binop]);
     if (!op) return CSINN_FALSE;
     op->binop = binop;
+    if (input1->is_const) {
+        /* one pixel's worth of channels, padding lanes 0 (their results are never read) */
+        uint8_t *row = calloc((size_t)d0.cp, (size_t)op->eb);
+        if (!row) {
+            free(op);
+            return CSINN_FALSE;
+        }
+        for (int c = 0; c < d0.c; c++)
+            memcpy(row + (size_t)c * op->eb, (const uint8_t *)input1->data + (size_t)(scalar ? 0 : c) * op->eb, (size_t)op->eb);
+        op->d_const = b200_warena_put(op->ctx, row, (size_t)d0.cp * op->eb);
+        op->const_count = d0.cp;
+        free(row);
+        if (!op->d_const) {
+            free(op);
+            return CSINN_FALSE;
+        }
+    }
     if (op->dtype == B200_I8) {
         if (!input0->qinfo || !input1->qinfo || !output->qinfo) {
             b200_fail("add: int8 tensors without qinfo");
@@ -890,7 +939,7 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
 int shl_b200_add(struct csinn_tensor *input0, struct csinn_tensor *input1,
                  struct csinn_tensor *output, struct csinn_diso_params *params)
 {
-    return layer_exec(params, input0, input1, output);
+    return layer_exec(params, input0, input1->is_const ? NULL : input1, output);
 }
 
 /* ---- pooling ------------------------------------------------------------------------------------------ */

@@ -119,7 +119,7 @@ __device__ __forceinline__ uint64_t bytes_to_f2(uint32_t wx, int e0, float off)
 __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a,
                                                      const uint4 *__restrict__ b,
                                                      uint4 *__restrict__ out, long long nvec,
-                                                     const AddArgs p)
+                                                     const AddArgs p, const int b_period)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
     const float zo = static_cast<float>(p.zp_out);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? i % b_period : i));
         const uint32_t wa[4] = {va.x ^ 0x80808080u, va.y ^ 0x80808080u, va.z ^ 0x80808080u, va.w ^ 0x80808080u};
         const uint32_t wb[4] = {vb.x ^ 0x80808080u, vb.y ^ 0x80808080u, vb.z ^ 0x80808080u, vb.w ^ 0x80808080u};
         uint32_t r[4];
@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
 __global__ void __launch_bounds__(256) add_f16_kernel(const uint4 *__restrict__ a,
                                                       const uint4 *__restrict__ b,
                                                       uint4 *__restrict__ out, long long nvec,
-                                                      int act, int binop)
+                                                      int act, int binop, const int b_period)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? i % b_period : i));
         const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
         const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
         uint4 vo;
@@ -266,6 +266,13 @@ extern "C" int b200_binary(int binop, int dtype, const void *a, const void *b, v
                            int zp_a, float s_b, int zp_b, float s_out, int zp_out,
                            const int8_t *post_lut, int act, void *stream)
 {
+    return b200_binary_bcast(binop, dtype, a, b, 0, out, count, s_a, zp_a, s_b, zp_b, s_out, zp_out, post_lut, act, stream);
+}
+
+extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void *b, size_t b_count, void *out,
+                                 size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                                 const int8_t *post_lut, int act, void *stream)
+{
     if (binop < B200_BINOP_ADD || binop > B200_BINOP_MUL) {
         set_error("b200_binary: unknown op %d", binop);
         return B200_ERR_ARG;
@@ -276,16 +283,21 @@ extern "C" int b200_binary(int binop, int dtype, const void *a, const void *b, v
         set_error("b200_add: bad arguments (dtype=%d count=%zu)", dtype, count);
         return B200_ERR_ARG;
     }
+    if (b_count % vec || b_count / vec >= (1u << 30)) {
+        set_error("b200_binary_bcast: period %zu of the second operand is not a multiple of %d elements", b_count, vec);
+        return B200_ERR_ARG;
+    }
+    const int b_period = static_cast<int>(b_count / vec);
     const long long nvec = static_cast<long long>(count / vec);
     if (dtype == B200_I8) {
         AddArgs p{s_a, s_b, s_out, zp_a, zp_b, zp_out, act, post_lut, binop, static_cast<float>(1.0 / static_cast<double>(s_out))};
         launch_kernel(add_i8_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
-            nvec, p);
+            nvec, p, b_period);
     } else {
         launch_kernel(add_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
-            nvec, act, binop);
+            nvec, act, binop, b_period);
     }
     B200_LAUNCH_CHECK();
     return B200_OK;

@@ -249,6 +249,12 @@ int b200_relu_f16(const void *in, void *out, size_t count, int act, void *stream
 typedef enum { B200_BINOP_ADD = 0, B200_BINOP_SUB = 1, B200_BINOP_MUL = 2 } b200_binop;
 int b200_binary(int binop, int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
                 float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act, void *stream);
+/* the same with a second operand that repeats every `b_count` elements (0 = same shape): a per-channel or
+ * scalar constant laid out as one pixel's channels ([cp] elements, padding lanes 0) -- the broadcasting
+ * shl_ref_add_f32 / sub / mul do for a [1, C, 1, 1] or one-element operand (source/reference/add.c:21) */
+int b200_binary_bcast(int binop, int dtype, const void *a, const void *b, size_t b_count, void *out, size_t count,
+                      float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
+                      void *stream);
 int b200_add(int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
              float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
              void *stream);

@@ -244,9 +244,10 @@ static int layer_init(h_net *net, int i)
             struct csinn_diso_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
             net->params[i] = p;
-            if (L->kind == H_SUB) return csinn_sub_init(in, net->t[L->in1], out, p);
-            if (L->kind == H_MUL) return csinn_mul_init(in, net->t[L->in1], out, p);
-            return csinn_add_init(in, net->t[L->in1], out, p);
+            struct csinn_tensor *rhs = L->w ? net->k[i] : net->t[L->in1];
+            if (L->kind == H_SUB) return csinn_sub_init(in, rhs, out, p);
+            if (L->kind == H_MUL) return csinn_mul_init(in, rhs, out, p);
+            return csinn_add_init(in, rhs, out, p);
         }
         case H_CONCAT: {
             struct csinn_concat_params *p = csinn_alloc_params(sizeof(*p), net->sess);
@@ -329,11 +330,11 @@ static int layer_call(h_net *net, int i)
         case H_ERF:
             return csinn_erf(in, out, p);
         case H_SUB:
-            return csinn_sub(in, net->t[L->in1], out, p);
+            return csinn_sub(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_MUL:
-            return csinn_mul(in, net->t[L->in1], out, p);
+            return csinn_mul(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_ADD:
-            return csinn_add(in, net->t[L->in1], out, p);
+            return csinn_add(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_CONCAT: {
             struct csinn_tensor *ins[3] = {in, net->t[L->in1], in};
             return csinn_concat(ins, out, p);
@@ -402,6 +403,17 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
         snprintf(nm, sizeof(nm), "output_%d", i);
         net->t[i + 1] = new_tensor(net, nm, L->out_dims, L->out_rank, dtype, act_layout(L->out_rank), 0, 1);
         net->t[i + 1]->qinfo->scale = L->s_out, net->t[i + 1]->qinfo->zero_point = L->zp_out;
+        if ((L->kind == H_ADD || L->kind == H_SUB || L->kind == H_MUL) && L->w) {
+            /* constant second operand: one element ([1]) or one value per channel ([1, C, 1, 1]) */
+            int32_t cd[4] = {1, L->o, 1, 1};
+            snprintf(nm, sizeof(nm), "const_%d", i);
+            net->k[i] = L->o == 1 ? new_tensor(net, nm, cd, 1, wdtype, CSINN_LAYOUT_O, 1, 1)
+                                  : new_tensor(net, nm, cd, 4, wdtype, CSINN_LAYOUT_NCHW, 1, 1);
+            net->k[i]->data = (void *)L->w;
+            net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+            net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f;
+            net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
+        }
         if (L->kind <= H_FC) {
             struct csinn_tensor *in = net->t[L->in0];
             int32_t kd[4];

@@ -740,3 +740,26 @@ def test_global_maxpool_int8_bit_exact_and_fp16(b200, oracle, rng):
         xh = rng.standard_normal(shape).astype(np.float16)
         got = b200.run(DT_F16, shape, [Layer(H_GMP, out_shape)], xh, run_mode=RM_GRAPH)
         assert np.array_equal(got.reshape(shape[0], shape[1]), xh.max(axis=(2, 3)))
+
+
+from test_oracle import BCAST_CASES, bcast_case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,op,scalar", BCAST_CASES)
+def test_binary_ops_with_a_constant_operand_int8_bit_exact(kind, op, scalar, b200, oracle, rng):
+    for shape in [(2, 24, 5, 7), (1, 64, 9, 9)]:
+        x, layer, want = bcast_case(kind, op, scalar, oracle, rng, shape)
+        for mode in (RM_LAYER, RM_GRAPH):
+            got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.04, zp_in=3, run_mode=mode)
+            assert np.array_equal(got, want), (shape, mode)
+
+
+@pytest.mark.gpu
+def test_binary_ops_with_a_constant_operand_fp16(b200, rng):
+    shape = (2, 24, 5, 7)
+    x = rng.standard_normal(shape).astype(np.float16)
+    k = rng.standard_normal(shape[1]).astype(np.float16)
+    for kind, fn in [(H_ADD, np.add), (17, np.subtract), (18, np.multiply)]:
+        got = b200.run(DT_F16, shape, [Layer(kind, shape, in0=0, w=k)], x, run_mode=RM_GRAPH)
+        f16_close(got, fn(x.astype(np.float32), k.astype(np.float32).reshape(1, -1, 1, 1)))

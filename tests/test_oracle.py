@@ -347,3 +347,26 @@ def test_global_maxpool_oracle_equals_the_reference(ref, oracle, rng):
         want = oracle.pool_i8(x, out_shape, avg=False, kernel=shape[2:], stride=(1, 1), pad=(0, 0), count_include_pad=0,
                               s_in=0.04, zp_in=3, s_out=0.03, zp_out=-9)
         assert np.array_equal(got, want)
+
+
+BCAST_CASES = [(H_ADD, 0, False), (17, 1, False), (18, 2, False), (18, 2, True), (H_ADD, 0, True)]
+
+
+def bcast_case(kind, op, scalar, oracle, rng, shape=(2, 24, 5, 7)):
+    """x (op) constant, the constant one value per channel ([1, C, 1, 1]) or a single element"""
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    k = rng.integers(-128, 128, size=(1 if scalar else shape[1],), dtype=np.int8)
+    layer = Layer(kind, shape, in0=0, s_out=0.05 if op != 2 else 0.03, zp_out=-11, w=k, s_w=np.float32([0.013]),
+                  zp_w=np.int32([7]))
+    kb = np.ascontiguousarray(np.broadcast_to(k.reshape(1, -1, 1, 1), shape))
+    want = oracle.binary_i8(op, x, kb, 0.04, 3, 0.013, 7, layer.s_out, -11)
+    return x, layer, want
+
+
+@pytest.mark.parametrize("kind,op,scalar", BCAST_CASES)
+def test_binary_ops_with_a_constant_operand_oracle_equals_the_reference(kind, op, scalar, ref, oracle, rng):
+    """csinn_add / sub / mul with a constant per-channel or one-element second operand: the numpy-style
+    broadcast of shl_ref_diso_broadcast_base (source/reference/utils.c:83) before the elementwise f32 op"""
+    x, layer, want = bcast_case(kind, op, scalar, oracle, rng)
+    got = ref.run(DT_INT8, x.shape, [layer], x, s_in=0.04, zp_in=3)
+    assert np.array_equal(got, want)
