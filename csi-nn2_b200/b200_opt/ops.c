@@ -860,6 +860,19 @@ static int mul_init(struct csinn_tensor *input0, struct csinn_tensor *input1, st
 {
     return binary_init(input0, input1, output, params, B200_BINOP_MUL);
 }
+/* prelu: replaces the shl_gref_prelu registration of source/thead_rvv/setup.c (source/reference/prelu.c:56):
+ * a binary op between the input and the constant per-channel slope, slope indexed along the channel axis */
+static int prelu_init(struct csinn_tensor *input, struct csinn_tensor *alpha, struct csinn_tensor *output,
+                      struct csinn_prelu_params *params)
+{
+    const int ch_axis = input->dim_count >= 2 ? 1 : 0;
+    if (!alpha->is_const || params->axis != ch_axis) {
+        b200_fail("prelu: the slope must be a constant indexed along the channel axis (axis %d given)", params->axis);
+        return CSINN_FALSE;
+    }
+    return binary_init(input, alpha, output, (struct csinn_diso_params *)params, B200_BINOP_PRELU);
+}
+void *shl_b200_prelu_init_fn(void) { return (void *)prelu_init; }
 void *shl_b200_sub_init_fn(void) { return (void *)sub_init; }
 void *shl_b200_mul_init_fn(void) { return (void *)mul_init; }
 static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
@@ -884,6 +897,8 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
         const int ch_from_end = input0->dim_count - 1 - (input0->dim_count >= 2 ? 1 : 0);
         scalar = elems == 1;
         per_channel = !scalar && big == 1 && elems == d0.c && from_end == ch_from_end;
+        /* prelu: the slope tensor is [C] whatever the rank of the input (indexed along params->axis) */
+        if (binop == B200_BINOP_PRELU) per_channel = !scalar && elems == d0.c, scalar = scalar && d0.c == 1;
         if (!input1->data || input1->dtype != input0->dtype || (!scalar && !per_channel)) {
             b200_fail("add: constant second operand must be one element or one value per channel of the same dtype");
             return CSINN_FALSE;
@@ -901,7 +916,7 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
                 return CSINN_FALSE;
             }
     }
-    static const char *const names[] = {"b200_add", "b200_sub", "b200_mul"};
+    static const char *const names[] = {"b200_add", "b200_sub", "b200_mul", "b200_prelu"};
     b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, names[binop]);
     if (!op) return CSINN_FALSE;
     op->binop = binop;

@@ -98,6 +98,7 @@ struct AddArgs {
 };
 __device__ __forceinline__ float binop_f(float a, float b, int binop)
 {
+    if (binop == B200_BINOP_PRELU) return a >= 0.f ? a : __fmul_rn(a, b);
     return binop == B200_BINOP_SUB ? __fsub_rn(a, b) : (binop == B200_BINOP_MUL ? __fmul_rn(a, b) : __fadd_rn(a, b));
 }
 
@@ -148,7 +149,14 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
                 const uint64_t xa = f2_fma(bytes_to_f2(wa[q], 2 * h, off_a), sa2, 0ull);
                 const uint64_t xb = f2_fma(bytes_to_f2(wb[q], 2 * h, off_b), sb2, 0ull);
                 uint64_t rr;
-                if (p.binop == B200_BINOP_MUL)
+                if (p.binop == B200_BINOP_PRELU) {
+                    int a0, a1, m0, m1;
+                    f2_unpack_bits(xa, a0, a1);
+                    f2_unpack_bits(f2_fma(xa, xb, 0ull), m0, m1);
+                    // input >= 0 keeps the input (-0.0 included: it compares equal to 0)
+                    rr = f2_pack_bits(static_cast<uint32_t>(__int_as_float(a0) >= 0.f ? a0 : m0),
+                                      static_cast<uint32_t>(__int_as_float(a1) >= 0.f ? a1 : m1));
+                } else if (p.binop == B200_BINOP_MUL)
                     rr = f2_fma(xa, xb, 0ull);
                 else if (p.binop == B200_BINOP_SUB)
                     rr = f2_add(xa, f2_pack_bits(static_cast<uint32_t>(xb) ^ 0x80000000u, static_cast<uint32_t>(xb >> 32) ^ 0x80000000u));
@@ -273,7 +281,7 @@ extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void
                                  size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
                                  const int8_t *post_lut, int act, void *stream)
 {
-    if (binop < B200_BINOP_ADD || binop > B200_BINOP_MUL) {
+    if (binop < B200_BINOP_ADD || binop > B200_BINOP_PRELU) {
         set_error("b200_binary: unknown op %d", binop);
         return B200_ERR_ARG;
     }

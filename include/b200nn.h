@@ -246,7 +246,12 @@ int b200_relu_f16(const void *in, void *out, size_t count, int act, void *stream
  * fused relu expressed as a post table (as in b200_epilogue). */
 /* elementwise binary ops between tensors of the same shape (shl_rvv_add/sub/mul_int8; semantics
  * source/reference/add.c:36, sub.c:36, mul.c:36 through shl_ref_diso_callback_base) */
-typedef enum { B200_BINOP_ADD = 0, B200_BINOP_SUB = 1, B200_BINOP_MUL = 2 } b200_binop;
+typedef enum {
+    B200_BINOP_ADD = 0,
+    B200_BINOP_SUB = 1,
+    B200_BINOP_MUL = 2,
+    B200_BINOP_PRELU = 3 /* a >= 0 ? a : a * b, b = the per-channel slope (source/reference/prelu.c:44-48) */
+} b200_binop;
 int b200_binary(int binop, int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
                 float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act, void *stream);
 /* the same with a second operand that repeats every `b_count` elements (0 = same shape): a per-channel or

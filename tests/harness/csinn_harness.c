@@ -45,6 +45,7 @@ enum {
     H_SILU,
     H_ERF,
     H_GMP, /* csinn_global_maxpool2d */
+    H_PRELU, /* csinn_prelu, slope = the constant operand ([C]) */
 };
 
 typedef struct {
@@ -249,6 +250,13 @@ static int layer_init(h_net *net, int i)
             if (L->kind == H_MUL) return csinn_mul_init(in, rhs, out, p);
             return csinn_add_init(in, rhs, out, p);
         }
+        case H_PRELU: {
+            struct csinn_prelu_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->axis = 1;
+            net->params[i] = p;
+            return csinn_prelu_init(in, net->k[i], out, p);
+        }
         case H_CONCAT: {
             struct csinn_concat_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -335,6 +343,8 @@ static int layer_call(h_net *net, int i)
             return csinn_mul(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_ADD:
             return csinn_add(in, L->w ? net->k[i] : net->t[L->in1], out, p);
+        case H_PRELU:
+            return csinn_prelu(in, net->k[i], out, p);
         case H_CONCAT: {
             struct csinn_tensor *ins[3] = {in, net->t[L->in1], in};
             return csinn_concat(ins, out, p);
@@ -403,6 +413,15 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
         snprintf(nm, sizeof(nm), "output_%d", i);
         net->t[i + 1] = new_tensor(net, nm, L->out_dims, L->out_rank, dtype, act_layout(L->out_rank), 0, 1);
         net->t[i + 1]->qinfo->scale = L->s_out, net->t[i + 1]->qinfo->zero_point = L->zp_out;
+        if (L->kind == H_PRELU && L->w) {
+            int32_t cd[1] = {L->o};
+            snprintf(nm, sizeof(nm), "alpha_%d", i);
+            net->k[i] = new_tensor(net, nm, cd, 1, wdtype, CSINN_LAYOUT_O, 1, 1);
+            net->k[i]->data = (void *)L->w;
+            net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+            net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f;
+            net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
+        }
         if ((L->kind == H_ADD || L->kind == H_SUB || L->kind == H_MUL) && L->w) {
             /* constant second operand: one element ([1]) or one value per channel ([1, C, 1, 1]) */
             int32_t cd[4] = {1, L->o, 1, 1};

@@ -760,6 +760,6 @@ def test_binary_ops_with_a_constant_operand_fp16(b200, rng):
     shape = (2, 24, 5, 7)
     x = rng.standard_normal(shape).astype(np.float16)
     k = rng.standard_normal(shape[1]).astype(np.float16)
-    for kind, fn in [(H_ADD, np.add), (17, np.subtract), (18, np.multiply)]:
+    for kind, fn in [(H_ADD, np.add), (17, np.subtract), (18, np.multiply), (23, lambda a, s: np.where(a >= 0, a, a * s))]:
         got = b200.run(DT_F16, shape, [Layer(kind, shape, in0=0, w=k)], x, run_mode=RM_GRAPH)
         f16_close(got, fn(x.astype(np.float32), k.astype(np.float32).reshape(1, -1, 1, 1)))

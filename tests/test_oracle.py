@@ -349,7 +349,7 @@ def test_global_maxpool_oracle_equals_the_reference(ref, oracle, rng):
         assert np.array_equal(got, want)
 
 
-BCAST_CASES = [(H_ADD, 0, False), (17, 1, False), (18, 2, False), (18, 2, True), (H_ADD, 0, True)]
+BCAST_CASES = [(H_ADD, 0, False), (17, 1, False), (18, 2, False), (18, 2, True), (H_ADD, 0, True), (23, 3, False)]  # 23 = H_PRELU
 
 
 def bcast_case(kind, op, scalar, oracle, rng, shape=(2, 24, 5, 7)):
