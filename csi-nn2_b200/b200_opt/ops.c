@@ -601,9 +601,24 @@ static int conv_act_of(struct csinn_params_base *base, int op_relu, int op_relu6
     return B200_ACT_NONE;
 }
 
+static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *kernel,
+                          struct csinn_tensor *bias, struct csinn_conv2d_params *params, int act);
 static int conv_init_common(struct csinn_tensor *input, struct csinn_tensor *output,
                             struct csinn_tensor *kernel, struct csinn_tensor *bias,
                             struct csinn_conv2d_params *params, int act)
+{
+    /* CSINN_QUANT_FLOAT16_W_INT8: fp16 activations over int8 weights */
+    if (input->dtype == CSINN_DTYPE_FLOAT16 && kernel->dtype == CSINN_DTYPE_INT8) {
+        struct csinn_tensor *kf = b200_dequant_weights_f16(kernel);
+        if (!kf) return CSINN_FALSE;
+        const int rc = conv_init_impl(input, output, kf, bias, params, act);
+        b200_free_dequant(kf);
+        return rc;
+    }
+    return conv_init_impl(input, output, kernel, bias, params, act);
+}
+static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *kernel,
+                          struct csinn_tensor *bias, struct csinn_conv2d_params *params, int act)
 {
     (void)conv_act_of;
     if (input->dim_count != 4 || kernel->dim_count != 4) {
@@ -722,9 +737,23 @@ int shl_b200_depthwise_conv2d(struct csinn_tensor *input, struct csinn_tensor *o
 }
 
 /* ---- fullyconnected ---------------------------------------------------------------------------- */
+static int fc_init_impl(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *weights,
+                        struct csinn_tensor *bias, struct csinn_fc_params *params);
 int shl_b200_fullyconnected_init(struct csinn_tensor *input, struct csinn_tensor *output,
                                  struct csinn_tensor *weights, struct csinn_tensor *bias,
                                  struct csinn_fc_params *params)
+{
+    if (input->dtype == CSINN_DTYPE_FLOAT16 && weights->dtype == CSINN_DTYPE_INT8) { /* CSINN_QUANT_FLOAT16_W_INT8 */
+        struct csinn_tensor *wf = b200_dequant_weights_f16(weights);
+        if (!wf) return CSINN_FALSE;
+        const int rc = fc_init_impl(input, output, wf, bias, params);
+        b200_free_dequant(wf);
+        return rc;
+    }
+    return fc_init_impl(input, output, weights, bias, params);
+}
+static int fc_init_impl(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *weights,
+                        struct csinn_tensor *bias, struct csinn_fc_params *params)
 {
     if (weights->dim_count != 2) {
         b200_fail("fullyconnected: expected [out][in] weights");

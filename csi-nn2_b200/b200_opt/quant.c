@@ -37,6 +37,71 @@ static float f16_to_f32(uint16_t h)
     return f;
 }
 
+/* IEEE round-to-nearest-even, what a hardware convert does */
+static uint16_t f32_to_f16_rne(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    const int32_t exp = (int32_t)((u >> 23) & 0xFF) - 127 + 15;
+    uint32_t man = u & 0x7FFFFFu;
+    if (((u >> 23) & 0xFF) == 0xFF) return (uint16_t)(sign | 0x7C00u | (man ? 0x200u : 0));
+    if (exp >= 31) return (uint16_t)(sign | 0x7C00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const int shift = 14 - exp;
+        uint32_t half = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        if (rem > mid || (rem == mid && (half & 1))) half++;
+        return (uint16_t)(sign | half);
+    }
+    uint32_t half = ((uint32_t)exp << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) half++; /* a carry into the exponent is the right answer */
+    return (uint16_t)(sign | half);
+}
+
+/* CSINN_QUANT_FLOAT16_W_INT8 (weight-only quantisation under fp16 activations): the int8 kernel is
+ * dequantised to fp16 once at init -- (q - zp) * scale with the per-channel qinfo of output channel
+ * dim[0], the float sequence of the reference's kernel transform (source/nn2/utils.c:920-931) -- as
+ * shl_rvv_conv_im2col_gemm_dequantize_per_channel_i8_to_f16 does for the C906 (c906_opt/fp16/convolution.c:77-81).
+ * Returns a heap copy of the tensor header with fp16 data; release with b200_free_dequant. */
+struct csinn_tensor *b200_dequant_weights_f16(const struct csinn_tensor *kernel)
+{
+    if (!kernel->data || !kernel->qinfo || kernel->dim_count < 1) {
+        b200_fail("int8 weights under fp16 activations need data and qinfo");
+        return NULL;
+    }
+    int64_t total = 1;
+    for (int i = 0; i < kernel->dim_count; i++) total *= kernel->dim[i];
+    const int64_t per_o = total / kernel->dim[0];
+    struct csinn_tensor *t = malloc(sizeof(*t));
+    uint16_t *h = malloc((size_t)total * sizeof(uint16_t));
+    if (!t || !h) {
+        free(t);
+        free(h);
+        b200_fail("out of host memory dequantising weights");
+        return NULL;
+    }
+    memcpy(t, kernel, sizeof(*t));
+    const int8_t *q = kernel->data;
+    for (int64_t i = 0; i < total; i++) {
+        const int qi = kernel->quant_channel > 1 ? (int)(i / per_o) : 0;
+        const float v = ((float)q[i] - (float)kernel->qinfo[qi].zero_point) * kernel->qinfo[qi].scale;
+        h[i] = f32_to_f16_rne(v);
+    }
+    t->dtype = CSINN_DTYPE_FLOAT16;
+    t->data = h;
+    return t;
+}
+void b200_free_dequant(struct csinn_tensor *t)
+{
+    if (!t) return;
+    free(t->data);
+    free(t);
+}
+
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 static int has_bias(const struct csinn_tensor *bias)
@@ -62,7 +127,10 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
     if (op->dtype == B200_F16) {
         if (has_bias(bias)) {
             const uint16_t *b = bias->data;
-            for (int o = 0; o < n_out; o++) badd[o] = f16_to_f32(b[o]);
+            /* the reference scales fp16 constants by qinfo->scale when it is not 1 (f16_to_float,
+             * source/nn2/utils.c:1183-1188) */
+            const float bs = bias->qinfo && fabsf(bias->qinfo->scale - 1.f) > 1.1920929e-7f ? bias->qinfo->scale : 1.f;
+            for (int o = 0; o < n_out; o++) badd[o] = f16_to_f32(b[o]) * bs;
         }
         op->d_mult = NULL;
         op->d_ibias = NULL;

@@ -64,6 +64,7 @@ typedef struct {
     const float *s_b;
     int32_t count_include_pad, ceil_mode, axis;
     float p0, p1; /* unary-op parameters */
+    int32_t w_int8; /* fp16 network: this layer's weights are int8 with qinfo s_w / zp_w (CSINN_QUANT_FLOAT16_W_INT8) */
 } h_layer;
 
 typedef struct {
@@ -447,18 +448,22 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
             }
             const int qch = L->w_channels > 0 ? L->w_channels : 1;
             snprintf(nm, sizeof(nm), "kernel_%d", i);
-            net->k[i] = new_tensor(net, nm, kd, krank, wdtype, klayout, 1, qch);
+            net->k[i] = new_tensor(net, nm, kd, krank, L->w_int8 ? CSINN_DTYPE_INT8 : wdtype, klayout, 1, qch);
             net->k[i]->data = (void *)L->w;
             net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
             int32_t bd[1] = {L->o};
             snprintf(nm, sizeof(nm), "bias_%d", i);
-            net->bias[i] = new_tensor(net, nm, bd, L->b ? 1 : 0, bdtype, CSINN_LAYOUT_O, 1, qch);
+            /* an fp16 bias under int8 weights carries one qinfo with scale 1: the reference multiplies fp16
+             * constants by qinfo->scale when it is not 1 (f16_to_float, source/nn2/utils.c:1175-1189) */
+            const int bqch = L->w_int8 ? 1 : qch;
+            net->bias[i] = new_tensor(net, nm, bd, L->b ? 1 : 0, bdtype, CSINN_LAYOUT_O, 1, bqch);
             net->bias[i]->data = (void *)L->b;
             for (int c = 0; c < qch; c++) {
                 net->k[i]->qinfo[c].scale = L->s_w ? L->s_w[c] : 1.0f;
                 net->k[i]->qinfo[c].zero_point = L->zp_w ? L->zp_w[c] : 0;
+                if (c >= bqch) continue;
                 net->bias[i]->qinfo[c].scale =
-                    L->s_b ? L->s_b[c] : in->qinfo->scale * net->k[i]->qinfo[c].scale;
+                    L->w_int8 ? 1.0f : (L->s_b ? L->s_b[c] : in->qinfo->scale * net->k[i]->qinfo[c].scale);
                 net->bias[i]->qinfo[c].zero_point = 0;
             }
         }

@@ -45,7 +45,7 @@ class HLayer(C.Structure):
         ("w", C.c_void_p), ("b", C.c_void_p), ("s_w", C.c_void_p), ("zp_w", C.c_void_p),
         ("w_channels", C.c_int32), ("s_b", C.c_void_p),
         ("count_include_pad", C.c_int32), ("ceil_mode", C.c_int32), ("axis", C.c_int32),
-        ("p0", C.c_float), ("p1", C.c_float),
+        ("p0", C.c_float), ("p1", C.c_float), ("w_int8", C.c_int32),
     ]
 
 
@@ -210,6 +210,7 @@ class Net:
                 self._keep += [w, s_w, zp_w, b, s_b]
                 a.w, a.b, a.s_w, a.zp_w, a.s_b = _ptr(w), _ptr(b), _ptr(s_w), _ptr(zp_w), _ptr(s_b)
                 a.w_channels = s_w.size
+                a.w_int8 = int(self.dtype == DT_F16 and w.dtype == np.int8)
             else:
                 a.kh, a.kw = int(l.kernel[0]), int(l.kernel[1])
             a.sh, a.sw = int(l.stride[0]), int(l.stride[1])

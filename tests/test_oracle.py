@@ -370,3 +370,18 @@ def test_binary_ops_with_a_constant_operand_oracle_equals_the_reference(kind, op
     x, layer, want = bcast_case(kind, op, scalar, oracle, rng)
     got = ref.run(DT_INT8, x.shape, [layer], x, s_in=0.04, zp_in=3)
     assert np.array_equal(got, want)
+
+
+def test_reference_takes_int8_weights_under_fp16_activations(ref, oracle, rng):
+    """CSINN_QUANT_FLOAT16_W_INT8 through the unmodified reference (kernel transform source/nn2/utils.c:920-931):
+    the harness path the GPU test compares against equals an f32 conv on (q - zp) * scale weights"""
+    n, c, h, w, o = 1, 16, 6, 7, 24
+    x = rng.standard_normal((n, c, h, w)).astype(np.float16)
+    wq = rng.integers(-127, 128, size=(o, c, 3, 3), dtype=np.int8)
+    s_w = ((1.0 + np.arange(o) / o) / (127.0 * 12.0)).astype(np.float32)
+    b = rng.standard_normal(o).astype(np.float16)
+    layer = Layer(H_CONV, (n, o, h, w), w=wq, b=b, s_w=s_w, pad=(1,) * 4)
+    got = ref.run(DT_F16, x.shape, [layer], x).astype(np.float32)
+    want = oracle.conv2d_f32(x.astype(np.float32), wq.astype(np.float32) * s_w.reshape(-1, 1, 1, 1), b.astype(np.float32),
+                             (n, o, h, w), stride=(1, 1), pad=(1,) * 4)
+    assert np.max(np.abs(got - want) / (np.abs(want) + 1.0)) < 2e-3
