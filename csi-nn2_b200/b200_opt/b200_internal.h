@@ -64,6 +64,7 @@ enum b200_op_kind {
     B200_OPK_SOFTMAX,
     B200_OPK_COPY,    /* reshape / flatten whose memory order is unchanged */
     B200_OPK_CONCAT,  /* one step per input: its slice of the output (b200_op_run's `part`) */
+    B200_OPK_SPLIT,   /* one step per output: its slice of the input (`part` = output index; cat_* fields) */
 };
 
 #define B200_CONCAT_MAX 32

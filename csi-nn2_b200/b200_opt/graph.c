@@ -264,7 +264,7 @@ static size_t weight_bound(struct shl_ref_graph *graph)
             size_t e = csinn_tensor_size(ct);
             total += e * 8 + (size_t)(ct->dim_count ? ct->dim[0] : 1) * 64 * 4 + 8192;
         }
-        total += 4096 + (size_t)l->in_num * 256; /* concat: one requant table per input */
+        total += 4096 + (size_t)(l->in_num + l->out_num) * 256; /* concat / split: one requant table per input / output */
     }
     return total;
 }
@@ -457,10 +457,12 @@ static int build_from_graph(struct csinn_session *sess)
     }
 
     b200_graph *g = calloc(1, sizeof(*g));
-    g->t = calloc((size_t)graph->layer_index * 2 + graph->input_num + graph->output_num + 4, sizeof(g_tensor));
+    size_t max_tensors = (size_t)graph->input_num + graph->output_num + 4;
+    for (int i = 0; i < graph->layer_index; i++) max_tensors += 1 + (size_t)graph->layer[i]->out_num;
+    g->t = calloc(max_tensors, sizeof(g_tensor));
     size_t max_steps = 1;
     for (int i = 0; i < graph->layer_index; i++)
-        max_steps += graph->layer[i]->in_num > 1 ? (size_t)graph->layer[i]->in_num : 1;
+        max_steps += (size_t)(graph->layer[i]->in_num > 1 ? graph->layer[i]->in_num : 1) + (size_t)graph->layer[i]->out_num;
     g->s = calloc(max_steps, sizeof(g_step));
     opt->g = g;
 
@@ -495,6 +497,31 @@ static int build_from_graph(struct csinn_session *sess)
                     strncat(g->s[g->ns].name, "+act", sizeof(g->s[g->ns].name) - strlen(g->s[g->ns].name) - 1);
                 }
             }
+        }
+        if (op->kind == B200_OPK_SPLIT) {
+            /* one step per output, each reading its slice of the shared input tensor */
+            const int in_idx = tensor_add(g, n->in[0]);
+            int bad = in_idx < 0 || n->out_num != op->cat_n || (g->t[in_idx].first_def < 0 && !g->t[in_idx].is_input);
+            for (int j = 0; !bad && j < n->out_num; j++) {
+                g_step *s = &g->s[g->ns];
+                if (j) snprintf(s->name, sizeof(s->name), "%s", n->name ? n->name : op->kname);
+                s->op = op, s->part = j, s->in1 = -1, s->in0 = in_idx;
+                s->out = tensor_add(g, n->out[j]);
+                if (s->out < 0) {
+                    bad = 1;
+                    break;
+                }
+                g->t[in_idx].last_use = g->ns;
+                if (g->t[s->out].first_def < 0) g->t[s->out].first_def = g->ns;
+                g->t[s->out].last_use = g->ns;
+                g->ns++;
+            }
+            if (bad) {
+                b200_fail("layer %d '%s': split input that no earlier layer produced, or bad outputs", i, n->name ? n->name : "?");
+                free(skip);
+                return CSINN_FALSE;
+            }
+            continue;
         }
         if (op->kind == B200_OPK_CONCAT) {
             /* one step per input, each writing its slice of the shared output tensor */

@@ -385,6 +385,21 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
                 void *scratch, void *stream)
 {
     switch (op->kind) {
+        case B200_OPK_SPLIT: {
+            if (part < 0 || part >= op->cat_n) {
+                b200_fail("split: output %d of %d", part, op->cat_n);
+                return CSINN_FALSE;
+            }
+            b200_concat_desc c;
+            memset(&c, 0, sizeof(c));
+            c.dtype = op->dtype, c.extract = 1;
+            c.n = out->n, c.c = out->c, c.h = out->h, c.w = out->w, c.cp_out = out->cp;
+            c.on = in0->n, c.oc = in0->c, c.oh = in0->h, c.ow = in0->w, c.cp_in = in0->cp;
+            c.axis = op->cat_axis, c.offset = op->cat_off[part];
+            c.in = in0->d, c.out = out->d, c.lut = op->cat_lut[part];
+            DEV_CHECK(b200_concat_slice(&c, stream));
+            return CSINN_TRUE;
+        }
         case B200_OPK_CONCAT: {
             if (part < 0 || part >= op->cat_n) {
                 b200_fail("concat: input %d of %d", part, op->cat_n);
@@ -1195,6 +1210,90 @@ int shl_b200_concat(struct csinn_tensor **input, struct csinn_tensor *output, st
     DEV_CHECK(b200_nhwc_to_nchw(dout.d, d_raw, dout.n, dout.c, dout.h, dout.w, dout.cp, dout.eb, stream));
     DEV_CHECK(b200_memcpy_d2h(output->data, d_raw, raw, stream));
     DEV_CHECK(b200_stream_sync(stream));
+    return CSINN_TRUE;
+}
+
+/* ---- split ---------------------------------------------------------------------------------------------- */
+/* replaces the shl_gref_split registration of source/thead_rvv/setup.c (which runs source/reference/split.c:81):
+ * output i is the slice [split_index[i-1], split_index[i]) of the input along `axis` (equal chunks when
+ * split_index is NULL, the last one shorter), requantised with its own qinfo -> one table per output */
+int shl_b200_split_init(struct csinn_tensor *input, struct csinn_tensor **output, struct csinn_split_params *params)
+{
+    const int k = params->output_num;
+    if (k < 1 || k > B200_CONCAT_MAX) {
+        b200_fail("split: %d outputs (1..%d supported)", k, B200_CONCAT_MAX);
+        return CSINN_FALSE;
+    }
+    int axis = params->axis;
+    if (axis < 0) axis += input->dim_count;
+    b200_dt din;
+    if (axis < 0 || axis >= input->dim_count || !b200_dt_from_tensor(&din, input)) {
+        b200_fail("split: axis %d of a rank-%d tensor (dtype %d)", params->axis, input->dim_count, input->dtype);
+        return CSINN_FALSE;
+    }
+    static const int dev_axis[5][4] = {{0}, {1}, {0, 1}, {0, 1, 3}, {0, 1, 2, 3}};
+    b200_op *op = op_new(&params->base, B200_OPK_SPLIT, input->dtype, "b200_split_slice");
+    if (!op) return CSINN_FALSE;
+    op->cat_n = k, op->cat_axis = dev_axis[input->dim_count][axis];
+    const int avg = (input->dim[axis] + k - 1) / k;
+    for (int i = 0; i < k; i++) {
+        const int begin = params->split_index ? (i == 0 ? 0 : params->split_index[i - 1]) : i * avg;
+        const int end = (i == k - 1) ? input->dim[axis] : (params->split_index ? params->split_index[i] : (i + 1) * avg);
+        const struct csinn_tensor *t = output[i];
+        int ok = t && t->dtype == input->dtype && t->dim_count == input->dim_count && begin >= 0 && end > begin &&
+                 end <= input->dim[axis] && t->dim[axis] == end - begin;
+        for (int d = 0; ok && d < input->dim_count; d++)
+            if (d != axis && t->dim[d] != input->dim[d]) ok = 0;
+        if (ok && op->dtype == B200_I8 && (!t->qinfo || !input->qinfo)) ok = 0;
+        if (!ok) {
+            b200_fail("split: output %d does not match slice [%d, %d) of the input (dtype, rank, dimensions, qinfo)", i,
+                      begin, end);
+            free(op);
+            return CSINN_FALSE;
+        }
+        op->cat_off[i] = begin;
+        if (op->dtype == B200_I8) {
+            int8_t lut[256];
+            b200_build_requant_lut(lut, B200_ACT_NONE, input->qinfo->scale, input->qinfo->zero_point, t->qinfo->scale,
+                                   t->qinfo->zero_point);
+            op->cat_lut[i] = b200_warena_put(op->ctx, lut, 256);
+            if (!op->cat_lut[i]) {
+                free(op);
+                return CSINN_FALSE;
+            }
+        }
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())shl_b200_split;
+    return CSINN_TRUE;
+}
+
+int shl_b200_split(struct csinn_tensor *input, struct csinn_tensor **output, struct csinn_split_params *params)
+{
+    b200_op *op = b200_op_find(params);
+    if (!op || op->kind != B200_OPK_SPLIT) {
+        b200_fail("split exec before init: no b200 operator bound to these params");
+        return CSINN_FALSE;
+    }
+    b200_set_device(op->ctx->device);
+    void *stream = op->ctx->stream;
+    b200_dt din;
+    if (upload_nchw(op, 0, input, &din, stream) != CSINN_TRUE) return CSINN_FALSE;
+    for (int i = 0; i < op->cat_n; i++) {
+        b200_dt dout;
+        if (!b200_dt_from_tensor(&dout, output[i]) || !output[i]->data) {
+            b200_fail("split: unsupported or unallocated output %d", i);
+            return CSINN_FALSE;
+        }
+        const size_t raw = (size_t)dout.n * dout.c * dout.h * dout.w * dout.eb;
+        dout.d = stage(op, 4, b200_dt_bytes(&dout));
+        void *d_raw = stage(op, 5, raw);
+        if (!dout.d || !d_raw) return CSINN_FALSE;
+        if (b200_op_run(op, i, &din, NULL, &dout, NULL, stream) != CSINN_TRUE) return CSINN_FALSE;
+        DEV_CHECK(b200_nhwc_to_nchw(dout.d, d_raw, dout.n, dout.c, dout.h, dout.w, dout.cp, dout.eb, stream));
+        DEV_CHECK(b200_memcpy_d2h(output[i]->data, d_raw, raw, stream));
+        DEV_CHECK(b200_stream_sync(stream)); /* the staging slots are reused by the next output */
+    }
     return CSINN_TRUE;
 }
 

@@ -314,6 +314,8 @@ struct ConcatArgs {
     int row_bytes;            // bytes copied per pixel (input channels)
     int out_byte_off;         // byte offset of the slice inside an output pixel
     int zero_bytes;           // bytes zeroed after the slice (padding lanes)
+    int in_byte_off;          // extract: byte offset of the slice inside an input pixel
+    int extract;              // 1: the input is the large tensor, the output the slice (split)
     int spatial;              // 1: a pixel offset has to be applied
 };
 
@@ -375,14 +377,15 @@ __global__ void __launch_bounds__(256) concat_slice_kernel(ConcatArgs a)
             const int b = static_cast<int>(r / a.h);
             po = (static_cast<long long>(b + a.n_off) * a.oh + (y + a.h_off)) * a.ow + (x + a.w_off);
         }
+        const long long ps = a.extract ? po : p, pd = a.extract ? p : po;  // source / destination pixel
         VT v;
         if (u < copy_units) {
-            v = *reinterpret_cast<const VT *>(a.in + p * a.in_pitch + static_cast<long long>(u) * V);
+            v = *reinterpret_cast<const VT *>(a.in + ps * a.in_pitch + a.in_byte_off + static_cast<long long>(u) * V);
             if constexpr (LUT) v = lut_apply<VT>(v, s_lut);
         } else {
             v = vec_zero<VT>();
         }
-        *reinterpret_cast<VT *>(a.out + po * a.out_pitch + a.out_byte_off + static_cast<long long>(u) * V) = v;
+        *reinterpret_cast<VT *>(a.out + pd * a.out_pitch + a.out_byte_off + static_cast<long long>(u) * V) = v;
     }
 }
 
@@ -407,7 +410,7 @@ extern "C" int b200_concat_slice(const b200_concat_desc *d, void *stream)
     using namespace b200;
     const int eb = !d ? 0 : (d->dtype == B200_I8 ? 1 : (d->dtype == B200_F16 ? 2 : 0));
     if (!d || !eb || !d->in || !d->out || d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c <= 0 || d->axis < 0 ||
-        d->axis > 3 || d->offset < 0 || d->cp_in < d->c || (d->cp_in * eb) % 16 || (d->cp_out * eb) % 16 ||
+        d->axis > 3 || d->offset < 0 || (d->extract ? d->cp_out : d->cp_in) < d->c || (d->cp_in * eb) % 16 || (d->cp_out * eb) % 16 ||
         (d->dtype != B200_I8 && d->lut)) {
         set_error("b200_concat_slice: bad descriptor");
         return B200_ERR_ARG;
@@ -421,8 +424,9 @@ extern "C" int b200_concat_slice(const b200_concat_desc *d, void *stream)
             return B200_ERR_ARG;
         }
     }
-    if (d->cp_out < d->oc) {
-        set_error("b200_concat_slice: output channel pitch %d below its channel count %d", d->cp_out, d->oc);
+    if ((d->extract ? d->cp_in : d->cp_out) < d->oc) {
+        set_error("b200_concat_slice: channel pitch %d of the whole tensor below its channel count %d",
+                  d->extract ? d->cp_in : d->cp_out, d->oc);
         return B200_ERR_ARG;
     }
     ConcatArgs a;
@@ -432,13 +436,16 @@ extern "C" int b200_concat_slice(const b200_concat_desc *d, void *stream)
     a.spatial = d->axis != 1;
     a.in_pitch = d->cp_in * eb, a.out_pitch = d->cp_out * eb;
     a.row_bytes = d->c * eb;
-    a.out_byte_off = d->axis == 1 ? d->offset * eb : 0;
-    // padding lanes: after the last channel slice, or after every pixel's channels on the other axes
+    a.extract = d->extract ? 1 : 0;
+    a.out_byte_off = (d->axis == 1 && !a.extract) ? d->offset * eb : 0;
+    a.in_byte_off = (d->axis == 1 && a.extract) ? d->offset * eb : 0;
+    // padding lanes: after the last channel slice, or after every pixel's channels on the other axes; an
+    // extracted slice is a whole tensor: always
     const int written_to = a.out_byte_off + a.row_bytes;
-    const int is_tail = d->axis != 1 || d->offset + d->c == d->oc;
+    const int is_tail = a.extract || d->axis != 1 || d->offset + d->c == d->oc;
     a.zero_bytes = is_tail ? a.out_pitch - written_to : 0;
     int v = 16;
-    while (v > eb && (a.row_bytes % v || a.out_byte_off % v || a.zero_bytes % v)) v = v == 16 ? 4 : eb;
+    while (v > eb && (a.row_bytes % v || a.out_byte_off % v || a.in_byte_off % v || a.zero_bytes % v)) v = v == 16 ? 4 : eb;
     const long long total = static_cast<long long>(d->n) * d->h * d->w * ((a.row_bytes + a.zero_bytes) / v);
     const int grid = grid_for(total, 256);
     cudaStream_t s = (cudaStream_t)stream;

@@ -278,6 +278,9 @@ typedef struct {
     const void *in;
     void *out;
     const int8_t *lut;
+    int32_t extract; /* 0: `in` is the slice (n, c, h, w, cp_in), `out` the whole tensor (on .. cp_out) -- concat;
+                        1: `in` is the whole tensor (on, oc, oh, ow, cp_in), `out` the slice (n, c, h, w, cp_out)
+                        -- split (source/reference/split.c:20), lut = requant_slice(dequant_whole(q)) */
 } b200_concat_desc;
 int b200_concat_slice(const b200_concat_desc *d, void *stream);
 

@@ -101,6 +101,9 @@ int shl_b200_softmax(struct csinn_tensor *input, struct csinn_tensor *output,
 int shl_b200_concat_init(struct csinn_tensor **input, struct csinn_tensor *output,
                          struct csinn_concat_params *params);
 int shl_b200_concat(struct csinn_tensor **input, struct csinn_tensor *output, struct csinn_concat_params *params);
+/* split along any axis of rank 1..4 tensors (source/reference/split.c:81; shl_gref_split in the RVV table) */
+int shl_b200_split_init(struct csinn_tensor *input, struct csinn_tensor **output, struct csinn_split_params *params);
+int shl_b200_split(struct csinn_tensor *input, struct csinn_tensor **output, struct csinn_split_params *params);
 int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *output, void *params);
 int shl_b200_reshape(struct csinn_tensor *input, struct csinn_tensor *output, void *params);
 /* perf callbacks: kernel name for the trace profiler (cf. source/thead_rvv/performance.c:442);

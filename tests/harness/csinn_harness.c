@@ -46,6 +46,8 @@ enum {
     H_ERF,
     H_GMP, /* csinn_global_maxpool2d */
     H_PRELU, /* csinn_prelu, slope = the constant operand ([C]) */
+    H_SPLIT, /* csinn_split of in0 in two at index (int)p0 along `axis`; the layer's output is slice (int)p1, the
+                other slice goes to a scratch tensor (net->k[i]) with the same qinfo */
 };
 
 typedef struct {
@@ -251,6 +253,16 @@ static int layer_init(h_net *net, int i)
             if (L->kind == H_MUL) return csinn_mul_init(in, rhs, out, p);
             return csinn_add_init(in, rhs, out, p);
         }
+        case H_SPLIT: {
+            struct csinn_split_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->output_num = 2, p->axis = L->axis;
+            p->split_index = calloc(2, sizeof(int32_t));
+            p->split_index[0] = (int32_t)L->p0, p->split_index[1] = in->dim[L->axis];
+            net->params[i] = p;
+            struct csinn_tensor *outs[2] = {L->p1 != 0.f ? net->k[i] : out, L->p1 != 0.f ? out : net->k[i]};
+            return csinn_split_init(in, outs, p);
+        }
         case H_PRELU: {
             struct csinn_prelu_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -344,6 +356,10 @@ static int layer_call(h_net *net, int i)
             return csinn_mul(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_ADD:
             return csinn_add(in, L->w ? net->k[i] : net->t[L->in1], out, p);
+        case H_SPLIT: {
+            struct csinn_tensor *outs[2] = {L->p1 != 0.f ? net->k[i] : out, L->p1 != 0.f ? out : net->k[i]};
+            return csinn_split(in, outs, p);
+        }
         case H_PRELU:
             return csinn_prelu(in, net->k[i], out, p);
         case H_CONCAT: {
@@ -414,6 +430,16 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
         snprintf(nm, sizeof(nm), "output_%d", i);
         net->t[i + 1] = new_tensor(net, nm, L->out_dims, L->out_rank, dtype, act_layout(L->out_rank), 0, 1);
         net->t[i + 1]->qinfo->scale = L->s_out, net->t[i + 1]->qinfo->zero_point = L->zp_out;
+        if (L->kind == H_SPLIT) {
+            const struct csinn_tensor *src = net->t[L->in0];
+            int32_t od[4];
+            for (int d = 0; d < src->dim_count; d++) od[d] = src->dim[d];
+            od[L->axis] = src->dim[L->axis] - L->out_dims[L->axis];
+            snprintf(nm, sizeof(nm), "split_other_%d", i);
+            net->k[i] = new_tensor(net, nm, od, src->dim_count, dtype, act_layout(src->dim_count), 0, 1);
+            net->k[i]->qinfo->scale = L->s_out, net->k[i]->qinfo->zero_point = L->zp_out;
+            net->k[i]->data = calloc(1, tsize(net->k[i]) * elem_bytes(dtype) + 64);
+        }
         if (L->kind == H_PRELU && L->w) {
             int32_t cd[1] = {L->o};
             snprintf(nm, sizeof(nm), "alpha_%d", i);

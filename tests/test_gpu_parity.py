@@ -804,3 +804,32 @@ def test_fullyconnected_fp16_activations_int8_weights(b200, rng):
     got = b200.run(DT_F16, (n, d), [Layer(H_FC, (n, o), w=wq, b=b, s_w=s_w)], x, run_mode=RM_GRAPH)
     want = x.astype(np.float32) @ (wq.astype(np.float32) * s_w.reshape(-1, 1)).T + b.astype(np.float32)
     f16_close(got, want, tol=2e-3)
+
+
+from test_oracle import SPLIT_CASES, split_case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("shape,axis,at", SPLIT_CASES)
+def test_split_int8_bit_exact(shape, axis, at, which, b200, oracle, rng):
+    x, layers, want = split_case(shape, axis, at, which, oracle, rng)
+    for mode in (RM_LAYER, RM_GRAPH):
+        got = b200.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3, run_mode=mode)
+        assert np.array_equal(got, want), mode
+
+
+@pytest.mark.gpu
+def test_split_fp16_is_a_copy(b200, rng):
+    from shl import H_SPLIT
+    for shape, axis, at in SPLIT_CASES:
+        x = rng.standard_normal(shape).astype(np.float16)
+        for which in (0, 1):
+            out_shape = list(shape)
+            out_shape[axis] = at if which == 0 else shape[axis] - at
+            layers = [Layer(H_RELU, shape), Layer(H_SPLIT, tuple(out_shape), axis=axis, p0=float(at), p1=float(which))]
+            got = b200.run(DT_F16, shape, layers, x, run_mode=RM_GRAPH)
+            sl = [slice(None)] * 4
+            sl[axis] = slice(0, at) if which == 0 else slice(at, None)
+            want = np.maximum(x, np.float16(0))[tuple(sl)]
+            assert np.array_equal(got.view(np.uint16), np.ascontiguousarray(want).view(np.uint16)), (shape, axis, which)

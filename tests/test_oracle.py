@@ -385,3 +385,30 @@ def test_reference_takes_int8_weights_under_fp16_activations(ref, oracle, rng):
     want = oracle.conv2d_f32(x.astype(np.float32), wq.astype(np.float32) * s_w.reshape(-1, 1, 1, 1), b.astype(np.float32),
                              (n, o, h, w), stride=(1, 1), pad=(1,) * 4)
     assert np.max(np.abs(got - want) / (np.abs(want) + 1.0)) < 2e-3
+
+
+SPLIT_CASES = [((2, 32, 5, 7), 1, 16), ((2, 24, 5, 7), 1, 7), ((1, 8, 9, 6), 2, 4), ((2, 5, 3, 11), 3, 10), ((4, 16, 2, 2), 0, 1)]
+
+
+def split_case(shape, axis, at, which, oracle, rng):
+    """relu(x) split in two at index `at` along `axis`; the network's output is slice `which`, requantised"""
+    from shl import H_SPLIT
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    out_shape = list(shape)
+    out_shape[axis] = at if which == 0 else shape[axis] - at
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128),
+              Layer(H_SPLIT, tuple(out_shape), s_out=0.017, zp_out=-100, axis=axis, p0=float(at), p1=float(which))]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    sl = [slice(None)] * 4
+    sl[axis] = slice(0, at) if which == 0 else slice(at, None)
+    piece = np.ascontiguousarray(r[tuple(sl)])
+    # requant(dequant(q)): concat of one input is exactly that (source/reference/split.c:81 converts the same way)
+    return x, layers, oracle.concat_i8([piece], [(0.021, -128)], axis, 0.017, -100)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("shape,axis,at", SPLIT_CASES)
+def test_split_oracle_equals_the_reference(shape, axis, at, which, ref, oracle, rng):
+    x, layers, want = split_case(shape, axis, at, which, oracle, rng)
+    got = ref.run(DT_INT8, shape, layers, x, s_in=0.04, zp_in=3)
+    assert np.array_equal(got, want)
