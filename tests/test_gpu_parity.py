@@ -833,3 +833,38 @@ def test_split_fp16_is_a_copy(b200, rng):
             sl[axis] = slice(0, at) if which == 0 else slice(at, None)
             want = np.maximum(x, np.float16(0))[tuple(sl)]
             assert np.array_equal(got.view(np.uint16), np.ascontiguousarray(want).view(np.uint16)), (shape, axis, which)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_shufflenet_style_unit_int8_bit_exact(mode, b200, oracle, rng):
+    """split -> (identity branch | 1x1 conv + relu -> depthwise 3x3 -> 1x1 conv) -> concat, the ShuffleNetV2 basic
+    unit without the shuffle: multi-output and multi-input nodes share tensors in the planned arena"""
+    from shl import H_CONCAT, H_SPLIT
+    n, c, h, w = 3, 48, 14, 14
+    half = c // 2
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    w1, sw1, b1, so1 = synth_conv_i8(rng, half, half, 1, 1)
+    wd, swd, bd, sod = synth_conv_i8(rng, half, half, 3, 3, depthwise=True)
+    w2, sw2, b2, so2 = synth_conv_i8(rng, half, half, 1, 1)
+    layers = [
+        Layer(H_RELU, (n, c, h, w), s_out=0.02, zp_out=-128),                                               # t1
+        Layer(H_SPLIT, (n, half, h, w), in0=1, s_out=0.02, zp_out=-128, axis=1, p0=float(half), p1=0.0),   # t2
+        Layer(H_SPLIT, (n, half, h, w), in0=1, s_out=0.02, zp_out=-128, axis=1, p0=float(half), p1=1.0),   # t3
+        Layer(H_CONV_RELU, (n, half, h, w), in0=3, w=w1, b=b1, s_w=sw1, s_out=so1, zp_out=-128),            # t4
+        Layer(H_CONV, (n, half, h, w), in0=4, w=wd, b=bd, s_w=swd, s_out=sod, zp_out=5, pad=(1,) * 4, group=half),  # t5
+        Layer(H_CONV_RELU, (n, half, h, w), in0=5, w=w2, b=b2, s_w=sw2, s_out=so2, zp_out=-128),            # t6
+        Layer(H_CONCAT, (n, c, h, w), in0=2, in1=6, s_out=0.03, zp_out=-128, axis=1),                        # t7
+    ]
+    got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.04, zp_in=3, run_mode=mode)
+    t1 = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.02, -128)
+    t2, t3 = np.ascontiguousarray(t1[:, :half]), np.ascontiguousarray(t1[:, half:])   # same qinfo: identity tables
+    kw = dict(stride=(1, 1), dilation=(1, 1), group=1, s_b=None)
+    t4 = oracle.conv2d_i8(t3, w1, b1, t3.shape, pad=(0,) * 4, s_in=0.02, zp_in=-128, s_w=sw1, s_out=so1, zp_out=-128,
+                          act=ACT_RELU, **kw)
+    t5 = oracle.conv2d_i8(t4, wd, bd, t4.shape, depthwise=True, pad=(1,) * 4, s_in=so1, zp_in=-128, s_w=swd, s_out=sod,
+                          zp_out=5, **kw)
+    t6 = oracle.conv2d_i8(t5, w2, b2, t5.shape, pad=(0,) * 4, s_in=sod, zp_in=5, s_w=sw2, s_out=so2, zp_out=-128,
+                          act=ACT_RELU, **kw)
+    want = oracle.concat_i8([t2, t6], [(0.02, -128), (so2, -128)], 1, 0.03, -128)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
