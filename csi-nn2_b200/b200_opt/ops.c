@@ -917,6 +917,13 @@ static int prelu_init(struct csinn_tensor *input, struct csinn_tensor *alpha, st
     return binary_init(input, alpha, output, (struct csinn_diso_params *)params, B200_BINOP_PRELU);
 }
 void *shl_b200_prelu_init_fn(void) { return (void *)prelu_init; }
+/* div: replaces the shl_gref_div registration of source/thead_rvv/setup.c (source/reference/div.c:36) */
+static int div_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
+                    struct csinn_diso_params *params)
+{
+    return binary_init(input0, input1, output, params, B200_BINOP_DIV);
+}
+void *shl_b200_div_init_fn(void) { return (void *)div_init; }
 void *shl_b200_sub_init_fn(void) { return (void *)sub_init; }
 void *shl_b200_mul_init_fn(void) { return (void *)mul_init; }
 static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1, struct csinn_tensor *output,
@@ -960,7 +967,7 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
                 return CSINN_FALSE;
             }
     }
-    static const char *const names[] = {"b200_add", "b200_sub", "b200_mul", "b200_prelu"};
+    static const char *const names[] = {"b200_add", "b200_sub", "b200_mul", "b200_prelu", "b200_div"};
     b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, names[binop]);
     if (!op) return CSINN_FALSE;
     op->binop = binop;

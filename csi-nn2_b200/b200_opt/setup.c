@@ -80,6 +80,7 @@ static void build_table(void)
         reg_op(dt, CSINN_OP_SUB, shl_b200_sub_init_fn(), shl_b200_add, shl_gref_sub, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_MUL, shl_b200_mul_init_fn(), shl_b200_add, shl_gref_mul, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_CONCAT, shl_b200_concat_init, shl_b200_concat, shl_gref_concat, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_DIV, shl_b200_div_init_fn(), shl_b200_add, shl_gref_div, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_PRELU, shl_b200_prelu_init_fn(), shl_b200_add, shl_gref_prelu, shl_b200_perf_diso);
         reg_op(dt, CSINN_OP_SPLIT, shl_b200_split_init, shl_b200_split, shl_gref_split, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_MAXPOOL2D, shl_b200_pool2d_init, shl_b200_pool2d, shl_gref_maxpool2d, shl_b200_perf_siso);

@@ -99,6 +99,7 @@ struct AddArgs {
 __device__ __forceinline__ float binop_f(float a, float b, int binop)
 {
     if (binop == B200_BINOP_PRELU) return a >= 0.f ? a : __fmul_rn(a, b);
+    if (binop == B200_BINOP_DIV) return __fdiv_rn(a, b);
     return binop == B200_BINOP_SUB ? __fsub_rn(a, b) : (binop == B200_BINOP_MUL ? __fmul_rn(a, b) : __fadd_rn(a, b));
 }
 
@@ -149,7 +150,12 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
                 const uint64_t xa = f2_fma(bytes_to_f2(wa[q], 2 * h, off_a), sa2, 0ull);
                 const uint64_t xb = f2_fma(bytes_to_f2(wb[q], 2 * h, off_b), sb2, 0ull);
                 uint64_t rr;
-                if (p.binop == B200_BINOP_PRELU) {
+                if (p.binop == B200_BINOP_DIV) {
+                    int a0, a1, d0, d1;
+                    f2_unpack_bits(xa, a0, a1);
+                    f2_unpack_bits(xb, d0, d1);
+                    rr = f2_pack(__fdiv_rn(__int_as_float(a0), __int_as_float(d0)), __fdiv_rn(__int_as_float(a1), __int_as_float(d1)));
+                } else if (p.binop == B200_BINOP_PRELU) {
                     int a0, a1, m0, m1;
                     f2_unpack_bits(xa, a0, a1);
                     f2_unpack_bits(f2_fma(xa, xb, 0ull), m0, m1);
@@ -175,6 +181,10 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
                 if (fabsf(t1 - n1) > 0.49951171875f || !(fabsf(t1) < 4194304.f)) n1 = rintf(__fdiv_rn(__int_as_float(rb1), p.s_out));
                 qo[2 * h] = static_cast<int>(fminf(fmaxf(__fadd_rn(n0, zo), -128.f), 127.f));
                 qo[2 * h + 1] = static_cast<int>(fminf(fmaxf(__fadd_rn(n1, zo), -128.f), 127.f));
+                if (p.binop == B200_BINOP_DIV) {  // 0 / 0: the reference's (int8_t)NaN is 0 on its x86 build
+                    if (__int_as_float(rb0) != __int_as_float(rb0)) qo[2 * h] = 0;
+                    if (__int_as_float(rb1) != __int_as_float(rb1)) qo[2 * h + 1] = 0;
+                }
             }
             if (has_lut) {
                 const uint32_t b0 = s_lut[qo[0] + 128], b1 = s_lut[qo[1] + 128], b2 = s_lut[qo[2] + 128], b3 = s_lut[qo[3] + 128];
@@ -281,7 +291,7 @@ extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void
                                  size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
                                  const int8_t *post_lut, int act, void *stream)
 {
-    if (binop < B200_BINOP_ADD || binop > B200_BINOP_PRELU) {
+    if (binop < B200_BINOP_ADD || binop > B200_BINOP_DIV) {
         set_error("b200_binary: unknown op %d", binop);
         return B200_ERR_ARG;
     }

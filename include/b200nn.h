@@ -250,7 +250,9 @@ typedef enum {
     B200_BINOP_ADD = 0,
     B200_BINOP_SUB = 1,
     B200_BINOP_MUL = 2,
-    B200_BINOP_PRELU = 3 /* a >= 0 ? a : a * b, b = the per-channel slope (source/reference/prelu.c:44-48) */
+    B200_BINOP_PRELU = 3, /* a >= 0 ? a : a * b, b = the per-channel slope (source/reference/prelu.c:44-48) */
+    B200_BINOP_DIV = 4    /* a / b (source/reference/div.c:22); int8: +-inf saturate, 0 / 0 gives 0 -- what the
+                             reference's (int8_t)NaN yields on its x86 build (source/nn2/utils.c:550-560) */
 } b200_binop;
 int b200_binary(int binop, int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
                 float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act, void *stream);

@@ -79,6 +79,7 @@ void *shl_b200_leaky_relu_init_fn(void);
 void *shl_b200_sigmoid_init_fn(void);
 void *shl_b200_clip_init_fn(void);
 void *shl_b200_global_maxpool_init_fn(void); /* csinn_global_maxpool2d, source/reference/global_maxpool.c:21 */
+void *shl_b200_div_init_fn(void);   /* csinn_div, source/reference/div.c:36 */
 void *shl_b200_prelu_init_fn(void); /* csinn_prelu with a constant per-channel slope, source/reference/prelu.c:21 */
 void *shl_b200_silu_init_fn(void); /* csinn_silu: val / (1 + exp(-val)), source/reference/silu.c:21 */
 void *shl_b200_erf_init_fn(void);  /* csinn_erf, source/reference/erf.c:21 */

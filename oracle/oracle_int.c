@@ -312,7 +312,10 @@ void oracle_binary_i8(int op, const int8_t *a, const int8_t *b, int8_t *out, int
     for (int64_t i = 0; i < count; i++) {
         float x = dequant_i8(a[i], s_a, zp_a), y = dequant_i8(b[i], s_b, zp_b);
         float r = op == 1 ? x - y : (op == 2 ? x * y : (op == 3 ? (x >= 0 ? x : x * y) /* prelu.c:44-48 */ : x + y));
-        out[i] = quant_i8(r, s_out, zp_out);
+        if (op == 4) r = x / y; /* div.c:22 */
+        /* 0 / 0: float_to_int8_base (source/nn2/utils.c:550) falls through both comparisons and casts NaN to
+         * int8_t -- 0 on the reference's x86 build (cvttss2si gives 0x80000000, the low byte is kept) */
+        out[i] = r != r ? 0 : quant_i8(r, s_out, zp_out);
     }
 }
 

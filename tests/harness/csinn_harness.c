@@ -48,6 +48,7 @@ enum {
     H_PRELU, /* csinn_prelu, slope = the constant operand ([C]) */
     H_SPLIT, /* csinn_split of in0 in two at index (int)p0 along `axis`; the layer's output is slice (int)p1, the
                 other slice goes to a scratch tensor (net->k[i]) with the same qinfo */
+    H_DIV,
 };
 
 typedef struct {
@@ -244,12 +245,14 @@ static int layer_init(h_net *net, int i)
         }
         case H_ADD:
         case H_SUB:
+        case H_DIV:
         case H_MUL: {
             struct csinn_diso_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
             net->params[i] = p;
             struct csinn_tensor *rhs = L->w ? net->k[i] : net->t[L->in1];
             if (L->kind == H_SUB) return csinn_sub_init(in, rhs, out, p);
+            if (L->kind == H_DIV) return csinn_div_init(in, rhs, out, p);
             if (L->kind == H_MUL) return csinn_mul_init(in, rhs, out, p);
             return csinn_add_init(in, rhs, out, p);
         }
@@ -352,6 +355,8 @@ static int layer_call(h_net *net, int i)
             return csinn_erf(in, out, p);
         case H_SUB:
             return csinn_sub(in, L->w ? net->k[i] : net->t[L->in1], out, p);
+        case H_DIV:
+            return csinn_div(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_MUL:
             return csinn_mul(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_ADD:
@@ -449,7 +454,7 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
             net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f;
             net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
         }
-        if ((L->kind == H_ADD || L->kind == H_SUB || L->kind == H_MUL) && L->w) {
+        if ((L->kind == H_ADD || L->kind == H_SUB || L->kind == H_MUL || L->kind == H_DIV) && L->w) {
             /* constant second operand: one element ([1]) or one value per channel ([1, C, 1, 1]) */
             int32_t cd[4] = {1, L->o, 1, 1};
             snprintf(nm, sizeof(nm), "const_%d", i);

@@ -28,7 +28,7 @@ API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
 RM_LAYER, RM_GRAPH = 0, 1
 
 (H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
- H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL, H_CONCAT, H_SILU, H_ERF, H_GMP, H_PRELU, H_SPLIT) = range(25)
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL, H_CONCAT, H_SILU, H_ERF, H_GMP, H_PRELU, H_SPLIT, H_DIV) = range(26)
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 UNARY_LEAKY_RELU, UNARY_SIGMOID, UNARY_CLIP, UNARY_SILU, UNARY_ERF = 3, 4, 5, 6, 7

@@ -635,7 +635,8 @@ def test_graph_mode_fuses_unary_nodes_into_their_producer(b200, rng):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30)], ids=["sub", "mul"])
+@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30), (25, 4, 0.09, 4)],
+                         ids=["sub", "mul", "div"])
 def test_sub_mul_int8_bit_exact(kind, op, s_out, zp_out, b200, oracle, rng):
     shape = (2, 24, 9, 11)
     x = rng.integers(-128, 128, size=shape, dtype=np.int8)

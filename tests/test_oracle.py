@@ -291,7 +291,8 @@ def test_unary_ops_oracle_equals_the_reference(kind, op, p0, p1, ref, oracle, rn
         assert np.array_equal(got, want), (s_in, zp_in, s_out, zp_out, int(np.count_nonzero(got != want)))
 
 
-@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30)], ids=["sub", "mul"])
+@pytest.mark.parametrize("kind,op,s_out,zp_out", [(17, 1, 0.05, -11), (18, 2, 0.012, -30), (25, 4, 0.09, 4)],
+                         ids=["sub", "mul", "div"])
 def test_sub_mul_oracle_equals_the_reference(kind, op, s_out, zp_out, ref, oracle, rng):
     """csinn_sub / csinn_mul between same-shape tensors (source/reference/sub.c:36, mul.c:36): oracle vs
     the reference library, bit for bit"""
@@ -349,7 +350,7 @@ def test_global_maxpool_oracle_equals_the_reference(ref, oracle, rng):
         assert np.array_equal(got, want)
 
 
-BCAST_CASES = [(H_ADD, 0, False), (17, 1, False), (18, 2, False), (18, 2, True), (H_ADD, 0, True), (23, 3, False)]  # 23 = H_PRELU
+BCAST_CASES = [(H_ADD, 0, False), (17, 1, False), (18, 2, False), (18, 2, True), (H_ADD, 0, True), (23, 3, False), (25, 4, False), (25, 4, True)]  # 23 = H_PRELU, 25 = H_DIV
 
 
 def bcast_case(kind, op, scalar, oracle, rng, shape=(2, 24, 5, 7)):
