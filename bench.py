@@ -368,9 +368,10 @@ def main():
         achieved = k["bytes"] / (k["ms"] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "mobilenet_v1_int8" and args.batch == 256:
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel class, from the
-            # committed `ncu --set full` capture of this same command (tools/ncu_summary.py traffic)
+            # committed `ncu --set full` capture of this same command (tools/ncu_summary.py traffic); the
+            # capture is of the batch-256 int8 MobileNetV1 step only: other workloads report null
             traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
