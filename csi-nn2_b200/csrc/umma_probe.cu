@@ -1,0 +1,90 @@
+// umma_probe.cu -- test hook: does a SWIZZLE_128B K-major shared-memory descriptor accept a start address
+// that is shifted by whole 128-byte rows which are NOT a multiple of the 8-row swizzle period?
+//
+// Why it matters: an implicit-GEMM 3x3 convolution (and a tensor-core depthwise kernel with a 128-byte pixel
+// pitch) can read the A operand of tap (ky, kx) straight out of ONE halo tile in shared memory -- a flat pixel
+// sequence [pixel][128 B] written by a swizzled TMA load -- by starting the descriptor (ky * row + kx) pixels
+// further on.  That only works if the tensor core applies the swizzle XOR to the absolute shared-memory
+// address (as TMA does when it writes), not to the row index relative to the descriptor's start.
+// csrc/dwconv3x3_umma.cu proved the shifted-start idea for the no-swizzle layout; this probe answers it for
+// SWIZZLE_128B.  One M128 N32 K32 kind::i8 MMA: D[m][n] = sum_k A[shift + m][k0*32 + k] * B[n][k0*32 + k].
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kProbeRows = 144;  // 128 + the largest shift
+
+__global__ void __launch_bounds__(128) umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                               const __grid_constant__ CUtensorMap tmap_b, int shift,
+                                                               int k0, int32_t *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sa = smem;                       // [kProbeRows][128 B], swizzled by the TMA
+    uint8_t *sb = smem + kProbeRows * 128 + ((1024 - (kProbeRows * 128) % 1024) % 1024);  // [32][128 B]
+    __shared__ uint64_t full_bar, done_bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_ptr, 32);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    if (tid == 0) {
+        mbar_expect_tx(&full_bar, kProbeRows * 128 + 32 * 128);
+        tma_load_2d(sa, &tmap_a, &full_bar, 0, 0);
+        tma_load_2d(sb, &tmap_b, &full_bar, 0, 0);
+        mbar_wait(&full_bar, 0);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sa) + shift * 128) + 2 * k0;
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sb)) + 2 * k0;
+        tc_mma_i8(tmem_base, adesc, bdesc, umma_idesc(2 /*S32*/, 1 /*S8*/, 128, 32), 0u);
+        tc_commit(&done_bar);
+    }
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j++) out[tid * 32 + j] = static_cast<int32_t>(r[j]);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 32);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// a_dev: [144][128] int8, b_dev: [32][128] int8, out_dev: [128][32] int32
+extern "C" int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev, int shift, int k0, void *out_dev,
+                                            void *stream)
+{
+    if (!a_dev || !b_dev || !out_dev || shift < 0 || shift > kProbeRows - 128 || k0 < 0 || k0 > 3) {
+        set_error("b200_test_umma_shifted_start: bad arguments (shift %d, k0 %d)", shift, k0);
+        return B200_ERR_ARG;
+    }
+    alignas(64) CUtensorMap ta, tb;
+    int rc = encode_tmap_2d(&ta, 1, a_dev, 128, kProbeRows, 128, 128, kProbeRows, 128);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tb, 1, b_dev, 128, 32, 128, 128, 32, 128);
+    if (rc) return rc;
+    const size_t smem = kProbeRows * 128 + 1024 + 32 * 128 + 1024;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CUDA_CHECK(launch_kernel(umma_shift_probe_kernel, dim3(1), dim3(128), smem, (cudaStream_t)stream, ta, tb, shift, k0,
+                                  static_cast<int32_t *>(out_dev)));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -869,3 +869,34 @@ def test_shufflenet_style_unit_int8_bit_exact(mode, b200, oracle, rng):
                           act=ACT_RELU, **kw)
     want = oracle.concat_i8([t2, t6], [(0.02, -128), (so2, -128)], 1, 0.03, -128)
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+
+
+@pytest.mark.gpu
+def test_swizzled_descriptor_start_may_be_shifted_by_any_number_of_rows():
+    """hardware fact the next kernels build on (csrc/umma_probe.cu, tools/umma_probe.py): a SWIZZLE_128B K-major A
+    descriptor whose start address is `shift` 128-byte rows into a TMA-written tile reads rows shift .. shift+127 for
+    EVERY shift, not only multiples of the 8-row swizzle period -- the swizzle follows the absolute shared-memory
+    address.  So the taps of a 3x3 convolution can be read from one flat halo tile by shifting the descriptor."""
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = C.CDLL(os.path.join(root, "csi-nn2_b200", "lib", "libb200nn.so"))
+    shim.b200_last_error.restype = C.c_char_p
+    rng = np.random.default_rng(0)
+    a = rng.integers(-128, 128, size=(144, 128), dtype=np.int8)
+    b = rng.integers(-128, 128, size=(32, 128), dtype=np.int8)
+    d_a, d_b, d_o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    for d, n in ((d_a, a.nbytes), (d_b, b.nbytes), (d_o, 128 * 32 * 4)):
+        assert shim.b200_malloc(C.byref(d), C.c_size_t(n)) == 0, shim.b200_last_error()
+    assert shim.b200_memcpy_h2d(d_a, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), None) == 0
+    assert shim.b200_memcpy_h2d(d_b, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.nbytes), None) == 0
+    for k0 in range(4):
+        for shift in (0, 1, 2, 3, 5, 7, 8, 9, 13, 16):
+            got = np.zeros((128, 32), np.int32)
+            assert shim.b200_test_umma_shifted_start(d_a, d_b, shift, k0, d_o, None) == 0, shim.b200_last_error()
+            assert shim.b200_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_o, C.c_size_t(got.nbytes), None) == 0
+            assert shim.b200_stream_sync(None) == 0, shim.b200_last_error()
+            ks = slice(32 * k0, 32 * k0 + 32)
+            want = a[shift:shift + 128, ks].astype(np.int32) @ b[:, ks].astype(np.int32).T
+            assert np.array_equal(got, want), (k0, shift)
+    for d in (d_a, d_b, d_o):
+        shim.b200_free(d)

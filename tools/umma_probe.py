@@ -1,0 +1,36 @@
+"""developer probe (GPU box): SWIZZLE_128B A descriptors whose start is shifted by whole 128-byte rows
+(csrc/umma_probe.cu) -- for which shifts does the MMA read the rows TMA wrote?"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+shim = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libb200nn.so"))
+shim.b200_last_error.restype = C.c_char_p
+rng = np.random.default_rng(0)
+a = rng.integers(-128, 128, size=(144, 128), dtype=np.int8)
+b = rng.integers(-128, 128, size=(32, 128), dtype=np.int8)
+d_a, d_b, d_o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+for d, n in ((d_a, a.nbytes), (d_b, b.nbytes), (d_o, 128 * 32 * 4)):
+    assert shim.b200_malloc(C.byref(d), C.c_size_t(n)) == 0, shim.b200_last_error()
+assert shim.b200_memcpy_h2d(d_a, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), None) == 0
+assert shim.b200_memcpy_h2d(d_b, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.nbytes), None) == 0
+ok = {}
+for k0 in range(4):
+    for shift in range(17):
+        got = np.zeros((128, 32), np.int32)
+        assert shim.b200_test_umma_shifted_start(d_a, d_b, shift, k0, d_o, None) == 0, shim.b200_last_error()
+        assert shim.b200_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_o, C.c_size_t(got.nbytes), None) == 0
+        assert shim.b200_stream_sync(None) == 0, shim.b200_last_error()
+        ks = slice(32 * k0, 32 * k0 + 32)
+        want = a[shift:shift + 128, ks].astype(np.int32) @ b[:, ks].astype(np.int32).T
+        ok[(k0, shift)] = bool(np.array_equal(got, want))
+        if not ok[(k0, shift)] and k0 == 0:
+            # which input row does each output row look like?
+            cand = a[:, ks].astype(np.int32) @ b[:, ks].astype(np.int32).T
+            rows = [int(np.argmax((cand == got[m]).all(axis=1))) if (cand == got[m]).all(axis=1).any() else -1 for m in range(16)]
+            print(f"k0 {k0} shift {shift}: first output rows read input rows {rows}")
+for k0 in range(4):
+    print("k0", k0, "shifts that match:", [s for s in range(17) if ok[(k0, s)]])
