@@ -381,6 +381,7 @@ using namespace b200;
 
 int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream);  // dwconv3x3_tma.cu
 int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_umma.cu
+int b200_dwconv3x3_umma128_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_umma128.cu
 
 extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
 {
@@ -408,6 +409,11 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         (d->ow - 1) * d->stride_w - d->pad_left + 2 <= d->w) {
         // stride 1 with "same" padding: the taps are accumulated on the tensor cores
         int handled = 0;
+        const char *tc = getenv("SHL_B200_DW_UMMA");
+        if (tc && atoi(tc) == 2) {
+            const int rc2 = b200_dwconv3x3_umma128_launch(d, d->wt_row3, stream, &handled);
+            if (rc2 || handled) return rc2;
+        }
         const int rc = b200_dwconv3x3_umma_launch(d, d->wt_row3, stream, &handled);
         if (rc || handled) return rc;
         return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);

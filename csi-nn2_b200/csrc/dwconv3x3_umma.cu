@@ -196,15 +196,17 @@ dw3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const DwUmmaArgs a)
                 tc_fence_after();
                 // start addresses in 16-byte units (= pixels); the whole ring lies below 256 KB
                 const uint32_t tile16 = (smem_u32(smem) + static_cast<uint32_t>(stage) * 2 * a.plane_stride) >> 4;
-                uint32_t d = tmem_base + buf * kUBufCols;
-                for (int mb = 0; mb < ((a.diag & 2) ? 0 : nmb); mb++) {
+                // tap-pair-major: consecutive MMAs go to different accumulators, so the accumulating MMAs of one
+                // accumulator never wait for each other's latency
+                const uint32_t d0 = tmem_base + buf * kUBufCols;
+                const int nmb_run = (a.diag & 2) ? 0 : nmb;
 #pragma unroll
-                    for (int pl = 0; pl < 2; pl++) {
-                        const uint32_t abase = tile16 + pl * plane16 + mb * 128;
+                for (int j = 0; j < 5; j++) {
+                    for (int mb = 0; mb < nmb_run; mb++) {
 #pragma unroll
-                        for (int j = 0; j < 5; j++)
-                            tc_mma_i8(d, a_tmpl[j] + (abase + a_off[j]), b_desc[pl][j], a.idesc, j > 0 ? 1u : 0u);
-                        d += 16;
+                        for (int pl = 0; pl < 2; pl++)
+                            tc_mma_i8(d0 + (mb * 2 + pl) * 16, a_tmpl[j] + (tile16 + pl * plane16 + mb * 128 + a_off[j]),
+                                      b_desc[pl][j], a.idesc, j > 0 ? 1u : 0u);
                     }
                 }
                 tc_commit(&empty_bar[stage]);  // the slot is free once these MMAs have read it
@@ -308,7 +310,7 @@ int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void
 {
     *handled = 0;
     const char *e_on = getenv("SHL_B200_DW_UMMA"), *e_swap = getenv("SHL_B200_DW_UMMA_SWAP");
-    const int enabled = e_on ? atoi(e_on) : 0, swap = e_swap ? atoi(e_swap) : 0;
+    const int enabled = e_on ? atoi(e_on) == 1 : 0, swap = e_swap ? atoi(e_swap) : 0;
     if (!enabled) return B200_OK;
     if (d->stride_h != 1 || d->stride_w != 1 || d->pad_top != 1 || d->pad_left != 1 || d->oh != d->h || d->ow != d->w)
         return B200_OK;

@@ -453,7 +453,7 @@ def test_resnet50_int8_narrow_bit_exact(b200):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
 
 
-@pytest.mark.parametrize("rows", ["umma", "tma", "generic"])
+@pytest.mark.parametrize("rows", ["umma128", "umma", "tma", "generic"])
 def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     """the tensor-core depthwise kernel (csrc/dwconv3x3_umma.cu: stride 1, "same" padding; other cases fall
     through), the TMA-fed dp4a kernel (csrc/dwconv3x3_tma.cu) and the generic one (csrc/dwconv.cu)
@@ -463,9 +463,13 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
         os.environ["SHL_B200_DW_GENERIC"] = "1"
     if rows == "umma":
         os.environ["SHL_B200_DW_UMMA"] = "1"
+    if rows == "umma128":  # csrc/dwconv3x3_umma128.cu: channel counts that are multiples of 128
+        os.environ["SHL_B200_DW_UMMA"] = "2"
     try:
         for (n, c, h, w, stride, pad, zp_in) in [(2, 32, 13, 29, 1, 1, -7), (7, 48, 7, 7, 1, 1, 5), (5, 16, 3, 2, 1, 1, -3),
-                                                 (1, 40, 1, 1, 1, 1, 9), (1, 16, 40, 200, 1, 1, -9), (1, 64, 56, 56, 1, 1, 0),
+                                                 (1, 40, 1, 1, 1, 1, 9), (1, 16, 40, 200, 1, 1, -9), (2, 128, 13, 29, 1, 1, -7),
+                                                 (5, 256, 7, 7, 1, 1, 3), (2, 128, 56, 56, 1, 1, -128), (1, 1024, 7, 7, 1, 1, 9),
+                                                 (300, 128, 14, 14, 1, 1, -6), (1, 64, 56, 56, 1, 1, 0),
                                                  (1, 48, 15, 15, 2, 1, 4), (1, 16, 7, 7, 1, 1, -128),
                                                  (1, 128, 9, 10, 2, 0, 2), (1, 20, 6, 5, 1, 0, 1),
                                                  (2, 96, 30, 33, 1, 1, -5), (1, 160, 57, 9, 2, 1, 7),

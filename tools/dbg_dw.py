@@ -6,7 +6,7 @@ from shl import DT_INT8, H_CONV, Harness, Layer, Oracle, synth_conv_i8
 
 b200, oracle = Harness("b200"), Oracle()
 rng = np.random.default_rng(0)
-cases = [(2, 32, 13, 29, -7), (1, 64, 56, 56, 0), (7, 48, 7, 7, 5), (1, 16, 7, 7, -128), (1, 512, 14, 14, -128),
+cases = [(2, 128, 13, 29, -7), (5, 256, 7, 7, 3), (2, 128, 56, 56, -128), (2, 32, 13, 29, -7), (1, 64, 56, 56, 0), (7, 48, 7, 7, 5), (1, 16, 7, 7, -128), (1, 512, 14, 14, -128),
          (3, 32, 112, 112, -128), (256, 32, 14, 14, 3)]
 for (n, c, h, w, zp_in) in cases:
     x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
