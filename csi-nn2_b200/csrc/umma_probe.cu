@@ -64,6 +64,48 @@ __global__ void __launch_bounds__(128) umma_shift_probe_kernel(const __grid_cons
     }
 }
 
+// rate probe: `reps` M128 x N x K32 kind::i8 MMAs over uninitialised swizzled operand tiles, round-robin over
+// `nacc` accumulators (1 = one dependent chain); cycles from the first issue to the completion of the last
+__global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, int reps, long long *cycles)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sa = smem;               // [128][128 B]
+    uint8_t *sb = smem + 128 * 128;   // [256][128 B]
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(i, 1, 2, 3);
+    if (tid == 0) {
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    if (tid == 0) {
+        const uint64_t a0 = umma_desc_sw128(smem_u32(sa)), b0 = umma_desc_sw128(smem_u32(sb));
+        const uint32_t idesc = umma_idesc(2, 1, 128, n);
+        const long long t0 = clock64();
+        for (int i = 0; i < reps; i++) tc_mma_i8(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
+        tc_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+        *cycles = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -86,5 +128,23 @@ extern "C" int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev
     B200_CUDA_CHECK(launch_kernel(umma_shift_probe_kernel, dim3(1), dim3(128), smem, (cudaStream_t)stream, ta, tb, shift, k0,
                                   static_cast<int32_t *>(out_dev)));
     B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// cycles for `reps` back-to-back M128 x n x K32 int8 MMAs on one SM, `nacc` accumulators in rotation
+extern "C" int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_host, void *stream)
+{
+    if (n < 16 || n > 256 || n % 16 || nacc < 1 || nacc * n > 512 || reps < 1 || !cycles_host) {
+        set_error("b200_test_umma_rate: bad arguments (n %d, nacc %d, reps %d)", n, nacc, reps);
+        return B200_ERR_ARG;
+    }
+    long long *d = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&d, sizeof(long long)));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CUDA_CHECK(launch_kernel(umma_rate_probe_kernel, dim3(1), dim3(128), (128 + 256) * 128 + 1024, (cudaStream_t)stream, n,
+                                  nacc, reps, d));
+    B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    B200_CUDA_CHECK(cudaMemcpy(cycles_host, d, sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return B200_OK;
 }

@@ -309,6 +309,9 @@ int b200_pool2d(const b200_pool_desc *d, void *stream);
  * 128-byte rows into a TMA-written tile: out[m][n] = sum_k a[shift + m][32 k0 + k] * b[n][32 k0 + k].
  * a_dev [144][128] int8, b_dev [32][128] int8, out_dev [128][32] int32 */
 int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev, int shift, int k0, void *out_dev, void *stream);
+/* test hook (csrc/umma_probe.cu): cycles one SM needs for `reps` back-to-back M128 x n x K32 kind::i8 MMAs with
+ * `nacc` accumulators in rotation (1 = one dependent chain) */
+int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_host, void *stream);
 /* test hook: the softmax denominator code alone (rows x c doubles -> rows floats), see csrc/softmax.cu */
 int b200_test_softmax_denominator(const void *e_dev, int rows, int c, void *out_dev, void *stream);
 int b200_softmax(int dtype, const void *in, void *out, int rows, int c, int cp_in, int cp_out,

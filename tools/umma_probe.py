@@ -34,3 +34,14 @@ for k0 in range(4):
             print(f"k0 {k0} shift {shift}: first output rows read input rows {rows}")
 for k0 in range(4):
     print("k0", k0, "shifts that match:", [s for s in range(17) if ok[(k0, s)]])
+
+# ---- issue rate of small MMAs on one SM ----
+shim.b200_test_umma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_void_p]
+print("cycles per M128 x N x K32 kind::i8 MMA (one SM, 2000 back to back):")
+for n in (16, 32, 64, 128, 256):
+    row = []
+    for nacc in (1, 2, 512 // n if 512 // n < 8 else 8):
+        cyc = C.c_longlong()
+        assert shim.b200_test_umma_rate(n, nacc, 2000, C.byref(cyc), None) == 0, shim.b200_last_error()
+        row.append(f"nacc {nacc}: {cyc.value / 2000:6.1f}")
+    print(f"  N {n:3d}   " + "   ".join(row))
