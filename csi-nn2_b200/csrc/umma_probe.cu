@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) umma_shift_probe_kernel(const __grid_cons
 
 // rate probe: `reps` M128 x N x K32 kind::i8 MMAs over uninitialised swizzled operand tiles, round-robin over
 // `nacc` accumulators (1 = one dependent chain); cycles from the first issue to the completion of the last
-__global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, int reps, long long *cycles)
+__global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, int reps, long long *cycles, int m, int f16)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -91,9 +91,12 @@ __global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, i
     const uint32_t tmem_base = tmem_ptr;
     if (tid == 0) {
         const uint64_t a0 = umma_desc_sw128(smem_u32(sa)), b0 = umma_desc_sw128(smem_u32(sb));
-        const uint32_t idesc = umma_idesc(2, 1, 128, n);
+        const uint32_t idesc = f16 ? umma_idesc(1, 0, m, n) : umma_idesc(2, 1, m, n);
         const long long t0 = clock64();
-        for (int i = 0; i < reps; i++) tc_mma_i8(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
+        if (f16)
+            for (int i = 0; i < reps; i++) tc_mma_f16(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
+        else
+            for (int i = 0; i < reps; i++) tc_mma_i8(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
         tc_commit(&done_bar);
         mbar_wait(&done_bar, 0);
         *cycles = clock64() - t0;
@@ -134,7 +137,13 @@ extern "C" int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev
 // cycles for `reps` back-to-back M128 x n x K32 int8 MMAs on one SM, `nacc` accumulators in rotation
 extern "C" int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_host, void *stream)
 {
-    if (n < 16 || n > 256 || n % 16 || nacc < 1 || nacc * n > 512 || reps < 1 || !cycles_host) {
+    return b200_test_umma_rate2(128, n, 0, nacc, reps, cycles_host, stream);
+}
+
+// the same for M = 64 / 128 and kind::i8 (f16 = 0, K = 32 bytes) / kind::f16 (f16 = 1, K = 16 halves)
+extern "C" int b200_test_umma_rate2(int m, int n, int f16, int nacc, int reps, long long *cycles_host, void *stream)
+{
+    if ((m != 64 && m != 128) || n < 16 || n > 256 || n % 16 || nacc < 1 || nacc * n > 512 || reps < 1 || !cycles_host) {
         set_error("b200_test_umma_rate: bad arguments (n %d, nacc %d, reps %d)", n, nacc, reps);
         return B200_ERR_ARG;
     }
@@ -142,7 +151,7 @@ extern "C" int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_
     B200_CUDA_CHECK(cudaMalloc(&d, sizeof(long long)));
     B200_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     B200_CUDA_CHECK(launch_kernel(umma_rate_probe_kernel, dim3(1), dim3(128), (128 + 256) * 128 + 1024, (cudaStream_t)stream, n,
-                                  nacc, reps, d));
+                                  nacc, reps, d, m, f16));
     B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     B200_CUDA_CHECK(cudaMemcpy(cycles_host, d, sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d);

@@ -45,3 +45,12 @@ for n in (16, 32, 64, 128, 256):
         assert shim.b200_test_umma_rate(n, nacc, 2000, C.byref(cyc), None) == 0, shim.b200_last_error()
         row.append(f"nacc {nacc}: {cyc.value / 2000:6.1f}")
     print(f"  N {n:3d}   " + "   ".join(row))
+
+shim.b200_test_umma_rate2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_void_p]
+for m, f16, name in ((64, 0, "M64 i8"), (128, 1, "M128 f16 (K = 16 halves)"), (64, 1, "M64 f16")):
+    row = []
+    for n in (16, 64, 128, 256):
+        cyc = C.c_longlong()
+        assert shim.b200_test_umma_rate2(m, n, f16, 2, 2000, C.byref(cyc), None) == 0, shim.b200_last_error()
+        row.append(f"N {n}: {cyc.value / 2000:6.1f}")
+    print(f"  {name:26s}" + "   ".join(row))
