@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) umma_shift_probe_kernel(const __grid_cons
 
 // rate probe: `reps` M128 x N x K32 kind::i8 MMAs over uninitialised swizzled operand tiles, round-robin over
 // `nacc` accumulators (1 = one dependent chain); cycles from the first issue to the completion of the last
-__global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, int reps, long long *cycles, int m, int f16)
+__global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, int reps, long long *cycles, int m, int f16, int issuers)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, i
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(i, 1, 2, 3);
     if (tid == 0) {
-        mbar_init(&done_bar, 1);
+        mbar_init(&done_bar, issuers);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -89,17 +89,21 @@ __global__ void __launch_bounds__(128) umma_rate_probe_kernel(int n, int nacc, i
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_ptr;
-    if (tid == 0) {
+    // `issuers` warps (lane 0 of warps 0 .. issuers-1) issue reps / issuers MMAs each, into disjoint accumulators
+    if ((tid & 31) == 0 && warp < issuers) {
         const uint64_t a0 = umma_desc_sw128(smem_u32(sa)), b0 = umma_desc_sw128(smem_u32(sb));
         const uint32_t idesc = f16 ? umma_idesc(1, 0, m, n) : umma_idesc(2, 1, m, n);
+        const int per = nacc / issuers > 0 ? nacc / issuers : 1;
+        const uint32_t tb = tmem_base + (issuers > 1 ? warp * per * n : 0);
+        const int mine = reps / issuers;
         const long long t0 = clock64();
         if (f16)
-            for (int i = 0; i < reps; i++) tc_mma_f16(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
+            for (int i = 0; i < mine; i++) tc_mma_f16(tb + (i % per) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
         else
-            for (int i = 0; i < reps; i++) tc_mma_i8(tmem_base + (i % nacc) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
+            for (int i = 0; i < mine; i++) tc_mma_i8(tb + (i % per) * n, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, 1u);
         tc_commit(&done_bar);
         mbar_wait(&done_bar, 0);
-        *cycles = clock64() - t0;
+        if (warp == 0) *cycles = clock64() - t0;
     }
     tc_fence_before();
     __syncthreads();
@@ -143,6 +147,17 @@ extern "C" int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_
 // the same for M = 64 / 128 and kind::i8 (f16 = 0, K = 32 bytes) / kind::f16 (f16 = 1, K = 16 halves)
 extern "C" int b200_test_umma_rate2(int m, int n, int f16, int nacc, int reps, long long *cycles_host, void *stream)
 {
+    return b200_test_umma_rate3(m, n, f16, nacc, reps, 1, cycles_host, stream);
+}
+
+// ... issued by `issuers` (1, 2 or 4) warps, each into its own accumulators
+extern "C" int b200_test_umma_rate3(int m, int n, int f16, int nacc, int reps, int issuers, long long *cycles_host,
+                                    void *stream)
+{
+    if (issuers != 1 && issuers != 2 && issuers != 4) {
+        set_error("b200_test_umma_rate3: issuers %d", issuers);
+        return B200_ERR_ARG;
+    }
     if ((m != 64 && m != 128) || n < 16 || n > 256 || n % 16 || nacc < 1 || nacc * n > 512 || reps < 1 || !cycles_host) {
         set_error("b200_test_umma_rate: bad arguments (n %d, nacc %d, reps %d)", n, nacc, reps);
         return B200_ERR_ARG;
@@ -151,7 +166,7 @@ extern "C" int b200_test_umma_rate2(int m, int n, int f16, int nacc, int reps, l
     B200_CUDA_CHECK(cudaMalloc(&d, sizeof(long long)));
     B200_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     B200_CUDA_CHECK(launch_kernel(umma_rate_probe_kernel, dim3(1), dim3(128), (128 + 256) * 128 + 1024, (cudaStream_t)stream, n,
-                                  nacc, reps, d, m, f16));
+                                  nacc, reps, d, m, f16, issuers));
     B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     B200_CUDA_CHECK(cudaMemcpy(cycles_host, d, sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d);

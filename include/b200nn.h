@@ -313,6 +313,7 @@ int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev, int shift
  * `nacc` accumulators in rotation (1 = one dependent chain) */
 int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_host, void *stream);
 int b200_test_umma_rate2(int m, int n, int f16, int nacc, int reps, long long *cycles_host, void *stream);
+int b200_test_umma_rate3(int m, int n, int f16, int nacc, int reps, int issuers, long long *cycles_host, void *stream);
 /* test hook: the softmax denominator code alone (rows x c doubles -> rows floats), see csrc/softmax.cu */
 int b200_test_softmax_denominator(const void *e_dev, int rows, int c, void *out_dev, void *stream);
 int b200_softmax(int dtype, const void *in, void *out, int rows, int c, int cp_in, int cp_out,

@@ -54,3 +54,13 @@ for m, f16, name in ((64, 0, "M64 i8"), (128, 1, "M128 f16 (K = 16 halves)"), (6
         assert shim.b200_test_umma_rate2(m, n, f16, 2, 2000, C.byref(cyc), None) == 0, shim.b200_last_error()
         row.append(f"N {n}: {cyc.value / 2000:6.1f}")
     print(f"  {name:26s}" + "   ".join(row))
+
+shim.b200_test_umma_rate3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_void_p]
+print("2000 M128 i8 MMAs in total, issued by 1 / 2 / 4 warps (cycles per MMA):")
+for n in (32, 128):
+    row = []
+    for issuers in (1, 2, 4):
+        cyc = C.c_longlong()
+        assert shim.b200_test_umma_rate3(128, n, 0, 4, 2000, issuers, C.byref(cyc), None) == 0, shim.b200_last_error()
+        row.append(f"{issuers} warps: {cyc.value / 2000:6.1f}")
+    print(f"  N {n:3d}   " + "   ".join(row))
