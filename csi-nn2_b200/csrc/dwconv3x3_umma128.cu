@@ -17,7 +17,7 @@ namespace b200 {
 constexpr int kVStagesMax = 3;
 constexpr int kVMaxMB = 2;                         // 128-pixel blocks per tile
 constexpr int kVEpiWarps = 16;
-constexpr int kVThreads = 64 + kVEpiWarps * 32;    // TMA warp, MMA warp, epilogue warps
+constexpr int kVThreads = 96 + kVEpiWarps * 32;    // TMA warp, MMA warp, epilogue warps, second MMA warp (last)
 constexpr int kVBufCols = kVMaxMB * 4 * 32;        // TMEM columns of one accumulator buffer
 constexpr int kVTmemCols = 2 * kVBufCols;          // 512
 constexpr int kVBBytes = 4 * 3 * 4096;             // diagonal B tiles: [slab][tap group][32 rows][128 B]
@@ -94,10 +94,10 @@ dw3x3_umma128_kernel(const __grid_constant__ CUtensorMap tmap, const DwV128Args 
         tma_prefetch_desc(&tmap);
         for (int i = 0; i < kVStagesMax; i++) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], 2);  // both MMA issuers have consumed the slot
         }
         for (int i = 0; i < 2; i++) {
-            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_full[i], 2);
             mbar_init(&acc_empty[i], kVEpiWarps);
         }
         mbar_fence_init();
@@ -133,8 +133,10 @@ dw3x3_umma128_kernel(const __grid_constant__ CUtensorMap tmap, const DwV128Args 
                 if (++stage == a.stages) stage = 0, phase ^= 1;
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || warp == 2 + kVEpiWarps) {
+        // ===== MMA issuers: one thread gets an MMA out every ~113 cycles whatever its shape (csrc/umma_probe.cu), so
+        // two warps issue, each the two 32-channel slabs (= accumulators) it owns =====
+        const int kq_lo = warp == 1 ? 0 : 2;
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -158,7 +160,7 @@ dw3x3_umma128_kernel(const __grid_constant__ CUtensorMap tmap, const DwV128Args 
                 for (int tp = 0; tp < 9; tp++) {
                     for (int mb = 0; mb < nmb_run; mb++) {
 #pragma unroll
-                        for (int kq = 0; kq < 4; kq++) {
+                        for (int kq = kq_lo; kq < kq_lo + 2; kq++) {
                             const uint64_t adesc = a0 + (static_cast<uint32_t>(mb) * 128 * 8 + a_off[tp] + 2 * kq);
                             const uint64_t bdesc = b0 + ((kq * 3 + (tp >> 2)) * (4096 >> 4) + 2 * (tp & 3));
                             tc_mma_i8(d0 + (mb * 4 + kq) * 32, adesc, bdesc, a.idesc, tp > 0 ? 1u : 0u);
