@@ -114,6 +114,10 @@ size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_d
 /* `part`: which input of a concat `in0` is (0 for every other kind) */
 int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
                 void *scratch, void *stream);
+/* depthwise 3x3 step + the 1x1 conv that is its only consumer as ONE kernel (csrc/dwpw_fused.cu);
+ * `mid` carries the shape of the depthwise output, which is never materialised */
+int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out);
+int b200_dwpw_run(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out, void *stream);
 /* fuse a following relu / relu6 node (with its own qinfo) into this op's epilogue */
 int b200_op_can_fuse_act(const b200_op *op);
 int b200_op_fuse_act(b200_op *op, int act, float p0, float p1, const struct csinn_tensor *act_in,

@@ -48,12 +48,15 @@ typedef struct {
     int uploaded;            /* the device input already holds the bytes of the current host pointer */
     void *d_out_nchw; /* graph outputs: compact NCHW copy for D2H */
     void *h_out;      /* graph outputs: host buffer handed to csinn_get_output */
+    int elided;       /* lives only inside a fused kernel (depthwise -> pointwise): no arena space */
 } g_tensor;
 
 typedef struct {
     b200_op *op;
     int in0, in1, out;
     int part; /* concat: which input in0 is */
+    b200_op *op2; /* depthwise step fused with the 1x1 conv that consumes it: the conv (else NULL) */
+    int mid;      /* ... and the tensor between them (shape only, never materialised) */
     size_t scratch;
     char name[96];
 } g_step;
@@ -285,6 +288,10 @@ static int plan_memory(b200_graph *g)
     int *placed = calloc(g->nt, sizeof(int));
     for (int oi = 0; oi < g->nt; oi++) {
         g_tensor *t = &g->t[order[oi]];
+        if (t->elided) {
+            t->off = 0; /* never dereferenced */
+            continue;
+        }
         if (t->is_input) t->first_def = -1;
         if (t->is_output) t->last_use = g->ns;
         const size_t sz = (b200_dt_bytes(&t->dt) + 1023) & ~(size_t)1023;
@@ -318,6 +325,18 @@ static int plan_memory(b200_graph *g)
     return CSINN_TRUE;
 }
 
+static const char *step_kname(const b200_graph *g, const g_step *s)
+{
+    return s->op2 ? "b200_dwpw_fused_tcgen05" : b200_op_kname(s->op, &g->t[s->in0].dt);
+}
+
+static int step_run(b200_graph *g, g_step *s, void *stream)
+{
+    if (s->op2) return b200_dwpw_run(s->op, s->op2, &g->t[s->in0].dt, &g->t[s->mid].dt, &g->t[s->out].dt, stream);
+    const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
+    return b200_op_run(s->op, s->part, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream);
+}
+
 static int run_steps(b200_graph *g, void *stream)
 {
     for (int i = 0; i < g->nt; i++) {
@@ -328,9 +347,7 @@ static int run_steps(b200_graph *g, void *stream)
     }
     for (int i = 0; i < g->ns; i++) {
         g_step *s = &g->s[i];
-        const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
-        if (b200_op_run(s->op, s->part, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
-            CSINN_TRUE) {
+        if (step_run(g, s, stream) != CSINN_TRUE) {
             shl_debug_error("b200: step %d (%s) failed: %s\n", i, s->name, shl_b200_last_error());
             return CSINN_FALSE;
         }
@@ -552,6 +569,26 @@ static int build_from_graph(struct csinn_session *sess)
         s->op = op;
         s->in0 = tensor_add(g, n->in[0]);
         s->in1 = -1;
+        /* depthwise 3x3 -> 1x1 conv: when the depthwise result has no other reader, the pair becomes ONE
+         * step whose intermediate tensor never leaves the SM (csrc/dwpw_fused.cu) */
+        if (op->kind == B200_OPK_CONV && g->ns > 0 && s->in0 >= 0) {
+            g_step *prev = &g->s[g->ns - 1];
+            g_tensor *mid = &g->t[s->in0];
+            const int out_idx = tensor_add(g, out_tn);
+            if (out_idx >= 0 && !prev->op2 && prev->op->kind == B200_OPK_DW && prev->out == s->in0 && !mid->is_input &&
+                !is_graph_output(graph, mid->node) && consumers(graph, mid->node, NULL) == 1 &&
+                b200_dwpw_can_fuse(prev->op, op, &g->t[prev->in0].dt, &mid->dt, &g->t[out_idx].dt)) {
+                prev->op2 = op, prev->mid = s->in0, prev->out = out_idx;
+                mid->elided = 1;
+                strncat(prev->name, " > ", sizeof(prev->name) - strlen(prev->name) - 1);
+                strncat(prev->name, s->name, sizeof(prev->name) - strlen(prev->name) - 1);
+                g_tensor *to2 = &g->t[out_idx];
+                if (to2->first_def < 0) to2->first_def = g->ns - 1;
+                to2->last_use = g->ns - 1;
+                memset(s, 0, sizeof(*s));
+                continue;
+            }
+        }
         const int two_inputs = op->kind == B200_OPK_ADD && !op->d_const; /* a constant operand lives in the weight arena */
         if (two_inputs) s->in1 = tensor_add(g, n->in[1]);
         s->out = tensor_add(g, out_tn);
@@ -846,7 +883,7 @@ int shl_b200_session_describe(struct csinn_session *sess, char *buf, int buflen)
     for (int i = 0; i < g->ns && n < buflen; i++) {
         const b200_dt *o = &g->t[g->s[i].out].dt;
         n += snprintf(buf + n, buflen - n, "%3d %-28s %s -> [%d,%d,%d,%d]\n", i,
-                      b200_op_kname(g->s[i].op, &g->t[g->s[i].in0].dt), g->s[i].name,
+                      step_kname(g, &g->s[i]), g->s[i].name,
                       o->n, o->c, o->h, o->w);
     }
     return n < buflen ? n : buflen - 1;
@@ -876,10 +913,7 @@ int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, 
         for (int i = 0; i < g->ns; i++) {
             g_step *s = &g->s[i];
             b200_event_record(ev[i], stream);
-            const b200_dt *in1 = s->in1 >= 0 ? &g->t[s->in1].dt : NULL;
-            if (b200_op_run(s->op, s->part, &g->t[s->in0].dt, in1, &g->t[s->out].dt, g->arena + g->scratch_off, stream) !=
-                CSINN_TRUE)
-                return 0;
+            if (step_run(g, s, stream) != CSINN_TRUE) return 0;
         }
         b200_event_record(ev[g->ns], stream);
         if (b200_stream_sync(stream) != B200_OK) return 0;
@@ -903,8 +937,13 @@ int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, 
             by += e * (double)p->o * p->kdim + 4.0 * p->o;
             op = 2.0 * o->n * o->h * o->w * (double)p->o * p->kdim;
         } else if (p->kind == B200_OPK_DW) {
+            const b200_dt *m = s->op2 ? &g->t[s->mid].dt : o; /* the depthwise output */
             by += e * (double)p->o * p->kh * p->kw + 4.0 * p->o;
-            op = 2.0 * o->n * o->h * o->w * (double)p->o * p->kh * p->kw;
+            op = 2.0 * m->n * m->h * m->w * (double)p->o * p->kh * p->kw;
+            if (s->op2) { /* fused block: depthwise input + pointwise output + both weight sets; the tensor between never moves */
+                by += e * (double)s->op2->o * s->op2->kdim + 4.0 * s->op2->o;
+                op += 2.0 * o->n * o->h * o->w * (double)s->op2->o * s->op2->kdim;
+            }
         }
         if (bytes) bytes[i] = by;
         if (ops) ops[i] = op;

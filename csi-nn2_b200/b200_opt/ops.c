@@ -492,6 +492,44 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
     return CSINN_FALSE;
 }
 
+/* ---- depthwise 3x3 -> pointwise 1x1 as one kernel ---------------------------- */
+static void dwpw_fill(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out,
+                      b200_dwpw_desc *f)
+{
+    memset(f, 0, sizeof(*f));
+    b200_dwconv_desc *d = &f->dw;
+    d->dtype = dw->dtype, d->n = in->n, d->c = in->c, d->cp = in->cp;
+    d->h = in->h, d->w = in->w, d->oh = mid->h, d->ow = mid->w;
+    d->kh = dw->kh, d->kw = dw->kw, d->stride_h = dw->sh, d->stride_w = dw->sw;
+    d->pad_top = dw->pt, d->pad_left = dw->pl, d->dil_h = dw->dh, d->dil_w = dw->dw;
+    d->in = in->d, d->wt = dw->d_w, d->wt_row3 = dw->d_w2, d->out = NULL, d->zp_in = dw->zp_in;
+    fill_epilogue(dw, &d->ep);
+    f->o = pw->o, f->w = pw->d_w, f->ldw = pw->ldk, f->out = out->d, f->ldo = out->cp;
+    fill_epilogue(pw, &f->ep);
+}
+
+/* `mid` = the depthwise output as the graph declares it (shape only: it is never materialised) */
+int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out)
+{
+    if (getenv("SHL_B200_NO_DWPW")) return 0;
+    if (dw->kind != B200_OPK_DW || pw->kind != B200_OPK_CONV || !pw->direct || dw->dtype != B200_I8 ||
+        pw->dtype != B200_I8 || in->is_nchw || pw->kdim != mid->c || mid->c != in->c || mid->n != out->n ||
+        mid->h != out->h || mid->w != out->w)
+        return 0;
+    b200_dwpw_desc f;
+    dwpw_fill(dw, pw, in, mid, out, &f);
+    f.dw.in = f.out = (void *)16; /* planning time: the arena is not allocated yet, only the shapes matter */
+    return b200_dwpw_supported(&f);
+}
+
+int b200_dwpw_run(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out, void *stream)
+{
+    b200_dwpw_desc f;
+    dwpw_fill(dw, pw, in, mid, out, &f);
+    DEV_CHECK(b200_dwpw_fused(&f, stream));
+    return CSINN_TRUE;
+}
+
 int b200_op_can_fuse_act(const b200_op *op)
 {
     return (op->kind == B200_OPK_CONV || op->kind == B200_OPK_DW || op->kind == B200_OPK_FC ||

@@ -83,6 +83,8 @@ int encode_tmap_nhwc_u8_nb(CUtensorMap *map, const void *base, int n, int h, int
                            int box_w, int box_h, int box_n);  // the same with box_n images per box
 int encode_tmap_nhwc_u8_sw128(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_w, int box_h,
                               int box_n);
+int encode_tmap_nhwc_u8_ex(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c, int box_w,
+                           int box_h, int box_n, int swizzle_bytes);
 int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
                    uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                    int swizzle_bytes = 128);

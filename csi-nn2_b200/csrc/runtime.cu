@@ -110,6 +110,32 @@ int encode_tmap_nhwc_u8_nb(CUtensorMap *map, const void *base, int n, int h, int
     return B200_OK;
 }
 
+// 4-D box of a pixel-major uint8 tensor with a choice of swizzle (0 / 32 / 64 / 128 bytes = the box's channel extent
+// for the swizzled modes): halo loads and clipped output-tile stores of csrc/dwpw_fused.cu, csrc/conv_igemm.cu
+int encode_tmap_nhwc_u8_ex(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c, int box_w, int box_h,
+                           int box_n, int swizzle_bytes)
+{
+    encode_tiled_fn fn = encode_entry();
+    if (!fn) return B200_ERR_CUDA;
+    cuuint64_t gdim[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t gstride[3] = {(cuuint64_t)cp, (cuuint64_t)cp * w, (cuuint64_t)cp * w * h};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                    : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                    : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                          : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(4d, swizzle %d) failed: CUresult %d (n %d h %d w %d cp %d box %d x %d x %d x %d)",
+                  swizzle_bytes, (int)r, n, h, w, cp, box_c, box_w, box_h, box_n);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
 // 4-D box {128 channels, box_w, box_h, box_n} of a pixel-major uint8 tensor, SWIZZLE_128B (csrc/dwconv3x3_umma128.cu)
 int encode_tmap_nhwc_u8_sw128(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_w, int box_h,
                               int box_n)

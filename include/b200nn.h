@@ -233,6 +233,29 @@ typedef struct {
 } b200_dwconv_desc;
 int b200_dwconv2d(const b200_dwconv_desc *d, void *stream);
 
+/* ---- depthwise 3x3 -> pointwise 1x1 in one kernel (a MobileNet block) -------------- */
+/* out = pw(dw(in)): the int8 result of the depthwise stage (requantised with dw.ep exactly as
+ * b200_dwconv2d would) is written into the tcgen05 GEMM's swizzled A operand tile in shared memory
+ * and never reaches HBM; the pointwise stage is b200_gemm's contract with `ep`.  Bit-identical to
+ * b200_dwconv2d followed by b200_gemm.  Covers int8, 3x3, stride 1 / 2, pads <= 1, o <= 256 and
+ * pointwise weights that stay resident in shared memory (b200_dwpw_supported tells).  dw.out is
+ * ignored.  Replaces the pair shl_rvv_dwconv3x3s1_int8 / s2
+ * (source/thead_rvv/int8/depthwise_convolution_3x3_int8.c:31,244) -> shl_rvv_conv1x1s1_gemm_int8
+ * (source/thead_rvv/int8/convolution_1x1_int8.c:56) of example/c906_mobilenetv1_f16.c. */
+typedef struct {
+    b200_dwconv_desc dw;
+    int32_t o;       /* pointwise output channels                                     */
+    const void *w;   /* device [o][ldw] int8, the b200_gemm weight layout (K = dw.c)  */
+    int32_t ldw;
+    void *out;       /* device [n][oh][ow][ldo]                                       */
+    int32_t ldo;
+    b200_epilogue ep; /* pointwise epilogue                                           */
+} b200_dwpw_desc;
+int b200_dwpw_supported(const b200_dwpw_desc *d);
+int b200_dwpw_fused(const b200_dwpw_desc *d, void *stream);
+/* the tile plan the fused kernel would use, as text (0 = the pair is not covered); tools and tests */
+int b200_dwpw_plan_describe(const b200_dwpw_desc *d, char *buf, int buflen);
+
 /* ---- bandwidth-bound ops ------------------------------------------------------ */
 /* q' = lut[q + 128] over `count` bytes: relu / relu6 / requantising identity with per-tensor
  * qinfo (source/reference/relu.c:39, relu6.c:42); count % 16 == 0 on pixel-major tensors. */

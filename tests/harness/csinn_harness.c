@@ -525,6 +525,9 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
             }
         }
         csinn_set_output(0, net->t[n], sess);
+        /* a zero-initialised session means CSINN_SAVE_AND_RUN (= 0) and would write shl.hhb.bm into the
+         * cwd at every session_setup: only save when a test asked for it */
+        sess->model.save_mode = CSINN_RUN_ONLY;
         if (g_save_path[0]) {
             sess->model.save_mode = CSINN_SAVE_AND_RUN;
             sess->model.bm_path = strdup(g_save_path);
