@@ -167,14 +167,6 @@ class ImportedNet:
         if not self.handle:
             raise RuntimeError(f"[{h.which}] model import failed: {h.error()}")
 
-    def describe(self) -> str:
-        """the b200 session's step list (kernel, node names, output shape per step)"""
-        shl = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libshl_b200.so"))
-        shl.shl_b200_session_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
-        buf = C.create_string_buffer(1 << 16)
-        shl.shl_b200_session_describe(self.session, buf, len(buf))
-        return buf.value.decode()
-
     def __call__(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=_np_dtype(self.dtype))
         assert x.shape == self.in_shape, (x.shape, self.in_shape)
@@ -238,6 +230,14 @@ class Net:
     @property
     def session(self) -> int:
         return self.h.lib.h_net_session(self.handle)
+
+    def describe(self) -> str:
+        """the b200 session's step list (kernel, node names, output shape per step)"""
+        shl = C.CDLL(os.path.join(ROOT, "csi-nn2_b200", "lib", "libshl_b200.so"))
+        shl.shl_b200_session_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        buf = C.create_string_buffer(1 << 16)
+        shl.shl_b200_session_describe(self.session, buf, len(buf))
+        return buf.value.decode()
 
     def __call__(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=_np_dtype(self.dtype))
