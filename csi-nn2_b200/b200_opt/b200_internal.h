@@ -117,6 +117,7 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
 /* depthwise 3x3 step + the 1x1 conv that is its only consumer as ONE kernel (csrc/dwpw_fused.cu);
  * `mid` carries the shape of the depthwise output, which is never materialised */
 int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out);
+int b200_dwpw_prefers_fusion(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out);
 int b200_dwpw_run(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out, void *stream);
 /* fuse a following relu / relu6 node (with its own qinfo) into this op's epilogue */
 int b200_op_can_fuse_act(const b200_op *op);

@@ -459,6 +459,9 @@ static int build_from_graph(struct csinn_session *sess)
     ctx->wused = 0;
     ctx->fixed_arena = 1;
     ctx->skip_upload = getenv("SHL_B200_SKIP_WEIGHT_UPLOAD") != NULL;
+    if (ctx->skip_upload)
+        fprintf(stderr, "[shl_b200] SHL_B200_SKIP_WEIGHT_UPLOAD is set: this session's weight arena stays ZERO until it is "
+                        "filled from another rank (shl_b200_session_weight_arena + a broadcast)\n");
     void *wb = NULL;
     DEV_CHECK(b200_malloc(&wb, ctx->wcap));
     ctx->wbase = wb;
@@ -577,7 +580,8 @@ static int build_from_graph(struct csinn_session *sess)
             const int out_idx = tensor_add(g, out_tn);
             if (out_idx >= 0 && !prev->op2 && prev->op->kind == B200_OPK_DW && prev->out == s->in0 && !mid->is_input &&
                 !is_graph_output(graph, mid->node) && consumers(graph, mid->node, NULL) == 1 &&
-                b200_dwpw_can_fuse(prev->op, op, &g->t[prev->in0].dt, &mid->dt, &g->t[out_idx].dt)) {
+                b200_dwpw_can_fuse(prev->op, op, &g->t[prev->in0].dt, &mid->dt, &g->t[out_idx].dt) &&
+                b200_dwpw_prefers_fusion(prev->op, op, &g->t[prev->in0].dt, &mid->dt, &g->t[out_idx].dt)) {
                 prev->op2 = op, prev->mid = s->in0, prev->out = out_idx;
                 mid->elided = 1;
                 strncat(prev->name, " > ", sizeof(prev->name) - strlen(prev->name) - 1);
@@ -597,7 +601,8 @@ static int build_from_graph(struct csinn_session *sess)
             return CSINN_FALSE;
         }
         g_tensor *ti = &g->t[s->in0], *to = &g->t[s->out];
-        if (ti->first_def < 0 && !ti->is_input) {
+        if ((ti->first_def < 0 && !ti->is_input) ||
+            (s->in1 >= 0 && g->t[s->in1].first_def < 0 && !g->t[s->in1].is_input)) {
             b200_fail("layer %d '%s' reads a tensor no earlier layer produced", i, n->name ? n->name : "?");
             free(skip);
             return CSINN_FALSE;

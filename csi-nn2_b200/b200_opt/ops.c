@@ -229,8 +229,17 @@ void b200_op_bind(void *params, b200_op *op)
         else
             g_reg_used++;
     }
+    if (g_reg[h].key == params && g_reg[h].op && g_reg[h].op != op) {
+        /* re-init of the same params (a second session_setup, a repeated layer-mode csinn_*_init): the old
+         * operator's staging buffers go, its constants stay in the arena they were bumped into */
+        b200_op *old = g_reg[h].op;
+        b200_set_device(old->ctx->device);
+        for (int i = 0; i < 8; i++)
+            if (old->stg[i]) b200_free(old->stg[i]);
+        free(old);
+    }
     g_reg[h].key = params;
-    g_reg[h].op = op; /* re-init of the same params replaces the op (constants stay in the arena) */
+    g_reg[h].op = op;
 }
 
 b200_op *b200_op_find(void *params)
@@ -300,9 +309,20 @@ static void fill_epilogue(const b200_op *op, b200_epilogue *ep)
  * direct dp4a kernel (csrc/conv_direct.cu) */
 static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
 {
-    return in0->is_nchw && op->group == 1 && op->kdim <= 160 &&
-           ((op->dtype == B200_I8 && op->o <= 256) || (op->dtype == B200_F16 && op->o <= 64)) &&
-           !getenv("SHL_B200_NO_DIRECT_CONV");
+    if (!(in0->is_nchw && op->group == 1 && op->kdim <= 160 &&
+          ((op->dtype == B200_I8 && op->o <= 256) || (op->dtype == B200_F16 && op->o <= 64)) &&
+          !getenv("SHL_B200_NO_DIRECT_CONV")))
+        return 0;
+    if (op->dtype == B200_I8) {
+        /* the dp4a kernel keeps the weights, the per-channel tables and (generic variant) one tap vector per
+         * thread in shared memory and refuses above 48 KB (csrc/conv_direct.cu, b200_conv2d_direct): such a
+         * layer takes im2col + GEMM instead.  kname, scratch planning and run_conv all decide through here. */
+        const size_t kwords = (size_t)(op->kdim + 3) / 4, o4 = (size_t)(op->o + 3) & ~(size_t)3;
+        const int special = in0->c == 3 && op->kh == op->kw && (op->kh == 3 || op->kh == 7) && op->dh == 1 && op->dw == 1;
+        const size_t smem = kwords * o4 * 4 + o4 * 12 + (special ? 0 : kwords * 128 * 4);
+        if (smem > 48 * 1024) return 0;
+    }
+    return 1;
 }
 
 /* the 3-channel 3x3 / 7x7 stems run as an implicit GEMM on the tensor core (csrc/conv_stem_tc.cu);
@@ -370,8 +390,11 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
         g.w = (const uint8_t *)op->d_w + (size_t)grp * og * op->ldk * op->eb;
         g.out = (uint8_t *)out->d + (size_t)grp * og * op->eb;
         if (op->group > 1) {
-            /* each group writes its own column window of the pixel-major output */
+            /* each group writes its own column window of the pixel-major output: tiles wider than the
+             * window are clipped at its end (the GEMM's n-tile may be wider than og, e.g. og = 48 in a 64-column
+             * tile), not at the row pitch -- beyond the window lie the next group's columns */
             g.ldo = out->cp;
+            g.out_cols = og;
             g.ep.mult = op->d_mult ? op->d_mult + grp * og : NULL;
             g.ep.badd = op->d_badd ? op->d_badd + grp * og : NULL;
             g.ep.ibias = op->d_ibias ? op->d_ibias + grp * og : NULL;
@@ -508,10 +531,14 @@ static void dwpw_fill(const b200_op *dw, const b200_op *pw, const b200_dt *in, c
     fill_epilogue(pw, &f->ep);
 }
 
-/* `mid` = the depthwise output as the graph declares it (shape only: it is never materialised) */
+/* `mid` = the depthwise output as the graph declares it (shape only: it is never materialised).
+ * SHL_B200_DWPW=0 never fuses, =1 fuses every pair the kernel covers; unset, the planner times both ways on
+ * scratch buffers of the real sizes and keeps the faster (b200_dwpw_prefers_fusion) -- the same policy the
+ * session applies to programmatic dependent launch. */
 int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out)
 {
-    if (getenv("SHL_B200_NO_DWPW")) return 0;
+    const char *mode = getenv("SHL_B200_DWPW");
+    if (getenv("SHL_B200_NO_DWPW") || (mode && atoi(mode) == 0)) return 0;
     if (dw->kind != B200_OPK_DW || pw->kind != B200_OPK_CONV || !pw->direct || dw->dtype != B200_I8 ||
         pw->dtype != B200_I8 || in->is_nchw || pw->kdim != mid->c || mid->c != in->c || mid->n != out->n ||
         mid->h != out->h || mid->w != out->w)
@@ -520,6 +547,60 @@ int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, 
     dwpw_fill(dw, pw, in, mid, out, &f);
     f.dw.in = f.out = (void *)16; /* planning time: the arena is not allocated yet, only the shapes matter */
     return b200_dwpw_supported(&f);
+}
+
+/* device time of `reps` runs of the pair, fused (one kernel) or not (two), on the given buffers; < 0 on error */
+static float dwpw_time(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out, int fused,
+                       int reps, void *stream, void *e0, void *e1)
+{
+    float ms = -1.f;
+    for (int r = -1; r < reps; r++) { /* r = -1: warm-up (function attributes, caches) */
+        if (r == 0 && b200_event_record(e0, stream) != B200_OK) return -1.f;
+        if (fused) {
+            if (b200_dwpw_run(dw, pw, in, mid, out, stream) != CSINN_TRUE) return -1.f;
+        } else if (b200_op_run(dw, 0, in, NULL, mid, NULL, stream) != CSINN_TRUE ||
+                   b200_op_run(pw, 0, mid, NULL, out, NULL, stream) != CSINN_TRUE)
+            return -1.f;
+    }
+    if (b200_event_record(e1, stream) != B200_OK || b200_stream_sync(stream) != B200_OK ||
+        b200_event_elapsed_ms(e0, e1, &ms) != B200_OK)
+        return -1.f;
+    return ms / reps;
+}
+
+/* 1: the fused kernel is at least as fast as depthwise + GEMM for this pair on this device (measured), 0: not */
+int b200_dwpw_prefers_fusion(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out)
+{
+    const char *mode = getenv("SHL_B200_DWPW");
+    if (mode) return atoi(mode) != 0;
+    b200_dt ti = *in, tm = *mid, to = *out;
+    void *e0 = NULL, *e1 = NULL;
+    void *stream = dw->ctx->stream;
+    int prefer = 0;
+    ti.d = tm.d = to.d = NULL;
+    const size_t bi = b200_dt_bytes(in);
+    uint8_t *host = malloc(bi);
+    if (!host) return 0;
+    uint32_t lcg = 12345u; /* bytes that look like activations: a table epilogue's bank conflicts depend on the data */
+    for (size_t i = 0; i < bi; i++) host[i] = (uint8_t)((lcg = lcg * 1664525u + 1013904223u) >> 24);
+    if (b200_malloc(&ti.d, bi) == B200_OK && b200_malloc(&tm.d, b200_dt_bytes(mid)) == B200_OK &&
+        b200_malloc(&to.d, b200_dt_bytes(out)) == B200_OK && b200_event_create(&e0) == B200_OK &&
+        b200_event_create(&e1) == B200_OK && b200_memcpy_h2d(ti.d, host, bi, stream) == B200_OK &&
+        b200_stream_sync(stream) == B200_OK) {
+        const float t_fused = dwpw_time(dw, pw, &ti, &tm, &to, 1, 3, stream, e0, e1);
+        const float t_plain = dwpw_time(dw, pw, &ti, &tm, &to, 0, 3, stream, e0, e1);
+        prefer = t_fused > 0.f && t_plain > 0.f && t_fused <= t_plain;
+        if (getenv("SHL_B200_DWPW_VERBOSE"))
+            fprintf(stderr, "[shl_b200] dw3x3 -> 1x1 pair c=%d o=%d %dx%d: fused %.1f us, two kernels %.1f us -> %s\n", in->c,
+                    out->c, out->h, out->w, t_fused * 1e3f, t_plain * 1e3f, prefer ? "fused" : "two kernels");
+    }
+    free(host);
+    if (e0) b200_event_destroy(e0);
+    if (e1) b200_event_destroy(e1);
+    if (ti.d) b200_free(ti.d);
+    if (tm.d) b200_free(tm.d);
+    if (to.d) b200_free(to.d);
+    return prefer;
 }
 
 int b200_dwpw_run(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out, void *stream)

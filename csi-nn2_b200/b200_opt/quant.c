@@ -166,16 +166,27 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
             const int bi = bias->quant_channel > 1 ? o : 0;
             if (bias->qinfo[bi].scale != 0) sb = bias->qinfo[bi].scale;
         }
-        int64_t wsum = 0;
-        for (int t = 0; t < taps_per_o; t++) wsum += w[(int64_t)o * taps_per_o + t];
+        int64_t wsum = 0, wabs = 0;
+        for (int t = 0; t < taps_per_o; t++) {
+            const int wv = w[(int64_t)o * taps_per_o + t];
+            wsum += wv;
+            wabs += wv < 0 ? -wv : wv;
+        }
         int64_t bq = b ? b[o] : 0;
         if (fuse_zp2bias) bq += (int64_t)zp_in * wsum; /* un-fold, cf. reference/convolution.c:375-395 */
         mult[o] = (float)(s_in * sw / s_out);
         badd[o] = (float)((double)bq * sb / s_out);
         ibias[o] = (int32_t)(-(int64_t)zp_in * wsum);
-        const double bound = (double)taps_per_o * 128.0 * 255.0 * fabs(mult[o]) + fabs(badd[o]);
-        if (!(bound < 4194304.0)) {
-            b200_fail("channel %d: |acc*mult+bias| may reach %.3g >= 2^22; qinfo out of the supported range",
+        /* The epilogues round through the 1.5 * 2^23 magic constant.  That is exact below 2^22, still lands on
+         * the right side of the int8 clamp for every larger POSITIVE value (the float's bit pattern only grows)
+         * and for negative values down to -1.5 * 2^23, where the sum changes sign and the integer reading of
+         * the bits would wrap.  So the requirement is |f| < 2^23, checked with this channel's own weights:
+         * |acc - zp_in * wsum| <= max|x - zp_in| * sum|w|, not the data-independent K * 128 * 255 (which refused
+         * e.g. a K = 25088 fullyconnected with ordinary scales). */
+        const int xmax = (127 - zp_in) > (zp_in + 128) ? (127 - zp_in) : (zp_in + 128);
+        const double bound = (double)wabs * xmax * fabs(mult[o]) + fabs(badd[o]);
+        if (!(bound < 8388608.0)) {
+            b200_fail("channel %d: |acc*mult+bias| may reach %.3g >= 2^23; qinfo out of the supported range",
                       o, bound);
             rc = CSINN_FALSE;
             goto done;

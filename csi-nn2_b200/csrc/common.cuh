@@ -151,6 +151,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// the same wait with a suspend-time hint: a failed try_wait parks the thread in hardware (it is woken when the
+// phase completes) instead of returning after ~20 cycles, so a waiting warp stops taking issue slots from the
+// warps that work (ncu on the fused block kernel: the three single-thread service warps alone spent 14 % of
+// the SM's issue slots in SYNCS / BRA / YIELD spin loops)
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680)
+        : "memory");
+}
+
 // TMA -----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
 {

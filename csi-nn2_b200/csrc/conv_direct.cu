@@ -353,12 +353,14 @@ extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
     long long g = (total + 127) / 128;
     const long long cap = static_cast<long long>(sm_count()) * 16;
     const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
-    if (smem > 48 * 1024) {
-        set_error("b200_conv2d_direct: weights + taps (%zu bytes) exceed the shared-memory budget", smem);
-        return B200_ERR_UNSUPPORTED;
-    }
     const bool unit_dil = d->dil_h == 1 && d->dil_w == 1;
     const size_t smem_sp = static_cast<size_t>(a.kwords) * o4 * 4 + static_cast<size_t>(o4) * 12;
+    const bool special = unit_dil && d->c == 3 && d->kh == d->kw && (d->kh == 3 || d->kh == 7);
+    // the same budget b200_opt/ops.c:conv_goes_direct applies before choosing this kernel over im2col + GEMM
+    if ((special ? smem_sp : smem) > 48 * 1024) {
+        set_error("b200_conv2d_direct: weights + taps (%zu bytes) exceed the shared-memory budget", special ? smem_sp : smem);
+        return B200_ERR_UNSUPPORTED;
+    }
     if (total >= (1ll << 31)) {
         set_error("b200_conv2d_direct: %lld output pixels exceed the 32-bit pixel index", total);
         return B200_ERR_UNSUPPORTED;

@@ -14,9 +14,15 @@
 //   warp 0        TMA producer: one 4-D box per (tile, channel chunk) into a ring of halo stages;
 //                 the pointwise weights once
 //   warp 1        MMA issuer (one elected lane) + TMEM allocation
-//   warps 2..9    pointwise epilogue: tcgen05.ld -> requantise -> staging (the GEMM's epilogue)
-//   warps 10..17  depthwise consumers: one output column x 4 channels per thread sliding down a
-//                 band of tile rows (the TMA depthwise kernel's inner loop), output = A operand rows
+//   warps 2..17   workers.  Each runs the depthwise stage of tile t -- one output column x 4 channels per
+//                 thread sliding down a band of tile rows (the TMA depthwise kernel's inner loop), output =
+//                 A operand rows -- and then, while the tensor core multiplies tile t, the pointwise
+//                 epilogue of tile t - 1 for its TMEM lane quadrant and a quarter of the columns
+//                 (tcgen05.ld -> requantise -> staging, the GEMM's epilogue).  Both halves are bound by
+//                 instruction issue, so every warp doing both keeps the two balanced whatever the ratio of
+//                 channels to outputs, and at any moment some warps are in the dp4a-heavy phase and others
+//                 in the float / table phase (first version: 8 depthwise + 8 epilogue warps -- the 8
+//                 depthwise warps alone paced the kernel, slower than the two separate kernels).
 //   warp 18       TMA-store warp
 // A tile = TW x TH output pixels (<= 256 = two M128 blocks) x ALL channels; pixel (y, x) of the tile is
 // A row / TMEM lane / staging row y * TW + x, which is also the order a 4-D TMA store box
@@ -42,16 +48,15 @@
 
 namespace b200 {
 
-constexpr int kFuDwWarps = 8;
-constexpr int kFuEpiWarps = 8;
-constexpr int kFuDwThreads = kFuDwWarps * 32;
-constexpr int kFuThreads = (3 + kFuDwWarps + kFuEpiWarps) * 32;  // + TMA producer, MMA issuer, store warp
+constexpr int kFuWorkers = 16;  // warps that run the depthwise stage of tile t, then the pointwise epilogue of tile t - 1
+constexpr int kFuWorkerThreads = kFuWorkers * 32;
+constexpr int kFuDwThreads = kFuWorkerThreads;
+constexpr int kFuThreads = (3 + kFuWorkers) * 32;  // + TMA producer, MMA issuer, store warp
 constexpr int kFuMaxStages = 6;
 constexpr int kFuAccStride = 256;  // TMEM columns per accumulator stage
 constexpr size_t kFuSmemLimit = 226 * 1024;
-constexpr int kFuFirstEpiWarp = 2;
-constexpr int kFuFirstDwWarp = kFuFirstEpiWarp + kFuEpiWarps;
-constexpr int kFuStoreWarp = kFuFirstDwWarp + kFuDwWarps;
+constexpr int kFuFirstWorker = 2;
+constexpr int kFuStoreWarp = kFuFirstWorker + kFuWorkers;
 
 struct DwPwArgs {
     // depthwise geometry
@@ -165,14 +170,14 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
         tma_prefetch_desc(&tm_out);
         for (int i = 0; i < a.stages; i++) {
             mbar_init(&halo_full[i], 1);
-            mbar_init(&halo_empty[i], kFuDwWarps);
+            mbar_init(&halo_empty[i], kFuWorkers);
         }
         for (int i = 0; i < 2; i++) {
-            mbar_init(&a_full[i], kFuDwWarps);
+            mbar_init(&a_full[i], kFuWorkers);
             mbar_init(&a_empty[i], 1);
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kFuEpiWarps);
-            mbar_init(&stg_full[i], kFuEpiWarps);
+            mbar_init(&tmem_empty[i], kFuWorkers);
+            mbar_init(&stg_full[i], kFuWorkers);
             mbar_init(&stg_empty[i], 1);
         }
         mbar_init(b_bar, 1);
@@ -182,13 +187,10 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
-    if (warp >= kFuFirstEpiWarp && warp < kFuFirstDwWarp && a.pep.post_lut != nullptr) {
-        const int t = threadIdx.x - kFuFirstEpiWarp * 32;
-        epi->lut[t] = static_cast<uint8_t>(a.pep.post_lut[t]);
-    }
-    if (warp >= kFuFirstDwWarp && warp < kFuStoreWarp && a.dep.post_lut != nullptr) {
-        const int t = threadIdx.x - kFuFirstDwWarp * 32;
-        s_dlut[t] = static_cast<uint8_t>(a.dep.post_lut[t]);
+    if (warp >= kFuFirstWorker && warp < kFuStoreWarp) {
+        const int t = threadIdx.x - kFuFirstWorker * 32;
+        if (t < 256 && a.pep.post_lut != nullptr) epi->lut[t] = static_cast<uint8_t>(a.pep.post_lut[t]);
+        if (t >= 256 && a.dep.post_lut != nullptr) s_dlut[t - 256] = static_cast<uint8_t>(a.dep.post_lut[t - 256]);
     }
     tc_fence_before();
     __syncthreads();
@@ -207,7 +209,7 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             for (FuWalk tw(a); tw.b < a.n; tw.next(a)) {
                 const int x0 = tw.xb * a.tw * S - a.pl, y0 = tw.yb * a.th * S - a.pt;
                 for (int c = 0; c < a.cchunks; c++) {
-                    mbar_wait(&halo_empty[stage], phase ^ 1);
+                    mbar_wait_parked(&halo_empty[stage], phase ^ 1);
                     mbar_expect_tx(&halo_full[stage], a.stage_bytes);
                     tma_load_4d(halo + static_cast<size_t>(stage) * a.stage_stride, &tm_in, &halo_full[stage], c * a.cc, x0,
                                 y0, tw.b);
@@ -218,13 +220,13 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one()) {
-            mbar_wait(b_bar, 0);
+            mbar_wait_parked(b_bar, 0);
             int local = 0;
             for (FuWalk tw(a); tw.b < a.n; tw.next(a), local++) {
                 const int buf = local & 1;
                 const uint32_t ph = (local >> 1) & 1;
-                mbar_wait(&tmem_empty[buf], ph);  // seeded (ph + 1) times
-                mbar_wait(&a_full[buf], ph);
+                mbar_wait_parked(&tmem_empty[buf], ph);  // seeded (ph + 1) times
+                mbar_wait_parked(&a_full[buf], ph);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(smem_a + buf * a.a_buf_bytes);
                 for (int m = 0; m < MT; m++) {
@@ -248,7 +250,7 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             for (FuWalk tw(a); tw.b < a.n; tw.next(a)) {
                 for (int hf = 0; hf < a.nhalves; hf++, unit++) {
                     const int sb = unit & 1;
-                    mbar_wait(&stg_full[sb], (unit >> 1) & 1);
+                    mbar_wait_parked(&stg_full[sb], (unit >> 1) & 1);
                     tma_store_4d(&tm_out, staging + sb * a.stg_half_bytes, hf * 128, tw.xb * a.tw, tw.yb * a.th, tw.b);
                     tma_store_commit();
                     tma_store_wait_read<0>();
@@ -257,48 +259,77 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             }
             tma_store_wait<0>();
         }
-    } else if (warp < kFuFirstDwWarp) {
-        // ===== pointwise epilogue: TMEM -> registers -> requantise -> swizzled staging =====
-        const int ew = warp - kFuFirstEpiWarp;
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        const int part = ew >> 2;   // 0..1: which 16-column chunks it owns
-        const int et = threadIdx.x - kFuFirstEpiWarp * 32;
-        const EpiScalars &ep = a.pep;
+    } else {
+        // ===== workers: depthwise for tile t, then the pointwise epilogue of tile t - 1 =====
+        const int wid = warp - kFuFirstWorker;
+        const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+        const int part = wid >> 2;   // 0..3: which 16-column chunks of a tile's accumulators it drains
+        const int tid = threadIdx.x - kFuFirstWorker * 32;
+        // ---- pointwise epilogue state ----
+        const EpiScalars &pe = a.pep;
         const int bn = a.bn;
         const int nsub = bn >> 4;
-        const int zp_m = ep.zp_out - kMagicI;
-        const int lut_base = static_cast<int>(smem_u32(epi->lut));
-        int lut_lo = kMagicI - ep.zp_out - 128 - lut_base;
-        asm("mov.b32 %0, %0;" : "+r"(lut_lo));
-        const bool has_lut = ep.post_lut != nullptr;
-        if (et < bn) {
-            const bool ok = et < a.o;
-            epi->mult[et] = ok ? ep.mult[et] : 0.f;
-            epi->badd[et] = ok ? ep.badd[et] : 0.f;
-            epi->ibias[et] = ((ok && ep.ibias) ? ep.ibias[et] : 0) + (MAGIC ? kMagicI : 0);
+        const int pzp_m = pe.zp_out - kMagicI;
+        const int plut_base = static_cast<int>(smem_u32(epi->lut));
+        int plut_lo = kMagicI - pe.zp_out - 128 - plut_base;
+        asm("mov.b32 %0, %0;" : "+r"(plut_lo));
+        const bool p_has_lut = pe.post_lut != nullptr;
+        if (tid < bn) {
+            const bool ok = tid < a.o;
+            epi->mult[tid] = ok ? pe.mult[tid] : 0.f;
+            epi->badd[tid] = ok ? pe.badd[tid] : 0.f;
+            epi->ibias[tid] = ((ok && pe.ibias) ? pe.ibias[tid] : 0) + (MAGIC ? kMagicI : 0);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kFuEpiWarps * 32) : "memory");
+        // ---- depthwise state: constants of the whole layer into shared memory ----
+        const int WORDS = 1 << a.words_log2;
+        const int cw = tid & (WORDS - 1);
+        const int xi = tid >> a.words_log2;
+        const int x = xi % a.tw;     // output column inside the tile
+        const int rbi = xi / a.tw;   // row band this thread walks
+        const bool item_ok = rbi < a.rb;
+        const EpiScalars &de = a.dep;
+        const bool d_has_lut = de.post_lut != nullptr;
+        const int dzp_m = de.zp_out - kMagicI;
+        const int dlut_base = static_cast<int>(smem_u32(s_dlut));
+        int dlut_lo = kMagicI - de.zp_out - 128 - dlut_base;
+        asm("mov.b32 %0, %0;" : "+r"(dlut_lo));
+        const bool top_pad = a.pt > 0;
+        const bool bot_pad = (a.oh - 1) * S - a.pt + 2 >= a.h;
+        for (int i = tid; i < 3 * cp; i += kFuWorkerThreads) s_wrow[i] = __ldg(a.wrow + i);
+        for (int i = tid; i < cp; i += kFuWorkerThreads) {
+            s_dmult[i] = __ldg(de.mult + i);
+            s_dbadd[i] = __ldg(de.badd + i);
+        }
+        // accumulator seeds [row class][column class][channel]: ibias + kMagicI + zp_in * (sum of the weights of
+        // the taps that fall into the padding), see dwconv3x3_tma.cu
+        for (int i = tid; i < 16 * cp; i += kFuWorkerThreads) {
+            const int c = i % cp, cls = i / cp;
+            int padsum = 0;
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const uint32_t wv = __ldg(a.wrow + ky * cp + c);
+                const bool rowpad = (ky == 0 && (cls & 4)) || (ky == 2 && (cls & 8));
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const bool colpad = (kx == 0 && (cls & 1)) || (kx == 2 && (cls & 2));
+                    if (rowpad || colpad) padsum += static_cast<int8_t>(wv >> (8 * kx));
+                }
+            }
+            s_seed[i] = __ldg(de.ibias + c) + kMagicI + a.zp_in * padsum;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kFuWorkerThreads) : "memory");
+
         const uint32_t scols = a.scols;
         const uint32_t swz_mask = scols >= 128 ? 7u : (scols == 64 ? 3u : (scols == 32 ? 1u : 0u));
         const uint32_t tquad = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        uint64_t mu2[8], ba2[8];
-        uint32_t ib[16];
-        int loaded_sub = -1;
-        auto load_sub = [&](int sub) {
+        // seed both accumulator stages with ibias (+ magic): the MMAs always accumulate
+        for (int sub = part; sub < nsub; sub += 4) {
+            uint32_t ib[16];
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-                const float4 m4 = *reinterpret_cast<const float4 *>(&epi->mult[sub * 16 + j4 * 4]);
-                const float4 b4 = *reinterpret_cast<const float4 *>(&epi->badd[sub * 16 + j4 * 4]);
                 const int4 i4 = *reinterpret_cast<const int4 *>(&epi->ibias[sub * 16 + j4 * 4]);
-                mu2[j4 * 2] = f2_pack(m4.x, m4.y), mu2[j4 * 2 + 1] = f2_pack(m4.z, m4.w);
-                ba2[j4 * 2] = f2_pack(b4.x, b4.y), ba2[j4 * 2 + 1] = f2_pack(b4.z, b4.w);
                 ib[j4 * 4 + 0] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
             }
-            loaded_sub = sub;
-        };
-        // seed both accumulator stages with ibias (+ magic): the MMAs always accumulate
-        for (int sub = part; sub < nsub; sub += 2) {
-            load_sub(sub);
             for (int a2 = 0; a2 < 2; a2++)
                 for (int m = 0; m < MT; m++) tmem_st_32x16(tquad + a2 * kFuAccStride + m * bn + sub * 16, ib);
         }
@@ -309,22 +340,32 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             mbar_arrive(&tmem_empty[0]);
             mbar_arrive(&tmem_empty[1]);
         }
-        int local = 0;
-        uint32_t unit = 0;
-        for (FuWalk tw(a); tw.b < a.n; tw.next(a), local++) {
+
+        uint32_t unit = 0;  // staging units handed to the store warp so far
+        auto epilogue_tile = [&](int local) {
             const int buf = local & 1;
             const uint32_t ph = (local >> 1) & 1;
-            mbar_wait(&tmem_full[buf], ph);
+            mbar_wait_parked(&tmem_full[buf], ph);
             tc_fence_after();
             const uint32_t taddr = tquad + buf * kFuAccStride;
             for (int hf = 0; hf < a.nhalves; hf++, unit++) {
                 const int sb = unit & 1;
                 uint8_t *stg = staging + sb * a.stg_half_bytes;
                 // the store issued from this staging unit two units ago must have finished reading it
-                mbar_wait(&stg_empty[sb], ((unit >> 1) & 1) ^ 1);
+                mbar_wait_parked(&stg_empty[sb], ((unit >> 1) & 1) ^ 1);
                 const int sub_end = min(nsub, hf * 8 + 8);
-                for (int sub = hf * 8 + part; sub < sub_end; sub += 2) {
-                    if (sub != loaded_sub) load_sub(sub);
+                for (int sub = hf * 8 + part; sub < sub_end; sub += 4) {
+                    uint64_t mu2[8], ba2[8];
+                    uint32_t ib[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const float4 m4 = *reinterpret_cast<const float4 *>(&epi->mult[sub * 16 + j4 * 4]);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&epi->badd[sub * 16 + j4 * 4]);
+                        const int4 i4 = *reinterpret_cast<const int4 *>(&epi->ibias[sub * 16 + j4 * 4]);
+                        mu2[j4 * 2] = f2_pack(m4.x, m4.y), mu2[j4 * 2 + 1] = f2_pack(m4.z, m4.w);
+                        ba2[j4 * 2] = f2_pack(b4.x, b4.y), ba2[j4 * 2 + 1] = f2_pack(b4.z, b4.w);
+                        ib[j4 * 4 + 0] = i4.x, ib[j4 * 4 + 1] = i4.y, ib[j4 * 4 + 2] = i4.z, ib[j4 * 4 + 3] = i4.w;
+                    }
                     const uint32_t colb = (static_cast<uint32_t>(sub) & 7u) * 16u;
 #pragma unroll 1
                     for (int m = 0; m < MT; m++) {
@@ -338,7 +379,7 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
                             int t[4];
                             requant_pair<MAGIC>(r[j4 * 4 + 0], r[j4 * 4 + 1], mu2[j4 * 2], ba2[j4 * 2], t[0], t[1]);
                             requant_pair<MAGIC>(r[j4 * 4 + 2], r[j4 * 4 + 3], mu2[j4 * 2 + 1], ba2[j4 * 2 + 1], t[2], t[3]);
-                            packed[j4] = finish4<PMODE>(t, ep, epi->lut, has_lut, zp_m, lut_lo, lut_base);
+                            packed[j4] = finish4<PMODE>(t, pe, epi->lut, p_has_lut, pzp_m, plut_lo, plut_base);
                         }
                         uint32_t off = static_cast<uint32_t>(m * 128 + quad * 32 + lane) * scols + colb;
                         off ^= ((off >> 7) & swz_mask) << 4;
@@ -357,49 +398,27 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stg_full[sb]);
             }
-        }
-    } else {
-        // ===== depthwise consumers =====
-        const int tid = threadIdx.x - kFuFirstDwWarp * 32;
-        const int WORDS = 1 << a.words_log2;
-        const int cw = tid & (WORDS - 1);
-        const int xi = tid >> a.words_log2;
-        const int x = xi % a.tw;     // output column inside the tile
-        const int rbi = xi / a.tw;   // row band this thread walks
-        const bool item_ok = rbi < a.rb;
-        const EpiScalars &ep = a.dep;
-        const bool has_lut = ep.post_lut != nullptr;
-        const int zp_m = ep.zp_out - kMagicI;
-        const int lut_base = static_cast<int>(smem_u32(s_dlut));
-        int lut_lo = kMagicI - ep.zp_out - 128 - lut_base;
-        asm("mov.b32 %0, %0;" : "+r"(lut_lo));
-        const bool top_pad = a.pt > 0;
-        const bool bot_pad = (a.oh - 1) * S - a.pt + 2 >= a.h;
-        // constants of the whole layer into shared memory: tap words, requantisation pairs, seed table
-        for (int i = tid; i < 3 * cp; i += kFuDwThreads) s_wrow[i] = __ldg(a.wrow + i);
-        for (int i = tid; i < cp; i += kFuDwThreads) {
-            s_dmult[i] = __ldg(ep.mult + i);
-            s_dbadd[i] = __ldg(ep.badd + i);
-        }
-        for (int i = tid; i < 16 * cp; i += kFuDwThreads) {
-            const int c = i % cp, cls = i / cp;
-            int padsum = 0;
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-                const uint32_t wv = __ldg(a.wrow + ky * cp + c);
-                const bool rowpad = (ky == 0 && (cls & 4)) || (ky == 2 && (cls & 8));
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    const bool colpad = (kx == 0 && (cls & 1)) || (kx == 2 && (cls & 2));
-                    if (rowpad || colpad) padsum += static_cast<int8_t>(wv >> (8 * kx));
-                }
-            }
-            s_seed[i] = __ldg(ep.ibias + c) + kMagicI + a.zp_in * padsum;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kFuDwThreads) : "memory");
+        };
 
         const int TWI_WORDS = a.twi << a.words_log2;  // words per halo row
         const int y0 = rbi * a.rpb;                    // first tile row of this thread's band
+        // byte offset of this thread's first tap word inside a halo stage, and of its first A operand row
+        const uint32_t halo_off = static_cast<uint32_t>((y0 * S) * TWI_WORDS + ((x * S) << a.words_log2) + cw) * 4u;
+        const uint32_t p0 = static_cast<uint32_t>(y0 * a.tw + x);
+        const uint32_t a_row_step = static_cast<uint32_t>(a.tw) << 7;
+        uint32_t wk[3][4];
+        uint64_t mu[2], ba[2];
+        auto load_chunk_consts = [&](int ch) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const uint4 wv = *reinterpret_cast<const uint4 *>(s_wrow + ky * cp + ch);
+                wk[ky][0] = wv.x, wk[ky][1] = wv.y, wk[ky][2] = wv.z, wk[ky][3] = wv.w;
+            }
+            const float4 m4 = *reinterpret_cast<const float4 *>(s_dmult + ch);
+            const float4 b4 = *reinterpret_cast<const float4 *>(s_dbadd + ch);
+            mu[0] = f2_pack(m4.x, m4.y), mu[1] = f2_pack(m4.z, m4.w);
+            ba[0] = f2_pack(b4.x, b4.y), ba[1] = f2_pack(b4.z, b4.w);
+        };
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
@@ -407,41 +426,34 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             const int buf = local & 1;
             const int ox = walk.xb * a.tw + x;
             const int oy0 = walk.yb * a.th;
-            const int rows_tile = min(a.th, a.oh - oy0);
-            const int rows_out = min(a.rpb, rows_tile - y0);  // rows of this thread's band inside the image
+            const int rows_out = min(a.rpb, min(a.th, a.oh - oy0) - y0);  // rows of this thread's band inside the image
             const bool work = item_ok && ox < a.ow && rows_out > 0;
             const int colc = ((ox * S - a.pl < 0) ? 1 : 0) | ((ox * S - a.pl + 2 >= a.w) ? 2 : 0);
             const int y_bot = bot_pad ? a.oh - 1 - oy0 - y0 : -1;  // band row that is the image's last row
             const uint32_t a_tile = smem_u32(smem_a + buf * a.a_buf_bytes);
             // the MMAs that read this A buffer two tiles ago must have retired
-            mbar_wait(&a_empty[buf], ((local >> 1) & 1) ^ 1);
+            mbar_wait_parked(&a_empty[buf], ((local >> 1) & 1) ^ 1);
             for (int c = 0; c < a.cchunks; c++) {
-                mbar_wait(&halo_full[stage], phase);
+                mbar_wait_parked(&halo_full[stage], phase);
                 const int ch = c * a.cc + cw * 4;  // first of this thread's four channels
                 if (work && ch < cp) {
-                    uint32_t wk[3][4];
-                    uint64_t mu[2], ba[2];
-#pragma unroll
-                    for (int ky = 0; ky < 3; ky++) {
-                        const uint4 wv = *reinterpret_cast<const uint4 *>(s_wrow + ky * cp + ch);
-                        wk[ky][0] = wv.x, wk[ky][1] = wv.y, wk[ky][2] = wv.z, wk[ky][3] = wv.w;
-                    }
-                    {
-                        const float4 m4 = *reinterpret_cast<const float4 *>(s_dmult + ch);
-                        const float4 b4 = *reinterpret_cast<const float4 *>(s_dbadd + ch);
-                        mu[0] = f2_pack(m4.x, m4.y), mu[1] = f2_pack(m4.z, m4.w);
-                        ba[0] = f2_pack(b4.x, b4.y), ba[1] = f2_pack(b4.z, b4.w);
-                    }
-                    const uint32_t *tile = reinterpret_cast<const uint32_t *>(halo + static_cast<size_t>(stage) * a.stage_stride);
-                    const uint32_t *tp = tile + (y0 * S) * TWI_WORDS + ((x * S) << a.words_log2) + cw;
-                    auto taps = [&](int r, uint32_t (&v)[4]) {
-                        const uint32_t *p = tp + r * TWI_WORDS;
-                        fu_taps3(p[0], p[WORDS], p[2 * WORDS], v);
+                    load_chunk_consts(ch);
+                    const uint32_t hbase = smem_u32(halo + static_cast<size_t>(stage) * a.stage_stride) + halo_off;
+                    const uint32_t pix = 4u << a.words_log2;     // bytes between horizontally adjacent pixels
+                    const uint32_t rowb = static_cast<uint32_t>(TWI_WORDS) * 4u;
+                    uint32_t rowp = hbase;                       // running address of the next input row's first tap
+                    auto taps = [&](uint32_t (&v)[4]) {
+                        uint32_t t0, t1, t2;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t0) : "r"(rowp));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t1) : "r"(rowp + pix));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t2) : "r"(rowp + 2 * pix));
+                        rowp += rowb;
+                        fu_taps3(t0, t1, t2, v);
                     };
+                    // seeds: interior rows from registers; the image's first / last row (padded ky = 0 / 2) from the table
                     const uint32_t seed_mid = smem_u32(s_seed + colc * cp + ch);
-                    const uint32_t seed_bot = seed_mid + 8 * cp * 4;
-                    const uint32_t seed_row0 =
-                        seed_mid + (((top_pad && oy0 + y0 == 0) ? 4 : 0) | (y_bot == 0 ? 8 : 0)) * cp * 4;
+                    int sm0, sm1, sm2, sm3;
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(sm0), "=r"(sm1), "=r"(sm2), "=r"(sm3) : "r"(seed_mid));
                     auto first_at = [&](int (&acc)[4], const uint32_t (&v)[4], uint32_t seed_addr) {
                         int s0, s1, s2, s3;
                         asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
@@ -453,56 +465,66 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
                         acc[3] = __dp4a(static_cast<int>(v[3]), static_cast<int>(wk[0][3]), s3);
                     };
                     auto first = [&](int (&acc)[4], const uint32_t (&v)[4], int yo) {
-                        first_at(acc, v, yo == y_bot ? seed_bot : seed_mid);
+                        if (yo == y_bot) {
+                            first_at(acc, v, seed_mid + 8 * cp * 4);
+                        } else {
+                            acc[0] = __dp4a(static_cast<int>(v[0]), static_cast<int>(wk[0][0]), sm0);
+                            acc[1] = __dp4a(static_cast<int>(v[1]), static_cast<int>(wk[0][1]), sm1);
+                            acc[2] = __dp4a(static_cast<int>(v[2]), static_cast<int>(wk[0][2]), sm2);
+                            acc[3] = __dp4a(static_cast<int>(v[3]), static_cast<int>(wk[0][3]), sm3);
+                        }
                     };
+                    const uint32_t seed_row0 =
+                        seed_mid + (((top_pad && oy0 + y0 == 0) ? 4 : 0) | (y_bot == 0 ? 8 : 0)) * cp * 4;
                     // A operand row of pixel (y0 + yy, x): p = (y0 + yy) * TW + x; 128-byte rows, 16-byte
                     // chunks XOR-swizzled with (p & 7); K block kb = ch / 128 holds MT * 128 rows
-                    const uint32_t a_row_base = a_tile + static_cast<uint32_t>(ch >> 7) * (MT * 16384) + (ch & 15);
+                    uint32_t a_lin = a_tile + static_cast<uint32_t>(ch >> 7) * (MT * 16384) + (ch & 15) + (p0 << 7);
                     const uint32_t c16 = (ch >> 4) & 7;
-                    uint32_t p = y0 * a.tw + x;
+                    uint32_t p = p0;
                     auto store = [&](const int (&acc)[4]) {
                         int t[4];
                         requant_pair<true>(acc[0], acc[1], mu[0], ba[0], t[0], t[1]);
                         requant_pair<true>(acc[2], acc[3], mu[1], ba[1], t[2], t[3]);
-                        const uint32_t q4 = finish4<DMODE>(t, ep, s_dlut, has_lut, zp_m, lut_lo, lut_base);
-                        const uint32_t addr = a_row_base + (p << 7) + (((c16 ^ p) & 7) << 4);
+                        const uint32_t q4 = finish4<DMODE>(t, de, s_dlut, d_has_lut, dzp_m, dlut_lo, dlut_base);
+                        const uint32_t addr = a_lin + (((c16 ^ p) & 7) << 4);
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(q4) : "memory");
                         p += a.tw;
+                        a_lin += a_row_step;
                     };
                     int accA[4], accB[4], accC[4];
                     uint32_t v[4];
                     if (S == 1) {
-                        taps(0, v);
+                        taps(v);
                         first_at(accA, v, seed_row0);
-                        taps(1, v);
+                        taps(v);
                         fu_dp4(accA, v, wk[1]), first(accB, v, 1);
                         for (int y = 0;; y += 3) {
-                            taps(y + 2, v);
+                            taps(v);
                             fu_dp4(accA, v, wk[2]), fu_dp4(accB, v, wk[1]), first(accC, v, y + 2);
                             store(accA);
                             if (y + 1 >= rows_out) break;
-                            taps(y + 3, v);
+                            taps(v);
                             fu_dp4(accB, v, wk[2]), fu_dp4(accC, v, wk[1]), first(accA, v, y + 3);
                             store(accB);
                             if (y + 2 >= rows_out) break;
-                            taps(y + 4, v);
+                            taps(v);
                             fu_dp4(accC, v, wk[2]), fu_dp4(accA, v, wk[1]), first(accB, v, y + 4);
                             store(accC);
                             if (y + 3 >= rows_out) break;
                         }
                     } else {
-                        taps(0, v);
+                        taps(v);
                         first_at(accA, v, seed_row0);
                         for (int y = 0;; y += 2) {
-                            taps(2 * y + 1, v);
+                            taps(v);
                             fu_dp4(accA, v, wk[1]);
-                            taps(2 * y + 2, v);
+                            taps(v);
                             fu_dp4(accA, v, wk[2]), first(accB, v, y + 1);
                             store(accA);
                             if (y + 1 >= rows_out) break;
-                            taps(2 * y + 3, v);
+                            taps(v);
                             fu_dp4(accB, v, wk[1]);
-                            taps(2 * y + 4, v);
+                            taps(v);
                             fu_dp4(accB, v, wk[2]), first(accA, v, y + 2);
                             store(accB);
                             if (y + 2 >= rows_out) break;
@@ -518,7 +540,10 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[buf]);
+            // while the tensor core works on this tile, drain the previous one
+            if (local > 0) epilogue_tile(local - 1);
         }
+        if (local > 0) epilogue_tile(local - 1);
     }
 
     tc_fence_before();
@@ -558,9 +583,13 @@ static bool fu_plan(const b200_dwpw_desc *d, FuPlan *out)
     const int mt_max = bn <= 128 ? 2 : 1;
     double best = -1;
     FuPlan bp = {};
+    // developer override: SHL_B200_DWPW_TILE="tw,th" pins the tile shape (tools/run_pair.py sweeps it)
+    int force_tw = 0, force_th = 0;
+    if (const char *e = getenv("SHL_B200_DWPW_TILE")) sscanf(e, "%d,%d", &force_tw, &force_th);
     for (int tw = 4; tw <= 64; tw++) {
         if (tw > 4 && tw > w.ow) break;
         for (int th = 2; th <= 64; th++) {
+            if (force_tw && (tw != force_tw || th != force_th)) continue;
             const int P = tw * th;
             const int mt = (P + 127) / 128;
             if (mt > mt_max) break;
@@ -588,9 +617,10 @@ static bool fu_plan(const b200_dwpw_desc *d, FuPlan *out)
             const int cchunks = (w.cp + cc - 1) / cc;
             const double busy = static_cast<double>(tw * (cc / 4) * p.rb) / kFuDwThreads * w.cp / (cchunks * cc);
             const double rows_norm = static_cast<double>(S * (p.rpb - 1) + 3) / (S * p.rpb);  // input rows per row needed
-            const double dw_cost = w.c * 13.0 * (0.2 * rows_norm + 0.8) / (col_util * row_util * busy);
+            // + the per-tile prologue of a thread (tile decode, constants, addresses: ~200 instructions per 4 channels)
+            const double dw_cost = w.c * (13.0 * (0.2 * rows_norm + 0.8) + 50.0 / p.rpb) / (col_util * row_util * busy);
             const double lane_util = static_cast<double>(w.ow) * w.oh / (static_cast<double>(xb) * yb * mt * 128.0);
-            const double pw_cost = d->o * 5.6 / lane_util;
+            const double pw_cost = d->o * (5.6 + 1.5 / mt) / lane_util;  // + the per-column parameters, loaded once per M128 pair
             const double halo = static_cast<double>(S * tw) * (S * th) / ((S * (tw - 1) + 3.0) * (S * (th - 1) + 3.0));
             double score = 1e4 / (dw_cost + pw_cost) * sqrt(sqrt(halo));
             if (p.stages < 3) score *= 0.9;

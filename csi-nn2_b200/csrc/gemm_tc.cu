@@ -575,6 +575,7 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     }
     const int eb = d->dtype == B200_I8 ? 1 : 2;
     if (d->m <= 0 || d->n <= 0 || d->k <= 0 || d->ldo < d->n || (d->lda * eb) % 16 ||
+        (d->out_cols != 0 && (d->out_cols < d->n || d->out_cols > d->ldo || (d->out_cols * eb) % 16)) ||
         (d->ldw * eb) % 16 || (d->ldo * eb) % 16 || d->lda < d->k || d->ldw < d->k ||
         (reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->w) & 15) ||
         (reinterpret_cast<uintptr_t>(d->out) & 15) ||
@@ -639,15 +640,17 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     if (rc) return rc;
     rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
     if (rc) return rc;
+    // columns a tile may touch: the row pitch, or the caller's window (a group of a grouped convolution)
+    const int out_cols = d->out_cols > 0 ? d->out_cols : d->ldo;
     if (d->dtype == B200_I8) {
-        // output tile: 128 rows x bn bytes, rows clipped at m, columns at the row pitch
-        rc = encode_tmap_2d(&to, 1, d->out, d->ldo, d->m, static_cast<uint64_t>(d->ldo), args.bn, kBM,
+        // output tile: 128 rows x bn bytes, rows clipped at m, columns at out_cols
+        rc = encode_tmap_2d(&to, 1, d->out, out_cols, d->m, static_cast<uint64_t>(d->ldo), args.bn, kBM,
                             args.bn >= 128 ? 128 : (args.bn >= 32 ? args.bn : 0));
         if (rc) return rc;
     } else {
         // fp16 output slab of one warp: 32 rows x (32 or 16) halves, 64B / 32B swizzle
         const int cw = args.bn >= 128 ? 32 : 16;
-        rc = encode_tmap_2d(&to, 2, d->out, d->ldo, d->m, static_cast<uint64_t>(d->ldo) * 2, cw, 32, cw * 2);
+        rc = encode_tmap_2d(&to, 2, d->out, out_cols, d->m, static_cast<uint64_t>(d->ldo) * 2, cw, 32, cw * 2);
         if (rc) return rc;
     }
 

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define B200NN_ABI_VERSION 2
+#define B200NN_ABI_VERSION 3
 
 typedef enum {
     B200_OK = 0,
@@ -168,6 +168,10 @@ typedef struct {
     int32_t ldw;     /* elements, ldw*elem % 16 == 0                                */
     void *out;       /* device [m][ldo]; columns [n, ldo) hold unspecified values    */
     int32_t ldo;     /* elements, ldo*elem % 16 == 0, ldo >= n                      */
+    int32_t out_cols; /* 0, or the number of columns of a row this call may write, starting at `out`
+                         (n <= out_cols <= ldo, out_cols*elem % 16 == 0): a group of a grouped convolution
+                         writes its own column window of the shared output, so whole tiles must be clipped
+                         there and not at the row pitch                                              */
     b200_epilogue ep;
 } b200_gemm_desc;
 int b200_gemm(const b200_gemm_desc *d, void *stream);

@@ -33,7 +33,7 @@ def test_shim_exports_every_declared_symbol():
     assert len(names) >= 35, names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == 3
 
 
 def test_backend_exports_every_declared_symbol():

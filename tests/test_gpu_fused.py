@@ -14,6 +14,15 @@ from shl import (DT_INT8, H_CONV, H_CONV_RELU, H_CONV_RELU6, H_RELU, H_RELU6, RM
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _always_fuse():
+    """the planner normally times the fused kernel against the two-kernel path and keeps the faster
+    (b200_dwpw_prefers_fusion); these tests are about the fused kernel, so they force it"""
+    os.environ["SHL_B200_DWPW"] = "1"
+    yield
+    os.environ.pop("SHL_B200_DWPW", None)
+
 # n, c, h, w, o, stride, pad, zp_in
 PAIRS = [
     (2, 32, 112, 112, 64, 1, 1, 0),        # MobileNetV1 block 1: 32-byte K, two M128 blocks per tile
@@ -87,13 +96,13 @@ def test_fused_block_equals_the_two_kernel_path(b200, rng):
     with b200.create(DT_INT8, x.shape, layers, s_in=0.02, zp_in=-9, run_mode=RM_GRAPH) as net:
         d_fused = net.describe()
         fused = net(x)
-    os.environ["SHL_B200_NO_DWPW"] = "1"
+    os.environ["SHL_B200_DWPW"] = "0"
     try:
         with b200.create(DT_INT8, x.shape, layers, s_in=0.02, zp_in=-9, run_mode=RM_GRAPH) as net:
             d_plain = net.describe()
             plain = net(x)
     finally:
-        os.environ.pop("SHL_B200_NO_DWPW", None)
+        os.environ["SHL_B200_DWPW"] = "1"
     assert "b200_dwpw_fused_tcgen05" in d_fused and "b200_dwpw_fused_tcgen05" not in d_plain
     assert d_fused.startswith("steps=1 ") and d_plain.startswith("steps=2 "), (d_fused, d_plain)
     assert np.array_equal(fused, plain)

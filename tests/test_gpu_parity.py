@@ -55,6 +55,10 @@ CONV_CASES = [
     (1, 3, 40, 40, 64, 7, 2, 3, 1, False, 0, H_CONV),        # ResNet stem shape
     (1, 64, 13, 13, 64, 1, 2, 0, 1, False, 0, H_CONV),       # strided 1x1 (ResNet downsample)
     (1, 64, 12, 12, 64, 3, 1, 1, 4, False, 0, H_CONV),       # group conv
+    (2, 32, 11, 13, 96, 3, 1, 1, 2, False, -3, H_CONV),      # group conv, 48 outputs per group: a 64-column tile clipped
+                                                             # at the group's window (it used to spill into the next group)
+    (1, 60, 9, 9, 240, 1, 1, 0, 3, False, 5, H_CONV),        # grouped 1x1, 80 outputs per group (128-column tile)
+    (1, 48, 10, 10, 320, 3, 2, 1, 2, False, 0, H_CONV_RELU), # 160 per group: one full and one clipped n-tile per group
     (2, 32, 20, 20, 32, 3, 1, 1, 1, True, -7, H_CONV),       # depthwise via csinn_conv2d
     (1, 64, 21, 21, 64, 3, 2, 1, 1, True, 0, H_DWCONV),      # depthwise via csinn_depthwise_conv2d
     (1, 24, 9, 11, 24, 3, 1, 1, 1, True, 2, H_CONV),         # depthwise, ragged channels / width
@@ -77,6 +81,51 @@ def test_conv_int8_bit_exact(case, b200, oracle, rng):
                             dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out,
                             zp_out=3, act=act)
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} outputs differ from the oracle"
+
+
+@pytest.mark.parametrize("case", [
+    # n, c, h, w, o, k, stride, pad, dilation, group, depthwise, zp_in
+    (2, 32, 19, 17, 48, 3, 1, 2, 2, 1, False, -7),     # dilation 2, "same" padding (im2col + GEMM)
+    (1, 16, 20, 20, 32, 3, 2, 3, 3, 1, False, 4),      # dilation 3 with stride 2
+    (1, 3, 33, 31, 16, 3, 1, 2, 2, 1, False, -5),      # dilated first layer read from the NCHW graph input
+    (2, 24, 15, 15, 24, 3, 1, 2, 2, 1, True, 6),       # dilated depthwise (generic kernel)
+    (1, 64, 14, 14, 64, 3, 1, 4, 4, 4, False, 0),      # dilated group conv
+], ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_d%d_g%d_dw%d_zp%d" % c)
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_dilated_conv_int8_bit_exact(case, mode, b200, oracle, ref_noavx, rng):
+    """dilation > 1 (source/reference/convolution.c:28-89 handles it; its AVX path ignores it,
+    conv_avx.h:109, so the reference is consulted through the non-AVX build)"""
+    n, c, h, w, o, k, stride, pad, dil, group, dw, zp_in = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, group=group, depthwise=dw)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4, (dil, dil))
+    layer = Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, stride=(stride, stride),
+                  pad=(pad,) * 4, dilation=(dil, dil), group=c if dw else group)
+    got = b200.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in, run_mode=mode)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), depthwise=dw, stride=(stride, stride), pad=(pad,) * 4,
+                            dilation=(dil, dil), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out,
+                            zp_out=3)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} outputs differ from the oracle"
+    if mode == RM_LAYER:
+        ref_band(got, ref_noavx.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in))
+
+
+@pytest.mark.parametrize("case", [(1, 32, 9, 9, 24, 3, 1, 1, 3), (2, 16, 10, 11, 48, 1, 1, 0, 2), (1, 24, 8, 8, 120, 3, 1, 1, 3)],
+                         ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d" % c)
+def test_group_conv_fp16_clips_tiles_at_the_group_window(case, b200, oracle, rng):
+    """fp16 group conv whose outputs per group (8, 24, 40) are narrower than the GEMM's n-tile: every group's tile
+    must be clipped at its own column window of the shared output"""
+    n, c, h, w, o, k, stride, pad, group = case
+    x = rng.standard_normal((n, c, h, w)).astype(np.float16)
+    cg = c // group
+    wt = (rng.standard_normal((o, cg, k, k)) / np.sqrt(cg * k * k)).astype(np.float16)
+    b = rng.standard_normal(o).astype(np.float16)
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layer = Layer(H_CONV, (n, o, oh, ow), w=wt, b=b, stride=(stride, stride), pad=(pad,) * 4, group=group)
+    got = b200.run(DT_F16, (n, c, h, w), [layer], x)
+    want = oracle.conv2d_f32(x.astype(np.float32), wt.astype(np.float32), b.astype(np.float32), (n, o, oh, ow),
+                             stride=(stride, stride), pad=(pad,) * 4, group=group)
+    f16_close(got, want)
 
 
 def test_conv_int8_against_the_reference_library(b200, ref, rng):
