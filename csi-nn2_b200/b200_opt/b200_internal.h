@@ -83,6 +83,7 @@ typedef struct b200_op {
     void *d_w2;  /* second packing of the same weights (int8 3x3 depthwise: ky-major dp4a words) */
     float *d_mult, *d_badd;
     int32_t *d_ibias;
+    int32_t *d_wzp; /* per-channel weight zero points when any is non-zero (asymmetric weights), else NULL */
     int8_t *d_lut; /* post table or the ACT table */
     int zp_in, zp_out, act, q6;
     float act_p0, act_p1; /* parameters of a unary op (leaky slope; clip min, max) */

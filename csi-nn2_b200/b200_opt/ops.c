@@ -309,6 +309,7 @@ static void fill_epilogue(const b200_op *op, b200_epilogue *ep)
  * direct dp4a kernel (csrc/conv_direct.cu) */
 static int conv_goes_direct(const b200_op *op, const b200_dt *in0)
 {
+    if (op->d_wzp) return 0; /* asymmetric weights need the row sums of the im2col matrix: im2col + GEMM */
     if (!(in0->is_nchw && op->group == 1 && op->kdim <= 160 &&
           ((op->dtype == B200_I8 && op->o <= 256) || (op->dtype == B200_F16 && op->o <= 64)) &&
           !getenv("SHL_B200_NO_DIRECT_CONV")))
@@ -341,11 +342,20 @@ const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
     return op->kname;
 }
 
-size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
+/* scratch layout: [im2col matrix of one group][row sums, int32 per output pixel (asymmetric weights only)] */
+static size_t im2col_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
     if (op->kind != B200_OPK_CONV || (op->direct && !in0->is_nchw)) return 0;
     if (conv_goes_direct(op, in0)) return 0;
-    return (size_t)out->n * out->h * out->w * op->ldk * op->eb;
+    return ((size_t)out->n * out->h * out->w * op->ldk * op->eb + 255) & ~(size_t)255;
+}
+
+size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
+{
+    if (op->kind != B200_OPK_CONV && op->kind != B200_OPK_FC) return 0;
+    size_t bytes = im2col_bytes(op, in0, out);
+    if (op->d_wzp) bytes += (size_t)out->n * out->h * out->w * sizeof(int32_t);
+    return bytes;
 }
 
 static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *scratch, void *stream)
@@ -385,6 +395,11 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
             c.in = in->d, c.col = scratch;
             DEV_CHECK(b200_im2col(&c, stream));
             g.a = scratch, g.lda = op->ldk;
+        }
+        if (op->d_wzp) {
+            int32_t *rs = (int32_t *)((uint8_t *)scratch + im2col_bytes(op, in, out));
+            DEV_CHECK(b200_rowsum_i8(g.a, g.lda, m, op->kdim, op->zp_in, rs, stream));
+            g.w_zp = op->d_wzp + grp * og, g.rowsum = rs;
         }
         g.n = og;
         g.w = (const uint8_t *)op->d_w + (size_t)grp * og * op->ldk * op->eb;
@@ -447,6 +462,10 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
             g.a = in0->d, g.lda = in0->cp, g.w = op->d_w, g.ldw = op->ldk;
             g.out = out->d, g.ldo = out->cp;
             fill_epilogue(op, &g.ep);
+            if (op->d_wzp) {
+                DEV_CHECK(b200_rowsum_i8(g.a, g.lda, g.m, op->kdim, op->zp_in, (int32_t *)scratch, stream));
+                g.w_zp = op->d_wzp, g.rowsum = (const int32_t *)scratch;
+            }
             DEV_CHECK(b200_gemm(&g, stream));
             return CSINN_TRUE;
         }
@@ -458,6 +477,7 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
             d.kh = op->kh, d.kw = op->kw, d.stride_h = op->sh, d.stride_w = op->sw;
             d.pad_top = op->pt, d.pad_left = op->pl, d.dil_h = op->dh, d.dil_w = op->dw;
             d.in = in0->d, d.wt = op->d_w, d.wt_row3 = op->d_w2, d.out = out->d, d.zp_in = op->zp_in;
+            d.w_zp = op->d_wzp;
             fill_epilogue(op, &d.ep);
             DEV_CHECK(b200_dwconv2d(&d, stream));
             return CSINN_TRUE;
@@ -539,6 +559,7 @@ int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, 
 {
     const char *mode = getenv("SHL_B200_DWPW");
     if (getenv("SHL_B200_NO_DWPW") || (mode && atoi(mode) == 0)) return 0;
+    if (dw->d_wzp || pw->d_wzp) return 0; /* asymmetric weights: two kernels (generic depthwise, row-sum GEMM) */
     if (dw->kind != B200_OPK_DW || pw->kind != B200_OPK_CONV || !pw->direct || dw->dtype != B200_I8 ||
         pw->dtype != B200_I8 || in->is_nchw || pw->kdim != mid->c || mid->c != in->c || mid->n != out->n ||
         mid->h != out->h || mid->w != out->w)

@@ -118,8 +118,10 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
     float *mult = calloc(n_alloc, sizeof(float));
     float *badd = calloc(n_alloc, sizeof(float));
     int32_t *ibias = calloc(n_alloc, sizeof(int32_t));
+    int32_t *wzp = calloc(n_alloc, sizeof(int32_t));
+    int any_wzp = 0;
     int rc = CSINN_TRUE;
-    if (!mult || !badd || !ibias) {
+    if (!mult || !badd || !ibias || !wzp) {
         b200_fail("out of host memory building requant tables");
         rc = CSINN_FALSE;
         goto done;
@@ -149,15 +151,16 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
     const int32_t *b = has_bias(bias) ? bias->data : NULL;
     for (int o = 0; o < n_out; o++) {
         const int qi = kernel->quant_channel > 1 ? o : 0;
-        if (kernel->qinfo[qi].zero_point != 0) {
-            /* same restriction as the reference's accelerated int8 path, which only takes
-             * CSINN_QUANT_INT8_ASYM_W_SYM (thead_rvv/int8/convolution.c:40-43) -- but with no
-             * CPU fallback behind it */
-            b200_fail("weight zero_point %d != 0 (channel %d): only symmetric weights are supported",
-                      kernel->qinfo[qi].zero_point, o);
-            rc = CSINN_UNSUPPORT_DTYPE;
+        /* asymmetric weights: acc = sum (x~ - zp_in) * (w - zw).  Contraction ops subtract zw * (row sum of x~ - zp_in)
+         * in the epilogue (include/b200nn.h); the depthwise kernel accumulates the window sum per channel. */
+        const int zw = kernel->qinfo[qi].zero_point;
+        if (zw < -128 || zw > 127) {
+            b200_fail("weight zero_point %d (channel %d) outside int8", zw, o);
+            rc = CSINN_FALSE;
             goto done;
         }
+        wzp[o] = zw;
+        any_wzp |= zw != 0;
         const double sw = kernel->qinfo[qi].scale;
         /* default bias scale: the float product, as it would sit in bias->qinfo[].scale */
         const float sb_default = input->qinfo->scale * kernel->qinfo[qi].scale;
@@ -170,10 +173,11 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
         for (int t = 0; t < taps_per_o; t++) {
             const int wv = w[(int64_t)o * taps_per_o + t];
             wsum += wv;
-            wabs += wv < 0 ? -wv : wv;
+            wabs += wv - zw < 0 ? zw - wv : wv - zw;
         }
         int64_t bq = b ? b[o] : 0;
-        if (fuse_zp2bias) bq += (int64_t)zp_in * wsum; /* un-fold, cf. reference/convolution.c:375-395 */
+        /* un-fold, cf. reference/convolution.c:375-395 (it sums the DEQUANTISED kernel, i.e. w - zw) */
+        if (fuse_zp2bias) bq += (int64_t)zp_in * (wsum - (int64_t)taps_per_o * zw);
         mult[o] = (float)(s_in * sw / s_out);
         badd[o] = (float)((double)bq * sb / s_out);
         ibias[o] = (int32_t)(-(int64_t)zp_in * wsum);
@@ -203,12 +207,16 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
     }
     op->d_mult = b200_warena_put(op->ctx, mult, n_alloc * sizeof(float));
     op->d_badd = b200_warena_put(op->ctx, badd, n_alloc * sizeof(float));
+    if (any_wzp && op->kind == B200_OPK_DW) /* the depthwise kernel multiplies (x~ - 0) by (w - zw) tap by tap */
+        for (int o = 0; o < n_out; o++) ibias[o] += zp_in * taps_per_o * wzp[o];
     op->d_ibias = b200_warena_put(op->ctx, ibias, n_alloc * sizeof(int32_t));
-    if (!op->d_mult || !op->d_badd || !op->d_ibias) rc = CSINN_FALSE;
+    op->d_wzp = any_wzp ? b200_warena_put(op->ctx, wzp, n_alloc * sizeof(int32_t)) : NULL;
+    if (!op->d_mult || !op->d_badd || !op->d_ibias || (any_wzp && !op->d_wzp)) rc = CSINN_FALSE;
 done:
     free(mult);
     free(badd);
     free(ibias);
+    free(wzp);
     return rc;
 }
 

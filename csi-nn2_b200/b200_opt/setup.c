@@ -63,6 +63,7 @@ static void build_table(void)
         const int dt = dts[i];
         reg_op(dt, CSINN_OP_CONV2D, shl_b200_conv2d_init, shl_b200_conv2d, shl_gref_conv2d, shl_b200_perf);
         reg_op(dt, CSINN_OP_GROUP_CONV2D, shl_b200_conv2d_init, shl_b200_conv2d, shl_gref_group_conv2d, shl_b200_perf);
+        reg_op(dt, CSINN_OP_GROUP_CONV2D_RELU, shl_b200_conv2d_relu_init_fn(), shl_b200_conv2d, shl_gref_group_conv2d_relu, shl_b200_perf);
         reg_op(dt, CSINN_OP_CONV2D_RELU, shl_b200_conv2d_relu_init_fn(), shl_b200_conv2d, shl_gref_conv2d_relu, shl_b200_perf);
         reg_op(dt, CSINN_OP_CONV2D_RELU6, shl_b200_conv2d_relu6_init_fn(), shl_b200_conv2d, shl_gref_conv2d_relu6, shl_b200_perf);
         reg_op(dt, CSINN_OP_DEPTHWISE_CONV2D, shl_b200_depthwise_conv2d_init, shl_b200_depthwise_conv2d, shl_gref_depthwise_conv2d, shl_b200_perf);

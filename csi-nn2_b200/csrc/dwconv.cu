@@ -26,8 +26,12 @@ struct DwArgs {
     void *out;
     int zp_in;
     EpiScalars ep;
+    const int32_t *wzp;  // int8 asymmetric weights: per-channel weight zero points, else null
 };
 
+// ASYM: weights with a zero point -- the window sum S of the (zero-point padded) taps is accumulated per channel
+// beside the products and acc - zw * S enters the epilogue (ibias carries the constant part, include/b200nn.h)
+template <bool ASYM>
 __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
 {
     pdl_launch_dependents();
@@ -55,10 +59,14 @@ __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
         const int ox0 = xg * kTW;
 
         int acc[kTW][16];
+        int xs[ASYM ? kTW : 1][ASYM ? 16 : 1];
 #pragma unroll
         for (int p = 0; p < kTW; p++)
 #pragma unroll
-            for (int j = 0; j < 16; j++) acc[p][j] = 0;
+            for (int j = 0; j < 16; j++) {
+                acc[p][j] = 0;
+                if (ASYM) xs[p][j] = 0;
+            }
 
         for (int ky = 0; ky < a.kh; ky++) {
             const int iy = oy * a.sh - a.pt + ky * a.dh;
@@ -84,10 +92,12 @@ __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
 #pragma unroll
                     for (int q = 0; q < 4; q++)
 #pragma unroll
-                        for (int e = 0; e < 4; e++)
+                        for (int e = 0; e < 4; e++) {
                             acc[p][q * 4 + e] = __dp4a(static_cast<int>(xw[q]),
                                                        static_cast<int>(wv[q * 4 + e]),
                                                        acc[p][q * 4 + e]);
+                            if (ASYM) xs[p][q * 4 + e] = __dp4a(static_cast<int>(xw[q]), 1 << (8 * e), xs[p][q * 4 + e]);
+                        }
                 }
             }
         }
@@ -103,6 +113,17 @@ __global__ void __launch_bounds__(128) dwconv_i8_kernel(const DwArgs a)
             mu[q * 4] = m4.x, mu[q * 4 + 1] = m4.y, mu[q * 4 + 2] = m4.z, mu[q * 4 + 3] = m4.w;
             ba[q * 4] = b4.x, ba[q * 4 + 1] = b4.y, ba[q * 4 + 2] = b4.z, ba[q * 4 + 3] = b4.w;
             ib[q * 4] = i4.x, ib[q * 4 + 1] = i4.y, ib[q * 4 + 2] = i4.z, ib[q * 4 + 3] = i4.w;
+        }
+        if (ASYM) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int4 z4 = __ldg(reinterpret_cast<const int4 *>(a.wzp + c0) + q);
+                const int z[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                for (int p = 0; p < kTW; p++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[p][q * 4 + e] -= z[e] * xs[p][q * 4 + e];
+            }
         }
 #pragma unroll
         for (int p = 0; p < kTW; p++) {
@@ -401,7 +422,7 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         return B200_ERR_ARG;
     }
     if (d->dtype == B200_I8 && d->wt_row3 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
-        !getenv("SHL_B200_DW_GENERIC") &&
+        !getenv("SHL_B200_DW_GENERIC") && !d->w_zp &&
         d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2) &&
         // the TMA kernel folds zero-point padding into per-class accumulator seeds: at most one
         // padded row / column on each side of any output's 3x3 window
@@ -419,6 +440,7 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);
     }
     DwArgs a;
+    a.wzp = nullptr;
     a.n = d->n, a.c = d->c, a.cp = d->cp, a.h = d->h, a.w = d->w, a.oh = d->oh, a.ow = d->ow;
     a.kh = d->kh, a.kw = d->kw, a.sh = d->stride_h, a.sw = d->stride_w;
     if (d->dtype == B200_F16 && d->kh == 3 && d->kw == 3 && d->dil_h == 1 && d->dil_w == 1 &&
@@ -447,14 +469,17 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
     a.pt = d->pad_top, a.pl = d->pad_left, a.dh = d->dil_h, a.dw = d->dil_w;
     a.in = d->in, a.wt = d->wt, a.out = d->out, a.zp_in = d->zp_in;
     a.ep = make_epi(d->ep);
+    a.wzp = d->dtype == B200_I8 ? d->w_zp : nullptr;
     const int vec = 16 / eb;
     const long long total = static_cast<long long>(d->n) * d->oh * ((d->ow + kTW - 1) / kTW) *
                             (d->cp / vec);
     long long g = (total + 127) / 128;
     const long long cap = static_cast<long long>(sm_count()) * 32;
     const int grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
-    if (d->dtype == B200_I8)
-        launch_kernel(dwconv_i8_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+    if (d->dtype == B200_I8 && a.wzp)
+        launch_kernel(dwconv_i8_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+    else if (d->dtype == B200_I8)
+        launch_kernel(dwconv_i8_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     else
         launch_kernel(dwconv_f16_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     B200_LAUNCH_CHECK();

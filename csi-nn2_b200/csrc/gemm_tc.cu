@@ -62,12 +62,15 @@ struct GemmArgs {
     void *out;
     uint32_t idesc;
     EpiScalars ep;
+    const int32_t *wzp;     // asymmetric weights: per-column weight zero points (else null)
+    const int32_t *rowsum;  // ... and the row sums b200_rowsum_i8 computed
 };
 
 struct __align__(16) EpiParams {
     float mult[256];
     float badd[256];
     int32_t ibias[256];  // + kMagicI when the kernel converts through the magic constant
+    int32_t wzp[256];    // asymmetric weights: the columns' weight zero points
     uint8_t lut[256];
 };
 
@@ -76,7 +79,9 @@ __device__ __forceinline__ void epi_bar_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 }
 
-template <int DT, int MODE, bool MAGIC>
+// ASYM: weights with zero points -- every accumulator is corrected by - w_zp[column] * rowsum[row] before the
+// requantisation (contract in include/b200nn.h); generic epilogue, no magic-number shortcut
+template <int DT, int MODE, bool MAGIC, bool ASYM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_o, const GemmArgs args)
@@ -287,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             epi->mult[et] = (ok && ep.mult) ? ep.mult[col] : 0.f;
             epi->badd[et] = (ok && ep.badd) ? ep.badd[col] : 0.f;
             epi->ibias[et] = ((ok && ep.ibias) ? ep.ibias[col] : 0) + (MAGIC ? kMagicI : 0);
+            if (ASYM) epi->wzp[et] = ok ? args.wzp[col] : 0;
         }
         epi_bar_sync();
         // a staging row is bn bytes = one TMA swizzle span (128B / 64B / 32B / none): XOR the
@@ -348,6 +354,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tmem_ld_32x16(taddr + g * bn + sub * 16, r);
                     tmem_ld_wait();
                     tmem_st_32x16(taddr + g * bn + sub * 16, ib);  // re-seed for the tile after next
+                    if (ASYM) {
+                        const int row = (mt0 + g) * kBM + quad * 32 + lane;
+                        const int rs = row < args.m ? __ldg(args.rowsum + row) : 0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const int4 z = *reinterpret_cast<const int4 *>(&epi->wzp[sub * 16 + j4 * 4]);
+                            r[j4 * 4 + 0] -= static_cast<uint32_t>(z.x * rs), r[j4 * 4 + 1] -= static_cast<uint32_t>(z.y * rs);
+                            r[j4 * 4 + 2] -= static_cast<uint32_t>(z.z * rs), r[j4 * 4 + 3] -= static_cast<uint32_t>(z.w * rs);
+                        }
+                    }
                     uint32_t packed[4];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; j4++) {
@@ -500,13 +516,13 @@ static int pick_bn(int n, int dtype)
     return ((n16 + tiles - 1) / tiles + 31) / 32 * 32;
 }
 
-template <int DT, int MODE, bool MAGIC>
+template <int DT, int MODE, bool MAGIC, bool ASYM = false>
 static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &ta,
                           const CUtensorMap &tb, const CUtensorMap &to, const GemmArgs &args, int dev)
 {
     static bool attr_set[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<DT, MODE, MAGIC>,
+        B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<DT, MODE, MAGIC, ASYM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSmemLimit));
         attr_set[dev] = true;
@@ -532,7 +548,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
             at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
             cfg.attrs = at, cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<DT, MODE, MAGIC>, &cfg) != cudaSuccess || n <= 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<DT, MODE, MAGIC, ASYM>, &cfg) != cudaSuccess || n <= 0) {
                 (void)cudaGetLastError();
                 n = -1;
             }
@@ -540,7 +556,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
         }
         if (dev < 0 || dev >= 64 || max_clusters[dev] * 2 < grid) la.cluster = 1;
     }
-    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC>, dim3(grid), dim3(kThreads), smem, stream,
+    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM>, dim3(grid), dim3(kThreads), smem, stream,
                                           la.cluster, ta, tb, to, la));
     if (tracing && la.trace) {  // diagnostic only: synchronous, prints a few CTAs' timelines (cycles from CTA start)
         static long long host[256 * 64];
@@ -579,7 +595,8 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
         (d->ldw * eb) % 16 || (d->ldo * eb) % 16 || d->lda < d->k || d->ldw < d->k ||
         (reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->w) & 15) ||
         (reinterpret_cast<uintptr_t>(d->out) & 15) ||
-        (d->dtype == B200_I8 && (!d->ep.mult || !d->ep.badd))) {
+        (d->dtype == B200_I8 && (!d->ep.mult || !d->ep.badd)) || ((d->w_zp != nullptr) != (d->rowsum != nullptr)) ||
+        (d->w_zp && d->dtype != B200_I8)) {
         set_error("b200_gemm: bad sizes m=%d n=%d k=%d lda=%d ldw=%d ldo=%d (pitches and bases must be 16-byte aligned)",
                   d->m, d->n, d->k, d->lda, d->ldw, d->ldo);
         return B200_ERR_ARG;
@@ -624,6 +641,7 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     args.ldo = d->ldo;
     args.out = d->out;
     args.ep = make_epi(d->ep);
+    args.wzp = d->w_zp, args.rowsum = d->rowsum;
     args.idesc = d->dtype == B200_I8 ? umma_idesc(2 /*S32*/, 1 /*S8*/, kBM, args.bn)
                                      : umma_idesc(1 /*F32*/, 0 /*F16*/, kBM, args.bn);
     // as many stages as fit: the ring also prefetches the next tiles' operands while the
@@ -679,6 +697,12 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
         // |acc + ibias| <= K * 2 * 128 * 127 < 2^22 lets the epilogue convert through the magic
         // constant (an FADD) instead of I2F
         const bool magic = d->k <= 128;
+        if (d->w_zp) {
+            rc = launch_variant<B200_I8, EPI_GENERIC, false, true>(grid, smem, s, ta, tb, to, args, dev);
+            if (rc) return rc;
+            B200_LAUNCH_CHECK();
+            return B200_OK;
+        }
         int mode;
         if (d->ep.post_lut)
             mode = d->ep.act == B200_ACT_NONE ? EPI_LUT : EPI_GENERIC;

@@ -460,3 +460,48 @@ extern "C" int b200_concat_slice(const b200_concat_desc *d, void *stream)
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+
+// ---- row sums for asymmetric weights -----------------------------------------------------------------------
+// rs[m] = sum_{k < K} a[m][k] - zp_in * K: one warp per row, 16 bytes per lane and step, dp4a against ones
+namespace b200 {
+__global__ void __launch_bounds__(256) rowsum_i8_kernel(const int8_t *__restrict__ a, int lda, int m, int k, int zp_in,
+                                                        int32_t *__restrict__ rs)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int k16 = k & ~15;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < m; row += warps) {
+        const int8_t *p = a + static_cast<size_t>(row) * lda;
+        int acc = 0;
+        for (int c = lane * 16; c < k16; c += 32 * 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + c));
+            acc = __dp4a(static_cast<int>(v.x), 0x01010101, acc);
+            acc = __dp4a(static_cast<int>(v.y), 0x01010101, acc);
+            acc = __dp4a(static_cast<int>(v.z), 0x01010101, acc);
+            acc = __dp4a(static_cast<int>(v.w), 0x01010101, acc);
+        }
+        for (int c = k16 + lane; c < k; c += 32) acc += p[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) rs[row] = acc - zp_in * k;
+    }
+}
+}  // namespace b200
+
+extern "C" int b200_rowsum_i8(const void *a, int32_t lda, int32_t m, int32_t k, int32_t zp_in, int32_t *rs, void *stream)
+{
+    if (!a || !rs || m <= 0 || k <= 0 || lda < k || lda % 16 || (reinterpret_cast<uintptr_t>(a) & 15)) {
+        b200::set_error("b200_rowsum_i8: bad arguments (m=%d k=%d lda=%d)", m, k, lda);
+        return B200_ERR_ARG;
+    }
+    long long blocks = (static_cast<long long>(m) + 7) / 8;
+    const long long cap = static_cast<long long>(b200::sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    b200::launch_kernel(b200::rowsum_i8_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, (cudaStream_t)stream,
+                        static_cast<const int8_t *>(a), lda, m, k, zp_in, rs);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -27,6 +27,9 @@
  * Quantised epilogue (the one arithmetic contract; oracle/oracle_int.c restates it):
  *     acc  = sum_k x~[k] * w[o][k]                        (int32, exact; x~ = zp_in at pads)
  *     acc += ibias[o]                                     (int32: -zp_in * sum_k w[o][k])
+ *     acc -= w_zp[o] * rs                                 (asymmetric weights only: rs = sum_k x~[k] - zp_in * K,
+ *                                                          so that acc = sum_k (x~ - zp_in) * (w - w_zp[o]);
+ *                                                          source/nn2/utils.c:920-931 dequantises kernels so)
  *     f    = fmaf((float)acc, mult[o], badd[o])           (one rounding)
  *     q    = clamp((int)rintf(f) + zp_out, -128, 127)     (round-half-even, like nearbyint in
  *                                                          source/nn2/utils.c:550 float_to_int8_base)
@@ -173,8 +176,16 @@ typedef struct {
                          writes its own column window of the shared output, so whole tiles must be clipped
                          there and not at the row pitch                                              */
     b200_epilogue ep;
+    /* asymmetric weights (both NULL for symmetric ones): per-output-channel weight zero points and the
+     * row sums rs[m] = sum_k a[m][k] - zp_in * k computed by b200_rowsum_i8 */
+    const int32_t *w_zp;   /* device [n] */
+    const int32_t *rowsum; /* device [m] */
 } b200_gemm_desc;
 int b200_gemm(const b200_gemm_desc *d, void *stream);
+/* rs[m] = sum_{k < K} a[m][k] - zp_in * K over int8 rows of pitch lda: the per-pixel term an asymmetric
+ * weight zero point multiplies (see the contract above).  On an im2col matrix the padded taps hold zp_in
+ * and cancel, as they must. */
+int b200_rowsum_i8(const void *a, int32_t lda, int32_t m, int32_t k, int32_t zp_in, int32_t *rs, void *stream);
 
 /* ---- im2col (the other half of "im2col + GEMM conv2d") ------------------------- */
 /* col[m][k], m = (b, oy, ox), k = (ky, kx, ci) with ci fastest, row pitch ldk elements;
@@ -234,6 +245,8 @@ typedef struct {
     void *out;       /* device [n][oh][ow][cp]                              */
     int32_t zp_in;   /* int8: value of a padded tap                         */
     b200_epilogue ep;
+    const int32_t *w_zp; /* device [cp] weight zero points, or NULL (symmetric weights); with them ep.ibias[o] must be
+                            -zp_in * (sum_taps w[o] - taps * w_zp[o]) and the generic kernel is used */
 } b200_dwconv_desc;
 int b200_dwconv2d(const b200_dwconv_desc *d, void *stream);
 

@@ -65,12 +65,17 @@ int oracle_requant_tables(const oracle_conv_params *p, const int8_t *wt, const i
         for (int t = 0; t < taps_per_o; t++) wsum += wt[(int64_t)o * taps_per_o + t];
         int64_t b = bias ? bias[o] : 0;
         /* a folded bias is un-folded exactly (reference does it in f32: convolution.c:375-395) */
-        if (p->fuse_zp2bias) b += (int64_t)p->zp_in * wsum;
+        const int zw = p->zp_w ? p->zp_w[qi] : 0;
+        /* the reference un-folds with the dequantised kernel, i.e. with sum (w - zp_w) (convolution.c:375-395) */
+        if (p->fuse_zp2bias) b += (int64_t)p->zp_in * (wsum - (int64_t)taps_per_o * zw);
         mult[o] = (float)((double)p->s_in * sw / (double)p->s_out);
         badd[o] = (float)((double)b * sb / (double)p->s_out);
         ibias[o] = (int32_t)(-(int64_t)p->zp_in * wsum);
-        double bound = (double)taps_per_o * 128.0 * 255.0 * fabs(mult[o]) + fabs(badd[o]);
-        if (!(bound < 4194304.0)) return -1; /* product refuses these too (b200_opt/quant.c) */
+        int64_t wabs = 0;
+        for (int t = 0; t < taps_per_o; t++) wabs += llabs((long long)wt[(int64_t)o * taps_per_o + t] - zw);
+        const int xmax = (127 - p->zp_in) > (p->zp_in + 128) ? (127 - p->zp_in) : (p->zp_in + 128);
+        double bound = (double)wabs * xmax * fabs(mult[o]) + fabs(badd[o]);
+        if (!(bound < 8388608.0)) return -1; /* product refuses these too (b200_opt/quant.c) */
     }
     return 0;
 }
@@ -89,7 +94,7 @@ int oracle_conv2d_i8(const oracle_conv_params *p, const int8_t *in, const int8_t
             const int g = o / og;
             for (int oy = 0; oy < p->oh; oy++) {
                 for (int ox = 0; ox < p->ow; ox++) {
-                    int32_t acc = 0;
+                    int32_t acc = 0, xsum = 0;
                     for (int ci = 0; ci < cg; ci++) {
                         const int c = g * cg + ci;
                         for (int ky = 0; ky < p->kh; ky++) {
@@ -100,10 +105,12 @@ int oracle_conv2d_i8(const oracle_conv_params *p, const int8_t *in, const int8_t
                                 if (iy >= 0 && iy < p->h && ix >= 0 && ix < p->w)
                                     x = in[(((int64_t)b * p->c + c) * p->h + iy) * p->w + ix];
                                 acc += x * wt[(((int64_t)o * cg + ci) * p->kh + ky) * p->kw + kx];
+                                xsum += x;
                             }
                         }
                     }
                     acc += ibias[o];
+                    if (p->zp_w) acc -= p->zp_w[p->w_channels > 1 ? o : 0] * (xsum - p->zp_in * taps);
                     out[(((int64_t)b * p->o + o) * p->oh + oy) * p->ow + ox] =
                         (int8_t)epilogue_i8(acc, mult[o], badd[o], p);
                 }
@@ -128,7 +135,7 @@ int oracle_dwconv2d_i8(const oracle_conv_params *p, const int8_t *in, const int8
             const int c = o / dm;
             for (int oy = 0; oy < p->oh; oy++) {
                 for (int ox = 0; ox < p->ow; ox++) {
-                    int32_t acc = 0;
+                    int32_t acc = 0, xsum = 0;
                     for (int ky = 0; ky < p->kh; ky++) {
                         for (int kx = 0; kx < p->kw; kx++) {
                             int iy = oy * p->stride_h - p->pad_top + ky * p->dil_h;
@@ -137,9 +144,11 @@ int oracle_dwconv2d_i8(const oracle_conv_params *p, const int8_t *in, const int8
                             if (iy >= 0 && iy < p->h && ix >= 0 && ix < p->w)
                                 x = in[(((int64_t)b * p->c + c) * p->h + iy) * p->w + ix];
                             acc += x * wt[((int64_t)o * p->kh + ky) * p->kw + kx];
+                            xsum += x;
                         }
                     }
                     acc += ibias[o];
+                    if (p->zp_w) acc -= p->zp_w[p->w_channels > 1 ? o : 0] * (xsum - p->zp_in * taps);
                     out[(((int64_t)b * p->o + o) * p->oh + oy) * p->ow + ox] =
                         (int8_t)epilogue_i8(acc, mult[o], badd[o], p);
                 }
@@ -159,10 +168,13 @@ int oracle_fc_i8(const oracle_conv_params *p, const int8_t *in, const int8_t *wt
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < p->n; b++) {
         for (int o = 0; o < p->o; o++) {
-            int32_t acc = 0;
-            for (int k = 0; k < p->c; k++)
+            int32_t acc = 0, xsum = 0;
+            for (int k = 0; k < p->c; k++) {
                 acc += (int)in[(int64_t)b * p->c + k] * wt[(int64_t)o * p->c + k];
+                xsum += in[(int64_t)b * p->c + k];
+            }
             acc += ibias[o];
+            if (p->zp_w) acc -= p->zp_w[p->w_channels > 1 ? o : 0] * (xsum - p->zp_in * p->c);
             out[(int64_t)b * p->o + o] = (int8_t)epilogue_i8(acc, mult[o], badd[o], p);
         }
     }

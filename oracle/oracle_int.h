@@ -22,6 +22,7 @@
  *              250-257; the RVV im2col writes zp_in at pads too,
  *              source/thead_rvv/int8/convolution_gemm_int8.c:116,125)
  *     acc  += ibias[o] = -zp_in * sum_taps w[o]            (zero-point fold)
+ *     acc  -= zp_w[o] * (sum_taps x~ - zp_in * taps)       (only with asymmetric weights, see zp_w below)
  *     f     = fmaf((float)acc, mult[o], badd[o])           (one rounding)
  *             mult[o] = (float)((double)s_in * s_w[o] / s_out)
  *             badd[o] = (float)((double)bias_q[o] * s_b[o] / s_out)   (s_b defaults to the float
@@ -69,6 +70,12 @@ typedef struct {
     int32_t post_act;
     float post_s_out;
     int32_t post_zp_out;
+    /* weight zero points, indexed like s_w, or NULL for symmetric weights (zero_point 0).  With them
+     *     acc = sum over taps of (x~ - zp_in) * (w - zp_w[o])
+     *         = sum x~ * w + ibias[o] - zp_w[o] * (sum_taps x~ - zp_in * taps)
+     * (a padded tap holds zp_in and contributes nothing); the reference dequantises the kernel with its
+     * zero point, source/nn2/utils.c:920-931 nchw_int8_to_float -> int8_to_float_base */
+    const int32_t *zp_w;
 } oracle_conv_params;
 
 /* requant tables shared by conv / dw / fc; returns 0, or -1 if a bound check fails */

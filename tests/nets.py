@@ -253,7 +253,7 @@ def oracle_forward(nb: NetBuilder, x: np.ndarray) -> np.ndarray:
             if i8:
                 y = orc.conv2d_i8(a, l.w, l.b, tuple(l.out_shape), depthwise=dw, stride=l.stride, pad=l.pad,
                                   dilation=l.dilation, group=1 if dw else l.group, s_in=s_in, zp_in=zp_in,
-                                  s_w=l.s_w, s_b=l.s_b, s_out=l.s_out, zp_out=l.zp_out, act=act)
+                                  s_w=l.s_w, s_b=l.s_b, s_out=l.s_out, zp_out=l.zp_out, act=act, zp_w=l.zp_w)
             else:
                 y = orc.conv2d_f32(a.astype(np.float32), l.w.astype(np.float32),
                                    None if l.b is None else l.b.astype(np.float32), tuple(l.out_shape),
@@ -262,7 +262,7 @@ def oracle_forward(nb: NetBuilder, x: np.ndarray) -> np.ndarray:
         elif l.kind == H_FC:
             if i8:
                 y = orc.fc_i8(a.reshape(a.shape[0], -1), l.w, l.b, s_in=s_in, zp_in=zp_in, s_w=l.s_w, s_b=l.s_b,
-                              s_out=l.s_out, zp_out=l.zp_out)
+                              s_out=l.s_out, zp_out=l.zp_out, zp_w=l.zp_w)
             else:
                 y = (a.reshape(a.shape[0], -1).astype(np.float32) @ l.w.astype(np.float32).T +
                      l.b.astype(np.float32)).astype(np.float16)

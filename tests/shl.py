@@ -294,7 +294,7 @@ class OConv(C.Structure):
         ("s_in", C.c_float), ("zp_in", C.c_int32), ("s_w", C.c_void_p), ("w_channels", C.c_int32),
         ("s_b", C.c_void_p), ("s_out", C.c_float), ("zp_out", C.c_int32), ("fuse_zp2bias", C.c_int32),
         ("act", C.c_int32), ("post", C.c_int32), ("post_act", C.c_int32), ("post_s_out", C.c_float),
-        ("post_zp_out", C.c_int32),
+        ("post_zp_out", C.c_int32), ("zp_w", C.c_void_p),
     ]
 
 
@@ -312,7 +312,7 @@ class Oracle:
         self.lib = C.CDLL(path)
 
     def _conv_params(self, x_shape, w, out_shape, *, stride, pad, dilation, group, s_in, zp_in, s_w, s_b, s_out,
-                     zp_out, fuse_zp2bias=0, act=ACT_NONE, post=None):
+                     zp_out, fuse_zp2bias=0, act=ACT_NONE, post=None, zp_w=None):
         p = OConv()
         if len(x_shape) == 4:
             p.n, p.c, p.h, p.w = x_shape
@@ -333,6 +333,11 @@ class Oracle:
         p.s_out, p.zp_out, p.fuse_zp2bias, p.act = s_out, zp_out, fuse_zp2bias, act
         if post is not None:
             p.post, p.post_act, p.post_s_out, p.post_zp_out = 1, post[0], post[1], post[2]
+        # weight zero points (indexed like s_w); None / all zero = symmetric weights
+        self._zw = None if zp_w is None else np.ascontiguousarray(zp_w, dtype=np.int32)
+        if self._zw is not None:
+            assert self._zw.size == self._sw.size, "zp_w must be indexed like s_w"
+            p.zp_w = _ptr(self._zw)
         return p
 
     def conv2d_i8(self, x, w, b, out_shape, *, depthwise=False, **kw):

@@ -243,12 +243,59 @@ def test_relu_keeping_its_producers_qinfo(kind, b200, oracle, rng):
         assert np.array_equal(got, want), (kind, c, o, k)
 
 
-def test_asymmetric_weights_are_refused_loudly(b200, rng):
-    x = rng.integers(-128, 128, size=(1, 16, 4, 4), dtype=np.int8)
-    wt, s_w, b, s_out = synth_conv_i8(rng, 16, 16, 1, 1)
-    layer = Layer(H_CONV, (1, 16, 4, 4), s_out=s_out, w=wt, b=b, s_w=s_w, zp_w=np.full(16, 3, np.int32))
-    with pytest.raises(RuntimeError, match="symmetric weights"):
-        b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02)
+ASYM_W_CASES = [
+    # n, c, h, w, o, k, stride, pad, group, depthwise, zp_in, per_channel
+    (2, 64, 14, 14, 96, 1, 1, 0, 1, False, -7, True),     # pointwise GEMM, per-channel weight zero points
+    (1, 512, 9, 9, 200, 1, 1, 0, 1, False, -128, True),   # 4 k-blocks, ragged N, extreme input zero point
+    (2, 32, 12, 12, 48, 3, 1, 1, 1, False, 5, True),      # 3x3 with padding through im2col: padded taps cancel
+    (1, 3, 32, 32, 32, 3, 2, 1, 1, False, 5, True),       # a first layer (NCHW input): im2col path, not the stem kernel
+    (2, 32, 10, 10, 64, 3, 2, 1, 2, False, 0, False),     # group conv, one zero point for the whole kernel
+    (1, 24, 11, 9, 24, 3, 1, 1, 1, True, -11, True),      # depthwise 3x3 (generic kernel)
+    (1, 128, 28, 28, 128, 3, 2, 1, 1, True, 3, False),    # depthwise stride 2, per-tensor
+]
+
+
+@pytest.mark.parametrize("case", ASYM_W_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d_dw%d_zp%d_pc%d" % c)
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_conv_int8_asymmetric_weights_bit_exact(case, mode, b200, oracle, ref_noavx, rng):
+    """weight zero_point != 0 (source/nn2/utils.c:920-931; BASELINE.json configs[4] "asymmetric quant"): the GEMM
+    epilogue subtracts w_zp[o] * (row sum of x~ - zp_in) per output (b200_rowsum_i8), the depthwise kernel
+    accumulates the window sum per channel; bit-exact against the oracle, in band against the reference"""
+    n, c, h, w, o, k, stride, pad, group, dw, zp_in, per_channel = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, group=group, depthwise=dw)
+    if per_channel:
+        zp_w = rng.integers(-20, 21, size=o).astype(np.int32)
+        zp_w[0], zp_w[-1] = -128, 127
+    else:
+        s_w, zp_w = s_w[:1], np.int32([9])
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layers = [Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, zp_w=zp_w, stride=(stride, stride),
+                    pad=(pad,) * 4, group=c if dw else group),
+              Layer(H_RELU, (n, o, oh, ow), s_out=s_out / 2, zp_out=-128)]
+    kw = dict(depthwise=dw, stride=(stride, stride), pad=(pad,) * 4, dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in,
+              s_w=s_w, s_b=None, s_out=s_out, zp_out=3, zp_w=zp_w)
+    got = b200.run(DT_INT8, x.shape, layers[:1], x, s_in=0.02, zp_in=zp_in, run_mode=mode)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), **kw)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} outputs differ from the oracle"
+    if mode == RM_GRAPH:  # with the relu node riding in the epilogue as a table
+        got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=zp_in, run_mode=mode)
+        want2 = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), post=(ACT_RELU, s_out / 2, -128), **kw)
+        assert np.array_equal(got, want2), "fused relu table"
+    else:
+        ref_band(got, ref_noavx.run(DT_INT8, x.shape, layers[:1], x, s_in=0.02, zp_in=zp_in))
+
+
+def test_fc_int8_asymmetric_weights_bit_exact(b200, oracle, rng):
+    batch, cin, units = 37, 600, 130
+    x = rng.integers(-128, 128, size=(batch, cin), dtype=np.int8)
+    wt4, s_w, b, s_out = synth_conv_i8(rng, cin, units, 1, 1)
+    wt = wt4.reshape(units, cin)
+    zp_w = rng.integers(-30, 31, size=units).astype(np.int32)
+    layer = Layer(H_FC, (batch, units), s_out=s_out, zp_out=-4, w=wt, b=b, s_w=s_w, zp_w=zp_w)
+    got = b200.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=6)
+    want = oracle.fc_i8(x, wt, b, s_in=0.02, zp_in=6, s_w=s_w, s_b=None, s_out=s_out, zp_out=-4, zp_w=zp_w)
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("batch,cin,units", [(1, 1024, 1000), (8, 31, 17), (300, 2048, 100)])

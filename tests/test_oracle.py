@@ -68,6 +68,52 @@ def test_conv_int8_against_reference(case, ref, ref_noavx, oracle, rng):
     assert (np.mean((want == 127) | (want == -128))) < 0.05  # the case is not degenerate
 
 
+ASYM_W_CASES = [
+    # n, c, h, w, o, k, stride, pad, group, depthwise, zp_in, per_channel
+    (1, 64, 14, 14, 96, 1, 1, 0, 1, False, -7, True),     # pointwise, per-channel weight zero points
+    (1, 32, 12, 12, 48, 3, 1, 1, 1, False, 5, True),      # 3x3 with padding: padded taps contribute nothing
+    (2, 32, 10, 10, 64, 3, 2, 1, 2, False, 0, False),     # group conv, one zero point for the whole kernel
+    (1, 24, 11, 9, 24, 3, 1, 1, 1, True, -11, True),      # depthwise
+    (1, 16, 9, 9, 16, 3, 2, 1, 1, True, 3, False),        # depthwise stride 2, per-tensor
+]
+
+
+@pytest.mark.parametrize("case", ASYM_W_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d_dw%d_zp%d_pc%d" % c)
+def test_conv_int8_asymmetric_weights_against_reference(case, ref, ref_noavx, oracle, rng):
+    """weight zero_point != 0 (BASELINE.json configs[4] "asymmetric quant"): the reference dequantises the
+    kernel with its zero point (source/nn2/utils.c:920-931); the oracle's integer form is
+    acc - zp_w * (sum x~ - zp_in * taps)"""
+    n, c, h, w, o, k, stride, pad, group, dw, zp_in, per_channel = case
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt, s_w, b, s_out = synth_conv_i8(rng, c, o, k, k, group=group, depthwise=dw)
+    if per_channel:
+        zp_w = rng.integers(-20, 21, size=o).astype(np.int32)
+    else:
+        s_w, zp_w = s_w[:1], np.int32([9])
+    oh, ow = conv_out_hw(h, w, k, k, (stride, stride), (pad,) * 4)
+    layer = Layer(H_CONV, (n, o, oh, ow), s_out=s_out, zp_out=3, w=wt, b=b, s_w=s_w, zp_w=zp_w, stride=(stride, stride),
+                  pad=(pad,) * 4, group=c if dw else group)
+    want = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), depthwise=dw, stride=(stride, stride), pad=(pad,) * 4,
+                            dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out,
+                            zp_out=3, zp_w=zp_w)
+    sym = oracle.conv2d_i8(x, wt, b, (n, o, oh, ow), depthwise=dw, stride=(stride, stride), pad=(pad,) * 4,
+                           dilation=(1, 1), group=group, s_in=0.02, zp_in=zp_in, s_w=s_w, s_b=None, s_out=s_out, zp_out=3)
+    assert np.mean(want != sym) > 0.2, "the zero points must matter in this case"
+    for lib in [ref_noavx] + ([ref] if n == 1 or dw else []):
+        close_int8(lib.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in), want, lib.which)
+
+
+def test_fc_int8_asymmetric_weights_against_reference(ref, oracle, rng):
+    batch, cin, units = 5, 200, 70
+    x = rng.integers(-128, 128, size=(batch, cin), dtype=np.int8)
+    wt4, s_w, b, s_out = synth_conv_i8(rng, cin, units, 1, 1)
+    wt = wt4.reshape(units, cin)
+    zp_w = rng.integers(-30, 31, size=units).astype(np.int32)
+    layer = Layer(H_FC, (batch, units), s_out=s_out, zp_out=-4, w=wt, b=b, s_w=s_w, zp_w=zp_w)
+    want = oracle.fc_i8(x, wt, b, s_in=0.02, zp_in=6, s_w=s_w, s_b=None, s_out=s_out, zp_out=-4, zp_w=zp_w)
+    close_int8(ref.run(DT_INT8, x.shape, [layer], x, s_in=0.02, zp_in=6), want, "reference fc, asymmetric weights")
+
+
 def test_reference_builds_disagree_like_the_oracle(ref, ref_noavx, oracle, rng):
     """The +-1 LSB band is the reference's own f32 accumulation noise: its two builds (AVX im2col
     sgemm, conv_avx.h:109, vs the scalar NHWC loop, convolution.c:28-89) differ from each other
