@@ -110,7 +110,7 @@ def test_dilated_conv_int8_bit_exact(case, mode, b200, oracle, ref_noavx, rng):
         ref_band(got, ref_noavx.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in))
 
 
-@pytest.mark.parametrize("case", [(1, 32, 9, 9, 24, 3, 1, 1, 3), (2, 16, 10, 11, 48, 1, 1, 0, 2), (1, 24, 8, 8, 120, 3, 1, 1, 3)],
+@pytest.mark.parametrize("case", [(1, 48, 9, 9, 24, 3, 1, 1, 3), (2, 16, 10, 11, 48, 1, 1, 0, 2), (1, 24, 8, 8, 120, 3, 1, 1, 3)],
                          ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d" % c)
 def test_group_conv_fp16_clips_tiles_at_the_group_window(case, b200, oracle, rng):
     """fp16 group conv whose outputs per group (8, 24, 40) are narrower than the GEMM's n-tile: every group's tile
