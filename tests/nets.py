@@ -191,7 +191,7 @@ class NetBuilder:
         return rng.standard_normal(self.in_shape).astype(np.float16)
 
 
-def mobilenet_v1(dtype=DT_INT8, batch=1, res=224, width=1.0, classes=1000, seed=0) -> NetBuilder:
+def mobilenet_v1(dtype=DT_INT8, batch=1, res=224, width=1.0, classes=1000, seed=0, softmax=True) -> NetBuilder:
     nb = NetBuilder(dtype, batch, (3, res, res), seed)
     t = 0
     for spec in mobilenet_v1_convs(res, width, classes):
@@ -202,7 +202,7 @@ def mobilenet_v1(dtype=DT_INT8, batch=1, res=224, width=1.0, classes=1000, seed=
                 t = nb.relu(t)
         elif spec[0] == "gap":
             t = nb.gap(t)
-        else:
+        elif softmax:
             t = nb.softmax(t)
     return nb
 
@@ -236,7 +236,7 @@ def resnet50(dtype=DT_INT8, batch=1, res=224, width=1.0, classes=1000, seed=0) -
     return nb
 
 
-def oracle_forward(nb: NetBuilder, x: np.ndarray) -> np.ndarray:
+def oracle_forward(nb: NetBuilder, x: np.ndarray, all_values: bool = False):
     """Whole-network result by chaining the oracle's per-op restatements (int8: the exact
     contract, so the product must match it bit for bit; fp16: f32 math rounded to f16 per layer)."""
     from shl import H_AVGPOOL, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_RELU6, H_RESHAPE, ACT_RELU, ACT_RELU6
@@ -307,4 +307,4 @@ def oracle_forward(nb: NetBuilder, x: np.ndarray) -> np.ndarray:
             raise NotImplementedError(l.kind)
         vals.append(np.ascontiguousarray(y))
         qs.append((l.s_out, l.zp_out))
-    return vals[-1]
+    return vals if all_values else vals[-1]  # vals[i] = tensor i (0 = the input, i = output of layer i - 1)

@@ -3,7 +3,7 @@ libshl_b200.so (registry -> b200_opt -> C-ABI shim -> sm_100a kernels) and is co
 oracle on the same seeded inputs.
 
 Bar: int8 results are BIT-EXACT against oracle/oracle_int.c (the arithmetic contract in
-include/b200nn.h) and within the reference's own f32-noise band (|d| <= 1 on <= 2e-4 of outputs,
+include/b200nn.h) and within the reference's own f32-noise band (|d| <= 1 on <= 1e-4 of outputs,
 see tests/test_oracle.py) against the unmodified reference library; fp16 is within 1e-3 relative
 (|d| / max(|want|, 1), the north-star tolerance) of f32-accumulated math.
 """
@@ -29,7 +29,10 @@ def f16_close(got, want, tol=F16_TOL):
 
 def ref_band(got, want):
     d = np.abs(got.astype(np.int32) - want.astype(np.int32))
-    assert d.max() <= 1 and np.count_nonzero(d) <= max(2e-4 * d.size, 2), (d.max(), np.count_nonzero(d), d.size)
+    # measured (tests/test_oracle.py prints it): the reference's f32 accumulation flips 2-6e-5 of the outputs by one
+    # LSB against exact integer accumulation; the gate is 1e-4 (at least 2 outputs on small tensors)
+    rate = np.count_nonzero(d) / d.size
+    assert d.max() <= 1 and np.count_nonzero(d) <= max(1e-4 * d.size, 2), (d.max(), np.count_nonzero(d), d.size, rate)
 
 
 CONV_CASES = [
@@ -529,14 +532,70 @@ def test_prefetched_inputs_give_the_same_bytes(first_op, b200, rng):
 
 
 def test_mobilenet_v1_fp16_graph(b200):
-    """BASELINE.json configs[2] shapes (c906_mobilenetv1_f16.c), fp16, at a size the oracle finishes"""
-    nb = nets.mobilenet_v1(DT_F16, batch=2, res=96, width=0.5, classes=200)
+    """BASELINE.json configs[2] shapes (c906_mobilenetv1_f16.c), fp16, at a size the oracle finishes: the class
+    scores BEFORE the softmax (probabilities of ~5e-3 hide everything behind an absolute tolerance), then the
+    probabilities.  28 layers each rounded to fp16 (the oracle chain rounds per layer too, but sums in another
+    order) accumulate, so the end-to-end bound on the scores is 4e-3; every layer on its own is held to the
+    north-star 1e-3 in test_mobilenet_v1_fp16_full_size_every_layer."""
+    nb = nets.mobilenet_v1(DT_F16, batch=2, res=96, width=0.5, classes=200, softmax=False)
     x = nb.input_batch()
     got = b200.run(DT_F16, nb.in_shape, nb.layers, x, run_mode=RM_GRAPH, api=API_C906)
     want = nets.oracle_forward(nb, x)
-    # softmax probabilities: absolute tolerance scaled like the relative one
-    assert np.max(np.abs(got.astype(np.float32) - want.astype(np.float32))) < 2e-3
+    f16_close(got, want, 4e-3)
+    assert float(np.abs(want.astype(np.float32)).max()) > 0.5, "degenerate scores"
+    nb = nets.mobilenet_v1(DT_F16, batch=2, res=96, width=0.5, classes=200)
+    got = b200.run(DT_F16, nb.in_shape, nb.layers, x, run_mode=RM_GRAPH, api=API_C906)
+    want = nets.oracle_forward(nb, x)
+    assert np.max(np.abs(got.astype(np.float32) - want.astype(np.float32))) < 1e-3
     assert abs(float(got.astype(np.float32).sum()) - 2.0) < 2e-2
+
+
+def test_mobilenet_v1_fp16_full_size_every_layer(b200):
+    """BASELINE.json configs[2] at its true layer shapes (224 x 224, width 1): every layer of the graph is run
+    on the device from the ORACLE's input for that layer and held to 1e-3 relative against f32 math -- the
+    north-star tolerance, per operator, at full size"""
+    nb = nets.mobilenet_v1(DT_F16, batch=1, softmax=False)
+    x = nb.input_batch()
+    vals = nets.oracle_forward(nb, x, all_values=True)
+    worst = 0.0
+    for i, l in enumerate(nb.layers):
+        a = vals[l.in0 if l.in0 >= 0 else i]
+        lone = Layer(**{**l.__dict__, "in0": -1})
+        got = b200.run(DT_F16, a.shape, [lone], a)
+        g, w = got.astype(np.float32), vals[i + 1].astype(np.float32)
+        err = float((np.abs(g - w) / np.maximum(np.abs(w), 1.0)).max())
+        worst = max(worst, err)
+        assert err <= F16_TOL, f"layer {i} (kind {l.kind}, out {l.out_shape}): max relative error {err:.3e}"
+    print(f"fp16 MobileNetV1 full size: worst per-layer relative error {worst:.2e}")
+
+
+def test_mobilenet_v1_fp16_batch_256_properties(b200):
+    """BASELINE.json configs[2] at its batch: every image of the batch equals the same image run alone (bytes),
+    replay is idempotent, and one image's class scores are within the end-to-end bound of the oracle chain"""
+    batch = 256
+    nb = nets.mobilenet_v1(DT_F16, batch=batch, softmax=False)
+    x = nb.input_batch()
+    x[9] = x[130]
+    with b200.create(DT_F16, nb.in_shape, nb.layers, run_mode=RM_GRAPH) as net:
+        y = net(x)
+        assert np.array_equal(y.view(np.uint16), net(x).view(np.uint16))
+    assert np.array_equal(y[9].view(np.uint16), y[130].view(np.uint16))
+    nb1 = nets.mobilenet_v1(DT_F16, batch=1, softmax=False)
+    with b200.create(DT_F16, nb1.in_shape, nb1.layers, run_mode=RM_GRAPH) as net1:
+        for i in (0, 9, 255):
+            assert np.array_equal(net1(x[i:i + 1])[0].view(np.uint16), y[i].view(np.uint16)), f"image {i}: batched != alone"
+    f16_close(y[3:4], nets.oracle_forward(nb1, x[3:4]), 4e-3)
+
+
+def test_resnet50_int8_full_size_bit_exact(b200):
+    """BASELINE.json configs[4] at its true layer shapes (224 x 224, width 1, 1000 classes), batch 2: all 16
+    bottlenecks, every 3x3 / strided / residual shape, bit-exact against the oracle chain"""
+    nb = nets.resnet50(DT_INT8, batch=2)
+    x = nb.input_batch()
+    got = b200.run(DT_INT8, nb.in_shape, nb.layers, x, s_in=nb.s_in, zp_in=nb.zp_in, run_mode=RM_GRAPH)
+    want = nets.oracle_forward(nb, x)
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
+    assert len(np.unique(got)) > 10, "degenerate output"
 
 
 def test_resnet50_int8_narrow_bit_exact(b200):

@@ -22,7 +22,7 @@ from shl import (ACT_NONE, ACT_RELU, ACT_RELU6, DT_F16, DT_F32, DT_INT8, H_ADD, 
                  H_CONV_RELU6, H_DWCONV, H_FC, H_GAP, H_MAXPOOL, H_RELU, H_RELU6, H_SOFTMAX, RM_GRAPH, Layer,
                  conv_out_hw, synth_conv_i8)
 
-TIE_RATE = 2e-4
+TIE_RATE = 1e-4  # measured 2-6e-5 (printed below); BASELINE.md gated 1e-5 on a single 401 408-output probe
 
 
 def close_int8(got, want, what):
@@ -30,6 +30,7 @@ def close_int8(got, want, what):
     assert d.max() <= 1, f"{what}: max |d| = {d.max()}"
     rate = np.count_nonzero(d) / d.size
     assert rate <= max(TIE_RATE, 2.0 / d.size), f"{what}: {np.count_nonzero(d)}/{d.size} outputs differ"
+    print(f"[tie rate] {what}: {np.count_nonzero(d)}/{d.size} = {rate:.2e}")
     return rate
 
 
