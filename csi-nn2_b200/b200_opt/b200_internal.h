@@ -83,6 +83,12 @@ typedef struct b200_op {
     void *d_w2;  /* second packing of the same weights (int8 3x3 depthwise: ky-major dp4a words) */
     float *d_mult, *d_badd;
     int32_t *d_ibias;
+    /* implicit-GEMM convolution (csrc/gemm_tc.cu IGEMM): border classes of the output positions and the
+     * accumulator seeds per (class, output channel); ig_ncls == 0: the op takes the explicit im2col path */
+    int ig_ncls;
+    int32_t *d_ig_seeds;
+    uint8_t *d_ig_clsmap;
+    int ig_h, ig_w, ig_oh, ig_ow; /* the geometry the tables were built for */
     int32_t *d_wzp; /* per-channel weight zero points when any is non-zero (asymmetric weights), else NULL */
     int8_t *d_lut; /* post table or the ACT table */
     int zp_in, zp_out, act, q6;
@@ -135,6 +141,7 @@ void b200_free_dequant(struct csinn_tensor *t);
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
 void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);
 void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int cp);
+int b200_make_igemm_tables(b200_op *op, const struct csinn_tensor *kernel, int h, int w, int oh, int ow);
 void *b200_pack_fc_weights(b200_op *op, const struct csinn_tensor *weights, size_t *bytes);
 
 /* graph.c */

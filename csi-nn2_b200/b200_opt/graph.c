@@ -266,6 +266,10 @@ static size_t weight_bound(struct shl_ref_graph *graph)
             if (!ct || !ct->is_const) continue;
             size_t e = csinn_tensor_size(ct);
             total += e * 8 + (size_t)(ct->dim_count ? ct->dim[0] : 1) * 64 * 4 + 8192;
+            if (ct->dim_count == 4) { /* implicit-GEMM tables: <= 64 seed rows (counted above) + the class map of the output */
+                struct csinn_tensor *ot = l->out[0]->data;
+                if (ot && ot->dim_count == 4) total += (size_t)ot->dim[2] * ot->dim[3] + 512;
+            }
         }
         total += 4096 + (size_t)(l->in_num + l->out_num) * 256; /* concat / split: one requant table per input / output */
     }

@@ -335,8 +335,17 @@ static int conv_stem_on_tc(const b200_op *op, const b200_dt *in0)
            !getenv("SHL_B200_NO_STEM_TC");
 }
 
+/* k > 1 convolutions whose channel count is a multiple of 64 gather their A operand by TMA im2col loads
+ * (csrc/gemm_tc.cu, IGEMM) instead of writing an im2col matrix to scratch */
+static int conv_uses_igemm(const b200_op *op, const b200_dt *in0)
+{
+    return op->kind == B200_OPK_CONV && op->ig_ncls >= 1 && !op->direct && !op->d_wzp && !in0->is_nchw &&
+           in0->h == op->ig_h && in0->w == op->ig_w && in0->c == op->cin && !getenv("SHL_B200_NO_IGEMM");
+}
+
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
 {
+    if (conv_uses_igemm(op, in0)) return "b200_conv_igemm_tcgen05";
     if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0))
         return (op->dtype == B200_I8 && conv_stem_on_tc(op, in0)) ? "b200_conv2d_stem_tcgen05" : "b200_conv2d_direct";
     return op->kname;
@@ -346,7 +355,7 @@ const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
 static size_t im2col_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
     if (op->kind != B200_OPK_CONV || (op->direct && !in0->is_nchw)) return 0;
-    if (conv_goes_direct(op, in0)) return 0;
+    if (conv_goes_direct(op, in0) || conv_uses_igemm(op, in0)) return 0;
     return ((size_t)out->n * out->h * out->w * op->ldk * op->eb + 255) & ~(size_t)255;
 }
 
@@ -375,6 +384,18 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
             DEV_CHECK(b200_conv2d_direct_f16(&c, stream));
         else
             DEV_CHECK(b200_conv2d_direct(&c, stream));
+        return CSINN_TRUE;
+    }
+    if (conv_uses_igemm(op, in)) {
+        b200_conv_igemm_desc c;
+        memset(&c, 0, sizeof(c));
+        c.n = in->n, c.h = in->h, c.w = in->w, c.c = in->c, c.cp_in = in->cp;
+        c.o = op->o, c.oh = out->h, c.ow = out->w, c.kh = op->kh, c.kw = op->kw;
+        c.stride_h = op->sh, c.stride_w = op->sw, c.pad_top = op->pt, c.pad_left = op->pl, c.dil_h = op->dh, c.dil_w = op->dw;
+        c.in = in->d, c.wt = op->d_w, c.ldw = op->ldk, c.out = out->d, c.ldo = out->cp;
+        fill_epilogue(op, &c.ep);
+        c.ncls = op->ig_ncls, c.seeds = op->d_ig_seeds, c.cls_map = op->d_ig_clsmap;
+        DEV_CHECK(b200_conv_igemm(&c, stream));
         return CSINN_TRUE;
     }
     b200_gemm_desc g;
@@ -836,6 +857,11 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
         if (op->direct) op->kname = "b200_gemm_tcgen05";
         rc = b200_make_requant(op, input, kernel, bias, output, op->kdim, params->conv_extra.fuse_zp2bias, O);
         if (rc == CSINN_TRUE && !(op->d_w = b200_pack_conv_weights(op, kernel, &wbytes))) rc = CSINN_FALSE;
+        /* k > 1, int8, group 1, channels a multiple of 64, symmetric weights: the implicit-GEMM kernel
+         * (the channel pitch of the input equals its channel count then, so K = taps x channels exactly) */
+        if (rc == CSINN_TRUE && !op->direct && op->dtype == B200_I8 && group == 1 && C % 64 == 0 && !op->d_wzp &&
+            kh * kw > 1 && output->dim_count == 4)
+            rc = b200_make_igemm_tables(op, kernel, input->dim[2], input->dim[3], output->dim[2], output->dim[3]);
     }
     if (rc != CSINN_TRUE) {
         free(op);

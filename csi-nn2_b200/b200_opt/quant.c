@@ -220,6 +220,97 @@ done:
     return rc;
 }
 
+/* Tables of the implicit-GEMM convolution (include/b200nn.h, b200_conv_igemm_desc): TMA zero-fills the taps that
+ * fall outside the image, the contract wants zp_in there.  Output row oy has the kernel rows {ky : oy*sh - pt +
+ * ky*dh outside [0, h)} in the padding, output column ox the kernel columns likewise; a position's class is the
+ * pair of those two sets, and its accumulator seed -zp_in * (sum of the weights of the taps INSIDE the image). */
+int b200_make_igemm_tables(b200_op *op, const struct csinn_tensor *kernel, int h, int w, int oh, int ow)
+{
+    op->ig_ncls = 0;
+    if (op->dtype != B200_I8 || op->group != 1 || op->kh > 16 || op->kw > 16 || (size_t)oh * ow > (1u << 20)) return CSINN_TRUE;
+    const int O = op->o, C = op->cin, kh = op->kh, kw = op->kw;
+    uint32_t rmasks[64], cmasks[64];
+    int nr = 0, nc = 0;
+    uint8_t *rcls = malloc((size_t)oh), *ccls = malloc((size_t)ow);
+    uint8_t *map = malloc((size_t)oh * ow);
+    int rc = CSINN_TRUE;
+    if (!rcls || !ccls || !map) goto fail;
+    for (int oy = 0; oy < oh; oy++) {
+        uint32_t m = 0;
+        for (int ky = 0; ky < kh; ky++) {
+            const int iy = oy * op->sh - op->pt + ky * op->dh;
+            if (iy < 0 || iy >= h) m |= 1u << ky;
+        }
+        int id = -1;
+        for (int i = 0; i < nr; i++)
+            if (rmasks[i] == m) id = i;
+        if (id < 0) {
+            if (nr == 64) goto toomany;
+            rmasks[id = nr++] = m;
+        }
+        rcls[oy] = (uint8_t)id;
+    }
+    for (int ox = 0; ox < ow; ox++) {
+        uint32_t m = 0;
+        for (int kx = 0; kx < kw; kx++) {
+            const int ix = ox * op->sw - op->pl + kx * op->dw;
+            if (ix < 0 || ix >= w) m |= 1u << kx;
+        }
+        int id = -1;
+        for (int i = 0; i < nc; i++)
+            if (cmasks[i] == m) id = i;
+        if (id < 0) {
+            if (nc == 64) goto toomany;
+            cmasks[id = nc++] = m;
+        }
+        ccls[ox] = (uint8_t)id;
+    }
+    if (nr * nc > 64) goto toomany;
+    {
+        const int ncls = nr * nc;
+        /* interior first would be nicer to read, but any numbering works: class = row class * nc + column class */
+        for (int oy = 0; oy < oh; oy++)
+            for (int ox = 0; ox < ow; ox++) map[(size_t)oy * ow + ox] = (uint8_t)(rcls[oy] * nc + ccls[ox]);
+        int32_t *seeds = calloc((size_t)ncls * O, sizeof(int32_t));
+        if (!seeds) goto fail;
+        const int8_t *wt = kernel->data; /* OIHW */
+        for (int o = 0; o < O; o++) {
+            int64_t tap_sum[256];
+            for (int t = 0; t < kh * kw; t++) tap_sum[t] = 0;
+            for (int ci = 0; ci < C; ci++)
+                for (int t = 0; t < kh * kw; t++) tap_sum[t] += wt[((size_t)o * C + ci) * kh * kw + t];
+            for (int r = 0; r < nr; r++)
+                for (int c = 0; c < nc; c++) {
+                    int64_t inside = 0;
+                    for (int ky = 0; ky < kh; ky++)
+                        for (int kx = 0; kx < kw; kx++)
+                            if (!((rmasks[r] >> ky) & 1) && !((cmasks[c] >> kx) & 1)) inside += tap_sum[ky * kw + kx];
+                    seeds[(size_t)(r * nc + c) * O + o] = (int32_t)(-(int64_t)op->zp_in * inside);
+                }
+        }
+        op->ig_ncls = (ncls > 1 && op->zp_in != 0) ? ncls : 1;
+        op->ig_h = h, op->ig_w = w, op->ig_oh = oh, op->ig_ow = ow;
+        if (op->ig_ncls > 1) {
+            op->d_ig_seeds = b200_warena_put(op->ctx, seeds, (size_t)ncls * O * sizeof(int32_t));
+            op->d_ig_clsmap = b200_warena_put(op->ctx, map, (size_t)oh * ow);
+            if (!op->d_ig_seeds || !op->d_ig_clsmap) rc = CSINN_FALSE;
+        }
+        free(seeds);
+    }
+    goto done;
+toomany:
+    op->ig_ncls = 0; /* more than 64 border classes (huge dilated kernels): the explicit im2col path handles it */
+    goto done;
+fail:
+    b200_fail("out of host memory building the implicit-GEMM tables");
+    rc = CSINN_FALSE;
+done:
+    free(rcls);
+    free(ccls);
+    free(map);
+    return rc;
+}
+
 /* OIHW -> [O][kh][kw][Cg] rows of pitch ldk: k = (ky, kx, ci), ci fastest = im2col's order */
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes)
 {

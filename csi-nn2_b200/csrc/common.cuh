@@ -85,6 +85,8 @@ int encode_tmap_nhwc_u8_sw128(CUtensorMap *map, const void *base, int n, int h, 
                               int box_n);
 int encode_tmap_nhwc_u8_ex(CUtensorMap *map, const void *base, int n, int h, int w, int cp, int box_c, int box_w,
                            int box_h, int box_n, int swizzle_bytes);
+int encode_tmap_im2col_u8(CUtensorMap *map, const void *base, int n, int h, int w, int c, int cp, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int stride_w, int stride_h, int chans, int pixels, int swizzle_bytes);
 int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
                    uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                    int swizzle_bytes = 128);
@@ -212,6 +214,17 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// im2col-mode load (tensor map from encode_tmap_im2col_u8): `pixels` output pixels starting at base pixel
+// (w, h, n) x the map's channel count starting at c, of the filter tap at offsets (woff, hoff)
+__device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c, int w, int h,
+                                                   int n, uint16_t woff, uint16_t hoff)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(woff), "h"(hoff)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0,
@@ -363,6 +376,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
     d |= static_cast<uint64_t>(1024 >> 4) << 32;             // SBO = 1024 B, bits [32,46)
     d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (sm_100)
     d |= static_cast<uint64_t>(2) << 61;                     // layout: SWIZZLE_128B
+    return d;
+}
+
+// the same for SWIZZLE_64B, rows of 64 bytes: 8-row x 64-byte atoms stacked every 512 bytes
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;              // SBO = 512 B
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;                     // layout: SWIZZLE_64B
     return d;
 }
 

@@ -64,6 +64,16 @@ struct GemmArgs {
     EpiScalars ep;
     const int32_t *wzp;     // asymmetric weights: per-column weight zero points (else null)
     const int32_t *rowsum;  // ... and the row sums b200_rowsum_i8 computed
+    // implicit-GEMM convolution (IGEMM): the A operand is gathered by TMA im2col loads, one filter tap x one channel
+    // slab per K block, straight from the pixel-major activation tensor
+    int kb_bytes;           // bytes of K per block: 128, or 64 (64-channel layers: SWIZZLE_64B operand tiles)
+    int slabs;              // channel slabs per tap = C / kb_bytes
+    int kw, dil_w, dil_h;   // tap index -> (ky, kx) -> load offsets
+    int ow, ohw;            // output width, output pixels per image (row index -> base pixel)
+    int stride_w, stride_h, lower_w, lower_h;
+    int ncls;               // border classes (1: no zero-point padding correction)
+    const int32_t *seeds;   // device [ncls][n]: ibias + zp_in * (weights of the taps the class has in the padding)
+    const uint8_t *cls_map; // device [ohw]: border class of an output pixel position
 };
 
 struct __align__(16) EpiParams {
@@ -81,7 +91,13 @@ __device__ __forceinline__ void epi_bar_sync()
 
 // ASYM: weights with zero points -- every accumulator is corrected by - w_zp[column] * rowsum[row] before the
 // requantisation (contract in include/b200nn.h); generic epilogue, no magic-number shortcut
-template <int DT, int MODE, bool MAGIC, bool ASYM = false>
+// IGEMM: implicit-GEMM convolution (int8): tma_a is an im2col-mode tensor map over the activation tensor and the
+// producer issues one im2col load per (128 output pixels, filter tap, channel slab) -- no im2col matrix in HBM.
+// TMA zero-fills the taps that fall into the padding where the contract wants zp_in; the difference,
+// zp_in * (sum of those taps' weights), depends on the output pixel's border class and the output channel and
+// enters through the accumulator seeds, which the epilogue threads (one TMEM lane = one output pixel each)
+// pick per row from a small table -- the depthwise kernels' fold, per row instead of per tile.
+template <int DT, int MODE, bool MAGIC, bool ASYM = false, bool IGEMM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_o, const GemmArgs args)
@@ -91,8 +107,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // access below compiles to LDS/STS rather than generic LD/ST
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int stages = args.stages;
-    const uint32_t a_stage_bytes = kBM * kBKBytes;
-    const uint32_t b_stage_bytes = args.bn * kBKBytes;
+    const uint32_t kbb = IGEMM ? static_cast<uint32_t>(args.kb_bytes) : static_cast<uint32_t>(kBKBytes);  // K bytes per block
+    const uint32_t a_stage_bytes = kBM * kbb;
+    const uint32_t b_stage_bytes = args.bn * kbb;
     // resident B: k_blocks slabs after the A ring; otherwise one B slab per ring slot
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + stages * a_stage_bytes;
@@ -107,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t *stg_full = b_bar + 1;    // epilogue warps -> store warp: staging buffer written
     uint64_t *stg_empty = stg_full + 2;  // store warp -> epilogue warps: the TMA store has read it
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(stg_empty + 2);
+    int32_t *seed_tab = reinterpret_cast<int32_t *>(tmem_ptr + 2);  // 16-byte aligned: 33 barriers + 8 bytes after the 16-byte aligned EpiParams
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -152,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_after();
     if (tr && threadIdx.x == 0) tr[1] = clock64();
     const uint32_t tmem_base = *tmem_ptr;
-    const int k_elems = DT == B200_I8 ? kBKBytes : kBKBytes / 2;
+    const int k_elems = DT == B200_I8 ? static_cast<int>(kbb) : kBKBytes / 2;
     // schedule: this CTA's n-tile is fixed; gridDim.x is a multiple of num_n_tiles (host)
     const int n0 = (blockIdx.x % args.num_n_tiles) * args.bn;
     const int ms0 = blockIdx.x / args.num_n_tiles;
@@ -185,7 +203,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         // the activation box is 64 rows: both halves from this CTA, or (pair) this CTA's
                         // half to both CTAs -- the peer sends the other half to both
                         uint8_t *a_dst = smem_a + stage * a_stage_bytes;
-                        if (args.cluster > 1) {
+                        if (IGEMM) {
+                            // K block kb = filter tap kb / slabs, channel slab kb % slabs; the 128 rows are the output
+                            // pixels m0 .. m0 + 127 in (image, oy, ox) order, the TMA unit walks them itself
+                            const int tap = kb / args.slabs, slab = kb - tap * args.slabs;
+                            const int ky = tap / args.kw, kx = tap - ky * args.kw;
+                            const int img = m0 / args.ohw, rem = m0 - img * args.ohw;
+                            const int oy = rem / args.ow, ox = rem - oy * args.ow;
+                            tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb),
+                                               ox * args.stride_w + args.lower_w, oy * args.stride_h + args.lower_h, img,
+                                               static_cast<uint16_t>(kx * args.dil_w), static_cast<uint16_t>(ky * args.dil_h));
+                        } else if (args.cluster > 1) {
                             const int half = static_cast<int>(cta_rank);
                             tma_load_2d_multicast(a_dst + half * (a_stage_bytes / 2), &tma_a, &full_bar[stage],
                                                   kb * k_elems, m0 + half * (kBM / 2), 3);
@@ -223,11 +251,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int kb = 0; kb < args.k_blocks; kb++) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes));
-                        const uint64_t bdesc = umma_desc_sw128(
-                            smem_u32(smem_b + (args.b_resident ? kb : stage) * b_stage_bytes));
+                        const bool sw64 = IGEMM && kbb == 64;
+                        const uint32_t a_addr = smem_u32(smem_a + stage * a_stage_bytes);
+                        const uint32_t b_addr = smem_u32(smem_b + (args.b_resident ? kb : stage) * b_stage_bytes);
+                        const uint64_t adesc = sw64 ? umma_desc_sw64(a_addr) : umma_desc_sw128(a_addr);
+                        const uint64_t bdesc = sw64 ? umma_desc_sw64(b_addr) : umma_desc_sw128(b_addr);
 #pragma unroll
                         for (int k = 0; k < kBKBytes / 32; k++) {
+                            if (IGEMM && k * 32 >= static_cast<int>(kbb)) break;
                             // advance 32 bytes of K inside the swizzle atom: +2 in 16-byte units
                             if (DT == B200_I8)
                                 tc_mma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, args.idesc, 1u);
@@ -316,12 +347,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             loaded_sub = sub;
         };
+        // IGEMM with zero-point padding: seeds depend on the border class of the row's output pixel
+        const bool by_class = IGEMM && args.ncls > 1;
+        if (by_class) {
+            for (int i = et; i < args.ncls * bn; i += kEpiWarps * 32) {
+                const int cls = i / bn, col = n0 + (i - cls * bn);
+                seed_tab[i] = col < args.n ? args.seeds[cls * args.n + col] : 0;
+            }
+            epi_bar_sync();
+        }
+        // border class of this thread's row in row block g of super tile ms_x (0 past the end of the tensor)
+        auto row_class = [&](int ms_x, int g) -> int {
+            const int row = (ms_x * G + g) * kBM + quad * 32 + lane;
+            if (ms_x >= args.num_m_super || row >= args.m) return 0;
+            return static_cast<int>(__ldg(args.cls_map + row % args.ohw));
+        };
+        auto class_seeds = [&](int cls, int sub, uint32_t (&sd)[16]) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+                const int4 i4 = *reinterpret_cast<const int4 *>(&seed_tab[cls * bn + sub * 16 + j4 * 4]);
+                sd[j4 * 4 + 0] = i4.x, sd[j4 * 4 + 1] = i4.y, sd[j4 * 4 + 2] = i4.z, sd[j4 * 4 + 3] = i4.w;
+            }
+        };
         // seed both accumulator stages: the MMAs always accumulate, which takes the "+ ibias" (and
         // the magic-number bias of the int -> float conversion) out of the per-output instruction count
-        for (int sub = part; sub < nsub; sub += 4) {
-            load_sub(sub);
+        if (by_class) {
             for (int a2 = 0; a2 < 2; a2++)
-                for (int g = 0; g < G; g++) tmem_st_32x16(tquad + a2 * kAccStride + g * bn + sub * 16, ib);
+                for (int g = 0; g < G; g++) {
+                    const int cls = row_class(ms0 + a2 * ms_step, g);
+                    for (int sub = part; sub < nsub; sub += 4) {
+                        uint32_t sd[16];
+                        class_seeds(cls, sub, sd);
+                        tmem_st_32x16(tquad + a2 * kAccStride + g * bn + sub * 16, sd);
+                    }
+                }
+        } else {
+            for (int sub = part; sub < nsub; sub += 4) {
+                load_sub(sub);
+                for (int a2 = 0; a2 < 2; a2++)
+                    for (int g = 0; g < G; g++) tmem_st_32x16(tquad + a2 * kAccStride + g * bn + sub * 16, ib);
+            }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -342,6 +407,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tquad + acc * kAccStride;
+            int cls_next[4] = {0, 0, 0, 0};  // classes of this thread's rows in the tile that uses this TMEM stage next
+            if (by_class) {
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    if (g < G) cls_next[g] = row_class(ms + 2 * ms_step, g);
+            }
             for (int sub = part; sub < nsub; sub += 4) {
                 // 16 columns x (mult, badd, ibias) -> 48 registers, reused for every row block of
                 // the super tile (and for the CTA's whole life when the n-tile has <= 64 columns)
@@ -353,7 +424,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint32_t r[16];
                     tmem_ld_32x16(taddr + g * bn + sub * 16, r);
                     tmem_ld_wait();
-                    tmem_st_32x16(taddr + g * bn + sub * 16, ib);  // re-seed for the tile after next
+                    if (by_class) {  // re-seed for the tile after next, by the border class its row will have
+                        uint32_t sd[16];
+                        class_seeds(g == 0 ? cls_next[0] : (g == 1 ? cls_next[1] : (g == 2 ? cls_next[2] : cls_next[3])), sub, sd);
+                        tmem_st_32x16(taddr + g * bn + sub * 16, sd);
+                    } else {
+                        tmem_st_32x16(taddr + g * bn + sub * 16, ib);  // re-seed for the tile after next
+                    }
                     if (ASYM) {
                         const int row = (mt0 + g) * kBM + quad * 32 + lane;
                         const int rs = row < args.m ? __ldg(args.rowsum + row) : 0;
@@ -491,11 +568,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident, size_t staging)
+static size_t gemm_smem_bytes(int stages, int bn, int k_blocks, bool resident, size_t staging, int kb_bytes = kBKBytes,
+                              size_t seed_bytes = 0)
 {
-    const size_t a = static_cast<size_t>(stages) * kBM * kBKBytes;
-    const size_t b = static_cast<size_t>(resident ? k_blocks : stages) * bn * kBKBytes;
-    return 1024 + a + b + 2 * staging + sizeof(EpiParams) + (2 * kMaxStages + 9) * sizeof(uint64_t) + 16;
+    const size_t a = static_cast<size_t>(stages) * kBM * kb_bytes;
+    const size_t b = static_cast<size_t>(resident ? k_blocks : stages) * bn * kb_bytes;
+    return 1024 + a + b + 2 * staging + sizeof(EpiParams) + (2 * kMaxStages + 9) * sizeof(uint64_t) + 16 + seed_bytes;
 }
 
 static int pick_bn(int n, int dtype)
@@ -516,13 +594,13 @@ static int pick_bn(int n, int dtype)
     return ((n16 + tiles - 1) / tiles + 31) / 32 * 32;
 }
 
-template <int DT, int MODE, bool MAGIC, bool ASYM = false>
+template <int DT, int MODE, bool MAGIC, bool ASYM = false, bool IGEMM = false>
 static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &ta,
                           const CUtensorMap &tb, const CUtensorMap &to, const GemmArgs &args, int dev)
 {
     static bool attr_set[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<DT, MODE, MAGIC, ASYM>,
+        B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSmemLimit));
         attr_set[dev] = true;
@@ -548,7 +626,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
             at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
             cfg.attrs = at, cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<DT, MODE, MAGIC, ASYM>, &cfg) != cudaSuccess || n <= 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>, &cfg) != cudaSuccess || n <= 0) {
                 (void)cudaGetLastError();
                 n = -1;
             }
@@ -556,7 +634,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
         }
         if (dev < 0 || dev >= 64 || max_clusters[dev] * 2 < grid) la.cluster = 1;
     }
-    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM>, dim3(grid), dim3(kThreads), smem, stream,
+    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>, dim3(grid), dim3(kThreads), smem, stream,
                                           la.cluster, ta, tb, to, la));
     if (tracing && la.trace) {  // diagnostic only: synchronous, prints a few CTAs' timelines (cycles from CTA start)
         static long long host[256 * 64];
@@ -579,7 +657,7 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
 
 using namespace b200;
 
-extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
+static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, void *stream)
 {
     if (!d || !d->a || !d->w || !d->out) {
         set_error("b200_gemm: null descriptor field");
@@ -601,15 +679,18 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
                   d->m, d->n, d->k, d->lda, d->ldw, d->ldo);
         return B200_ERR_ARG;
     }
-    GemmArgs args;
+    GemmArgs args = {};
     args.m = d->m;
     args.n = d->n;
-    args.k_blocks = (d->k * eb + kBKBytes - 1) / kBKBytes;
+    // implicit GEMM: one K block = one filter tap x one channel slab of 128 (or, for 64-channel layers, 64) bytes
+    const int kb_bytes = ig ? (ig->c % 128 == 0 ? 128 : 64) : kBKBytes;
+    args.kb_bytes = kb_bytes;
+    args.k_blocks = (d->k * eb + kb_bytes - 1) / kb_bytes;
     args.bn = pick_bn(d->n, d->dtype);
     // prefer an n-tile whose weights stay resident in shared memory: halve a 256-wide tile when
     // that makes K * bn fit
-    if (d->dtype == B200_F16 && args.k_blocks * args.bn * kBKBytes > kResidentBBytes && args.bn > 128 &&
-        args.k_blocks * 128 * kBKBytes <= kResidentBBytes)
+    if (d->dtype == B200_F16 && args.k_blocks * args.bn * kb_bytes > kResidentBBytes && args.bn > 128 &&
+        args.k_blocks * 128 * kb_bytes <= kResidentBBytes)
         args.bn = 128;
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
     // few rows (classifier layers, small batches): narrower int8 n-tiles so that more SMs get a tile
@@ -634,8 +715,9 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
                                                : static_cast<size_t>(kEpiWarps) * 2048;
     args.stage_bytes = static_cast<uint32_t>(staging);
     // weights stay resident when they fit beside the staging and at least three A stages
-    args.b_resident = args.k_blocks * args.bn * kBKBytes <= kResidentBBytes &&
-                      gemm_smem_bytes(3, args.bn, args.k_blocks, true, staging) <= kSmemLimit &&
+    const size_t seed_bytes = (ig && ig->ncls > 1) ? static_cast<size_t>(ig->ncls) * args.bn * sizeof(int32_t) : 0;
+    args.b_resident = args.k_blocks * args.bn * kb_bytes <= kResidentBBytes &&
+                      gemm_smem_bytes(3, args.bn, args.k_blocks, true, staging, kb_bytes, seed_bytes) <= kSmemLimit &&
                       !getenv("SHL_B200_GEMM_NO_RESIDENT");
     args.trace = nullptr;
     args.ldo = d->ldo;
@@ -647,16 +729,36 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     // as many stages as fit: the ring also prefetches the next tiles' operands while the
     // epilogue drains, which is what keeps HBM busy on the short-K (memory-bound) layers
     int stages = kMaxStages;
-    while (stages > 2 && gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging) > kSmemLimit)
+    while (stages > 2 &&
+           gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging, kb_bytes, seed_bytes) > kSmemLimit)
         stages--;
     args.stages = stages;
-    const size_t smem = gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging);
+    const size_t smem = gemm_smem_bytes(stages, args.bn, args.k_blocks, args.b_resident, staging, kb_bytes, seed_bytes);
+    if (smem > kSmemLimit) {
+        set_error("b200_gemm: %zu bytes of shared memory needed (bn=%d, %d K blocks)", smem, args.bn, args.k_blocks);
+        return B200_ERR_UNSUPPORTED;
+    }
 
     alignas(64) CUtensorMap ta, tb, to;
-    const int box_k = kBKBytes / eb;
-    int rc = encode_tmap_2d(&ta, eb, d->a, d->k, d->m, static_cast<uint64_t>(d->lda) * eb, box_k, kBM / 2);
+    const int box_k = kb_bytes / eb;
+    int rc;
+    if (ig) {
+        // base pixels: ow x oh per image, the first at (-pad_left, -pad_top), stepping by the stride; the box's far
+        // corner is put exactly on the last base pixel so that the walk agrees with (oh, ow) whatever the far pads are
+        const int lower_w = -ig->pad_left, lower_h = -ig->pad_top;
+        const int upper_w = lower_w + (ig->ow - 1) * ig->stride_w - (ig->w - 1);
+        const int upper_h = lower_h + (ig->oh - 1) * ig->stride_h - (ig->h - 1);
+        rc = encode_tmap_im2col_u8(&ta, ig->in, ig->n, ig->h, ig->w, ig->c, ig->cp_in, lower_w, lower_h, upper_w, upper_h,
+                                   ig->stride_w, ig->stride_h, kb_bytes, kBM, kb_bytes);
+        args.slabs = ig->c / kb_bytes, args.kw = ig->kw, args.dil_w = ig->dil_w, args.dil_h = ig->dil_h;
+        args.ow = ig->ow, args.ohw = ig->oh * ig->ow;
+        args.stride_w = ig->stride_w, args.stride_h = ig->stride_h, args.lower_w = lower_w, args.lower_h = lower_h;
+        args.ncls = ig->ncls > 1 ? ig->ncls : 1, args.seeds = ig->seeds, args.cls_map = ig->cls_map;
+    } else {
+        rc = encode_tmap_2d(&ta, eb, d->a, d->k, d->m, static_cast<uint64_t>(d->lda) * eb, box_k, kBM / 2);
+    }
     if (rc) return rc;
-    rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn);
+    rc = encode_tmap_2d(&tb, eb, d->w, d->k, d->n, static_cast<uint64_t>(d->ldw) * eb, box_k, args.bn, kb_bytes);
     if (rc) return rc;
     // columns a tile may touch: the row pitch, or the caller's window (a group of a grouped convolution)
     const int out_cols = d->out_cols > 0 ? d->out_cols : d->ldo;
@@ -683,7 +785,7 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     // 14x14x512 -> 512 layers, batch 256): 25.2 us per layer paired against 23.9 us unpaired -- those
     // layers are not bound by L2 bandwidth (ncu: xbar -> L1 at 15 % of peak) -- so it is opt-in
     // (SHL_B200_GEMM_CLUSTER=1); parity-tested either way.
-    args.cluster = (args.num_n_tiles % 2 == 0 && grid % 2 == 0 && getenv("SHL_B200_GEMM_CLUSTER")) ? 2 : 1;
+    args.cluster = (!ig && args.num_n_tiles % 2 == 0 && grid % 2 == 0 && getenv("SHL_B200_GEMM_CLUSTER")) ? 2 : 1;
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t s = (cudaStream_t)stream;
@@ -697,6 +799,23 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
         // |acc + ibias| <= K * 2 * 128 * 127 < 2^22 lets the epilogue convert through the magic
         // constant (an FADD) instead of I2F
         const bool magic = d->k <= 128;
+        if (ig) {
+            int mode;
+            if (d->ep.post_lut)
+                mode = d->ep.act == B200_ACT_NONE ? EPI_LUT : EPI_GENERIC;
+            else
+                mode = d->ep.act == B200_ACT_NONE ? EPI_PLAIN : (d->ep.act == B200_ACT_RELU ? EPI_RELU : EPI_RELU6);
+            switch (mode) {
+                case EPI_PLAIN: rc = launch_variant<B200_I8, EPI_PLAIN, false, false, true>(grid, smem, s, ta, tb, to, args, dev); break;
+                case EPI_RELU: rc = launch_variant<B200_I8, EPI_RELU, false, false, true>(grid, smem, s, ta, tb, to, args, dev); break;
+                case EPI_RELU6: rc = launch_variant<B200_I8, EPI_RELU6, false, false, true>(grid, smem, s, ta, tb, to, args, dev); break;
+                case EPI_LUT: rc = launch_variant<B200_I8, EPI_LUT, false, false, true>(grid, smem, s, ta, tb, to, args, dev); break;
+                default: rc = launch_variant<B200_I8, EPI_GENERIC, false, false, true>(grid, smem, s, ta, tb, to, args, dev); break;
+            }
+            if (rc) return rc;
+            B200_LAUNCH_CHECK();
+            return B200_OK;
+        }
         if (d->w_zp) {
             rc = launch_variant<B200_I8, EPI_GENERIC, false, true>(grid, smem, s, ta, tb, to, args, dev);
             if (rc) return rc;
@@ -728,4 +847,36 @@ extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream)
     if (rc) return rc;
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+extern "C" int b200_gemm(const b200_gemm_desc *d, void *stream) { return gemm_run(d, nullptr, stream); }
+
+static bool igemm_shape_ok(const b200_conv_igemm_desc *c)
+{
+    if (!c || !c->in || !c->wt || !c->out || !c->ep.mult || !c->ep.badd) return false;
+    const int upper_w = -c->pad_left + (c->ow - 1) * c->stride_w - (c->w - 1);
+    const int upper_h = -c->pad_top + (c->oh - 1) * c->stride_h - (c->h - 1);
+    return c->n > 0 && c->c > 0 && c->c % 64 == 0 && c->cp_in >= c->c && c->cp_in % 16 == 0 && c->o > 0 && c->kh >= 1 &&
+           c->kw >= 1 && c->kh * c->kw > 1 && c->stride_w >= 1 && c->stride_w <= 8 && c->stride_h >= 1 && c->stride_h <= 8 &&
+           c->dil_w >= 1 && c->dil_h >= 1 && (c->kw - 1) * c->dil_w <= 255 && (c->kh - 1) * c->dil_h <= 255 &&
+           c->pad_left <= 128 && c->pad_top <= 128 && c->pad_left >= 0 && c->pad_top >= 0 && upper_w >= -128 && upper_w <= 127 &&
+           upper_h >= -128 && upper_h <= 127 && c->ldw >= c->kh * c->kw * c->c && c->ldw % 16 == 0 && c->ldo >= c->o &&
+           c->ldo % 16 == 0 && static_cast<long long>(c->n) * c->oh * c->ow < (1ll << 31) &&
+           (c->ncls <= 1 || (c->seeds && c->cls_map && c->ncls <= 64));
+}
+
+extern "C" int b200_conv_igemm_supported(const b200_conv_igemm_desc *c) { return igemm_shape_ok(c) ? 1 : 0; }
+
+extern "C" int b200_conv_igemm(const b200_conv_igemm_desc *c, void *stream)
+{
+    if (!igemm_shape_ok(c)) {
+        set_error("b200_conv_igemm: descriptor outside the implicit-GEMM kernel's domain (int8, channels a multiple of 64, k > 1)");
+        return B200_ERR_UNSUPPORTED;
+    }
+    b200_gemm_desc g = {};
+    g.dtype = B200_I8;
+    g.m = c->n * c->oh * c->ow, g.n = c->o, g.k = c->kh * c->kw * c->c;
+    g.a = c->in, g.lda = (g.k + 15) / 16 * 16;  // unused by the im2col producer; kept valid for the argument checks
+    g.w = c->wt, g.ldw = c->ldw, g.out = c->out, g.ldo = c->ldo, g.ep = c->ep;
+    return gemm_run(&g, c, stream);
 }

@@ -157,6 +157,49 @@ int encode_tmap_nhwc_u8_sw128(CUtensorMap *map, const void *base, int n, int h, 
     return B200_OK;
 }
 
+// im2col-mode tensor map over a pixel-major uint8 tensor [n][h][w][cp] (cuTensorMapEncodeIm2col): one load
+// delivers `pixels` consecutive OUTPUT pixels of a convolution (walking W, then H, then N with the
+// convolution's stride, the base pixel box shrunk by the corners so that exactly ow x oh base pixels exist per
+// image) x `chans` channels of ONE filter tap, the tap given per load as (w, h) offsets; taps that fall outside
+// the image are zero-filled.  lower = -pad, upper = pad_far - (k - 1) * dilation.
+typedef CUresult (*encode_im2col_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+int encode_tmap_im2col_u8(CUtensorMap *map, const void *base, int n, int h, int w, int c, int cp, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int stride_w, int stride_h, int chans, int pixels, int swizzle_bytes)
+{
+    static encode_im2col_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeIm2col entry point unavailable (%s)", cudaGetErrorString(e));
+            return B200_ERR_CUDA;
+        }
+        fn = reinterpret_cast<encode_im2col_fn>(p);
+    }
+    cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t gstride[3] = {(cuuint64_t)cp, (cuuint64_t)cp * w, (cuuint64_t)cp * w * h};
+    int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), gdim, gstride, lower, upper,
+                    (cuuint32_t)chans, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                    : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                    : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                          : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed: CUresult %d (n %d h %d w %d c %d cp %d corners %d %d %d %d stride %d %d "
+                  "chans %d pixels %d)", (int)r, n, h, w, c, cp, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, chans,
+                  pixels);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
 int encode_tmap_2d(CUtensorMap *map, int elem_bytes, const void *base, uint64_t inner,
                    uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                    int swizzle_bytes)

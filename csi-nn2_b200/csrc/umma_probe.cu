@@ -172,3 +172,46 @@ extern "C" int b200_test_umma_rate3(int m, int n, int f16, int nacc, int reps, i
     cudaFree(d);
     return B200_OK;
 }
+
+
+// ---- TMA im2col-mode probe ---------------------------------------------------------------------------------
+// One im2col load of `pixels` (<= 256) output pixels x `chans` channels of one filter tap, no swizzle, copied
+// out as it lies in shared memory: pins the coordinate / corner / offset conventions the implicit-GEMM
+// convolution (csrc/conv_igemm.cu) is built on against a numpy gather (tests/test_gpu_igemm.py).
+namespace b200 {
+__global__ void __launch_bounds__(128) tma_im2col_probe_kernel(const __grid_constant__ CUtensorMap tmap, int c0, int w0,
+                                                               int h0, int n0, int woff, int hoff, int bytes, uint8_t *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, bytes);
+        tma_load_im2col_4d(smem, &tmap, &bar, c0, w0, h0, n0, static_cast<uint16_t>(woff), static_cast<uint16_t>(hoff));
+    }
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+}  // namespace b200
+
+extern "C" int b200_test_tma_im2col(const void *in_dev, int n, int h, int w, int c, int cp, int lower_w, int lower_h,
+                                    int upper_w, int upper_h, int stride_w, int stride_h, int chans, int pixels, int c0, int w0,
+                                    int h0, int n0, int woff, int hoff, void *out_dev, void *stream)
+{
+    using namespace b200;
+    alignas(64) CUtensorMap tm;
+    int rc = encode_tmap_im2col_u8(&tm, in_dev, n, h, w, c, cp, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, chans,
+                                   pixels, 0);
+    if (rc) return rc;
+    const int bytes = chans * pixels;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(tma_im2col_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    tma_im2col_probe_kernel<<<1, 128, bytes + 1024, (cudaStream_t)stream>>>(tm, c0, w0, h0, n0, woff, hoff, bytes,
+                                                                           static_cast<uint8_t *>(out_dev));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -187,6 +187,34 @@ int b200_gemm(const b200_gemm_desc *d, void *stream);
  * and cancel, as they must. */
 int b200_rowsum_i8(const void *a, int32_t lda, int32_t m, int32_t k, int32_t zp_in, int32_t *rs, void *stream);
 
+/* ---- implicit-GEMM conv2d: k > 1 convolutions without an im2col matrix ---------------------- */
+/* out[(b, oy, ox)][o] = epilogue( sum over taps and channels of x~ * w ): the same contract and packed weights
+ * ([o][ldw], k = (ky, kx, ci)) as b200_im2col + b200_gemm, but the GEMM's A operand is gathered by TMA in im2col
+ * mode (cuTensorMapEncodeIm2col: one load = 128 output pixels x one filter tap x one channel slab) straight
+ * from the pixel-major activation tensor -- the [M][K] matrix never exists in HBM.  TMA zero-fills padded taps
+ * where the contract wants zp_in; the difference enters through per-border-class accumulator seeds:
+ *   cls_map[oy * ow + ox] = class of the output position (which taps fall into the padding),
+ *   seeds[cls][o]         = ibias[o] + zp_in * sum of w[o] over those taps (all channels)
+ * (ncls <= 1: no correction -- zp_in == 0 or no padding; ep.ibias is used as it is).
+ * int8, group 1, channels a multiple of 64.  Replaces shl_rvv_conv_im2col_gemm_int8
+ * (source/thead_rvv/int8/convolution_gemm_int8.c:106-170) without its im2col buffer. */
+typedef struct {
+    int32_t n, h, w, c, cp_in;  /* input [n][h][w][cp_in], c channels                         */
+    int32_t o, oh, ow;
+    int32_t kh, kw, stride_h, stride_w, pad_top, pad_left, dil_h, dil_w;
+    const void *in;
+    const void *wt;             /* device [o][ldw] int8                                       */
+    int32_t ldw;
+    void *out;                  /* device [n][oh][ow][ldo]                                    */
+    int32_t ldo;
+    b200_epilogue ep;
+    int32_t ncls;
+    const int32_t *seeds;       /* device [ncls][o]                                           */
+    const uint8_t *cls_map;     /* device [oh * ow]                                           */
+} b200_conv_igemm_desc;
+int b200_conv_igemm_supported(const b200_conv_igemm_desc *d);
+int b200_conv_igemm(const b200_conv_igemm_desc *d, void *stream);
+
 /* ---- im2col (the other half of "im2col + GEMM conv2d") ------------------------- */
 /* col[m][k], m = (b, oy, ox), k = (ky, kx, ci) with ci fastest, row pitch ldk elements;
  * padded taps and k >= kh*kw*cg are written as `pad_value` (= zp_in for int8) / 0.
@@ -354,6 +382,12 @@ int b200_test_umma_shifted_start(const void *a_dev, const void *b_dev, int shift
 int b200_test_umma_rate(int n, int nacc, int reps, long long *cycles_host, void *stream);
 int b200_test_umma_rate2(int m, int n, int f16, int nacc, int reps, long long *cycles_host, void *stream);
 int b200_test_umma_rate3(int m, int n, int f16, int nacc, int reps, int issuers, long long *cycles_host, void *stream);
+/* test hook (csrc/umma_probe.cu): one TMA im2col-mode load (cuTensorMapEncodeIm2col map over [n][h][w][cp] uint8) of
+ * `pixels` output pixels x `chans` channels of the tap at (woff, hoff), starting at base pixel (w0, h0, n0), channel c0;
+ * out_dev receives the [pixels][chans] bytes as they lie in shared memory (no swizzle) */
+int b200_test_tma_im2col(const void *in_dev, int n, int h, int w, int c, int cp, int lower_w, int lower_h, int upper_w,
+                         int upper_h, int stride_w, int stride_h, int chans, int pixels, int c0, int w0, int h0, int n0, int woff,
+                         int hoff, void *out_dev, void *stream);
 /* test hook: the softmax denominator code alone (rows x c doubles -> rows floats), see csrc/softmax.cu */
 int b200_test_softmax_denominator(const void *e_dev, int rows, int c, void *out_dev, void *stream);
 int b200_softmax(int dtype, const void *in, void *out, int rows, int c, int cp_in, int cp_out,
