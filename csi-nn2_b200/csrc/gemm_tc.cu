@@ -39,7 +39,8 @@ namespace b200 {
 constexpr int kBM = 128;        // UMMA M (cta_group::1)
 constexpr int kBKBytes = 128;   // one swizzle atom of K per stage
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (3 + kEpiWarps) * 32;  // + TMA producer, MMA issuer, TMA-store warp
+constexpr int kThreads = (4 + kEpiWarps) * 32;  // + TMA producer, MMA issuer, TMA-store warp, second MMA issuer
+constexpr int kIssuer2Warp = 3 + kEpiWarps;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kMaxStages = 12;
 constexpr size_t kSmemLimit = 226 * 1024;
@@ -66,6 +67,9 @@ struct GemmArgs {
     const int32_t *rowsum;  // ... and the row sums b200_rowsum_i8 computed
     // implicit-GEMM convolution (IGEMM): the A operand is gathered by TMA im2col loads, one filter tap x one channel
     // slab per K block, straight from the pixel-major activation tensor
+    int issuers;            // 1, or 2: a second warp issues the MMAs of every other K block (int8, long K: one thread
+                            // issues an MMA every ~113-155 cycles whatever its shape, the pipe takes an N = 128 one
+                            // every 64 -- csrc/umma_probe.cu)
     int kb_bytes;           // bytes of K per block: 128, or 64 (64-channel layers: SWIZZLE_64B operand tiles)
     int slabs;              // channel slabs per tap = C / kb_bytes
     int kw, dil_w, dil_h;   // tap index -> (ky, kx) -> load offsets
@@ -147,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(&empty_bar[i], args.cluster);  // a slot is free when every CTA of the pair has consumed it
         }
         for (int i = 0; i < 2; i++) {
-            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_full[i], args.issuers);
             mbar_init(&tmem_empty[i], kEpiWarps);
             mbar_init(&stg_full[i], kEpiWarps);
             mbar_init(&stg_empty[i], 1);
@@ -187,53 +191,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             pdl_wait();  // the activations are the predecessor's output
             int stage = 0;
             uint32_t phase = 0;
+            // slot order: row block major (one issuer), or K block major with the row blocks of the super tile
+            // interleaved (two issuers: issuer i owns the row blocks g = i mod 2, i.e. its own accumulators, and
+            // both find their operands side by side in the ring)
+            const bool kmajor = args.issuers == 2;
             for (int ms = ms0; ms < args.num_m_super; ms += ms_step) {
                 const int mt0 = ms * G;
-                for (int g = 0; g < G; g++) {
-                    if (mt0 + g >= args.num_m_tiles) break;
+                const int gmax = min(G, args.num_m_tiles - mt0);
+                // IGEMM: base pixel of each row block's first row
+                int bw[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0}, bimg[4] = {0, 0, 0, 0};
+                if (IGEMM) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        if (g >= gmax) break;
+                        const int m0 = (mt0 + g) * kBM;
+                        bimg[g] = m0 / args.ohw;
+                        const int rem = m0 - bimg[g] * args.ohw;
+                        const int oy = rem / args.ow;
+                        bw[g] = (rem - oy * args.ow) * args.stride_w + args.lower_w, bh[g] = oy * args.stride_h + args.lower_h;
+                    }
+                }
+                const int n_slots = gmax * args.k_blocks;
+                int g = 0, kb = 0, slab = 0, tkx = 0, tky = 0;  // (tap, slab) of K block kb, kept incrementally
+                for (int it = 0; it < n_slots; it++) {
                     const int m0 = (mt0 + g) * kBM;
-                    for (int kb = 0; kb < args.k_blocks; kb++) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (args.b_resident) {
-                            mbar_expect_tx(&full_bar[stage], a_stage_bytes);
-                        } else {
-                            mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
-                            tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], kb * k_elems, n0);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (args.b_resident) {
+                        mbar_expect_tx(&full_bar[stage], a_stage_bytes);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
+                        tma_load_2d(smem_b + stage * b_stage_bytes, &tma_b, &full_bar[stage], kb * k_elems, n0);
+                    }
+                    // the activation box is 64 rows: both halves from this CTA, or (pair) this CTA's
+                    // half to both CTAs -- the peer sends the other half to both
+                    uint8_t *a_dst = smem_a + stage * a_stage_bytes;
+                    if (IGEMM) {
+                        // K block kb = filter tap (tky, tkx), channel slab `slab`; the 128 rows are the output pixels
+                        // m0 .. m0 + 127 in (image, oy, ox) order, the TMA unit walks them itself
+                        const int bwg = g == 0 ? bw[0] : (g == 1 ? bw[1] : (g == 2 ? bw[2] : bw[3]));
+                        const int bhg = g == 0 ? bh[0] : (g == 1 ? bh[1] : (g == 2 ? bh[2] : bh[3]));
+                        const int big = g == 0 ? bimg[0] : (g == 1 ? bimg[1] : (g == 2 ? bimg[2] : bimg[3]));
+                        tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb), bwg, bhg, big,
+                                           static_cast<uint16_t>(tkx * args.dil_w), static_cast<uint16_t>(tky * args.dil_h));
+                    } else if (args.cluster > 1) {
+                        const int half = static_cast<int>(cta_rank);
+                        tma_load_2d_multicast(a_dst + half * (a_stage_bytes / 2), &tma_a, &full_bar[stage],
+                                              kb * k_elems, m0 + half * (kBM / 2), 3);
+                    } else {
+                        tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * k_elems, m0);
+                        tma_load_2d(a_dst + a_stage_bytes / 2, &tma_a, &full_bar[stage], kb * k_elems, m0 + kBM / 2);
+                    }
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    // next slot
+                    bool next_kb;
+                    if (kmajor) {
+                        next_kb = ++g == gmax;
+                        if (next_kb) g = 0;
+                    } else {
+                        next_kb = true;
+                    }
+                    if (next_kb) {
+                        if (++slab == args.slabs) {
+                            slab = 0;
+                            if (++tkx == args.kw) tkx = 0, tky++;
                         }
-                        // the activation box is 64 rows: both halves from this CTA, or (pair) this CTA's
-                        // half to both CTAs -- the peer sends the other half to both
-                        uint8_t *a_dst = smem_a + stage * a_stage_bytes;
-                        if (IGEMM) {
-                            // K block kb = filter tap kb / slabs, channel slab kb % slabs; the 128 rows are the output
-                            // pixels m0 .. m0 + 127 in (image, oy, ox) order, the TMA unit walks them itself
-                            const int tap = kb / args.slabs, slab = kb - tap * args.slabs;
-                            const int ky = tap / args.kw, kx = tap - ky * args.kw;
-                            const int img = m0 / args.ohw, rem = m0 - img * args.ohw;
-                            const int oy = rem / args.ow, ox = rem - oy * args.ow;
-                            tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb),
-                                               ox * args.stride_w + args.lower_w, oy * args.stride_h + args.lower_h, img,
-                                               static_cast<uint16_t>(kx * args.dil_w), static_cast<uint16_t>(ky * args.dil_h));
-                        } else if (args.cluster > 1) {
-                            const int half = static_cast<int>(cta_rank);
-                            tma_load_2d_multicast(a_dst + half * (a_stage_bytes / 2), &tma_a, &full_bar[stage],
-                                                  kb * k_elems, m0 + half * (kBM / 2), 3);
-                        } else {
-                            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * k_elems, m0);
-                            tma_load_2d(a_dst + a_stage_bytes / 2, &tma_a, &full_bar[stage], kb * k_elems, m0 + kBM / 2);
-                        }
-                        if (++stage == stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        if (++kb == args.k_blocks) kb = 0, slab = 0, tkx = 0, tky = 0, g += kmajor ? 0 : 1;
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || (warp == kIssuer2Warp && args.issuers == 2)) {
+        // ===== MMA issuer(s): with two, the ring carries the super tile's row blocks interleaved per K block and
+        // issuer i takes the row blocks g = i mod 2 -- its own accumulators: MMAs of different threads are not
+        // ordered against each other, so two issuers must never accumulate into the same TMEM columns (a first
+        // version that split the K blocks of ONE accumulator passed the parity suite and then raced under
+        // compute-sanitizer's timing).  Each commits the slots it consumed and, once per super tile, the
+        // accumulator barrier (count = issuers) =====
         if (elect_one()) {
+            const int me = warp == 1 ? 0 : 1;
+            const int nis = args.issuers;
             if (args.b_resident) mbar_wait(b_bar, 0);
-            if (tr) tr[2] = clock64();
+            if (tr && me == 0) tr[2] = clock64();
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -245,10 +286,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // use and again after each drain, so completion #n of tmem_empty means "seeded n times"
                 mbar_wait(&tmem_empty[acc], DT == B200_I8 ? acc_phase : (acc_phase ^ 1));
                 tc_fence_after();
-                for (int g = 0; g < G; g++) {
-                    if (mt0 + g >= args.num_m_tiles) break;
-                    const uint32_t tmem_d = tmem_base + acc * kAccStride + g * args.bn;
-                    for (int kb = 0; kb < args.k_blocks; kb++) {
+                const int gmax = min(G, args.num_m_tiles - mt0);
+                const int n_slots = gmax * args.k_blocks;
+                int g = 0, kb = 0;
+                for (int it = 0; it < n_slots; it++) {
+                    // two issuers: the slots come K block major and issuer i takes the row blocks g = i mod 2
+                    if (nis == 1 || (g & 1) == me) {
+                        const uint32_t tmem_d = tmem_base + acc * kAccStride + g * args.bn;
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const bool sw64 = IGEMM && kbb == 64;
@@ -270,16 +314,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             tc_commit_multicast(&empty_bar[stage], 3);
                         else
                             tc_commit(&empty_bar[stage]);
-                        if (++stage == stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                    }
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (nis == 2) {
+                        if (++g == gmax) g = 0, kb++;
+                    } else if (++kb == args.k_blocks) {
+                        kb = 0, g++;
                     }
                 }
-                tc_commit(&tmem_full[acc]);  // accumulators complete -> epilogue
-                if (tr && local < 28) tr[8 + 2 * local] = clock64();
+                tc_commit(&tmem_full[acc]);  // this issuer's share of the accumulators complete -> epilogue
+                if (tr && me == 0 && local < 28) tr[8 + 2 * local] = clock64();
             }
         }
+    } else if (warp == kIssuer2Warp) {
+        // second issuer not in use for this launch
     } else if (warp == 2 + kEpiWarps) {
         // ===== TMA-store warp (int8): hands finished staging tiles to the store engine, so that the
         // epilogue warps never meet at a CTA-wide barrier -- a fast warp runs up to two super tiles
@@ -724,6 +775,11 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     args.out = d->out;
     args.ep = make_epi(d->ep);
     args.wzp = d->w_zp, args.rowsum = d->rowsum;
+    // a second MMA issuer when the layer is long enough in K to be bound by one thread's issue rate
+    // (SHL_B200_GEMM_ISSUERS=1/2 forces it); int8 only: the fp16 accumulation order stays one thread's
+    args.issuers = (d->dtype == B200_I8 && args.k_blocks >= 8) ? 2 : 1;
+    if (const char *e = getenv("SHL_B200_GEMM_ISSUERS")) args.issuers = (d->dtype == B200_I8 && atoi(e) == 2) ? 2 : 1;
+    if (args.issuers == 2 && (args.group & 1)) args.issuers = 1;  // the issuers split the super tile's row blocks
     args.idesc = d->dtype == B200_I8 ? umma_idesc(2 /*S32*/, 1 /*S8*/, kBM, args.bn)
                                      : umma_idesc(1 /*F32*/, 0 /*F16*/, kBM, args.bn);
     // as many stages as fit: the ring also prefetches the next tiles' operands while the
