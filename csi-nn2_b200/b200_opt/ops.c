@@ -857,10 +857,10 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
         if (op->direct) op->kname = "b200_gemm_tcgen05";
         rc = b200_make_requant(op, input, kernel, bias, output, op->kdim, params->conv_extra.fuse_zp2bias, O);
         if (rc == CSINN_TRUE && !(op->d_w = b200_pack_conv_weights(op, kernel, &wbytes))) rc = CSINN_FALSE;
-        /* k > 1, int8, group 1, channels a multiple of 64, symmetric weights: the implicit-GEMM kernel
-         * (the channel pitch of the input equals its channel count then, so K = taps x channels exactly) */
+        /* every convolution that is not a plain GEMM (k > 1, strided or padded 1x1), int8, group 1, channels a
+         * multiple of 64, symmetric weights: the implicit-GEMM kernel (K = taps x channels exactly) */
         if (rc == CSINN_TRUE && !op->direct && op->dtype == B200_I8 && group == 1 && C % 64 == 0 && !op->d_wzp &&
-            kh * kw > 1 && output->dim_count == 4)
+            output->dim_count == 4)
             rc = b200_make_igemm_tables(op, kernel, input->dim[2], input->dim[3], output->dim[2], output->dim[3]);
     }
     if (rc != CSINN_TRUE) {

@@ -685,7 +685,8 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
         }
         if (dev < 0 || dev >= 64 || max_clusters[dev] * 2 < grid) la.cluster = 1;
     }
-    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>, dim3(grid), dim3(kThreads), smem, stream,
+    B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>, dim3(grid),
+                                          dim3(la.issuers == 2 ? kThreads : kThreads - 32), smem, stream,
                                           la.cluster, ta, tb, to, la));
     if (tracing && la.trace) {  // diagnostic only: synchronous, prints a few CTAs' timelines (cycles from CTA start)
         static long long host[256 * 64];
@@ -777,7 +778,7 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     args.wzp = d->w_zp, args.rowsum = d->rowsum;
     // a second MMA issuer when the layer is long enough in K to be bound by one thread's issue rate
     // (SHL_B200_GEMM_ISSUERS=1/2 forces it); int8 only: the fp16 accumulation order stays one thread's
-    args.issuers = (d->dtype == B200_I8 && args.k_blocks >= 8) ? 2 : 1;
+    args.issuers = (d->dtype == B200_I8 && args.k_blocks >= 9) ? 2 : 1;
     if (const char *e = getenv("SHL_B200_GEMM_ISSUERS")) args.issuers = (d->dtype == B200_I8 && atoi(e) == 2) ? 2 : 1;
     if (args.issuers == 2 && (args.group & 1)) args.issuers = 1;  // the issuers split the super tile's row blocks
     args.idesc = d->dtype == B200_I8 ? umma_idesc(2 /*S32*/, 1 /*S8*/, kBM, args.bn)
@@ -913,7 +914,7 @@ static bool igemm_shape_ok(const b200_conv_igemm_desc *c)
     const int upper_w = -c->pad_left + (c->ow - 1) * c->stride_w - (c->w - 1);
     const int upper_h = -c->pad_top + (c->oh - 1) * c->stride_h - (c->h - 1);
     return c->n > 0 && c->c > 0 && c->c % 64 == 0 && c->cp_in >= c->c && c->cp_in % 16 == 0 && c->o > 0 && c->kh >= 1 &&
-           c->kw >= 1 && c->kh * c->kw > 1 && c->stride_w >= 1 && c->stride_w <= 8 && c->stride_h >= 1 && c->stride_h <= 8 &&
+           c->kw >= 1 && c->stride_w >= 1 && c->stride_w <= 8 && c->stride_h >= 1 && c->stride_h <= 8 &&
            c->dil_w >= 1 && c->dil_h >= 1 && (c->kw - 1) * c->dil_w <= 255 && (c->kh - 1) * c->dil_h <= 255 &&
            c->pad_left <= 128 && c->pad_top <= 128 && c->pad_left >= 0 && c->pad_top >= 0 && upper_w >= -128 && upper_w <= 127 &&
            upper_h >= -128 && upper_h <= 127 && c->ldw >= c->kh * c->kw * c->c && c->ldw % 16 == 0 && c->ldo >= c->o &&
@@ -926,7 +927,7 @@ extern "C" int b200_conv_igemm_supported(const b200_conv_igemm_desc *c) { return
 extern "C" int b200_conv_igemm(const b200_conv_igemm_desc *c, void *stream)
 {
     if (!igemm_shape_ok(c)) {
-        set_error("b200_conv_igemm: descriptor outside the implicit-GEMM kernel's domain (int8, channels a multiple of 64, k > 1)");
+        set_error("b200_conv_igemm: descriptor outside the implicit-GEMM kernel's domain (int8, channels a multiple of 64)");
         return B200_ERR_UNSUPPORTED;
     }
     b200_gemm_desc g = {};

@@ -95,6 +95,8 @@ IGEMM_CASES = [
     (1, 64, 19, 17, 64, 3, 3, 1, 2, 2, -5),      # dilation 2
     (1, 128, 15, 13, 32, 5, 3, 2, 2, 2, 3),      # 5 x 3 kernel, stride 2, more border classes
     (5, 512, 7, 7, 512, 3, 3, 1, 1, 1, -128),    # ResNet layer4 3x3: 36 K blocks, 4 n-tiles
+    (2, 256, 28, 28, 512, 1, 1, 2, 0, 1, -128),  # ResNet downsample shortcut: strided 1x1 (one tap, no im2col buffer either)
+    (3, 64, 13, 13, 64, 1, 1, 2, 0, 1, 0),       # strided 1x1, odd size, 64-byte K blocks
 ]
 
 
