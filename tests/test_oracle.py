@@ -278,6 +278,30 @@ def test_golden_reference_library_agrees(golden, ref):
     _f32_close(got, want)
 
 
+def test_baseline_config_1_f32_conv_on_the_x86_reference(ref, ref_noavx, oracle, rng):
+    """BASELINE.json configs[0]: a single csinn_conv2d, f32, 3x3 stride 1, 1x3x224x224 -> 64 channels, on the x86_ref
+    backend of the host CPU (plumbing: registry -> shl_ref_conv2d_f32 -> conv_im2col_sgemm_avx,
+    source/reference/convolution.c:91, conv_avx.h:109).  The AVX im2col + sgemm build and the scalar NHWC build
+    must agree with each other and with the oracle's f32 loop; the wall time is printed, not asserted."""
+    import time
+    x = rng.standard_normal((1, 3, 224, 224)).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 3, 3)) / np.sqrt(27.0)).astype(np.float32)
+    b = rng.standard_normal(64).astype(np.float32)
+    layer = Layer(H_CONV, (1, 64, 224, 224), w=w, b=b, pad=(1,) * 4)
+    t0 = time.perf_counter()
+    got = ref.run(DT_F32, x.shape, [layer], x)
+    t_avx = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    got2 = ref_noavx.run(DT_F32, x.shape, [layer], x)
+    t_scalar = time.perf_counter() - t0
+    want = oracle.conv2d_f32(x, w, b, (1, 64, 224, 224), pad=(1,) * 4)
+    _f32_close(got, want)
+    _f32_close(got2, want)
+    ops = 2.0 * 64 * 224 * 224 * 27
+    print(f"config 1 (f32 3x3, 1x3x224x224 -> 64) on x86_ref: AVX build {t_avx * 1e3:.1f} ms ({ops / t_avx / 1e9:.1f} GFLOP/s, "
+          f"8 OpenMP threads), scalar build {t_scalar * 1e3:.1f} ms, incl. session + tensor set-up")
+
+
 def test_network_oracle_chain_equals_reference_graph(ref, ref_noavx):
     """A whole (narrow) MobileNetV1 through the reference in graph mode (GREF,
     source/graph_ref/setup.c:1305) equals the chained oracle ops."""
