@@ -299,18 +299,44 @@ def main():
     sess = net.session
     stream = shl.shl_b200_session_stream(sess)
 
-    # one-time weight broadcast over NVLink (rank 0 holds the packed weights + tables)
-    bcast_ms = None
+    # one-time weight broadcast over NVLink (rank 0 holds the packed weights + tables): the library's own C entry
+    # (b200_opt/dist.c: ncclBroadcast on its own communicator; torch.distributed only carries the 128-byte id);
+    # if NCCL cannot be bound from C, the torch path (pyhost/b200_dist.py) does the same broadcast
+    bcast_ms, bcast_how = None, None
     if dist is not None:
         import torch
-        ptr, nbytes = C.c_void_p(), C.c_uint64()
-        assert shl.shl_b200_session_weight_arena(sess, C.byref(ptr), C.byref(nbytes)) == 1
-        arena = b200_dist.device_bytes_as_tensor(ptr.value, nbytes.value, local_rank)
+        shl.shl_b200_nccl_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        shl.shl_b200_session_broadcast_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        shl.shl_b200_nccl_comm_destroy.argtypes = [C.c_void_p]
+        uid = (C.c_uint8 * 128)()
+        ok = 1
+        if rank == 0:
+            ok = int(shl.shl_b200_nccl_unique_id(uid) == 1)
+        t_uid = torch.tensor(list(bytes(uid)) + [ok], dtype=torch.uint8, device=torch.device("cuda", local_rank))
+        dist.broadcast(t_uid, src=0)
+        got = bytes(t_uid.cpu().tolist())
+        comm = C.c_void_p()
+        c_path = bool(got[128])
+        if c_path:
+            C.memmove(uid, got[:128], 128)
+            c_path = shl.shl_b200_nccl_comm_init(sess, uid, rank, world, C.byref(comm)) == 1
+        flags = b200_dist.max_over_ranks([0.0 if c_path else 1.0], device=torch.device("cuda", local_rank))
+        c_path = flags[0] == 0.0  # every rank must have its communicator, or nobody uses the C path
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        b200_dist.broadcast_arena(arena, src=0)
+        if c_path:
+            assert shl.shl_b200_session_broadcast_weights(sess, comm, 0) == 1, b200.error()
+            bcast_how = "shl_b200_session_broadcast_weights: one ncclBroadcast of the weight arena on the library's own communicator (C)"
+        else:
+            ptr, nbytes = C.c_void_p(), C.c_uint64()
+            assert shl.shl_b200_session_weight_arena(sess, C.byref(ptr), C.byref(nbytes)) == 1
+            arena = b200_dist.device_bytes_as_tensor(ptr.value, nbytes.value, local_rank)
+            b200_dist.broadcast_arena(arena, src=0)
+            bcast_how = "torch.distributed broadcast of the arena (pyhost/b200_dist.py): NCCL could not be bound from C"
         torch.cuda.synchronize()
         bcast_ms = 1e3 * (time.perf_counter() - t0)
+        if c_path:
+            shl.shl_b200_nccl_comm_destroy(comm)
 
     # pinned host buffers for the end-to-end path
     # two of them, holding different batches (the second is the first rotated by one image), so that
@@ -621,7 +647,7 @@ def main():
                 "cpu_baseline": cpu,
                 "tensor_tops": (sum(k["ops"] for k in per_kernel.values()) * world * steps / (dev_ms * 1e-3) / 1e12)
                 if per_kernel else None,
-                "weight_broadcast_ms": bcast_ms, "batch1": batch1,
+                "weight_broadcast_ms": bcast_ms, "weight_broadcast_how": bcast_how, "batch1": batch1,
                 "session": desc[0] if rank == 0 and per_kernel else None}
         emit(line)
     net.close()

@@ -400,6 +400,8 @@ static int save_binary_model(struct csinn_session *sess, struct shl_ref_graph *g
 }
 
 static int build_from_graph(struct csinn_session *sess);
+int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, double *ms, double *bytes, double *ops,
+                             int cap);
 
 int shl_b200_session_setup(struct csinn_session *sess)
 {
@@ -803,6 +805,27 @@ int shl_b200_session_run(struct csinn_session *sess)
                                            (size_t)t->dt.n, opt->ctx.stream));
     }
     DEV_CHECK(b200_stream_sync(opt->ctx.stream));
+    /* sess->profiler_level = CSINN_PROFILER_LEVEL_TIMER / _ALL: the per-layer report the reference prints from its
+     * run loop (source/graph_ref/setup.c:1383-1392 + shl_benchmark_layer, source/utils/debug.c:1037), here with
+     * device times (CUDA events around each step's kernels, one extra eager pass) instead of a host clock */
+    if (sess->profiler_level == CSINN_PROFILER_LEVEL_TIMER || sess->profiler_level == CSINN_PROFILER_LEVEL_ALL) {
+        double *ms = calloc((size_t)g->ns * 3, sizeof(double));
+        if (ms) {
+            double *by = ms + g->ns, *op = by + g->ns, total = 0;
+            const int n = shl_b200_session_profile(sess, 1, 3, ms, by, op, g->ns);
+            for (int i = 0; i < n; i++) {
+                const b200_dt *a = &g->t[g->s[i].in0].dt, *o = &g->t[g->s[i].out].dt;
+                printf("[%3d]: %-28s %8.3fms  ^*^: [%d, %d, %d, %d] ==> [%d, %d, %d, %d] | %.1f GB/s", i,
+                       step_kname(g, &g->s[i]), ms[i], a->n, a->c, a->h, a->w, o->n, o->c, o->h, o->w,
+                       ms[i] > 0 ? by[i] / ms[i] / 1e6 : 0.0);
+                if (op[i] > 0) printf(" | %.4f GOPS | %.1f TOPS", op[i] / 1e9, op[i] / ms[i] / 1e9);
+                printf(" | %s\n", g->s[i].name);
+                total += ms[i];
+            }
+            printf("[layer-benchmark]: network device time = %.3fms (%d steps)\n", total, n);
+            free(ms);
+        }
+    }
     return CSINN_TRUE;
 }
 

@@ -544,6 +544,10 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
                                    op->s_in, op->zp_in, op->s_out, op->zp_out, stream));
             return CSINN_TRUE;
         case B200_OPK_COPY:
+            if (op->direct) { /* flatten of an N x C x H x W tensor: back to NCHW order = the flattened rows */
+                DEV_CHECK(b200_nhwc_to_nchw(in0->d, out->d, in0->n, in0->c, in0->h, in0->w, in0->cp, in0->eb, stream));
+                return CSINN_TRUE;
+            }
             if (b200_dt_bytes(in0) != b200_dt_bytes(out)) {
                 b200_fail("reshape changes the device footprint (%zu -> %zu bytes)", b200_dt_bytes(in0),
                           b200_dt_bytes(out));
@@ -1275,14 +1279,25 @@ int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *outpu
 {
     struct csinn_params_base *base = params;
     b200_dt din, dout;
-    if (!b200_dt_from_tensor(&din, input) || !b200_dt_from_tensor(&dout, output) ||
-        din.h * din.w != 1 || dout.h * dout.w != 1 || din.n != dout.n || din.c != dout.c) {
-        /* with H*W > 1 an NCHW reshape permutes the pixel-major buffer */
-        b200_fail("reshape/flatten: only N x C x 1 x 1 <-> N x C is supported on the device layout");
+    if (!b200_dt_from_tensor(&din, input) || !b200_dt_from_tensor(&dout, output)) {
+        b200_fail("reshape/flatten: unsupported tensor rank / dtype");
         return CSINN_FALSE;
     }
-    b200_op *op = op_new(base, B200_OPK_COPY, input->dtype, "b200_reshape_copy");
+    /* N x C x 1 x 1 <-> N x C: the pixel-major buffer already is the result.  N x C x H x W -> N x (C*H*W) (the
+     * flatten in front of a VGG / AlexNet classifier; source/reference/flatten.c / reshape.c copy the NCHW bytes):
+     * the pixel-major buffer is permuted back into NCHW order, which IS the flattened row when C*H*W fills the
+     * output's row pitch.  Other reshapes with H*W > 1 would need a general permutation and are refused. */
+    const int plain = din.h * din.w == 1 && dout.h * dout.w == 1 && din.n == dout.n && din.c == dout.c;
+    const long long flat = (long long)din.c * din.h * din.w;
+    const int to_rows = !plain && dout.h * dout.w == 1 && din.n == dout.n && flat == dout.c && dout.cp == dout.c;
+    if (!plain && !to_rows) {
+        b200_fail("reshape/flatten: only N x C x 1 x 1 <-> N x C, or N x C x H x W -> N x (C*H*W) with C*H*W a multiple of "
+                  "%d, is supported on the device layout", 16 / din.eb);
+        return CSINN_FALSE;
+    }
+    b200_op *op = op_new(base, B200_OPK_COPY, input->dtype, to_rows ? "b200_flatten_to_nchw" : "b200_reshape_copy");
     if (!op) return CSINN_FALSE;
+    op->direct = to_rows; /* B200_OPK_COPY: 1 = permute pixel-major -> NCHW order */
     b200_op_bind(params, op);
     base->cb->exec = (int (*)())shl_b200_reshape;
     return CSINN_TRUE;

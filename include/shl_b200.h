@@ -154,6 +154,15 @@ int shl_b200_session_profile(struct csinn_session *sess, int warmup, int iters, 
  * device allocation): exposed so that multi-GPU launchers can broadcast it once over NCCL
  * instead of re-uploading per rank. */
 int shl_b200_session_weight_arena(struct csinn_session *sess, void **dev_ptr, uint64_t *bytes);
+/* Multi-GPU start-up in C (b200_opt/dist.c): batch sharding has no collective on the inference path; the ONE
+ * exchange is the weight arena of rank `root` into the arenas of the other ranks (created with
+ * SHL_B200_SKIP_WEIGHT_UPLOAD=1) by a single ncclBroadcast over NVLink.  NCCL is bound at run time (dlopen), the
+ * communicator is the library's own: shl_b200_nccl_unique_id on one rank, the 128 bytes carried to the others by
+ * the host's launcher (MPI, torch.distributed, a file), shl_b200_nccl_comm_init everywhere. */
+int shl_b200_nccl_unique_id(void *id128);
+int shl_b200_nccl_comm_init(struct csinn_session *sess, const void *id128, int rank, int world, void **comm);
+int shl_b200_session_broadcast_weights(struct csinn_session *sess, void *comm, int root);
+int shl_b200_nccl_comm_destroy(void *comm);
 /* drop the device operator bound to a params struct (staging buffers of layer mode) */
 void shl_b200_op_release(void *params);
 /* Errors.  The reference's front ends drop the status init / exec return

@@ -1059,3 +1059,19 @@ def test_swizzled_descriptor_start_may_be_shifted_by_any_number_of_rows():
             assert np.array_equal(got, want), (k0, shift)
     for d in (d_a, d_b, d_o):
         shim.b200_free(d)
+
+
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_flatten_of_a_feature_map_feeds_fullyconnected(mode, b200, oracle, rng):
+    """N x C x H x W -> N x (C*H*W) (the flatten in front of a VGG / AlexNet classifier, source/reference/flatten.c):
+    the pixel-major device tensor is permuted back into NCHW order, then the fullyconnected GEMM runs on the rows"""
+    n, c, h, w, units = 3, 32, 5, 4, 40
+    x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
+    wt4, s_w, b, s_out = synth_conv_i8(rng, c * h * w, units, 1, 1)
+    layers = [Layer(H_RELU, (n, c, h, w), s_out=0.02, zp_out=-3),
+              Layer(H_FLATTEN, (n, c * h * w), s_out=0.02, zp_out=-3),
+              Layer(H_FC, (n, units), s_out=s_out, zp_out=2, w=wt4.reshape(units, c * h * w), b=b, s_w=s_w)]
+    from types import SimpleNamespace
+    want = nets.oracle_forward(SimpleNamespace(layers=layers, orc=oracle, dtype=DT_INT8, s_in=0.02, zp_in=-3), x)
+    got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=-3, run_mode=mode)
+    assert np.array_equal(got, want)
