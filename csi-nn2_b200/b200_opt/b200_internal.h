@@ -137,6 +137,7 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
                       const struct csinn_tensor *output, int taps_per_o, int fuse_zp2bias,
                       int n_out);
 struct csinn_tensor *b200_dequant_weights_f16(const struct csinn_tensor *kernel); /* fp16 activations, int8 weights */
+struct csinn_tensor *b200_int8_weights_as_f16(const struct csinn_tensor *kernel); /* exact integers + scales for the epilogue */
 void b200_free_dequant(struct csinn_tensor *t);
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
 void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);

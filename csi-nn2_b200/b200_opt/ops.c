@@ -789,7 +789,13 @@ static int conv_init_common(struct csinn_tensor *input, struct csinn_tensor *out
 {
     /* CSINN_QUANT_FLOAT16_W_INT8: fp16 activations over int8 weights */
     if (input->dtype == CSINN_DTYPE_FLOAT16 && kernel->dtype == CSINN_DTYPE_INT8) {
-        struct csinn_tensor *kf = b200_dequant_weights_f16(kernel);
+        /* the tcgen05 GEMM path multiplies exact integer weights and scales per channel in the epilogue; depthwise
+         * and the shapes that may take the first-layer kernel (K <= 160, O <= 64) keep weights dequantised to fp16 */
+        const int grp = params->group > 0 ? params->group : 1;
+        const int dwise = grp == input->dim[1] && kernel->dim[1] == 1 && grp > 1;
+        const int kd = kernel->dim[1] * kernel->dim[2] * kernel->dim[3];
+        const int gemm_only = !dwise && !(grp == 1 && kd <= 160 && kernel->dim[0] <= 64);
+        struct csinn_tensor *kf = gemm_only ? b200_int8_weights_as_f16(kernel) : b200_dequant_weights_f16(kernel);
         if (!kf) return CSINN_FALSE;
         const int rc = conv_init_impl(input, output, kf, bias, params, act);
         b200_free_dequant(kf);
@@ -929,7 +935,7 @@ int shl_b200_fullyconnected_init(struct csinn_tensor *input, struct csinn_tensor
                                  struct csinn_fc_params *params)
 {
     if (input->dtype == CSINN_DTYPE_FLOAT16 && weights->dtype == CSINN_DTYPE_INT8) { /* CSINN_QUANT_FLOAT16_W_INT8 */
-        struct csinn_tensor *wf = b200_dequant_weights_f16(weights);
+        struct csinn_tensor *wf = b200_int8_weights_as_f16(weights); /* exact integers, scale in the GEMM epilogue */
         if (!wf) return CSINN_FALSE;
         const int rc = fc_init_impl(input, output, wf, bias, params);
         b200_free_dequant(wf);

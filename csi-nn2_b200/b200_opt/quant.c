@@ -95,6 +95,37 @@ struct csinn_tensor *b200_dequant_weights_f16(const struct csinn_tensor *kernel)
     t->data = h;
     return t;
 }
+/* The same tensor as EXACT integers in fp16 (q - zp, |v| <= 255) with the per-channel scales handed to the next
+ * b200_make_requant call, which uploads them as the GEMM epilogue's per-column multiplier: products of fp16
+ * activations with integer weights are exact in the f32 accumulator and the scale is applied once, in f32 --
+ * what the reference's f32 path computes up to summation order -- instead of rounding every weight to fp16 first
+ * (5e-4 relative each).  Used for the tcgen05 GEMM path; depthwise and first-layer kernels keep dequantised weights. */
+static float *g_pending_wscale;
+static int g_pending_wscale_n;
+struct csinn_tensor *b200_int8_weights_as_f16(const struct csinn_tensor *kernel)
+{
+    struct csinn_tensor *t = b200_dequant_weights_f16(kernel);
+    if (!t) return NULL;
+    int64_t total = 1;
+    for (int i = 0; i < kernel->dim_count; i++) total *= kernel->dim[i];
+    const int O = kernel->dim[0];
+    const int64_t per_o = total / O;
+    float *sc = malloc((size_t)O * sizeof(float));
+    if (!sc) {
+        b200_free_dequant(t);
+        return NULL;
+    }
+    const int8_t *q = kernel->data;
+    uint16_t *h = t->data;
+    for (int64_t i = 0; i < total; i++) {
+        const int qi = kernel->quant_channel > 1 ? (int)(i / per_o) : 0;
+        h[i] = f32_to_f16_rne((float)q[i] - (float)kernel->qinfo[qi].zero_point);
+    }
+    for (int o = 0; o < O; o++) sc[o] = kernel->qinfo[kernel->quant_channel > 1 ? o : 0].scale;
+    free(g_pending_wscale);
+    g_pending_wscale = sc, g_pending_wscale_n = O;
+    return t;
+}
 void b200_free_dequant(struct csinn_tensor *t)
 {
     if (!t) return;
@@ -138,6 +169,18 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
         op->d_ibias = NULL;
         op->d_badd = b200_warena_put(op->ctx, badd, n_alloc * sizeof(float));
         if (!op->d_badd) rc = CSINN_FALSE;
+        if (g_pending_wscale) { /* integer weights in fp16 (b200_int8_weights_as_f16): per-column scale in the epilogue */
+            if (g_pending_wscale_n == n_out) {
+                for (int o = 0; o < n_out; o++) mult[o] = g_pending_wscale[o];
+                op->d_mult = b200_warena_put(op->ctx, mult, n_alloc * sizeof(float));
+                if (!op->d_mult) rc = CSINN_FALSE;
+            } else {
+                b200_fail("weight scales for %d channels handed to an operator with %d outputs", g_pending_wscale_n, n_out);
+                rc = CSINN_FALSE;
+            }
+            free(g_pending_wscale);
+            g_pending_wscale = NULL;
+        }
         goto done;
     }
     if (!input->qinfo || !kernel->qinfo || !output->qinfo) {

@@ -532,6 +532,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (et < args.bn) {
             const int col = n0 + et;
             epi->badd[et] = (col < args.n && ep.badd) ? ep.badd[col] : 0.f;
+            // per-column scale (integer weights in fp16, CSINN_QUANT_FLOAT16_W_INT8); fma(acc, 1, b) == acc + b
+            epi->mult[et] = (col < args.n && ep.mult) ? ep.mult[col] : 1.f;
         }
         epi_bar_sync();
         pdl_wait();  // the output buffer may alias a tensor the predecessor still reads
@@ -568,8 +570,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int j2 = 0; j2 < 16; j2++) {
                         const float2 ba = *reinterpret_cast<const float2 *>(&epi->badd[c0 + j2 * 2]);
-                        float f0 = act_f(__uint_as_float(r[j2 * 2]) + ba.x, act);
-                        float f1 = act_f(__uint_as_float(r[j2 * 2 + 1]) + ba.y, act);
+                        const float2 mu = *reinterpret_cast<const float2 *>(&epi->mult[c0 + j2 * 2]);
+                        float f0 = act_f(fmaf(__uint_as_float(r[j2 * 2]), mu.x, ba.x), act);
+                        float f1 = act_f(fmaf(__uint_as_float(r[j2 * 2 + 1]), mu.y, ba.y), act);
                         const int cb = n0 + c0 + j2 * 2;
                         f0 = cb < args.n ? f0 : 0.f;
                         f1 = cb + 1 < args.n ? f1 : 0.f;
