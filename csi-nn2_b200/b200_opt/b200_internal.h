@@ -65,6 +65,7 @@ enum b200_op_kind {
     B200_OPK_COPY,    /* reshape / flatten whose memory order is unchanged */
     B200_OPK_CONCAT,  /* one step per input: its slice of the output (b200_op_run's `part`) */
     B200_OPK_SPLIT,   /* one step per output: its slice of the input (`part` = output index; cat_* fields) */
+    B200_OPK_TENSOR,  /* transpose / gather / reduce_sum / layer_norm / rms_norm / matmul (t_* fields, csrc/tensor_ops.cu) */
 };
 
 #define B200_CONCAT_MAX 32
@@ -106,10 +107,22 @@ typedef struct b200_op {
     float s_in, s_in1;
     int zp_in1;
     int pool_avg, pool_global, count_include_pad;
+    /* B200_OPK_TENSOR */
+    int t_op;            /* enum b200_tensor_op */
+    int t_axis, t_perm[4];
+    float t_eps;
+    int32_t *d_idx;      /* gather: constant indices */
+    int n_idx, oob_q;
+    float *d_gamma, *d_beta;
+    int in_rank, in_dim[4], in1_rank, in1_dim[4], out_rank, out_dim[4]; /* logical shapes (the API's) */
+    int mm_batches, mm_batches_b, mm_i, mm_k, mm_j, mm_trans_a, mm_trans_b, mm_const_b;
+    int two_inputs;      /* the second operand is an activation (matmul of two activations) */
     /* layer-mode staging buffers, grown on demand */
     void *stg[8];
     size_t stg_bytes[8];
 } b200_op;
+
+enum b200_tensor_op { B200_T_TRANSPOSE = 1, B200_T_GATHER, B200_T_REDUCE_SUM, B200_T_LAYER_NORM, B200_T_RMS_NORM, B200_T_MATMUL };
 
 /* registry params* -> op (ops.c) */
 void b200_op_bind(void *params, b200_op *op);
@@ -139,6 +152,7 @@ int b200_make_requant(b200_op *op, const struct csinn_tensor *input,
 struct csinn_tensor *b200_dequant_weights_f16(const struct csinn_tensor *kernel); /* fp16 activations, int8 weights */
 struct csinn_tensor *b200_int8_weights_as_f16(const struct csinn_tensor *kernel); /* exact integers + scales for the epilogue */
 void b200_free_dequant(struct csinn_tensor *t);
+float b200_f16_to_f32(uint16_t h);
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
 void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);
 void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int cp);

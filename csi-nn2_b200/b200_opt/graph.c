@@ -599,7 +599,8 @@ static int build_from_graph(struct csinn_session *sess)
                 continue;
             }
         }
-        const int two_inputs = op->kind == B200_OPK_ADD && !op->d_const; /* a constant operand lives in the weight arena */
+        /* a constant second operand lives in the weight arena; a matmul of two activations reads two tensors */
+        const int two_inputs = (op->kind == B200_OPK_ADD && !op->d_const) || (op->kind == B200_OPK_TENSOR && op->two_inputs);
         if (two_inputs) s->in1 = tensor_add(g, n->in[1]);
         s->out = tensor_add(g, out_tn);
         if (s->in0 < 0 || s->out < 0 || (two_inputs && s->in1 < 0)) {

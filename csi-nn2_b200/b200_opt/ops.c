@@ -359,8 +359,10 @@ static size_t im2col_bytes(const b200_op *op, const b200_dt *in0, const b200_dt 
     return ((size_t)out->n * out->h * out->w * op->ldk * op->eb + 255) & ~(size_t)255;
 }
 
+static size_t matmul_scratch(const b200_op *op, size_t *off_b, size_t *off_o, size_t *off_rs);
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
+    if (op->kind == B200_OPK_TENSOR && op->t_op == B200_T_MATMUL) return matmul_scratch(op, NULL, NULL, NULL);
     if (op->kind != B200_OPK_CONV && op->kind != B200_OPK_FC) return 0;
     size_t bytes = im2col_bytes(op, in0, out);
     if (op->d_wzp) bytes += (size_t)out->n * out->h * out->w * sizeof(int32_t);
@@ -438,6 +440,108 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
         DEV_CHECK(b200_gemm(&g, stream));
     }
     return CSINN_TRUE;
+}
+
+/* ---- transpose / gather / reduce_sum / layer_norm / rms_norm / matmul ---------------------------------------- */
+static void view_of(b200_view *v, int rank, const int *dim, const b200_dt *dt)
+{
+    memset(v, 0, sizeof(*v));
+    v->rank = rank;
+    for (int i = 0; i < rank; i++) v->dim[i] = dim[i];
+    v->cp = dt->cp;
+}
+
+/* scratch of a matmul: [A rows (M x ldk)][B rows (batches_b x J x ldk, when mat1 is an activation)][output rows (M x ldo)]
+ * [row sums (M int32, int8 with a mat1 zero point)] */
+static size_t matmul_scratch(const b200_op *op, size_t *off_b, size_t *off_o, size_t *off_rs)
+{
+    const size_t M = (size_t)op->mm_batches * op->mm_i;
+    const size_t ldo = (size_t)b200_round_channels(op->mm_j, op->eb);
+    size_t o = 0;
+    o += (M * op->ldk * op->eb + 255) & ~(size_t)255;
+    if (off_b) *off_b = o;
+    if (!op->mm_const_b) o += ((size_t)op->mm_batches_b * op->mm_j * op->ldk * op->eb + 255) & ~(size_t)255;
+    if (off_o) *off_o = o;
+    o += (M * ldo * op->eb + 255) & ~(size_t)255;
+    if (off_rs) *off_rs = o;
+    if (op->d_wzp) o += M * sizeof(int32_t);
+    return o;
+}
+
+static int run_tensor_op(b200_op *op, const b200_dt *in0, const b200_dt *in1, const b200_dt *out, void *scratch, void *stream)
+{
+    b200_view vi, vo;
+    view_of(&vi, op->in_rank, op->in_dim, in0);
+    view_of(&vo, op->out_rank, op->out_dim, out);
+    /* the padding lanes of the output's channel pitch are not covered by the logical walks */
+    DEV_CHECK(b200_memset(out->d, 0, b200_dt_bytes(out), stream));
+    switch (op->t_op) {
+        case B200_T_TRANSPOSE:
+            DEV_CHECK(b200_permute(&vi, in0->d, &vo, out->d, op->t_perm, op->eb, op->d_lut, stream));
+            return CSINN_TRUE;
+        case B200_T_GATHER:
+            DEV_CHECK(b200_gather(&vi, in0->d, &vo, out->d, op->t_axis, op->d_idx, op->n_idx, op->eb, op->d_lut, op->oob_q,
+                                  stream));
+            return CSINN_TRUE;
+        case B200_T_REDUCE_SUM:
+            DEV_CHECK(b200_reduce_sum(&vi, in0->d, &vo, out->d, op->t_axis, op->eb, op->s_in, op->zp_in, op->s_out,
+                                      op->zp_out, stream));
+            return CSINN_TRUE;
+        case B200_T_LAYER_NORM:
+        case B200_T_RMS_NORM:
+            DEV_CHECK(b200_norm(op->t_op == B200_T_RMS_NORM, &vi, in0->d, out->d, op->t_axis, op->t_eps, op->d_gamma,
+                                op->d_beta, op->eb, op->s_in, op->zp_in, op->s_out, op->zp_out, stream));
+            return CSINN_TRUE;
+        case B200_T_MATMUL: {
+            /* rows of mat0 -> K-major A, the tcgen05 GEMM against the packed mat1 (constant: packed at init like
+             * fullyconnected weights; activation: packed per run), rows back into the output tensor */
+            size_t off_b = 0, off_o = 0, off_rs = 0;
+            matmul_scratch(op, &off_b, &off_o, &off_rs);
+            uint8_t *sc = scratch;
+            if (!sc) {
+                b200_fail("matmul: no scratch");
+                return CSINN_FALSE;
+            }
+            const int M = op->mm_batches * op->mm_i;
+            const int ldo = b200_round_channels(op->mm_j, op->eb);
+            DEV_CHECK(b200_pack_rows(&vi, in0->d, op->mm_batches, op->mm_i, op->mm_k, op->mm_trans_a, sc, op->ldk, op->eb, stream));
+            const void *w = op->d_w;
+            if (!op->mm_const_b) {
+                b200_view v1;
+                if (!in1) {
+                    b200_fail("matmul: second operand missing");
+                    return CSINN_FALSE;
+                }
+                view_of(&v1, op->in1_rank, op->in1_dim, in1);
+                /* mat1 is [.., K, J] (rows = j need a transposing walk) or, with trans_b, [.., J, K] */
+                DEV_CHECK(b200_pack_rows(&v1, in1->d, op->mm_batches_b, op->mm_j, op->mm_k, !op->mm_trans_b, sc + off_b, op->ldk,
+                                         op->eb, stream));
+                w = sc + off_b;
+            }
+            b200_gemm_desc g;
+            memset(&g, 0, sizeof(g));
+            g.dtype = op->dtype, g.n = op->mm_j, g.k = op->mm_k, g.lda = op->ldk, g.ldw = op->ldk, g.ldo = ldo;
+            fill_epilogue(op, &g.ep);
+            const int per_batch = !op->mm_const_b && op->mm_batches_b > 1;
+            const int calls = per_batch ? op->mm_batches : 1;
+            for (int b = 0; b < calls; b++) {
+                g.m = per_batch ? op->mm_i : M;
+                g.a = sc + (size_t)b * op->mm_i * op->ldk * op->eb;
+                g.w = (const uint8_t *)w + (per_batch ? (size_t)b * op->mm_j * op->ldk * op->eb : 0);
+                g.out = sc + off_o + (size_t)b * op->mm_i * ldo * op->eb;
+                if (op->d_wzp) {
+                    int32_t *rs = (int32_t *)(sc + off_rs) + (size_t)b * op->mm_i;
+                    DEV_CHECK(b200_rowsum_i8(g.a, g.lda, g.m, op->mm_k, op->zp_in, rs, stream));
+                    g.w_zp = op->d_wzp, g.rowsum = rs;
+                }
+                DEV_CHECK(b200_gemm(&g, stream));
+            }
+            DEV_CHECK(b200_unpack_rows(&vo, out->d, M, op->mm_j, sc + off_o, ldo, op->eb, stream));
+            return CSINN_TRUE;
+        }
+    }
+    b200_fail("unknown tensor op %d", op->t_op);
+    return CSINN_FALSE;
 }
 
 int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, const b200_dt *out,
@@ -543,6 +647,8 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
             DEV_CHECK(b200_softmax(op->dtype, in0->d, out->d, in0->n, in0->c, in0->cp, out->cp,
                                    op->s_in, op->zp_in, op->s_out, op->zp_out, stream));
             return CSINN_TRUE;
+        case B200_OPK_TENSOR:
+            return run_tensor_op(op, in0, in1, out, scratch, stream);
         case B200_OPK_COPY:
             if (op->direct) { /* flatten of an N x C x H x W tensor: back to NCHW order = the flattened rows */
                 DEV_CHECK(b200_nhwc_to_nchw(in0->d, out->d, in0->n, in0->c, in0->h, in0->w, in0->cp, in0->eb, stream));
@@ -1520,3 +1626,293 @@ int shl_b200_perf_diso(struct csinn_tensor *input0, struct csinn_tensor *input1,
     (void)input0, (void)input1, (void)output;
     return perf_set(params, perf_info);
 }
+
+/* ---- transpose / gather / reduce_sum / layer_norm / rms_norm / matmul (source/thead_rvv/setup.c:316-470) ---------- */
+static b200_op *tensor_op_new(struct csinn_params_base *base, const struct csinn_tensor *input,
+                              const struct csinn_tensor *output, int t_op, const char *kname)
+{
+    if (input->dim_count < 1 || input->dim_count > 4 || output->dim_count < 1 || output->dim_count > 4) {
+        b200_fail("%s: tensors of rank 1..4 only (got %d -> %d)", kname, input->dim_count, output->dim_count);
+        return NULL;
+    }
+    b200_op *op = op_new(base, B200_OPK_TENSOR, input->dtype, kname);
+    if (!op) return NULL;
+    op->t_op = t_op;
+    op->in_rank = input->dim_count, op->out_rank = output->dim_count;
+    for (int i = 0; i < input->dim_count; i++) op->in_dim[i] = input->dim[i];
+    for (int i = 0; i < output->dim_count; i++) op->out_dim[i] = output->dim[i];
+    if (op->dtype == B200_I8) {
+        if (!input->qinfo || !output->qinfo) {
+            b200_fail("%s: int8 tensors without qinfo", kname);
+            free(op);
+            return NULL;
+        }
+        op->s_in = input->qinfo->scale, op->zp_in = input->qinfo->zero_point;
+        op->s_out = output->qinfo->scale, op->zp_out = output->qinfo->zero_point;
+    }
+    return op;
+}
+
+/* int8 copies: requant_out(dequant_in(q)) as a table when the two qinfos differ (what the reference's
+ * siso_callback_base does around the f32 copy), else a plain copy */
+static int tensor_op_copy_lut(b200_op *op)
+{
+    if (op->dtype != B200_I8 || (op->s_in == op->s_out && op->zp_in == op->zp_out)) return CSINN_TRUE;
+    op->d_lut = upload_lut(op->ctx, B200_ACT_NONE, 0.f, 0.f, op->s_in, op->zp_in, op->s_out, op->zp_out);
+    return op->d_lut ? CSINN_TRUE : CSINN_FALSE;
+}
+
+static int tensor_exec1(struct csinn_tensor *input, struct csinn_tensor *output, void *params)
+{
+    return layer_exec(params, input, NULL, output);
+}
+
+static int transpose_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_transpose_params *params)
+{
+    b200_op *op = tensor_op_new(&params->base, input, output, B200_T_TRANSPOSE, "b200_transpose");
+    if (!op) return CSINN_FALSE;
+    if (params->permute_num != input->dim_count || output->dim_count != input->dim_count) {
+        b200_fail("transpose: %d permutation entries for a rank-%d tensor", params->permute_num, input->dim_count);
+        free(op);
+        return CSINN_FALSE;
+    }
+    for (int k = 0; k < params->permute_num; k++) op->t_perm[k] = params->permute[k];
+    if (tensor_op_copy_lut(op) != CSINN_TRUE) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())tensor_exec1;
+    return CSINN_TRUE;
+}
+
+static int gather_exec(struct csinn_tensor *input, struct csinn_tensor *indices, struct csinn_tensor *output, void *params)
+{
+    (void)indices;
+    return layer_exec(params, input, NULL, output);
+}
+static int gather_init(struct csinn_tensor *input, struct csinn_tensor *indices, struct csinn_tensor *output,
+                       struct csinn_gather_params *params)
+{
+    if (!indices->is_const || !indices->data || (indices->dtype != CSINN_DTYPE_INT64 && indices->dtype != CSINN_DTYPE_INT32)) {
+        b200_fail("gather: the indices must be a constant int64 / int32 tensor");
+        return CSINN_FALSE;
+    }
+    b200_op *op = tensor_op_new(&params->base, input, output, B200_T_GATHER, "b200_gather");
+    if (!op) return CSINN_FALSE;
+    op->t_axis = params->axis < 0 ? params->axis + input->dim_count : params->axis;
+    int64_t n = 1;
+    for (int i = 0; i < indices->dim_count; i++) n *= indices->dim[i];
+    if (op->t_axis < 0 || op->t_axis >= input->dim_count || n <= 0 || n > (1 << 24)) {
+        b200_fail("gather: axis %d / %lld indices", params->axis, (long long)n);
+        free(op);
+        return CSINN_FALSE;
+    }
+    int32_t *idx = malloc((size_t)n * sizeof(int32_t));
+    if (!idx) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t v = indices->dtype == CSINN_DTYPE_INT64 ? ((const int64_t *)indices->data)[i] : ((const int32_t *)indices->data)[i];
+        idx[i] = v > INT32_MAX ? INT32_MAX : (v < INT32_MIN / 2 ? INT32_MIN / 2 : (int32_t)v); /* out of range stays out of range */
+    }
+    op->d_idx = b200_warena_put(op->ctx, idx, (size_t)n * sizeof(int32_t));
+    op->n_idx = (int)n;
+    free(idx);
+    if (op->dtype == B200_I8) {
+        int8_t one[256];
+        b200_build_unary_lut(one, B200_ACT_NONE, 0.f, 0.f, 1.0f, 0, op->s_out, op->zp_out); /* quantise 0.0: index of q = 0 */
+        op->oob_q = one[128];
+    }
+    if (!op->d_idx || tensor_op_copy_lut(op) != CSINN_TRUE) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())gather_exec;
+    return CSINN_TRUE;
+}
+
+static int reduce_sum_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_reduce_params *params)
+{
+    if (params->axis_count != 1) { /* the reference asserts the same, source/reference/reduce_sum.c:25 */
+        b200_fail("reduce_sum: exactly one axis (got %d)", params->axis_count);
+        return CSINN_FALSE;
+    }
+    b200_op *op = tensor_op_new(&params->base, input, output, B200_T_REDUCE_SUM, "b200_reduce_sum");
+    if (!op) return CSINN_FALSE;
+    op->t_axis = params->axis[0]; /* -1 = over everything, as in the reference */
+    if (op->t_axis < -1 || op->t_axis >= input->dim_count) {
+        b200_fail("reduce_sum: axis %d of a rank-%d tensor", op->t_axis, input->dim_count);
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())tensor_exec1;
+    return CSINN_TRUE;
+}
+
+/* gamma / beta / weight constants as dequantised f32 (what shl_ref_tensor_transform_f32 hands the f32 kernels) */
+static float *const_as_f32(b200_op *op, const struct csinn_tensor *t, int64_t want, const char *what)
+{
+    int64_t n = 1;
+    for (int i = 0; i < t->dim_count; i++) n *= t->dim[i];
+    if (!t->data || n != want) {
+        b200_fail("%s: constant of %lld elements expected (got %lld)", what, (long long)want, (long long)n);
+        return NULL;
+    }
+    float *f = malloc((size_t)n * sizeof(float));
+    if (!f) return NULL;
+    for (int64_t i = 0; i < n; i++) {
+        if (t->dtype == CSINN_DTYPE_INT8)
+            f[i] = ((float)((const int8_t *)t->data)[i] - (float)t->qinfo->zero_point) * t->qinfo->scale;
+        else if (t->dtype == CSINN_DTYPE_FLOAT16)
+            f[i] = b200_f16_to_f32(((const uint16_t *)t->data)[i]) *
+                   (t->qinfo && fabsf(t->qinfo->scale - 1.f) > 1.1920929e-7f ? t->qinfo->scale : 1.f);
+        else if (t->dtype == CSINN_DTYPE_FLOAT32)
+            f[i] = ((const float *)t->data)[i];
+        else {
+            b200_fail("%s: constant dtype %d", what, t->dtype);
+            free(f);
+            return NULL;
+        }
+    }
+    float *d = b200_warena_put(op->ctx, f, (size_t)n * sizeof(float));
+    free(f);
+    return d;
+}
+
+static int norm_exec4(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *g, struct csinn_tensor *b,
+                      void *params)
+{
+    (void)g, (void)b;
+    return layer_exec(params, input, NULL, output);
+}
+static int layer_norm_init(struct csinn_tensor *input, struct csinn_tensor *output, struct csinn_tensor *gamma,
+                           struct csinn_tensor *beta, struct csinn_layer_norm_params *params)
+{
+    b200_op *op = tensor_op_new(&params->base, input, output, B200_T_LAYER_NORM, "b200_layer_norm");
+    if (!op) return CSINN_FALSE;
+    op->t_axis = params->axis >= 0 ? params->axis : params->axis + input->dim_count;
+    op->t_eps = params->epsilon;
+    int64_t norm = 1;
+    for (int i = op->t_axis; i >= 0 && i < input->dim_count; i++) norm *= input->dim[i];
+    if (op->t_axis < 0 || op->t_axis >= input->dim_count || !(op->d_gamma = const_as_f32(op, gamma, norm, "layer_norm gamma")) ||
+        !(op->d_beta = const_as_f32(op, beta, norm, "layer_norm beta"))) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())norm_exec4;
+    return CSINN_TRUE;
+}
+static int rms_norm_exec(struct csinn_tensor *input, struct csinn_tensor *w, struct csinn_tensor *output, void *params)
+{
+    (void)w;
+    return layer_exec(params, input, NULL, output);
+}
+static int rms_norm_init(struct csinn_tensor *input, struct csinn_tensor *weights, struct csinn_tensor *output,
+                         struct csinn_rms_norm_params *params)
+{
+    b200_op *op = tensor_op_new(&params->base, input, output, B200_T_RMS_NORM, "b200_rms_norm");
+    if (!op) return CSINN_FALSE;
+    op->t_axis = params->axis >= 0 ? params->axis : params->axis + input->dim_count;
+    op->t_eps = params->epsilon;
+    int64_t norm = 1;
+    for (int i = op->t_axis; i >= 0 && i < input->dim_count; i++) norm *= input->dim[i];
+    if (op->t_axis < 0 || op->t_axis >= input->dim_count || !(op->d_gamma = const_as_f32(op, weights, norm, "rms_norm weight"))) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())rms_norm_exec;
+    return CSINN_TRUE;
+}
+
+/* csinn_matmul (source/reference/matmul.c:21; replaces shl_rvv_matmul_int8 / _fp16): out[b][i][j] = sum_k a[b][i][k] *
+ * m1[b][k][j] with optional transposes; mat1 shared by all batches when it has none.  A constant mat1 is packed once as
+ * [J][K] rows (the fullyconnected weight layout) with the zero-point fold of the requantise contract; an activation mat1
+ * (fp16 only: its column sums would be run-time data) is packed per run. */
+static int matmul_exec(struct csinn_tensor *mat0, struct csinn_tensor *mat1, struct csinn_tensor *output, void *params)
+{
+    return layer_exec(params, mat0, mat1->is_const ? NULL : mat1, output);
+}
+static int matmul_init(struct csinn_tensor *mat0, struct csinn_tensor *mat1, struct csinn_tensor *output,
+                       struct csinn_matmul_params *params)
+{
+    if (mat0->dim_count < 2 || mat1->dim_count < 2 || mat1->dim_count > 4 || mat0->dtype != mat1->dtype) {
+        b200_fail("matmul: operands of rank 2..4 and one dtype");
+        return CSINN_FALSE;
+    }
+    b200_op *op = tensor_op_new(&params->base, mat0, output, B200_T_MATMUL, "b200_matmul_tcgen05");
+    if (!op) return CSINN_FALSE;
+    const int ra = mat0->dim_count, rb = mat1->dim_count;
+    op->mm_trans_a = params->trans_a ? 1 : 0, op->mm_trans_b = params->trans_b ? 1 : 0;
+    op->mm_i = mat0->dim[ra - (params->trans_a ? 1 : 2)];
+    op->mm_k = mat0->dim[ra - (params->trans_a ? 2 : 1)];
+    op->mm_j = mat1->dim[rb - (params->trans_b ? 2 : 1)];
+    const int kb = mat1->dim[rb - (params->trans_b ? 1 : 2)];
+    op->mm_batches = 1, op->mm_batches_b = 1;
+    for (int i = 0; i < ra - 2; i++) op->mm_batches *= mat0->dim[i];
+    for (int i = 0; i < rb - 2; i++) op->mm_batches_b *= mat1->dim[i];
+    op->in1_rank = rb;
+    for (int i = 0; i < rb; i++) op->in1_dim[i] = mat1->dim[i];
+    op->mm_const_b = mat1->is_const ? 1 : 0;
+    op->kdim = op->mm_k, op->ldk = b200_round_channels(op->mm_k, op->eb), op->o = op->mm_j, op->cin = op->mm_k;
+    int rc = CSINN_TRUE;
+    if (kb != op->mm_k || (op->mm_batches_b != 1 && op->mm_batches_b != op->mm_batches)) {
+        b200_fail("matmul: inner extents %d vs %d, batches %d vs %d", op->mm_k, kb, op->mm_batches, op->mm_batches_b);
+        rc = CSINN_FALSE;
+    } else if (!op->mm_const_b && op->dtype == B200_I8) {
+        b200_fail("matmul: int8 needs a constant second operand (its zero-point fold is precomputed)");
+        rc = CSINN_FALSE;
+    } else if (op->mm_const_b && op->mm_batches_b != 1) {
+        b200_fail("matmul: a constant second operand with batches is not supported");
+        rc = CSINN_FALSE;
+    }
+    if (rc == CSINN_TRUE && op->mm_const_b) {
+        /* [J][K] copy of mat1, then exactly the fullyconnected machinery: requantise tables + packed rows */
+        const int J = op->mm_j, K = op->mm_k, eb = op->eb;
+        struct csinn_tensor wt = *mat1;
+        uint8_t *rows = malloc((size_t)J * K * eb);
+        if (!rows) {
+            free(op);
+            return CSINN_FALSE;
+        }
+        const uint8_t *src = mat1->data;
+        for (int j = 0; j < J; j++)
+            for (int k = 0; k < K; k++)
+                memcpy(rows + ((size_t)j * K + k) * eb, src + (params->trans_b ? ((size_t)j * K + k) : ((size_t)k * J + j)) * eb, (size_t)eb);
+        wt.data = rows, wt.dim_count = 2, wt.dim[0] = J, wt.dim[1] = K;
+        size_t wbytes = 0;
+        rc = b200_make_requant(op, mat0, &wt, NULL, output, K, 0, J);
+        if (rc == CSINN_TRUE && !(op->d_w = b200_pack_fc_weights(op, &wt, &wbytes))) rc = CSINN_FALSE;
+        free(rows);
+    } else if (rc == CSINN_TRUE) {
+        struct csinn_tensor none = *mat1; /* fp16 x fp16 activations: no tables, no bias */
+        none.data = NULL;
+        op->d_mult = op->d_badd = NULL, op->d_ibias = NULL;
+        op->two_inputs = 1;
+        (void)none;
+    }
+    if (rc != CSINN_TRUE) {
+        free(op);
+        return CSINN_FALSE;
+    }
+    b200_op_bind(params, op);
+    params->base.cb->exec = (int (*)())matmul_exec;
+    return CSINN_TRUE;
+}
+
+void *shl_b200_transpose_init_fn(void) { return (void *)transpose_init; }
+void *shl_b200_gather_init_fn(void) { return (void *)gather_init; }
+void *shl_b200_reduce_sum_init_fn(void) { return (void *)reduce_sum_init; }
+void *shl_b200_layer_norm_init_fn(void) { return (void *)layer_norm_init; }
+void *shl_b200_rms_norm_init_fn(void) { return (void *)rms_norm_init; }
+void *shl_b200_matmul_init_fn(void) { return (void *)matmul_init; }
+void *shl_b200_tensor_exec1_fn(void) { return (void *)tensor_exec1; }
+void *shl_b200_gather_exec_fn(void) { return (void *)gather_exec; }
+void *shl_b200_norm_exec4_fn(void) { return (void *)norm_exec4; }
+void *shl_b200_rms_norm_exec_fn(void) { return (void *)rms_norm_exec; }
+void *shl_b200_matmul_exec_fn(void) { return (void *)matmul_exec; }

@@ -13,6 +13,7 @@
 
 #include "b200_internal.h"
 
+float b200_f16_to_f32(uint16_t h);
 static float f16_to_f32(uint16_t h)
 {
     uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 0x1F, man = h & 0x3FF, u;
@@ -36,6 +37,8 @@ static float f16_to_f32(uint16_t h)
     memcpy(&f, &u, 4);
     return f;
 }
+
+float b200_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
 
 /* IEEE round-to-nearest-even, what a hardware convert does */
 static uint16_t f32_to_f16_rne(float f)

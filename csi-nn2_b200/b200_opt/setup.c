@@ -16,7 +16,7 @@
 
 #include "b200_internal.h"
 
-#define B200_CB_MAX 64
+#define B200_CB_MAX 160
 static struct shl_cb_table g_cb_table[B200_CB_MAX];
 static int g_cb_n;
 static struct csinn_callback g_cb_unset; /* all NULL: csinn_<op>() -> CSINN_CALLBACK_UNSET */
@@ -91,6 +91,12 @@ static void build_table(void)
         reg_op(dt, CSINN_OP_SOFTMAX, shl_b200_softmax_init, shl_b200_softmax, shl_gref_softmax, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_RESHAPE, shl_b200_reshape_init, shl_b200_reshape, shl_gref_reshape, shl_b200_perf_siso);
         reg_op(dt, CSINN_OP_FLATTEN, shl_b200_reshape_init, shl_b200_reshape, shl_gref_flatten, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_TRANSPOSE, shl_b200_transpose_init_fn(), shl_b200_tensor_exec1_fn(), shl_gref_transpose, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_GATHER, shl_b200_gather_init_fn(), shl_b200_gather_exec_fn(), shl_gref_gather, shl_b200_perf_diso);
+        reg_op(dt, CSINN_OP_REDUCE_SUM, shl_b200_reduce_sum_init_fn(), shl_b200_tensor_exec1_fn(), shl_gref_reduce_sum, shl_b200_perf_siso);
+        reg_op(dt, CSINN_OP_LAYER_NORM, shl_b200_layer_norm_init_fn(), shl_b200_norm_exec4_fn(), shl_gref_layer_norm, NULL);
+        reg_op(dt, CSINN_OP_RMS_NORM, shl_b200_rms_norm_init_fn(), shl_b200_rms_norm_exec_fn(), shl_gref_rms_norm, NULL);
+        reg_op(dt, CSINN_OP_MATMUL, shl_b200_matmul_init_fn(), shl_b200_matmul_exec_fn(), shl_gref_matmul, shl_b200_perf_diso);
     }
 }
 

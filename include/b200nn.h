@@ -354,6 +354,40 @@ typedef struct {
 } b200_concat_desc;
 int b200_concat_slice(const b200_concat_desc *d, void *stream);
 
+/* ---- structural / normalisation operators of the RVV table (csrc/tensor_ops.cu) ---------------------------- */
+/* A tensor of logical rank 1..4 in the device layout: rank 4 (d0..d3) = (n, c, h, w), rank 3 = (n, c, w), rank 2 =
+ * (n, c), rank 1 = (c); element (n, c, h, w) at ((n*H + h)*W + w)*cp + c.  The kernels below walk LOGICAL row-major
+ * indices -- the order the reference's loops define the semantics in -- and map them to device offsets. */
+typedef struct {
+    int32_t rank;
+    int32_t dim[4];
+    int32_t cp; /* channel pitch in elements */
+} b200_view;
+/* transpose: out[o] = in[i] with i[perm[k]] = o[k] (source/reference/transpose.c:57; replaces shl_rvv_transpose_int8 /
+ * _fp16).  int8 with differing qinfo: lut = requant_out(dequant_in(q)) as for concat, else NULL. */
+int b200_permute(const b200_view *in, const void *src, const b200_view *out, void *dst, const int32_t *perm,
+                 int elem_bytes, const int8_t *lut_dev, void *stream);
+/* gather along `axis` with n_idx constant indices (negative = from the end, out of range = 0.0:
+ * source/reference/gather.c:21-60; replaces shl_rvv_gather_int8 / _fp16); oob_q = the quantised 0.0 */
+int b200_gather(const b200_view *in, const void *src, const b200_view *out, void *dst, int axis, const int32_t *idx_dev,
+                int n_idx, int elem_bytes, const int8_t *lut_dev, int oob_q, void *stream);
+/* sum over one axis (axis < 0: over everything), sequential f32 in index order like source/reference/reduce_sum.c:21
+ * (replaces shl_rvv_reduce_sum_int8) */
+int b200_reduce_sum(const b200_view *in, const void *src, const b200_view *out, void *dst, int axis, int elem_bytes,
+                    float s_in, int zp_in, float s_out, int zp_out, void *stream);
+/* layer_norm (rms = 0: (x - mean) / sqrt(var + eps) * gamma + beta) / rms_norm (rms = 1: x / sqrt(mean(x^2) + eps) *
+ * gamma) over the axes [axis, rank): source/reference/layer_norm.c:21, rms_norm.c:21, the float sequence verbatim;
+ * gamma / beta = dequantised f32 device arrays of the normalised extent (replaces shl_rvv_layer_norm_int8 / _fp16,
+ * shl_rvv_rms_norm_fp16) */
+int b200_norm(int rms, const b200_view *v, const void *src, void *dst, int axis, float eps, const float *gamma_dev,
+              const float *beta_dev, int elem_bytes, float s_in, int zp_in, float s_out, int zp_out, void *stream);
+/* csinn_matmul on the tcgen05 GEMM: logical matrices [.., R, K] (trans = 0) or [.., K, R] (trans = 1) <-> dense K-major
+ * rows [(batch * R + r)][ld] that b200_gemm takes as A or W; and the GEMM's output rows back into a tensor */
+int b200_pack_rows(const b200_view *t, const void *src, int batches, int rows, int k, int trans, void *rows_dev, int ld,
+                   int elem_bytes, void *stream);
+int b200_unpack_rows(const b200_view *t, void *dst, long long nrows, int cols, const void *rows_dev, int ld, int elem_bytes,
+                     void *stream);
+
 /* maxpool / avgpool on pixel-major tensors; reference: source/reference/maxpool.c:64,
  * averagepool.c:71 (sequential f32 sum in (y,x) order, divided by the valid-tap count unless
  * count_include_pad). global average pool = kh=h, kw=w (global_averagepool.c:21). */

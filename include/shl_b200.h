@@ -80,6 +80,19 @@ void *shl_b200_sigmoid_init_fn(void);
 void *shl_b200_clip_init_fn(void);
 void *shl_b200_global_maxpool_init_fn(void); /* csinn_global_maxpool2d, source/reference/global_maxpool.c:21 */
 void *shl_b200_div_init_fn(void);   /* csinn_div, source/reference/div.c:36 */
+/* transpose / gather / reduce_sum / layer_norm / rms_norm / matmul (source/thead_rvv/setup.c:316-470; semantics
+ * source/reference/transpose.c, gather.c, reduce_sum.c, layer_norm.c, rms_norm.c, matmul.c) */
+void *shl_b200_transpose_init_fn(void);
+void *shl_b200_gather_init_fn(void);
+void *shl_b200_reduce_sum_init_fn(void);
+void *shl_b200_layer_norm_init_fn(void);
+void *shl_b200_rms_norm_init_fn(void);
+void *shl_b200_matmul_init_fn(void);
+void *shl_b200_tensor_exec1_fn(void);
+void *shl_b200_gather_exec_fn(void);
+void *shl_b200_norm_exec4_fn(void);
+void *shl_b200_rms_norm_exec_fn(void);
+void *shl_b200_matmul_exec_fn(void);
 void *shl_b200_prelu_init_fn(void); /* csinn_prelu with a constant per-channel slope, source/reference/prelu.c:21 */
 void *shl_b200_silu_init_fn(void); /* csinn_silu: val / (1 + exp(-val)), source/reference/silu.c:21 */
 void *shl_b200_erf_init_fn(void);  /* csinn_erf, source/reference/erf.c:21 */

@@ -49,6 +49,13 @@ enum {
     H_SPLIT, /* csinn_split of in0 in two at index (int)p0 along `axis`; the layer's output is slice (int)p1, the
                 other slice goes to a scratch tensor (net->k[i]) with the same qinfo */
     H_DIV,
+    H_TRANSPOSE,  /* csinn_transpose, permutation in (kh, kw, sh, sw) */
+    H_GATHER,     /* csinn_gather along `axis`, `o` constant int64 indices in w */
+    H_REDUCE_SUM, /* csinn_reduce_sum over `axis` (-1: everything); keepdims when the ranks agree */
+    H_LAYER_NORM, /* csinn_layer_norm from `axis` on, eps = p0, gamma = w, beta = b (o elements, qinfo s_w / zp_w) */
+    H_RMS_NORM,   /* csinn_rms_norm from `axis` on, eps = p0, weight = w */
+    H_MATMUL,     /* csinn_matmul(in0, mat1): mat1 = constant w with the pt dims (kh, kw, sh, sw), or tensor in1 when w is
+                     NULL; trans_a = pd, trans_b = pr */
 };
 
 typedef struct {
@@ -273,6 +280,53 @@ static int layer_init(h_net *net, int i)
             net->params[i] = p;
             return csinn_prelu_init(in, net->k[i], out, p);
         }
+        case H_TRANSPOSE: {
+            struct csinn_transpose_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->permute_num = in->dim_count;
+            p->permute = calloc(4, sizeof(int32_t));
+            p->permute[0] = L->kh, p->permute[1] = L->kw, p->permute[2] = L->sh, p->permute[3] = L->sw;
+            net->params[i] = p;
+            return csinn_transpose_init(in, out, p);
+        }
+        case H_GATHER: {
+            struct csinn_gather_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->axis = L->axis;
+            net->params[i] = p;
+            return csinn_gather_init(in, net->k[i], out, p);
+        }
+        case H_REDUCE_SUM: {
+            struct csinn_reduce_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->axis_count = 1;
+            p->axis = calloc(1, sizeof(int32_t));
+            p->axis[0] = L->axis;
+            p->keepdims = out->dim_count == in->dim_count;
+            net->params[i] = p;
+            return csinn_reduce_sum_init(in, out, p);
+        }
+        case H_LAYER_NORM: {
+            struct csinn_layer_norm_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->epsilon = L->p0, p->axis = L->axis, p->center = true, p->scale = true;
+            net->params[i] = p;
+            return csinn_layer_norm_init(in, out, net->k[i], net->bias[i], p);
+        }
+        case H_RMS_NORM: {
+            struct csinn_rms_norm_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->epsilon = L->p0, p->axis = L->axis;
+            net->params[i] = p;
+            return csinn_rms_norm_init(in, net->k[i], out, p);
+        }
+        case H_MATMUL: {
+            struct csinn_matmul_params *p = csinn_alloc_params(sizeof(*p), net->sess);
+            base_init(net, &p->base, nm);
+            p->trans_a = L->pd != 0, p->trans_b = L->pr != 0;
+            net->params[i] = p;
+            return csinn_matmul_init(in, L->w ? net->k[i] : net->t[L->in1], out, p);
+        }
         case H_CONCAT: {
             struct csinn_concat_params *p = csinn_alloc_params(sizeof(*p), net->sess);
             base_init(net, &p->base, nm);
@@ -367,6 +421,18 @@ static int layer_call(h_net *net, int i)
         }
         case H_PRELU:
             return csinn_prelu(in, net->k[i], out, p);
+        case H_TRANSPOSE:
+            return csinn_transpose(in, out, p);
+        case H_GATHER:
+            return csinn_gather(in, net->k[i], out, p);
+        case H_REDUCE_SUM:
+            return csinn_reduce_sum(in, out, p);
+        case H_LAYER_NORM:
+            return csinn_layer_norm(in, out, net->k[i], net->bias[i], p);
+        case H_RMS_NORM:
+            return csinn_rms_norm(in, net->k[i], out, p);
+        case H_MATMUL:
+            return csinn_matmul(in, L->w ? net->k[i] : net->t[L->in1], out, p);
         case H_CONCAT: {
             struct csinn_tensor *ins[3] = {in, net->t[L->in1], in};
             return csinn_concat(ins, out, p);
@@ -464,6 +530,32 @@ void *h_net_create(int api, int dtype, int run_mode, const int32_t *in_dims, int
             net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
             net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f;
             net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
+        }
+        if ((L->kind == H_LAYER_NORM || L->kind == H_RMS_NORM) && L->w) {
+            int32_t cd[1] = {L->o};
+            snprintf(nm, sizeof(nm), "gamma_%d", i);
+            net->k[i] = new_tensor(net, nm, cd, 1, wdtype, CSINN_LAYOUT_O, 1, 1);
+            net->k[i]->data = (void *)L->w, net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+            net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f, net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
+            if (L->b) {
+                snprintf(nm, sizeof(nm), "beta_%d", i);
+                net->bias[i] = new_tensor(net, nm, cd, 1, wdtype, CSINN_LAYOUT_O, 1, 1);
+                net->bias[i]->data = (void *)L->b, net->bias[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+                net->bias[i]->qinfo->scale = net->k[i]->qinfo->scale, net->bias[i]->qinfo->zero_point = net->k[i]->qinfo->zero_point;
+            }
+        }
+        if (L->kind == H_GATHER) {
+            int32_t cd[1] = {L->o};
+            snprintf(nm, sizeof(nm), "indices_%d", i);
+            net->k[i] = new_tensor(net, nm, cd, 1, CSINN_DTYPE_INT64, CSINN_LAYOUT_N, 1, 1);
+            net->k[i]->data = (void *)L->w, net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+        }
+        if (L->kind == H_MATMUL && L->w) {
+            int32_t cd[4] = {L->kh, L->kw, L->sh, L->sw};
+            snprintf(nm, sizeof(nm), "mat1_%d", i);
+            net->k[i] = new_tensor(net, nm, cd, L->pt, wdtype, act_layout(L->pt), 1, 1);
+            net->k[i]->data = (void *)L->w, net->k[i]->mtype = CSINN_MEM_TYPE_CPU_ALIGNED;
+            net->k[i]->qinfo->scale = L->s_w ? L->s_w[0] : 1.0f, net->k[i]->qinfo->zero_point = L->zp_w ? L->zp_w[0] : 0;
         }
         if (L->kind <= H_FC) {
             struct csinn_tensor *in = net->t[L->in0];

@@ -28,7 +28,8 @@ API_REF, API_C906, API_C920, API_C908, API_RVV, API_C920V2 = 0, 3, 4, 12, 15, 18
 RM_LAYER, RM_GRAPH = 0, 1
 
 (H_CONV, H_CONV_RELU, H_CONV_RELU6, H_DWCONV, H_FC, H_RELU, H_RELU6, H_ADD, H_MAXPOOL, H_AVGPOOL,
- H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL, H_CONCAT, H_SILU, H_ERF, H_GMP, H_PRELU, H_SPLIT, H_DIV) = range(26)
+ H_GAP, H_SOFTMAX, H_FLATTEN, H_RESHAPE, H_LEAKY_RELU, H_SIGMOID, H_CLIP, H_SUB, H_MUL, H_CONCAT, H_SILU, H_ERF, H_GMP, H_PRELU, H_SPLIT, H_DIV, H_TRANSPOSE, H_GATHER,
+ H_REDUCE_SUM, H_LAYER_NORM, H_RMS_NORM, H_MATMUL) = range(32)
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 UNARY_LEAKY_RELU, UNARY_SIGMOID, UNARY_CLIP, UNARY_SILU, UNARY_ERF = 3, 4, 5, 6, 7
@@ -219,6 +220,11 @@ class Net:
             a.group, a.fuse_zp2bias = int(l.group), int(l.fuse_zp2bias)
             a.count_include_pad, a.ceil_mode, a.axis = int(l.count_include_pad), int(l.ceil_mode), int(l.axis)
             a.p0, a.p1 = float(l.p0), float(l.p1)
+            if l.kind == H_TRANSPOSE:  # permutation in (kernel, stride)
+                a.kh, a.kw, a.sh, a.sw = (list(l.kernel) + list(l.stride))[:4]
+            if l.kind == H_MATMUL and l.w is not None:  # constant mat1: its dims in (kh, kw, sh, sw), rank in pt
+                shp = list(np.asarray(l.w).shape) + [1, 1, 1]
+                a.kh, a.kw, a.sh, a.sw, a.pt = shp[0], shp[1], shp[2], shp[3], np.asarray(l.w).ndim
         dims = (C.c_int32 * len(self.in_shape))(*self.in_shape)
         self._arr = arr
         self.handle = h.lib.h_net_create(api, dtype, run_mode, dims, len(self.in_shape), float(s_in), int(zp_in),
