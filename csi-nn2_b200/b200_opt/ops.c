@@ -521,6 +521,7 @@ static int run_tensor_op(b200_op *op, const b200_dt *in0, const b200_dt *in1, co
             b200_gemm_desc g;
             memset(&g, 0, sizeof(g));
             g.dtype = op->dtype, g.n = op->mm_j, g.k = op->mm_k, g.lda = op->ldk, g.ldw = op->ldk, g.ldo = ldo;
+            g.w_dynamic = !op->mm_const_b; /* packed by the kernel just before: no weight prefetch under dependent launch */
             fill_epilogue(op, &g.ep);
             const int per_batch = !op->mm_const_b && op->mm_batches_b > 1;
             const int calls = per_batch ? op->mm_batches : 1;

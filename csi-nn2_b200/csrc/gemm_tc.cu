@@ -67,6 +67,7 @@ struct GemmArgs {
     const int32_t *rowsum;  // ... and the row sums b200_rowsum_i8 computed
     // implicit-GEMM convolution (IGEMM): the A operand is gathered by TMA im2col loads, one filter tap x one channel
     // slab per K block, straight from the pixel-major activation tensor
+    int b_dynamic;          // the B operand is the predecessor's output: no prefetch before griddepcontrol.wait
     int issuers;            // 1, or 2: a second warp issues the MMAs of every other K block (int8, long K: one thread
                             // issues an MMA every ~113-155 cycles whatever its shape, the pipe takes an N = 128 one
                             // every 64 -- csrc/umma_probe.cu)
@@ -183,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
+            if (args.b_dynamic) pdl_wait();  // B is an activation: it does not exist before the predecessor completes
             if (args.b_resident) {
                 mbar_expect_tx(b_bar, args.k_blocks * b_stage_bytes);
                 for (int kb = 0; kb < args.k_blocks; kb++)
@@ -779,6 +781,7 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     args.out = d->out;
     args.ep = make_epi(d->ep);
     args.wzp = d->w_zp, args.rowsum = d->rowsum;
+    args.b_dynamic = d->w_dynamic != 0;
     // a second MMA issuer when the layer is long enough in K to be bound by one thread's issue rate
     // (SHL_B200_GEMM_ISSUERS=1/2 forces it); int8 only: the fp16 accumulation order stays one thread's
     args.issuers = (d->dtype == B200_I8 && args.k_blocks >= 9) ? 2 : 1;

@@ -180,6 +180,9 @@ typedef struct {
      * row sums rs[m] = sum_k a[m][k] - zp_in * k computed by b200_rowsum_i8 */
     const int32_t *w_zp;   /* device [n] */
     const int32_t *rowsum; /* device [m] */
+    int32_t w_dynamic;     /* != 0: `w` was written by the preceding kernel of the stream (matmul of two activations), not at
+                              init: under programmatic dependent launch the kernel must not prefetch it before its
+                              predecessor has completed */
 } b200_gemm_desc;
 int b200_gemm(const b200_gemm_desc *d, void *stream);
 /* rs[m] = sum_{k < K} a[m][k] - zp_in * K over int8 rows of pitch lda: the per-pixel term an asymmetric
