@@ -87,6 +87,8 @@ typedef struct b200_op {
     /* implicit-GEMM convolution (csrc/gemm_tc.cu IGEMM): border classes of the output positions and the
      * accumulator seeds per (class, output channel); ig_ncls == 0: the op takes the explicit im2col path */
     int ig_ncls;
+    void *d_w_diag;  /* depthwise as an implicit GEMM: [cp][taps * 64] rows, diagonal per tap (quant.c b200_pack_dw_diag) */
+    int ldk_diag;
     int32_t *d_ig_seeds;
     uint8_t *d_ig_clsmap;
     int ig_h, ig_w, ig_oh, ig_ow; /* the geometry the tables were built for */
@@ -156,6 +158,7 @@ float b200_f16_to_f32(uint16_t h);
 void *b200_pack_conv_weights(b200_op *op, const struct csinn_tensor *kernel, size_t *bytes);
 void *b200_pack_dw_weights(b200_op *op, const struct csinn_tensor *kernel, int cp, size_t *bytes);
 void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int cp);
+void *b200_pack_dw_diag(b200_op *op, const struct csinn_tensor *kernel, int cp, int *ldk);
 int b200_make_igemm_tables(b200_op *op, const struct csinn_tensor *kernel, int h, int w, int oh, int ow);
 void *b200_pack_fc_weights(b200_op *op, const struct csinn_tensor *weights, size_t *bytes);
 

@@ -266,6 +266,8 @@ static size_t weight_bound(struct shl_ref_graph *graph)
             if (!ct || !ct->is_const) continue;
             size_t e = csinn_tensor_size(ct);
             total += e * 8 + (size_t)(ct->dim_count ? ct->dim[0] : 1) * 64 * 4 + 8192;
+            if (ct->dim_count == 4 && ct->dim[1] == 1) /* depthwise: the tap-diagonal weight matrix of the implicit GEMM */
+                total += (size_t)ct->dim[0] * ct->dim[2] * ct->dim[3] * 64 + 1024;
             if (ct->dim_count == 4) { /* implicit-GEMM tables: <= 64 seed rows (counted above) + the class map of the output */
                 struct csinn_tensor *ot = l->out[0]->data;
                 if (ot && ot->dim_count == 4) total += (size_t)ot->dim[2] * ot->dim[3] + 512;

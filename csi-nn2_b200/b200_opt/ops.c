@@ -343,9 +343,23 @@ static int conv_uses_igemm(const b200_op *op, const b200_dt *in0)
            in0->h == op->ig_h && in0->w == op->ig_w && in0->c == op->cin && !getenv("SHL_B200_NO_IGEMM");
 }
 
+/* depthwise convolutions with channels a multiple of 64 run on the same implicit-GEMM kernel against tap-diagonal
+ * weights (SHL_B200_DW_IGEMM=0 keeps the dp4a kernels; =1 forces it where it applies; default: see dw_igemm_rule) */
+static int dw_uses_igemm(const b200_op *op, const b200_dt *in0)
+{
+    if (op->kind != B200_OPK_DW || !op->d_w_diag || op->ig_ncls < 1 || in0->is_nchw || in0->h != op->ig_h ||
+        in0->w != op->ig_w)
+        return 0;
+    if (getenv("SHL_B200_DW_GENERIC") || getenv("SHL_B200_DW_UMMA")) return 0; /* another kernel was asked for */
+    const char *e = getenv("SHL_B200_DW_IGEMM");
+    if (e) return atoi(e) != 0;
+    return 1;
+}
+
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0)
 {
     if (conv_uses_igemm(op, in0)) return "b200_conv_igemm_tcgen05";
+    if (dw_uses_igemm(op, in0)) return "b200_dwconv_igemm_tcgen05";
     if (op->kind == B200_OPK_CONV && conv_goes_direct(op, in0))
         return (op->dtype == B200_I8 && conv_stem_on_tc(op, in0)) ? "b200_conv2d_stem_tcgen05" : "b200_conv2d_direct";
     return op->kname;
@@ -596,6 +610,18 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
             return CSINN_TRUE;
         }
         case B200_OPK_DW: {
+            if (dw_uses_igemm(op, in0)) {
+                b200_conv_igemm_desc c;
+                memset(&c, 0, sizeof(c));
+                c.n = in0->n, c.h = in0->h, c.w = in0->w, c.c = in0->c, c.cp_in = in0->cp;
+                c.o = op->o, c.oh = out->h, c.ow = out->w, c.kh = op->kh, c.kw = op->kw;
+                c.stride_h = op->sh, c.stride_w = op->sw, c.pad_top = op->pt, c.pad_left = op->pl, c.dil_h = op->dh, c.dil_w = op->dw;
+                c.in = in0->d, c.wt = op->d_w_diag, c.ldw = op->ldk_diag, c.out = out->d, c.ldo = out->cp;
+                fill_epilogue(op, &c.ep);
+                c.ncls = op->ig_ncls, c.seeds = op->d_ig_seeds, c.cls_map = op->d_ig_clsmap, c.dw_slab = 1;
+                DEV_CHECK(b200_conv_igemm(&c, stream));
+                return CSINN_TRUE;
+            }
             b200_dwconv_desc d;
             memset(&d, 0, sizeof(d));
             d.dtype = op->dtype, d.n = in0->n, d.c = in0->c, d.cp = in0->cp;
@@ -960,6 +986,13 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
         if (rc == CSINN_TRUE && op->dtype == B200_I8 && kh == 3 && kw == 3 &&
             !(op->d_w2 = b200_pack_dw3x3_rows(op, kernel, cp)))
             rc = CSINN_FALSE;
+        /* int8, channels a multiple of 64, symmetric weights: the depthwise convolution can run as an implicit GEMM on
+         * the tensor cores against tap-diagonal weights (b200_conv_igemm, dw_slab) */
+        if (rc == CSINN_TRUE && op->dtype == B200_I8 && C % 64 == 0 && !op->d_wzp && kh * kw <= 25 && output->dim_count == 4) {
+            rc = b200_make_igemm_tables(op, kernel, input->dim[2], input->dim[3], output->dim[2], output->dim[3]);
+            if (rc == CSINN_TRUE && op->ig_ncls >= 1 && !(op->d_w_diag = b200_pack_dw_diag(op, kernel, cp, &op->ldk_diag)))
+                rc = CSINN_FALSE;
+        }
     } else {
         const int og = O / group;
         if (group > 1 && (og * op->eb) % 16) {

@@ -274,7 +274,8 @@ int b200_make_igemm_tables(b200_op *op, const struct csinn_tensor *kernel, int h
 {
     op->ig_ncls = 0;
     if (op->dtype != B200_I8 || op->group != 1 || op->kh > 16 || op->kw > 16 || (size_t)oh * ow > (1u << 20)) return CSINN_TRUE;
-    const int O = op->o, C = op->cin, kh = op->kh, kw = op->kw;
+    /* a depthwise kernel is O1HW: one input channel per output */
+    const int O = op->o, C = op->kind == B200_OPK_DW ? 1 : op->cin, kh = op->kh, kw = op->kw;
     uint32_t rmasks[64], cmasks[64];
     int nr = 0, nc = 0;
     uint8_t *rcls = malloc((size_t)oh), *ccls = malloc((size_t)ow);
@@ -424,6 +425,23 @@ void *b200_pack_dw3x3_rows(b200_op *op, const struct csinn_tensor *kernel, int c
         }
     void *dev = b200_warena_put(op->ctx, buf, (size_t)3 * cp * sizeof(uint32_t));
     free(buf);
+    return dev;
+}
+
+/* depthwise as an implicit GEMM (b200_conv_igemm_desc.dw_slab): row o = [tap][64] bytes, zero except w[o][tap] at
+ * column o % 64 of its tap -- a matrix that is diagonal per (64-channel slab, tap) */
+void *b200_pack_dw_diag(b200_op *op, const struct csinn_tensor *kernel, int cp, int *ldk)
+{
+    const int C = kernel->dim[0], taps = kernel->dim[2] * kernel->dim[3];
+    const int ld = taps * 64;
+    uint8_t *buf = calloc((size_t)cp * ld, 1);
+    if (!buf) return NULL;
+    const int8_t *src = kernel->data;
+    for (int c = 0; c < C; c++)
+        for (int t = 0; t < taps; t++) buf[(size_t)c * ld + t * 64 + (c & 63)] = (uint8_t)src[(size_t)c * taps + t];
+    void *dev = b200_warena_put(op->ctx, buf, (size_t)cp * ld);
+    free(buf);
+    *ldk = ld;
     return dev;
 }
 

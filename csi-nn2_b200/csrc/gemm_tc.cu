@@ -71,6 +71,8 @@ struct GemmArgs {
     int issuers;            // 1, or 2: a second warp issues the MMAs of every other K block (int8, long K: one thread
                             // issues an MMA every ~113-155 cycles whatever its shape, the pipe takes an N = 128 one
                             // every 64 -- csrc/umma_probe.cu)
+    int dw_slab;            // depthwise as an implicit GEMM: n-tile j multiplies ITS OWN 64 input channels (the A
+                            // channel coordinate follows n0) with a B that is diagonal per filter tap
     int kb_bytes;           // bytes of K per block: 128, or 64 (64-channel layers: SWIZZLE_64B operand tiles)
     int slabs;              // channel slabs per tap = C / kb_bytes
     int kw, dil_w, dil_h;   // tap index -> (ky, kx) -> load offsets
@@ -233,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const int bwg = g == 0 ? bw[0] : (g == 1 ? bw[1] : (g == 2 ? bw[2] : bw[3]));
                         const int bhg = g == 0 ? bh[0] : (g == 1 ? bh[1] : (g == 2 ? bh[2] : bh[3]));
                         const int big = g == 0 ? bimg[0] : (g == 1 ? bimg[1] : (g == 2 ? bimg[2] : bimg[3]));
-                        tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb), bwg, bhg, big,
+                        tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb) + (args.dw_slab ? n0 : 0), bwg, bhg, big,
                                            static_cast<uint16_t>(tkx * args.dil_w), static_cast<uint16_t>(tky * args.dil_h));
                     } else if (args.cluster > 1) {
                         const int half = static_cast<int>(cta_rank);
@@ -740,10 +742,10 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     args.m = d->m;
     args.n = d->n;
     // implicit GEMM: one K block = one filter tap x one channel slab of 128 (or, for 64-channel layers, 64) bytes
-    const int kb_bytes = ig ? (ig->c % 128 == 0 ? 128 : 64) : kBKBytes;
+    const int kb_bytes = ig ? ((ig->c % 128 == 0 && !ig->dw_slab) ? 128 : 64) : kBKBytes;
     args.kb_bytes = kb_bytes;
     args.k_blocks = (d->k * eb + kb_bytes - 1) / kb_bytes;
-    args.bn = pick_bn(d->n, d->dtype);
+    args.bn = (ig && ig->dw_slab) ? 64 : pick_bn(d->n, d->dtype);  // depthwise: one n-tile = one 64-channel slab
     // prefer an n-tile whose weights stay resident in shared memory: halve a 256-wide tile when
     // that makes K * bn fit
     if (d->dtype == B200_F16 && args.k_blocks * args.bn * kb_bytes > kResidentBBytes && args.bn > 128 &&
@@ -752,7 +754,7 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     args.num_m_tiles = (d->m + kBM - 1) / kBM;
     // few rows (classifier layers, small batches): narrower int8 n-tiles so that more SMs get a tile
     // -- the kernel is latency-bound there and every CTA streams only its own slice of the weights
-    if (d->dtype == B200_I8 && !getenv("SHL_B200_GEMM_NO_NARROW"))
+    if (d->dtype == B200_I8 && !(ig && ig->dw_slab) && !getenv("SHL_B200_GEMM_NO_NARROW"))
         while (args.bn > 32 && static_cast<long long>(args.num_m_tiles) * ((d->n + args.bn - 1) / args.bn) * 2 <= sm_count())
             args.bn /= 2;
     args.num_n_tiles = (d->n + args.bn - 1) / args.bn;
@@ -813,7 +815,8 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
         const int upper_h = lower_h + (ig->oh - 1) * ig->stride_h - (ig->h - 1);
         rc = encode_tmap_im2col_u8(&ta, ig->in, ig->n, ig->h, ig->w, ig->c, ig->cp_in, lower_w, lower_h, upper_w, upper_h,
                                    ig->stride_w, ig->stride_h, kb_bytes, kBM, kb_bytes);
-        args.slabs = ig->c / kb_bytes, args.kw = ig->kw, args.dil_w = ig->dil_w, args.dil_h = ig->dil_h;
+        args.slabs = ig->dw_slab ? 1 : ig->c / kb_bytes, args.kw = ig->kw, args.dil_w = ig->dil_w, args.dil_h = ig->dil_h;
+        args.dw_slab = ig->dw_slab != 0;
         args.ow = ig->ow, args.ohw = ig->oh * ig->ow;
         args.stride_w = ig->stride_w, args.stride_h = ig->stride_h, args.lower_w = lower_w, args.lower_h = lower_h;
         args.ncls = ig->ncls > 1 ? ig->ncls : 1, args.seeds = ig->seeds, args.cls_map = ig->cls_map;
@@ -923,7 +926,8 @@ static bool igemm_shape_ok(const b200_conv_igemm_desc *c)
            c->kw >= 1 && c->stride_w >= 1 && c->stride_w <= 8 && c->stride_h >= 1 && c->stride_h <= 8 &&
            c->dil_w >= 1 && c->dil_h >= 1 && (c->kw - 1) * c->dil_w <= 255 && (c->kh - 1) * c->dil_h <= 255 &&
            c->pad_left <= 128 && c->pad_top <= 128 && c->pad_left >= 0 && c->pad_top >= 0 && upper_w >= -128 && upper_w <= 127 &&
-           upper_h >= -128 && upper_h <= 127 && c->ldw >= c->kh * c->kw * c->c && c->ldw % 16 == 0 && c->ldo >= c->o &&
+           upper_h >= -128 && upper_h <= 127 && c->ldw >= c->kh * c->kw * (c->dw_slab ? 64 : c->c) && c->ldw % 16 == 0 &&
+           (!c->dw_slab || c->o == c->c) && c->ldo >= c->o &&
            c->ldo % 16 == 0 && static_cast<long long>(c->n) * c->oh * c->ow < (1ll << 31) &&
            (c->ncls <= 1 || (c->seeds && c->cls_map && c->ncls <= 64));
 }
@@ -938,7 +942,9 @@ extern "C" int b200_conv_igemm(const b200_conv_igemm_desc *c, void *stream)
     }
     b200_gemm_desc g = {};
     g.dtype = B200_I8;
-    g.m = c->n * c->oh * c->ow, g.n = c->o, g.k = c->kh * c->kw * c->c;
+    // depthwise (dw_slab): every 64-channel n-tile contracts over taps x ITS 64 channels; `wt` holds, per output channel,
+    // the row [tap][64] that is zero except w[o][tap] at column o % 64
+    g.m = c->n * c->oh * c->ow, g.n = c->o, g.k = c->kh * c->kw * (c->dw_slab ? 64 : c->c);
     g.a = c->in, g.lda = (g.k + 15) / 16 * 16;  // unused by the im2col producer; kept valid for the argument checks
     g.w = c->wt, g.ldw = c->ldw, g.out = c->out, g.ldo = c->ldo, g.ep = c->ep;
     return gemm_run(&g, c, stream);

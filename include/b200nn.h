@@ -214,6 +214,12 @@ typedef struct {
     int32_t ncls;
     const int32_t *seeds;       /* device [ncls][o]                                           */
     const uint8_t *cls_map;     /* device [oh * ow]                                           */
+    int32_t dw_slab;            /* != 0: DEPTHWISE convolution (o == c) on the same kernel: every 64-channel n-tile
+                                   contracts over taps x its own 64 input channels against a B that is diagonal per tap --
+                                   wt = [o][kh*kw*64] int8, zero except w[o][tap] at column tap*64 + o % 64.  The tensor
+                                   pipe spends 64x the useful MACs, and still beats the dp4a kernels: what a depthwise
+                                   output costs on the CUDA cores is its requantise epilogue plus 13 instructions of tap
+                                   transposition and dp4a, here only the epilogue is left */
 } b200_conv_igemm_desc;
 int b200_conv_igemm_supported(const b200_conv_igemm_desc *d);
 int b200_conv_igemm(const b200_conv_igemm_desc *d, void *stream);

@@ -608,12 +608,15 @@ def test_resnet50_int8_narrow_bit_exact(b200):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
 
 
-@pytest.mark.parametrize("rows", ["umma128", "umma", "tma", "generic"])
+@pytest.mark.parametrize("rows", ["igemm", "umma128", "umma", "tma", "generic"])
 def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     """the tensor-core depthwise kernel (csrc/dwconv3x3_umma.cu: stride 1, "same" padding; other cases fall
     through), the TMA-fed dp4a kernel (csrc/dwconv3x3_tma.cu) and the generic one (csrc/dwconv.cu)
     on shapes that hit ragged rows / columns / channel chunks, both strides, zero-point patching of
     the halo, unpadded borders and a fused relu table"""
+    # "igemm" = the default where channels are a multiple of 64: the implicit-GEMM kernel against tap-diagonal weights
+    if rows == "tma":
+        os.environ["SHL_B200_DW_IGEMM"] = "0"
     if rows == "generic":
         os.environ["SHL_B200_DW_GENERIC"] = "1"
     if rows == "umma":
@@ -644,6 +647,7 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     finally:
         os.environ.pop("SHL_B200_DW_GENERIC", None)
         os.environ.pop("SHL_B200_DW_UMMA", None)
+        os.environ.pop("SHL_B200_DW_IGEMM", None)
 
 
 def test_dwconv_sweep_shapes(b200, oracle, rng):
