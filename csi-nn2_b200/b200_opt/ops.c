@@ -343,8 +343,10 @@ static int conv_uses_igemm(const b200_op *op, const b200_dt *in0)
            in0->h == op->ig_h && in0->w == op->ig_w && in0->c == op->cin && !getenv("SHL_B200_NO_IGEMM");
 }
 
-/* depthwise convolutions with channels a multiple of 64 run on the same implicit-GEMM kernel against tap-diagonal
- * weights (SHL_B200_DW_IGEMM=0 keeps the dp4a kernels; =1 forces it where it applies; default: see dw_igemm_rule) */
+/* Depthwise convolutions with channels a multiple of 64 CAN run on the implicit-GEMM kernel against tap-diagonal
+ * weights (SHL_B200_DW_IGEMM=1; bit-exact, in the parity suite).  Off by default: measured 2x slower than the dp4a
+ * kernel (14 x 14 x 512 at batch 256: 53 vs 26 us) -- nine im2col-mode TMA loads of 128 pixels per tile cost ~4.5 cycles
+ * per pixel request in the TMA unit, the same rate that bounds the dense implicit GEMM. */
 static int dw_uses_igemm(const b200_op *op, const b200_dt *in0)
 {
     if (op->kind != B200_OPK_DW || !op->d_w_diag || op->ig_ncls < 1 || in0->is_nchw || in0->h != op->ig_h ||
@@ -352,8 +354,7 @@ static int dw_uses_igemm(const b200_op *op, const b200_dt *in0)
         return 0;
     if (getenv("SHL_B200_DW_GENERIC") || getenv("SHL_B200_DW_UMMA")) return 0; /* another kernel was asked for */
     const char *e = getenv("SHL_B200_DW_IGEMM");
-    if (e) return atoi(e) != 0;
-    return 1;
+    return e && atoi(e) != 0;
 }
 
 const char *b200_op_kname(const b200_op *op, const b200_dt *in0)

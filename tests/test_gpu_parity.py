@@ -614,9 +614,9 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     through), the TMA-fed dp4a kernel (csrc/dwconv3x3_tma.cu) and the generic one (csrc/dwconv.cu)
     on shapes that hit ragged rows / columns / channel chunks, both strides, zero-point patching of
     the halo, unpadded borders and a fused relu table"""
-    # "igemm" = the default where channels are a multiple of 64: the implicit-GEMM kernel against tap-diagonal weights
-    if rows == "tma":
-        os.environ["SHL_B200_DW_IGEMM"] = "0"
+    # "igemm": the implicit-GEMM kernel against tap-diagonal weights where channels are a multiple of 64 (opt-in)
+    if rows == "igemm":
+        os.environ["SHL_B200_DW_IGEMM"] = "1"
     if rows == "generic":
         os.environ["SHL_B200_DW_GENERIC"] = "1"
     if rows == "umma":
