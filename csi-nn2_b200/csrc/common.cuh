@@ -227,6 +227,17 @@ __device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, const CUtenso
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(woff), "h"(hoff)
         : "memory");
 }
+// the same im2col load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster in cta_mask
+__device__ __forceinline__ void tma_load_im2col_4d_multicast(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c, int w,
+                                                             int h, int n, uint16_t woff, uint16_t hoff, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(woff), "h"(hoff),
+        "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0,
                                              int c1)
 {

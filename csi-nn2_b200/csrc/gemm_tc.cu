@@ -208,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         if (g >= gmax) break;
-                        const int m0 = (mt0 + g) * kBM;
+                        // (pair: this CTA fetches its 64-row half of every A tile and multicasts it to both)
+                        const int m0 = (mt0 + g) * kBM + (args.cluster > 1 ? static_cast<int>(cta_rank) * (kBM / 2) : 0);
                         bimg[g] = m0 / args.ohw;
                         const int rem = m0 - bimg[g] * args.ohw;
                         const int oy = rem / args.ow;
@@ -235,8 +236,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const int bwg = g == 0 ? bw[0] : (g == 1 ? bw[1] : (g == 2 ? bw[2] : bw[3]));
                         const int bhg = g == 0 ? bh[0] : (g == 1 ? bh[1] : (g == 2 ? bh[2] : bh[3]));
                         const int big = g == 0 ? bimg[0] : (g == 1 ? bimg[1] : (g == 2 ? bimg[2] : bimg[3]));
-                        tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb) + (args.dw_slab ? n0 : 0), bwg, bhg, big,
-                                           static_cast<uint16_t>(tkx * args.dil_w), static_cast<uint16_t>(tky * args.dil_h));
+                        if (args.cluster > 1)
+                            tma_load_im2col_4d_multicast(a_dst + cta_rank * (a_stage_bytes / 2), &tma_a, &full_bar[stage],
+                                                         slab * static_cast<int>(kbb) + (args.dw_slab ? n0 : 0), bwg, bhg, big,
+                                                         static_cast<uint16_t>(tkx * args.dil_w),
+                                                         static_cast<uint16_t>(tky * args.dil_h), 3);
+                        else
+                            tma_load_im2col_4d(a_dst, &tma_a, &full_bar[stage], slab * static_cast<int>(kbb) + (args.dw_slab ? n0 : 0), bwg, bhg, big,
+                                               static_cast<uint16_t>(tkx * args.dil_w), static_cast<uint16_t>(tky * args.dil_h));
                     } else if (args.cluster > 1) {
                         const int half = static_cast<int>(cta_rank);
                         tma_load_2d_multicast(a_dst + half * (a_stage_bytes / 2), &tma_a, &full_bar[stage],
@@ -690,7 +697,10 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
             }
             max_clusters[dev] = n;
         }
-        if (dev < 0 || dev >= 64 || max_clusters[dev] * 2 < grid) la.cluster = 1;
+        if (dev < 0 || dev >= 64 || max_clusters[dev] * 2 < grid) {
+            if (IGEMM) return 1;  // the A tensor map was encoded for 64-pixel halves: the caller re-plans without pairs
+            la.cluster = 1;
+        }
     }
     B200_CUDA_CHECK(launch_kernel_cluster(gemm_tc_kernel<DT, MODE, MAGIC, ASYM, IGEMM>, dim3(grid),
                                           dim3(la.issuers == 2 ? kThreads : kThreads - 32), smem, stream,
@@ -716,7 +726,14 @@ static int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUte
 
 using namespace b200;
 
+static int gemm_run_impl(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, void *stream, bool allow_cluster);
 static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, void *stream)
+{
+    int rc = gemm_run_impl(d, ig, stream, true);
+    if (rc == 1) rc = gemm_run_impl(d, ig, stream, false);  // the device cannot co-schedule the CTA pairs
+    return rc;
+}
+static int gemm_run_impl(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, void *stream, bool allow_cluster)
 {
     if (!d || !d->a || !d->w || !d->out) {
         set_error("b200_gemm: null descriptor field");
@@ -804,6 +821,17 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
         return B200_ERR_UNSUPPORTED;
     }
 
+    // CTA pairs (same rows, neighbouring n-tiles) that fetch each A tile once and multicast it: opt-in for the plain GEMM
+    // (measured slower there: not L2-bound), and for the implicit GEMM, whose producer is bound by the TMA unit's im2col
+    // request rate (~4.5 cycles per pixel row whatever its width): a pair halves the requests per CTA
+    int ctas_per_n0 = sm_count() / args.num_n_tiles;
+    if (ctas_per_n0 < 1) ctas_per_n0 = 1;
+    if (ctas_per_n0 > args.num_m_super) ctas_per_n0 = args.num_m_super;
+    const int grid0 = ctas_per_n0 * args.num_n_tiles;
+    const char *cl_env = getenv("SHL_B200_GEMM_CLUSTER");
+    const bool cl_default = ig != nullptr && !ig->dw_slab;
+    const int want_cluster =
+        (allow_cluster && args.num_n_tiles % 2 == 0 && grid0 % 2 == 0 && (cl_env ? atoi(cl_env) != 0 : cl_default)) ? 2 : 1;
     alignas(64) CUtensorMap ta, tb, to;
     const int box_k = kb_bytes / eb;
     int rc;
@@ -814,7 +842,7 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
         const int upper_w = lower_w + (ig->ow - 1) * ig->stride_w - (ig->w - 1);
         const int upper_h = lower_h + (ig->oh - 1) * ig->stride_h - (ig->h - 1);
         rc = encode_tmap_im2col_u8(&ta, ig->in, ig->n, ig->h, ig->w, ig->c, ig->cp_in, lower_w, lower_h, upper_w, upper_h,
-                                   ig->stride_w, ig->stride_h, kb_bytes, kBM, kb_bytes);
+                                   ig->stride_w, ig->stride_h, kb_bytes, want_cluster > 1 ? kBM / 2 : kBM, kb_bytes);
         args.slabs = ig->dw_slab ? 1 : ig->c / kb_bytes, args.kw = ig->kw, args.dil_w = ig->dil_w, args.dil_h = ig->dil_h;
         args.dw_slab = ig->dw_slab != 0;
         args.ow = ig->ow, args.ohw = ig->oh * ig->ow;
@@ -851,7 +879,8 @@ static int gemm_run(const b200_gemm_desc *d, const b200_conv_igemm_desc *ig, voi
     // 14x14x512 -> 512 layers, batch 256): 25.2 us per layer paired against 23.9 us unpaired -- those
     // layers are not bound by L2 bandwidth (ncu: xbar -> L1 at 15 % of peak) -- so it is opt-in
     // (SHL_B200_GEMM_CLUSTER=1); parity-tested either way.
-    args.cluster = (!ig && args.num_n_tiles % 2 == 0 && grid % 2 == 0 && getenv("SHL_B200_GEMM_CLUSTER")) ? 2 : 1;
+    // (decided before the tensor maps: a paired implicit GEMM loads 64-pixel im2col boxes)
+    args.cluster = want_cluster;
     int dev = 0;
     B200_CUDA_CHECK(cudaGetDevice(&dev));
     cudaStream_t s = (cudaStream_t)stream;
