@@ -839,6 +839,12 @@ def test_binary_ops_on_rounding_ties_and_saturation(kind, op, b200, oracle, rng)
         want = oracle.binary_i8(op, x, r, s_a, zp_a, s_r, zp_r, s_out, zp_out)
         got = b200.run(DT_INT8, shape, layers, x, s_in=s_a, zp_in=zp_a, run_mode=RM_GRAPH)
         assert np.array_equal(got, want), (s_a, s_r, s_out, int(np.count_nonzero(got != want)))
+        # the same op with a relu behind it: the graph planner folds the relu into the binary kernel as a 256-entry
+        # table (for add / sub this is the specialised residual-add kernel's table variant)
+        layers2 = layers + [Layer(H_RELU, shape, s_out=s_out * 0.7, zp_out=-128)]
+        want2 = oracle.relu_i8(want, ACT_RELU, s_out, zp_out, s_out * 0.7, -128)
+        got2 = b200.run(DT_INT8, shape, layers2, x, s_in=s_a, zp_in=zp_a, run_mode=RM_GRAPH)
+        assert np.array_equal(got2, want2), ("relu", s_a, s_r, s_out, int(np.count_nonzero(got2 != want2)))
 
 
 from test_oracle import CONCAT_CASES, concat_case
