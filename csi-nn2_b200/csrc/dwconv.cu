@@ -403,6 +403,7 @@ using namespace b200;
 int b200_dwconv3x3_tma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream);  // dwconv3x3_tma.cu
 int b200_dwconv3x3_umma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_umma.cu
 int b200_dwconv3x3_umma128_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_umma128.cu
+int b200_dwconv3x3_imma_launch(const b200_dwconv_desc *d, const void *wrow, void *stream, int *handled);  // dwconv3x3_imma.cu
 
 extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
 {
@@ -437,6 +438,9 @@ extern "C" int b200_dwconv2d(const b200_dwconv_desc *d, void *stream)
         }
         const int rc = b200_dwconv3x3_umma_launch(d, d->wt_row3, stream, &handled);
         if (rc || handled) return rc;
+        // the default: taps on the warp-level tensor path (diagonal-B IMMA); maps / channel counts it leaves alone go on
+        const int rc3 = b200_dwconv3x3_imma_launch(d, d->wt_row3, stream, &handled);
+        if (rc3 || handled) return rc3;
         return b200_dwconv3x3_tma_launch(d, d->wt_row3, stream);
     }
     DwArgs a;

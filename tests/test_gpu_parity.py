@@ -608,12 +608,15 @@ def test_resnet50_int8_narrow_bit_exact(b200):
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)}/{got.size} differ"
 
 
-@pytest.mark.parametrize("rows", ["igemm", "umma128", "umma", "tma", "generic"])
+@pytest.mark.parametrize("rows", ["imma", "igemm", "umma128", "umma", "tma", "generic"])
 def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
     """the tensor-core depthwise kernel (csrc/dwconv3x3_umma.cu: stride 1, "same" padding; other cases fall
     through), the TMA-fed dp4a kernel (csrc/dwconv3x3_tma.cu) and the generic one (csrc/dwconv.cu)
     on shapes that hit ragged rows / columns / channel chunks, both strides, zero-point patching of
     the halo, unpadded borders and a fused relu table"""
+    # "imma" (the default path): taps as diagonal-B warp MMAs (csrc/dwconv3x3_imma.cu) where channels are a multiple of
+    # 32 and the map is at least 12 wide; everything else falls through to the dp4a kernel, which "tma" forces
+    os.environ["SHL_B200_DW_IMMA"] = "2" if rows == "imma" else "0"  # 2: wherever it applies, not only where it is faster
     # "igemm": the implicit-GEMM kernel against tap-diagonal weights where channels are a multiple of 64 (opt-in)
     if rows == "igemm":
         os.environ["SHL_B200_DW_IGEMM"] = "1"
@@ -631,7 +634,11 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
                                                  (1, 48, 15, 15, 2, 1, 4), (1, 16, 7, 7, 1, 1, -128),
                                                  (1, 128, 9, 10, 2, 0, 2), (1, 20, 6, 5, 1, 0, 1),
                                                  (2, 96, 30, 33, 1, 1, -5), (1, 160, 57, 9, 2, 1, 7),
-                                                 (1, 512, 14, 14, 1, 1, -128), (3, 32, 112, 112, 1, 1, -128)]:
+                                                 (1, 512, 14, 14, 1, 1, -128), (3, 32, 112, 112, 1, 1, -128),
+                                                 (2, 64, 30, 33, 2, 1, -9), (1, 128, 57, 40, 2, 1, 11), (2, 32, 28, 28, 2, 1, -128),
+                                                 (1, 256, 28, 28, 1, 1, 6), (1, 64, 112, 112, 2, 1, -128), (1, 128, 9, 30, 1, 0, -4),
+                                                 (2, 256, 29, 31, 2, 0, 8), (1, 64, 17, 12, 1, 1, -2), (3, 512, 14, 14, 2, 1, 5),
+                                                 (1, 192, 20, 45, 1, 1, -11), (1, 96, 33, 18, 2, 1, 3)]:
             x = rng.integers(-128, 128, size=(n, c, h, w), dtype=np.int8)
             wt, s_w, b, s_out = synth_conv_i8(rng, c, c, 3, 3, depthwise=True)
             oh, ow = conv_out_hw(h, w, 3, 3, (stride, stride), (pad,) * 4)
@@ -648,6 +655,7 @@ def test_dwconv3x3_kernel_variants(rows, b200, oracle, rng):
         os.environ.pop("SHL_B200_DW_GENERIC", None)
         os.environ.pop("SHL_B200_DW_UMMA", None)
         os.environ.pop("SHL_B200_DW_IGEMM", None)
+        os.environ.pop("SHL_B200_DW_IMMA", None)
 
 
 def test_dwconv_sweep_shapes(b200, oracle, rng):
