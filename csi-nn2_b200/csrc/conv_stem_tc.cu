@@ -63,10 +63,16 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
     constexpr int JR = (ROWS + 3) / 4;                    // rows per warp of a group
     constexpr uint32_t STG = ROWS * WROW;                 // staging bytes per group
     constexpr int K = C * KH * KW;
-    constexpr int KP = (K + 31) / 32 * 32;      // K padded to whole MMA k-steps
+    // K order of the A tile: one group of KWP = KW rounded up to whole words per staged row (ky, c), the group's bytes
+    // being kx = 0 .. KWP - 1 -- i.e. a pixel's A row is ROWS unaligned word reads out of the staged rows, not K byte
+    // reads.  The bytes kx >= KW (the next pixels) meet zero weights.
+    constexpr int KWP = (KW + 3) / 4 * 4;
+    constexpr int GW = KWP / 4;                 // words per group
+    constexpr int KG = ROWS * KWP;              // K as laid out
+    constexpr int KP = (KG + 31) / 32 * 32;     // padded to whole MMA k-steps
     constexpr int KSTEPS = KP / 32;
     constexpr int ATOMS = (KP + 127) / 128;     // 128-byte swizzle atoms per row
-    constexpr int KWORDS = KP / 4;
+    constexpr int KCHUNKS = (KG + 15) / 16;     // 16-byte chunks of an A row that hold data
     constexpr int N = NCH * 16;
     constexpr bool MAGIC = K <= 128;
     constexpr uint32_t A_TILE = ATOMS * 128 * 128;   // bytes
@@ -98,8 +104,11 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
         if (row < a.o) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                const int k = k0 + e;
-                if (k < K) wv[e >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(a.wt[row * a.ldw + k])) << (8 * (e & 3));
+                const int k = k0 + e;                       // = (ky * C + c) * KWP + kx
+                const int grp = k / KWP, kx = k - grp * KWP;
+                const int ky = grp / C, c = grp - ky * C;
+                if (grp < ROWS && kx < KW)                   // a.wt: k = (ky, kx, c)
+                    wv[e >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(a.wt[row * a.ldw + (ky * KW + kx) * C + c])) << (8 * (e & 3));
             }
         }
         *reinterpret_cast<uint4 *>(smem_b + atom * (N * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) =
@@ -297,27 +306,27 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
                     tp_next = decode(tile_of(i + 1, g));
                     prefetch(tp_next);
                 }
-                // ---- gather this thread's pixel: K bytes, (ky, kx, c) order, out of the staged rows
-                const int shift = (tp_cur.ox0 * SW - a.pl) & 3;
-                const uint8_t *src = stg + r * SW + shift;
-                uint32_t xw[KWORDS];
+                // ---- gather this thread's pixel: per staged row (ky, c) the KWP bytes from its window's first column on,
+                // as GW unaligned words (two aligned loads + one byte permute each; the sub-word offset is the same on
+                // every row because rows start word-aligned)
+                const int boff = r * SW + ((tp_cur.ox0 * SW - a.pl) & 3);
+                const uint32_t sel = 0x3210u + 0x1111u * static_cast<uint32_t>(boff & 3);
+                const uint32_t *srow = reinterpret_cast<const uint32_t *>(stg) + (boff >> 2);
+                uint32_t xw[KCHUNKS * 4];
 #pragma unroll
-                for (int j = 0; j < KWORDS; j++) xw[j] = 0;
+                for (int j = ROWS * GW; j < KCHUNKS * 4; j++) xw[j] = 0;
 #pragma unroll
-                for (int ky = 0; ky < KH; ky++) {
+                for (int row = 0; row < ROWS; row++) {
+                    uint32_t w[GW + 1];
 #pragma unroll
-                    for (int kx = 0; kx < KW; kx++) {
+                    for (int j = 0; j <= GW; j++) w[j] = srow[row * WW + j];
 #pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const int k = (ky * KW + kx) * C + c;
-                            const uint32_t v = src[(ky * C + c) * WROW + kx];
-                            xw[k >> 2] |= v << (8 * (k & 3));
-                        }
-                    }
+                    for (int j = 0; j < GW; j++) xw[row * GW + j] = __byte_perm(w[j], w[j + 1], sel);
                 }
                 uint8_t *arow = smem_a + (g * 2 + (i & 1)) * A_TILE + r * 128;
+                // chunks past KCHUNKS are never written: whatever they hold multiplies the zero weights of k >= KG
 #pragma unroll
-                for (int j = 0; j < KWORDS / 4; j++) {
+                for (int j = 0; j < KCHUNKS; j++) {
                     const int atom = j >> 3, chunk = j & 7;
                     *reinterpret_cast<uint4 *>(arow + atom * (128 * 128) + ((chunk ^ (r & 7)) << 4)) =
                         make_uint4(xw[j * 4], xw[j * 4 + 1], xw[j * 4 + 2], xw[j * 4 + 3]);
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(stem_threads(C * KH * KW, NCH), 1) conv_stem_t
 template <int C, int KH, int KW, int SW, int NCH>
 static int stem_launch(int mode, int grid, cudaStream_t s, const StemArgs &a, int dev)
 {
-    constexpr int KP = (C * KH * KW + 31) / 32 * 32;
+    constexpr int KP = (KH * C * ((KW + 3) / 4 * 4) + 31) / 32 * 32;
     constexpr int ATOMS = (KP + 127) / 128;
     constexpr int N = NCH * 16;
     constexpr int STG = (KH * C * ((128 * SW + KW - 1 + 3 + 3) / 4) * 4 + 15) & ~15;

@@ -49,7 +49,7 @@ struct DwImmaArgs {
     int row_bytes; // TWI * CC
     int stages;
     int ybands, xbands, cchunks;
-    int dxb, dyb, db;  // the grid's stride over spatial tiles as (x band, y band, image) digits
+    int dyb, db;  // the grid's stride over (row band, image) as two digits
     int stage_bytes, stage_stride;
     const uint32_t *wrow;  // [3 (ky)][cp] words: (w[ky][0][c], w[ky][1][c], w[ky][2][c], 0)
     int8_t *out;
@@ -57,21 +57,24 @@ struct DwImmaArgs {
     EpiScalars ep;
 };
 
+// This CTA's walk over the tile space: the channel chunk AND the column band are blockIdx.x % (cchunks * xbands) for good
+// (the grid is a multiple of that), so everything that depends on them -- per-channel constants, B fragments, seeds, the
+// threads' output columns and their border classes -- is set up once; (row band, image) advance by a fixed stride, applied as
+// two digits with a carry.
 struct ImmaWalk {
     int cc, xb, yb, b;
     __device__ __forceinline__ explicit ImmaWalk(const DwImmaArgs &a)
     {
-        cc = blockIdx.x % a.cchunks;
-        uint32_t q = blockIdx.x / a.cchunks;
-        xb = q % a.xbands;
-        q /= a.xbands;
+        const uint32_t lanes = a.cchunks * a.xbands;
+        const uint32_t l = blockIdx.x % lanes;
+        cc = l % a.cchunks;
+        xb = l / a.cchunks;
+        const uint32_t q = blockIdx.x / lanes;
         yb = q % a.ybands;
         b = q / a.ybands;
     }
     __device__ __forceinline__ void next(const DwImmaArgs &a)
     {
-        xb += a.dxb;
-        if (xb >= a.xbands) xb -= a.xbands, yb++;
         yb += a.dyb;
         if (yb >= a.ybands) yb -= a.ybands, b++;
         b += a.db;
@@ -174,6 +177,8 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
     // thread's accumulators (columns 2q, 2q + 1 of both MMAs) are the four adjacent channels 4q .. 4q + 3.
     // K halves: Bf[ky] = (w[ky][0], w[ky][1]); Bg01 = (w[0][2], w[1][2]); Bg12 = (w[1][2], w[2][2]); Bg2 = (w[2][2], 0)
     uint64_t Bf[3][2], Bg01[2], Bg2[2];
+    uint32_t zero;  // opaque to the compiler: the (w, 0) pairs stay resident instead of being re-made before every MMA
+    asm volatile("mov.u32 %0, 0;" : "=r"(zero));
     {
         const int cgrp = cc * CC + chunk * 16 + 4 * (g >> 1);
 #pragma unroll
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
                 w2[ky] = ((wv >> 16) & 0xFFu) << (8 * j);
             }
             Bg01[nh] = f2_pack_bits(w2[0], w2[1]);
-            Bg2[nh] = f2_pack_bits(w2[2], 0u);
+            Bg2[nh] = f2_pack_bits(w2[2], zero);
         }
     }
     const int ch = cc * CC + chunk * 16 + 4 * q;  // first of this thread's four output channels
@@ -223,30 +228,34 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
     const size_t orow = static_cast<size_t>(a.ow) * a.cp;
     const uint32_t zpw = 0x01010101u * static_cast<uint32_t>(a.zp_in & 0xFF);
     const int xband = a.sp * (kImWarps / NCH);  // output columns of a tile
+    const int xb = walk.xb;
+    // this thread's two output pixels: columns g and g + 8 of the strip (fixed for the CTA's life, like the chunk)
+    const int ox0 = xb * xband + strip * a.sp + g;
+    const int ox1 = ox0 + 8;
+    const bool ok0 = ch_ok && g < a.sp && ox0 < a.ow;
+    const bool ok1 = ch_ok && g + 8 < a.sp && ox1 < a.ow;
+    // seeds in the layout of the two MMAs' C operands: sq[nh] = channels 2nh, 2nh + 1 of pixel g, then of pixel g + 8
+    int sq[2][4];
+    {
+        const int col0 = ((ox0 * S - a.pl < 0) ? 1 : 0) | ((ox0 * S - a.pl + 2 >= a.w) ? 2 : 0);
+        const int col1 = ((ox1 * S - a.pl < 0) ? 1 : 0) | ((ox1 * S - a.pl + 2 >= a.w) ? 2 : 0);
+        const int *s0 = s_seed + col0 * CC + chunk * 16 + 4 * q, *s1 = s_seed + col1 * CC + chunk * 16 + 4 * q;
+        sq[0][0] = s0[0], sq[0][1] = s0[1], sq[1][0] = s0[2], sq[1][1] = s0[3];
+        sq[0][2] = s1[0], sq[0][3] = s1[1], sq[1][2] = s1[2], sq[1][3] = s1[3];
+    }
+    int8_t *const pcol = a.out + static_cast<size_t>(ox0) * a.cp + ch;
+    // the image's columns inside a tile row, as 16-byte chunks (for the zero-point patch of padded rows)
+    const int x_start = xb * xband * S - a.pl;            // image column of tile column 0
+    const int tx0 = max(0, -x_start);
+    const int per_row = (min(static_cast<int>(row_bytes / CC), a.w - x_start) - tx0) * (CC / 16);
     int stage = 0;
     uint32_t phase = 0;
 
     for (; walk.b < a.n; walk.next(a)) {
-        const int xb = walk.xb, yb = walk.yb, b = walk.b;
-        const int oy0 = yb * a.th;
+        const int oy0 = walk.yb * a.th;
         const int rows_out = min(a.th, a.oh - oy0);
-        // this thread's two output pixels: columns g and g + 8 of the strip
-        const int ox0 = xb * xband + strip * a.sp + g;
-        const int ox1 = ox0 + 8;
-        const bool ok0 = ch_ok && g < a.sp && ox0 < a.ow;
-        const bool ok1 = ch_ok && g + 8 < a.sp && ox1 < a.ow;
-        const int col0 = ((ox0 * S - a.pl < 0) ? 1 : 0) | ((ox0 * S - a.pl + 2 >= a.w) ? 2 : 0);
-        const int col1 = ((ox1 * S - a.pl < 0) ? 1 : 0) | ((ox1 * S - a.pl + 2 >= a.w) ? 2 : 0);
-        const uint32_t seed0 = smem_u32(s_seed + col0 * CC + chunk * 16 + 4 * q);
-        const uint32_t seed1 = smem_u32(s_seed + col1 * CC + chunk * 16 + 4 * q);
-        int8_t *po0 = a.out + ((static_cast<size_t>(b) * a.oh + oy0) * a.ow + ox0) * a.cp + ch;
+        int8_t *po0 = pcol + (static_cast<size_t>(walk.b) * a.oh + oy0) * orow;
         int8_t *po1 = po0 + 8 * a.cp;
-        // seeds in the layout of the two MMAs' C operands: sq[nh] = channels 2nh, 2nh + 1 of pixel g, then of pixel g + 8
-        int sq[2][4];
-        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sq[0][0]), "=r"(sq[0][1]) : "r"(seed0));
-        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sq[1][0]), "=r"(sq[1][1]) : "r"(seed0 + 8));
-        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sq[0][2]), "=r"(sq[0][3]) : "r"(seed1));
-        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sq[1][2]), "=r"(sq[1][3]) : "r"(seed1 + 8));
 
         pdl_wait();  // the output buffer may alias a tensor the predecessor still reads
         mbar_wait(&full_bar[stage], phase);
@@ -260,10 +269,6 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
             const int rows_in = S * (rows_out - 1) + 3;           // tile rows the valid outputs read
             const bool top = iy0 < 0, bot = iy0 + rows_in > a.h;
             if ((top || bot) && zpw != 0u) {
-                const int x_start = xb * xband * S - a.pl;        // image column of tile column 0
-                const int twi = row_bytes / CC;
-                const int tx0 = max(0, -x_start), tx1 = min(twi, a.w - x_start);
-                const int per_row = (tx1 - tx0) * (CC / 16);
                 if (per_row > 0) {
                     const uint4 z4 = make_uint4(zpw, zpw, zpw, zpw);
                     for (int i = tid; i < 2 * per_row; i += kConsumers) {
@@ -321,6 +326,23 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
             po0 += orow, po1 += orow;
         };
 
+        // one input row of the stride-1 walk: last row of `lst`, middle row of `mid`, first row of `nw`.  The six MMAs over
+        // the F operand are independent; the four over G each continue an accumulator started at least four MMAs earlier
+        // (a dependent MMA issued back to back waits out the whole tensor latency).
+        auto step1 = [&](int (&lst)[2][4], int (&mid)[2][4], int (&nw)[2][4]) {
+            load_f(), load_g();
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) imma16832(lst[nh], lst[nh], Af, Bf[2][nh]);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) imma16832(mid[nh], mid[nh], Af, Bf[1][nh]);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) imma16832(nw[nh], sq[nh], Af, Bf[0][nh]);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) imma16832(lst[nh], lst[nh], Ag, Bg2[nh]);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) imma16832(nw[nh], nw[nh], Ag, Bg01[nh]);
+            store(lst);
+        };
         int accA[2][4], accB[2][4], accC[2][4];
         if (S == 1) {
             // input row r: first row of output row r, middle row of r - 1, last row of r - 2
@@ -329,17 +351,11 @@ __global__ void __launch_bounds__(kImWarps * 32 + 32, 2) dw3x3_imma_kernel(const
             load_f(), load_g();
             mm_f(accA, 1), first(accB);
             for (int y = 0;; y += 3) {
-                load_f(), load_g();
-                last(accA), mm_f(accB, 1), first(accC);
-                store(accA);
+                step1(accA, accB, accC);
                 if (y + 1 >= rows_out) break;
-                load_f(), load_g();
-                last(accB), mm_f(accC, 1), first(accA);
-                store(accB);
+                step1(accB, accC, accA);
                 if (y + 2 >= rows_out) break;
-                load_f(), load_g();
-                last(accC), mm_f(accA, 1), first(accB);
-                store(accC);
+                step1(accC, accA, accB);
                 if (y + 3 >= rows_out) break;
             }
         } else {
@@ -414,7 +430,7 @@ int b200_dwconv3x3_imma_launch(const b200_dwconv_desc *d, const void *wrow, void
     const int enabled = getenv("SHL_B200_DW_IMMA") ? atoi(getenv("SHL_B200_DW_IMMA")) : 1;
     if (!enabled) return B200_OK;
     const int S = d->stride_h;
-    if (enabled == 1 && !(S == 2 && d->ow >= 28)) return B200_OK;
+    if (enabled == 1 && !(S == 2 && d->ow >= 28 && d->cp <= 64)) return B200_OK;
     const int CC = d->cp % 128 == 0 ? 128 : (d->cp % 64 == 0 ? 64 : (d->cp % 32 == 0 ? 32 : 0));
     if (!CC || d->ow < 12) return B200_OK;
     const int ns = kImWarps / (CC / 16);  // strips per tile
@@ -468,14 +484,13 @@ int b200_dwconv3x3_imma_launch(const b200_dwconv_desc *d, const void *wrow, void
     int rc = encode_tmap_nhwc_u8_ex(&tm, d->in, d->n, d->h, d->w, d->cp, CC, twi, thi, 1, CC);
     if (rc) return rc;
 
+    const int lanes = cchunks * xbands;
     long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
-    if (cap > cchunks) cap -= cap % cchunks;
-    if (cap < cchunks) cap = cchunks;
-    const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+    if (cap > lanes) cap -= cap % lanes;
+    if (cap < lanes) cap = lanes;
+    const int grid = static_cast<int>(tiles < cap ? tiles : cap);  // tiles is a multiple of lanes
     {
-        int qd = grid / cchunks;
-        a.dxb = qd % xbands;
-        qd /= xbands;
+        const int qd = grid / lanes;
         a.dyb = qd % ybands;
         a.db = qd / ybands;
     }
