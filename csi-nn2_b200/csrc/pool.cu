@@ -7,6 +7,8 @@
 // 128-bit vector.
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -185,6 +187,69 @@ __global__ void __launch_bounds__(128) maxpool_i8_bytes_kernel(const PoolArgs a)
     }
 }
 
+// The same for K x K windows that always overlap the image (pad < K, no window entirely in the padding): a padded tap
+// is replaced by the nearest tap INSIDE the window (clamped coordinates), which cannot change a maximum, so the K * K
+// 128-bit loads are unconditional and issued back to back; one block row per (image, output row), no division but the
+// one by the chunk count.  With equal input / output qinfo the requantisation table is the identity and is skipped.
+// (ResNet-50's 3x3 stride-2 stem pool, 256 x 64 x 112 x 112: see DESIGN.md.)
+template <int K, bool IDENT>
+__global__ void __launch_bounds__(256) maxpool_kxk_i8_kernel(const PoolArgs a)
+{
+    pdl_launch_dependents();
+    __shared__ uint8_t s_lut[256];
+    if (!IDENT)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            s_lut[i] = static_cast<uint8_t>(quant_i8_exact(dequant_i8(i - 128, a.s_in, a.zp_in), a.s_out, a.zp_out));
+    pdl_wait();  // inputs and the output buffer belong to the predecessor until here
+    __syncthreads();
+    const int chunks = a.cp / 16;
+    const int per_row = a.ow * chunks;
+    const int8_t *in = static_cast<const int8_t *>(a.in);
+    int8_t *out = static_cast<int8_t *>(a.out);
+    const int rows = a.n * a.oh;
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int b = row / a.oh, oy = row - b * a.oh;
+        const int y0 = oy * a.sh - a.pt;
+        int yy[K];
+#pragma unroll
+        for (int f = 0; f < K; f++) yy[f] = min(max(y0 + f, 0), a.h - 1);
+        const int8_t *img = in + static_cast<size_t>(b) * a.h * a.w * a.cp;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+            const int ox = i / chunks, ch = i - ox * chunks;
+            const int x0 = ox * a.sw - a.pl;
+            uint4 v[K * K];
+#pragma unroll
+            for (int fy = 0; fy < K; fy++)
+#pragma unroll
+                for (int fx = 0; fx < K; fx++) {
+                    const int xx = min(max(x0 + fx, 0), a.w - 1);
+                    v[fy * K + fx] = __ldg(reinterpret_cast<const uint4 *>(img + (static_cast<size_t>(yy[fy]) * a.w + xx) * a.cp + ch * 16));
+                }
+            uint32_t m[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+            for (int t = 1; t < K * K; t++) {
+                m[0] = __vmaxs4(m[0], v[t].x), m[1] = __vmaxs4(m[1], v[t].y);
+                m[2] = __vmaxs4(m[2], v[t].z), m[3] = __vmaxs4(m[3], v[t].w);
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t o = m[q];
+                if (!IDENT) {
+                    const uint32_t u = m[q] ^ 0x80808080u;  // table index = value + 128
+                    const uint32_t b0 = s_lut[u & 0xFF], b1 = s_lut[(u >> 8) & 0xFF], b2 = s_lut[(u >> 16) & 0xFF], b3 = s_lut[u >> 24];
+                    o = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+                }
+                // channels past c (padding lanes of the last chunk) are stored as zeros
+                const int left = a.c - (ch * 16 + q * 4);
+                if (left < 4) o = left <= 0 ? 0u : (o & (0xFFFFFFFFu >> (8 * (4 - left))));
+                pk[q] = o;
+            }
+            *reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(row)) * a.ow + ox) * a.cp + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
 // Global average pool, int8: one thread per 32-bit word of channels (four channels), so that a
 // 7x7x1024 map spreads over n*256 threads instead of n*64, every load is a coalesced word and the
 // h*w loads of a thread are independent (only the four f32 sums are sequential, in (y, x) order
@@ -258,6 +323,22 @@ extern "C" int b200_pool2d(const b200_pool_desc *d, void *stream)
         d->pad_top == 0 && d->pad_left == 0) {
         const int tot = d->n * (d->cp / 4);
         launch_kernel(gap_i8_kernel, dim3((tot + 127) / 128), dim3(128), 0, (cudaStream_t)stream, a);
+    } else if (d->dtype == B200_I8 && !d->is_avg && d->kh == d->kw && (d->kh == 3 || d->kh == 2) && d->pad_top < d->kh &&
+               d->pad_left < d->kw && (d->oh - 1) * d->stride_h - d->pad_top < d->h && (d->ow - 1) * d->stride_w - d->pad_left < d->w &&
+               !getenv("SHL_B200_POOL_GENERIC")) {
+        // every window overlaps the image: the unrolled kernel with clamped taps
+        const bool ident = d->s_in == d->s_out && d->zp_in == d->zp_out;
+        const int per_row = d->ow * (d->cp / 16);
+        const long long rows = static_cast<long long>(d->n) * d->oh;
+        const dim3 g2((per_row + 255) / 256, static_cast<unsigned>(rows < 65535 ? rows : 65535));
+        cudaStream_t st = (cudaStream_t)stream;
+        if (d->kh == 3) {
+            if (ident) launch_kernel(maxpool_kxk_i8_kernel<3, true>, g2, dim3(256), 0, st, a);
+            else launch_kernel(maxpool_kxk_i8_kernel<3, false>, g2, dim3(256), 0, st, a);
+        } else {
+            if (ident) launch_kernel(maxpool_kxk_i8_kernel<2, true>, g2, dim3(256), 0, st, a);
+            else launch_kernel(maxpool_kxk_i8_kernel<2, false>, g2, dim3(256), 0, st, a);
+        }
     } else if (d->dtype == B200_I8 && !d->is_avg && total < (1ll << 31)) {
         launch_kernel(maxpool_i8_bytes_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
     } else if (d->dtype == B200_I8)
