@@ -374,6 +374,21 @@ static size_t im2col_bytes(const b200_op *op, const b200_dt *in0, const b200_dt 
     return ((size_t)out->n * out->h * out->w * op->ldk * op->eb + 255) & ~(size_t)255;
 }
 
+/* group convolutions whose outputs per group are not a multiple of 16 bytes (this includes depthwise convolutions with a
+ * depth multiplier, which are group convolutions with one input channel per group): a group's GEMM cannot store into
+ * its column window of the output directly (the TMA store wants 16-byte aligned rows), so it writes a staging tensor
+ * [pixels][og rounded up] that a slice copy then places -- slow, exact, and only on this rare path */
+static int group_needs_stage(const b200_op *op)
+{
+    return op->kind == B200_OPK_CONV && op->group > 1 && ((op->o / op->group) * op->eb) % 16 != 0;
+}
+static size_t group_stage_bytes(const b200_op *op, const b200_dt *out)
+{
+    if (!group_needs_stage(op)) return 0;
+    const size_t ldo = (size_t)b200_round_channels(op->o / op->group, op->eb);
+    return ((size_t)out->n * out->h * out->w * ldo * op->eb + 255) & ~(size_t)255;
+}
+
 static size_t matmul_scratch(const b200_op *op, size_t *off_b, size_t *off_o, size_t *off_rs);
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
@@ -381,6 +396,7 @@ size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_d
     if (op->kind != B200_OPK_CONV && op->kind != B200_OPK_FC) return 0;
     size_t bytes = im2col_bytes(op, in0, out);
     if (op->d_wzp) bytes += (size_t)out->n * out->h * out->w * sizeof(int32_t);
+    bytes += group_stage_bytes(op, out);
     return bytes;
 }
 
@@ -442,6 +458,23 @@ static int run_conv(b200_op *op, const b200_dt *in, const b200_dt *out, void *sc
         g.n = og;
         g.w = (const uint8_t *)op->d_w + (size_t)grp * og * op->ldk * op->eb;
         g.out = (uint8_t *)out->d + (size_t)grp * og * op->eb;
+        if (group_needs_stage(op)) {
+            /* the group's columns go through a staging tensor and a slice copy (see group_needs_stage) */
+            uint8_t *stage_buf = (uint8_t *)scratch + im2col_bytes(op, in, out) + (op->d_wzp ? (size_t)m * sizeof(int32_t) : 0);
+            const int ldo = b200_round_channels(og, op->eb);
+            g.out = stage_buf, g.ldo = ldo, g.out_cols = 0;
+            g.ep.mult = op->d_mult ? op->d_mult + grp * og : NULL;
+            g.ep.badd = op->d_badd ? op->d_badd + grp * og : NULL;
+            g.ep.ibias = op->d_ibias ? op->d_ibias + grp * og : NULL;
+            DEV_CHECK(b200_gemm(&g, stream));
+            b200_concat_desc cd;
+            memset(&cd, 0, sizeof(cd));
+            cd.dtype = op->dtype, cd.n = out->n, cd.c = og, cd.h = out->h, cd.w = out->w, cd.cp_in = ldo;
+            cd.on = out->n, cd.oc = out->c, cd.oh = out->h, cd.ow = out->w, cd.cp_out = out->cp;
+            cd.axis = 1, cd.offset = grp * og, cd.in = stage_buf, cd.out = out->d, cd.lut = NULL, cd.extract = 0;
+            DEV_CHECK(b200_concat_slice(&cd, stream));
+            continue;
+        }
         if (op->group > 1) {
             /* each group writes its own column window of the pixel-major output: tiles wider than the
              * window are clipped at its end (the GEMM's n-tile may be wider than og, e.g. og = 48 in a 64-column
@@ -952,7 +985,9 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
     const int C = input->dim[1], O = kernel->dim[0], cg = kernel->dim[1];
     const int kh = kernel->dim[2], kw = kernel->dim[3];
     int group = params->group > 0 ? params->group : 1;
-    const int is_dw = group == C && cg == 1 && group > 1;
+    /* a depthwise convolution with a depth multiplier (O = m * C, source/reference/convolution.c:229: output channel
+     * ic * m + j reads input channel ic) is the group convolution group = C, one input channel per group */
+    const int is_dw = group == C && cg == 1 && group > 1 && O == C;
     if (!is_dw && (C % group || O % group || cg != C / group)) {
         b200_fail("conv2d: inconsistent group=%d for C=%d O=%d kernel I=%d", group, C, O, cg);
         return CSINN_FALSE;
@@ -976,11 +1011,6 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
     int rc;
     size_t wbytes = 0;
     if (is_dw) {
-        if (O != C) {
-            b200_fail("depthwise conv2d: depth multiplier %d/%d != 1 is not supported", O, C);
-            free(op);
-            return CSINN_FALSE;
-        }
         const int cp = b200_round_channels(C, op->eb);
         rc = b200_make_requant(op, input, kernel, bias, output, kh * kw, params->conv_extra.fuse_zp2bias, O);
         if (rc == CSINN_TRUE && !(op->d_w = b200_pack_dw_weights(op, kernel, cp, &wbytes))) rc = CSINN_FALSE;
@@ -995,12 +1025,6 @@ static int conv_init_impl(struct csinn_tensor *input, struct csinn_tensor *outpu
                 rc = CSINN_FALSE;
         }
     } else {
-        const int og = O / group;
-        if (group > 1 && (og * op->eb) % 16) {
-            b200_fail("group conv2d: %d output channels per group is not a multiple of %d", og, 16 / op->eb);
-            free(op);
-            return CSINN_FALSE;
-        }
         op->kdim = cg * kh * kw;
         op->ldk = b200_round_channels(op->kdim, op->eb);
         op->direct = kh == 1 && kw == 1 && op->sh == 1 && op->sw == 1 && op->pt == 0 && op->pl == 0 &&

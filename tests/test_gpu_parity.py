@@ -67,6 +67,11 @@ CONV_CASES = [
     (1, 24, 9, 11, 24, 3, 1, 1, 1, True, 2, H_CONV),         # depthwise, ragged channels / width
     (1, 16, 12, 12, 16, 5, 1, 2, 1, True, 4, H_CONV),        # depthwise 5x5
     (1, 512, 14, 14, 512, 3, 1, 1, 1, True, -128, H_CONV),   # MobileNetV1 depthwise shape
+    # outputs per group that are not a multiple of 16 bytes go through a staging tensor and a slice copy per group
+    (1, 48, 9, 10, 72, 3, 1, 1, 3, False, -5, H_CONV),       # 24 per group
+    (2, 32, 7, 7, 80, 1, 1, 0, 2, False, 0, H_CONV_RELU),    # 40 per group, 1x1
+    (1, 16, 11, 9, 32, 3, 1, 1, 16, False, 6, H_CONV),       # depthwise with depth multiplier 2 (group = C, O = 2C)
+    (1, 8, 10, 10, 24, 3, 2, 1, 8, False, -3, H_DWCONV),     # depth multiplier 3 through csinn_depthwise_conv2d
 ]
 
 
@@ -113,7 +118,8 @@ def test_dilated_conv_int8_bit_exact(case, mode, b200, oracle, ref_noavx, rng):
         ref_band(got, ref_noavx.run(DT_INT8, (n, c, h, w), [layer], x, s_in=0.02, zp_in=zp_in))
 
 
-@pytest.mark.parametrize("case", [(1, 48, 9, 9, 24, 3, 1, 1, 3), (2, 16, 10, 11, 48, 1, 1, 0, 2), (1, 24, 8, 8, 120, 3, 1, 1, 3)],
+@pytest.mark.parametrize("case", [(1, 48, 9, 9, 24, 3, 1, 1, 3), (2, 16, 10, 11, 48, 1, 1, 0, 2), (1, 24, 8, 8, 120, 3, 1, 1, 3),
+                                  (1, 16, 8, 8, 16, 3, 1, 1, 4), (1, 8, 9, 9, 16, 3, 1, 1, 8)],  # 4 per group (staged); depth multiplier 2
                          ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d_g%d" % c)
 def test_group_conv_fp16_clips_tiles_at_the_group_window(case, b200, oracle, rng):
     """fp16 group conv whose outputs per group (8, 24, 40) are narrower than the GEMM's n-tile: every group's tile

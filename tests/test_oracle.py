@@ -46,6 +46,9 @@ CONV_CASES = [
     (2, 32, 20, 20, 32, 3, 1, 1, 1, True, -7, H_CONV),          # depthwise through csinn_conv2d
     (1, 64, 21, 21, 64, 3, 2, 1, 1, True, 0, H_DWCONV),         # depthwise through csinn_depthwise_conv2d
     (1, 16, 12, 12, 16, 5, 1, 2, 1, True, 4, H_CONV),
+    (1, 48, 9, 10, 72, 3, 1, 1, 3, False, -5, H_CONV),          # group conv, 24 outputs per group (not a multiple of 16)
+    (1, 16, 11, 9, 32, 3, 1, 1, 16, False, 6, H_CONV),          # depthwise with depth multiplier 2 (group = C, O = 2C)
+    (1, 8, 10, 10, 24, 3, 2, 1, 8, False, -3, H_DWCONV),        # depth multiplier 3 through csinn_depthwise_conv2d
 ]
 
 
