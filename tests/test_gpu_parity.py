@@ -174,7 +174,11 @@ def test_pointwise_conv_with_cluster_multicast(case, b200, oracle, rng):
 
 FIRST_LAYER = [(2, 3, 32, 32, 32, 3, 2, 1, 5), (1, 3, 40, 40, 64, 7, 2, 3, 0), (1, 4, 17, 19, 24, 3, 1, 1, -9),
                (1, 1, 16, 16, 8, 5, 1, 2, 3), (3, 3, 224, 224, 32, 3, 2, 1, 0),
-               (1, 3, 33, 35, 48, 3, 2, 1, -7), (5, 3, 30, 30, 16, 3, 1, 1, 11), (2, 3, 61, 47, 24, 7, 2, 3, -128)]
+               (1, 3, 33, 35, 48, 3, 2, 1, -7), (5, 3, 30, 30, 16, 3, 1, 1, 11), (2, 3, 61, 47, 24, 7, 2, 3, -128),
+               # row pitches that are multiples of 16 bytes: the TMA-staged tensor-core stem (others take the dp4a kernel)
+               (2, 3, 48, 48, 64, 7, 2, 3, -5), (1, 3, 64, 80, 48, 7, 2, 3, 9), (2, 3, 32, 48, 16, 3, 1, 1, 11),
+               (1, 3, 20, 160, 16, 3, 1, 1, 7), (1, 3, 18, 288, 32, 3, 2, 1, -3), (1, 3, 32, 32, 64, 3, 2, 1, 4),
+               (3, 3, 17, 16, 8, 3, 2, 1, -128), (1, 3, 9, 272, 64, 7, 2, 3, 6)]
 
 
 @pytest.mark.parametrize("direct", ["stem_tc", "dp4a", "im2col"])
