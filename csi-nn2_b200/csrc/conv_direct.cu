@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(kDirectThreads) conv_direct_f16_kernel(const D
 
 using namespace b200;
 
-int b200_conv_stem_tc_launch(const b200_conv_direct_desc *d, void *stream);  // conv_stem_tc.cu
+int b200_conv_stem_tc_launch(const b200_conv_direct_desc *d, void *stream);      // conv_stem_tc.cu
+int b200_conv_stem_f16_tc_launch(const b200_conv_direct_desc *d, void *stream);  // conv_stem_f16_tc.cu
 
 extern "C" int b200_conv2d_direct(const b200_conv_direct_desc *d, void *stream)
 {
@@ -391,6 +392,11 @@ extern "C" int b200_conv2d_direct_f16(const b200_conv_direct_desc *d, void *stre
         static_cast<long long>(d->n) * d->c * d->h * d->w >= (1ll << 31)) {
         set_error("b200_conv2d_direct_f16: unsupported shape (C*kh*kw=%d must be <= 160, O=%d <= 64)", K, d->o);
         return B200_ERR_UNSUPPORTED;
+    }
+    // the 3-channel 3x3 stem runs as an implicit GEMM on the tensor core (conv_stem_f16_tc.cu)
+    if (!getenv("SHL_B200_NO_STEM_TC")) {
+        const int rc = b200_conv_stem_f16_tc_launch(d, stream);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
     DirectArgs a;
     a.n = d->n, a.c = d->c, a.h = d->h, a.w = d->w, a.o = d->o, a.oh = d->oh, a.ow = d->ow, a.cp_out = d->cp_out;

@@ -429,13 +429,16 @@ def test_conv_fp16_within_tolerance(case, b200, oracle, rng):
 
 
 @pytest.mark.parametrize("case", [(2, 3, 32, 32, 32, 3, 2, 1), (1, 3, 40, 40, 64, 7, 2, 3), (3, 3, 33, 35, 48, 3, 1, 1),
-                                  (1, 4, 17, 19, 24, 3, 1, 1), (2, 1, 16, 16, 8, 5, 1, 2)],
+                                  (1, 4, 17, 19, 24, 3, 1, 1), (2, 1, 16, 16, 8, 5, 1, 2),
+                                  # 3-channel 3x3 with a row pitch of a multiple of 16 bytes: the tensor-core fp16 stem
+                                  (3, 3, 224, 224, 32, 3, 2, 1), (2, 3, 24, 40, 16, 3, 1, 1), (1, 3, 18, 288, 64, 3, 2, 1),
+                                  (1, 3, 20, 160, 48, 3, 1, 1), (2, 3, 17, 16, 8, 3, 2, 0)],
                          ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_p%d" % c)
-@pytest.mark.parametrize("direct", ["direct", "im2col"])
+@pytest.mark.parametrize("direct", ["direct", "cuda_cores", "im2col"])
 def test_first_layer_conv_fp16_from_nchw(case, direct, b200, oracle, rng):
-    """graph mode, fp16: the first conv reads the NCHW graph input directly (csrc/conv_direct.cu,
-    conv_direct_f16_kernel: f32 accumulation in registers) or, forced, through im2col + GEMM; a relu
-    node rides in the epilogue either way"""
+    """graph mode, fp16: the first conv reads the NCHW graph input directly (csrc/conv_stem_f16_tc.cu: 3-channel 3x3 on
+    tcgen05 kind::f16; csrc/conv_direct.cu, conv_direct_f16_kernel: f32 accumulation in registers -- every other small-K
+    shape, or forced by "cuda_cores") or, forced, through im2col + GEMM; a relu node rides in the epilogue either way"""
     n, c, h, w, o, k, stride, pad = case
     x = rng.standard_normal((n, c, h, w)).astype(np.float16)
     wt = (rng.standard_normal((o, c, k, k)) / np.sqrt(c * k * k)).astype(np.float16)
@@ -445,10 +448,13 @@ def test_first_layer_conv_fp16_from_nchw(case, direct, b200, oracle, rng):
               Layer(H_RELU, (n, o, oh, ow))]
     if direct == "im2col":
         os.environ["SHL_B200_NO_DIRECT_CONV"] = "1"
+    if direct == "cuda_cores":
+        os.environ["SHL_B200_NO_STEM_TC"] = "1"
     try:
         got = b200.run(DT_F16, x.shape, layers, x, run_mode=RM_GRAPH)
     finally:
         os.environ.pop("SHL_B200_NO_DIRECT_CONV", None)
+        os.environ.pop("SHL_B200_NO_STEM_TC", None)
     want = np.maximum(oracle.conv2d_f32(x.astype(np.float32), wt.astype(np.float32), b.astype(np.float32),
                                         (n, o, oh, ow), stride=(stride, stride), pad=(pad,) * 4), 0)
     f16_close(got, want)
