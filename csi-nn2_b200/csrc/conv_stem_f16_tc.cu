@@ -22,7 +22,7 @@
 namespace b200 {
 
 // worker groups per CTA: TMEM holds groups x 2 accumulators x N columns <= 512
-__host__ __device__ constexpr int f16_stem_groups(int nch) { return nch <= 2 ? 5 : 4; }
+__host__ __device__ constexpr int f16_stem_groups(int nch) { return nch <= 2 ? 6 : 4; }
 __host__ __device__ constexpr int f16_stem_threads(int nch) { return (f16_stem_groups(nch) * 4 + 1) * 32; }
 
 struct StemF16Args {

@@ -33,7 +33,7 @@ namespace b200 {
 // worker groups per CTA: 5 when the tiles are small (K <= 128, N <= 32: 20 worker warps keep the
 // schedulers busy through the shared-memory and TMEM latencies of gather and epilogue), else 4
 // (TMEM: groups x 2 x N columns <= 512; shared memory: groups x (A tile + 2 staging buffers))
-__host__ __device__ constexpr int stem_groups(int k, int nch) { return (k <= 128 && nch <= 2) ? 5 : 4; }
+__host__ __device__ constexpr int stem_groups(int k, int nch) { return (k <= 128 && nch <= 2) ? 6 : 4; }
 // staging geometry: bytes of an image row one TMA box covers, boxes per tile, bytes between boxes / buffers
 __host__ __device__ constexpr int stem_hb() { return 160; }
 __host__ __device__ constexpr int stem_boxes(int sw) { return sw == 2 ? 2 : 1; }
