@@ -749,8 +749,10 @@ static void dwpw_fill(const b200_op *dw, const b200_op *pw, const b200_dt *in, c
  * session applies to programmatic dependent launch. */
 int b200_dwpw_can_fuse(const b200_op *dw, const b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out)
 {
+    /* SHL_B200_DWPW: unset / 0 = two kernels (the default since the fused kernel measured slower on every MobileNetV1
+     * pair at batch 256), 1 = fuse every covered pair, "auto" = time both per pair at session_setup */
     const char *mode = getenv("SHL_B200_DWPW");
-    if (getenv("SHL_B200_NO_DWPW") || (mode && atoi(mode) == 0)) return 0;
+    if (getenv("SHL_B200_NO_DWPW") || !mode || (strcmp(mode, "auto") != 0 && atoi(mode) == 0)) return 0;
     if (dw->d_wzp || pw->d_wzp) return 0; /* asymmetric weights: two kernels (generic depthwise, row-sum GEMM) */
     if (dw->kind != B200_OPK_DW || pw->kind != B200_OPK_CONV || !pw->direct || dw->dtype != B200_I8 ||
         pw->dtype != B200_I8 || in->is_nchw || pw->kdim != mid->c || mid->c != in->c || mid->n != out->n ||
@@ -785,7 +787,8 @@ static float dwpw_time(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_d
 int b200_dwpw_prefers_fusion(b200_op *dw, b200_op *pw, const b200_dt *in, const b200_dt *mid, const b200_dt *out)
 {
     const char *mode = getenv("SHL_B200_DWPW");
-    if (mode) return atoi(mode) != 0;
+    if (!mode) return 0;
+    if (strcmp(mode, "auto") != 0) return atoi(mode) != 0;
     b200_dt ti = *in, tm = *mid, to = *out;
     void *e0 = NULL, *e1 = NULL;
     void *stream = dw->ctx->stream;

@@ -85,7 +85,7 @@ def launch_list(path, dst):
     print(f"wrote {dst}: {n} launches")
 
 
-CLASSES = [("gemm_tc_kernel", "b200_gemm_tcgen05"), ("dw3x3_tma_kernel", "b200_dwconv2d"), ("dwconv_", "b200_dwconv2d"),
+CLASSES = [("gemm_tc_kernel", "b200_gemm_tcgen05"), ("dw3x3_tma_kernel", "b200_dwconv2d"), ("dw3x3_imma_kernel", "b200_dwconv2d"), ("dwconv_", "b200_dwconv2d"),
            ("conv_direct", "b200_conv2d_direct"), ("conv_stem_tc", "b200_conv2d_stem_tcgen05"), ("im2col", "b200_im2col_gemm_tcgen05"), ("gap_i8", "b200_global_avgpool"),
            ("pool_", "b200_pool"), ("softmax", "b200_softmax")]
 
