@@ -97,6 +97,7 @@ typedef struct b200_op {
     int zp_in, zp_out, act, q6;
     float act_p0, act_p1; /* parameters of a unary op (leaky slope; clip min, max) */
     int binop;            /* B200_OPK_ADD: b200_binop (add / sub / mul) */
+    int bcast_nc;         /* B200_OPK_ADD with a second ACTIVATION of shape [N, C, 1, 1]: one value per image and channel */
     void *d_const;        /* B200_OPK_ADD: constant second operand, one pixel's channels ([cp] elements); NULL = tensor */
     int const_count;      /* its length in elements */
     /* B200_OPK_CONCAT: device axis (0..3 = n, c, h, w), per-input offset along it and requant table */

@@ -685,6 +685,17 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
                 b200_fail("%s: constant operand packed for %d channels, the activation has %d", op->kname, op->const_count, in0->cp);
                 return CSINN_FALSE;
             }
+            if (op->bcast_nc) { /* second activation: one pixel of channels per image */
+                if (in1->cp != in0->cp || in1->h * in1->w != 1) {
+                    b200_fail("%s: broadcast operand is not [N or 1, C, 1, 1]", op->kname);
+                    return CSINN_FALSE;
+                }
+                DEV_CHECK(b200_binary_bcast_nc(op->binop, op->dtype, in0->d, in1->d, (size_t)in0->cp,
+                                               (size_t)in0->h * in0->w * in0->cp, out->d,
+                                               b200_dt_bytes(out) / op->eb, op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out,
+                                               op->zp_out, op->d_lut, op->act, stream));
+                return CSINN_TRUE;
+            }
             DEV_CHECK(b200_binary_bcast(op->binop, op->dtype, in0->d, op->d_const ? op->d_const : in1->d,
                                         op->d_const ? (size_t)op->const_count : 0, out->d, b200_dt_bytes(out) / op->eb,
                                         op->s_in, op->zp_in, op->s_in1, op->zp_in1, op->s_out, op->zp_out, op->d_lut,
@@ -1275,7 +1286,7 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
 {
     /* a constant second operand may be one element or one value per channel ([C], [C,1,1], [1,C,1,1]):
      * the broadcasting of shl_ref_add_f32 (source/reference/add.c:21); anything else must match in0 */
-    int per_channel = 0, scalar = 0;
+    int per_channel = 0, scalar = 0, bcast_nc = 0;
     b200_dt d0;
     if (input0->is_const || !b200_dt_from_tensor(&d0, input0)) {
         b200_fail("add: first operand must be a non-constant int8 / fp16 tensor of rank 1..4");
@@ -1299,22 +1310,26 @@ static int binary_init(struct csinn_tensor *input0, struct csinn_tensor *input1,
             return CSINN_FALSE;
         }
     } else {
-        if (input0->dim_count != input1->dim_count) {
-            b200_fail("add: broadcasting between activations is not supported (ranks %d vs %d)", input0->dim_count,
-                      input1->dim_count);
-            return CSINN_FALSE;
-        }
-        for (int i = 0; i < input0->dim_count; i++)
-            if (input0->dim[i] != input1->dim[i]) {
-                b200_fail("add: broadcasting between activations is not supported (dim %d: %d vs %d)", i, input0->dim[i],
-                          input1->dim[i]);
+        /* two activations: the same shape, or [N, C, H, W] against [N, C, 1, 1] (one value per image and
+         * channel -- a squeeze-and-excitation scale; source/reference/utils.c:83) */
+        int same = input0->dim_count == input1->dim_count;
+        for (int i = 0; same && i < input0->dim_count; i++) same = input0->dim[i] == input1->dim[i];
+        if (!same) {
+            const int ok = input0->dim_count == 4 && input1->dim_count == 4 && input1->dim[1] == input0->dim[1] &&
+                           input1->dim[2] == 1 && input1->dim[3] == 1 && input1->dim[0] == input0->dim[0] &&
+                           input1->dtype == input0->dtype && binop != B200_BINOP_PRELU;
+            if (!ok) {
+                b200_fail("add: broadcasting between two activations is supported for [N, C, H, W] against [N, C, 1, 1] only");
                 return CSINN_FALSE;
             }
+            bcast_nc = 1;
+        }
     }
     static const char *const names[] = {"b200_add", "b200_sub", "b200_mul", "b200_prelu", "b200_div"};
     b200_op *op = op_new(&params->base, B200_OPK_ADD, input0->dtype, names[binop]);
     if (!op) return CSINN_FALSE;
     op->binop = binop;
+    op->bcast_nc = bcast_nc;
     if (input1->is_const) {
         /* one pixel's worth of channels, padding lanes 0 (their results are never read) */
         uint8_t *row = calloc((size_t)d0.cp, (size_t)op->eb);

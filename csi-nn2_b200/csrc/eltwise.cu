@@ -121,7 +121,7 @@ __device__ __forceinline__ uint64_t bytes_to_f2(uint32_t wx, int e0, float off)
 __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a,
                                                      const uint4 *__restrict__ b,
                                                      uint4 *__restrict__ out, long long nvec,
-                                                     const AddArgs p, const int b_period)
+                                                     const AddArgs p, const int b_period, const long long b_outer)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) add_i8_kernel(const uint4 *__restrict__ a
     const float zo = static_cast<float>(p.zp_out);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? i % b_period : i));
+        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? (b_outer ? i / b_outer * b_period : 0) + i % b_period : i));
         const uint32_t wa[4] = {va.x ^ 0x80808080u, va.y ^ 0x80808080u, va.z ^ 0x80808080u, va.w ^ 0x80808080u};
         const uint32_t wb[4] = {vb.x ^ 0x80808080u, vb.y ^ 0x80808080u, vb.z ^ 0x80808080u, vb.w ^ 0x80808080u};
         uint32_t r[4];
@@ -273,13 +273,13 @@ __global__ void __launch_bounds__(256) add_i8_fast_kernel(const uint4 *__restric
 __global__ void __launch_bounds__(256) add_f16_kernel(const uint4 *__restrict__ a,
                                                       const uint4 *__restrict__ b,
                                                       uint4 *__restrict__ out, long long nvec,
-                                                      int act, int binop, const int b_period)
+                                                      int act, int binop, const int b_period, const long long b_outer)
 {
     pdl_launch_dependents();
     pdl_wait();  // inputs and the output buffer belong to the predecessor until here
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? i % b_period : i));
+        const uint4 va = __ldg(a + i), vb = __ldg(b + (b_period ? (b_outer ? i / b_outer * b_period : 0) + i % b_period : i));
         const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
         const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
         uint4 vo;
@@ -346,6 +346,25 @@ extern "C" int b200_unary_f16(const void *in, void *out, size_t count, int act, 
     return B200_OK;
 }
 
+static int binary_impl(int binop, int dtype, const void *a, const void *b, size_t b_count, size_t a_per_instance, void *out,
+                       size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                       const int8_t *post_lut, int act, void *stream);
+
+extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void *b, size_t b_count, void *out,
+                                 size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                                 const int8_t *post_lut, int act, void *stream)
+{
+    return binary_impl(binop, dtype, a, b, b_count, 0, out, count, s_a, zp_a, s_b, zp_b, s_out, zp_out, post_lut, act, stream);
+}
+
+extern "C" int b200_binary_bcast_nc(int binop, int dtype, const void *a, const void *b, size_t b_count, size_t a_per_instance,
+                                    void *out, size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                                    const int8_t *post_lut, int act, void *stream)
+{
+    return binary_impl(binop, dtype, a, b, b_count, a_per_instance, out, count, s_a, zp_a, s_b, zp_b, s_out, zp_out, post_lut, act,
+                       stream);
+}
+
 extern "C" int b200_add(int dtype, const void *a, const void *b, void *out, size_t count, float s_a,
                         int zp_a, float s_b, int zp_b, float s_out, int zp_out,
                         const int8_t *post_lut, int act, void *stream)
@@ -360,9 +379,12 @@ extern "C" int b200_binary(int binop, int dtype, const void *a, const void *b, v
     return b200_binary_bcast(binop, dtype, a, b, 0, out, count, s_a, zp_a, s_b, zp_b, s_out, zp_out, post_lut, act, stream);
 }
 
-extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void *b, size_t b_count, void *out,
-                                 size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
-                                 const int8_t *post_lut, int act, void *stream)
+// b_count = elements after which the second operand repeats (0 = same shape), a_per_instance = elements of the first operand
+// that share one instance of that period (0 = one instance for the whole tensor: a constant; H * W * cp = one per image: a
+// [N, C, 1, 1] activation against [N, C, H, W])
+static int binary_impl(int binop, int dtype, const void *a, const void *b, size_t b_count, size_t a_per_instance, void *out,
+                       size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                       const int8_t *post_lut, int act, void *stream)
 {
     if (binop < B200_BINOP_ADD || binop > B200_BINOP_DIV) {
         set_error("b200_binary: unknown op %d", binop);
@@ -379,6 +401,11 @@ extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void
         return B200_ERR_ARG;
     }
     const int b_period = static_cast<int>(b_count / vec);
+    if (a_per_instance % vec || (a_per_instance && !b_period)) {
+        set_error("b200_binary_bcast_nc: %zu elements per instance of the second operand's period %zu", a_per_instance, b_count);
+        return B200_ERR_ARG;
+    }
+    const long long b_outer = static_cast<long long>(a_per_instance / vec);
     const long long nvec = static_cast<long long>(count / vec);
     if (dtype == B200_I8) {
         AddArgs p{s_a, s_b, s_out, zp_a, zp_b, zp_out, act, post_lut, binop, static_cast<float>(1.0 / static_cast<double>(s_out))};
@@ -402,11 +429,11 @@ extern "C" int b200_binary_bcast(int binop, int dtype, const void *a, const void
         }
         launch_kernel(add_i8_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
-            nvec, p, b_period);
+            nvec, p, b_period, b_outer);
     } else {
         launch_kernel(add_f16_kernel, dim3(ew_grid(nvec)), dim3(256), 0, (cudaStream_t)stream, 
             static_cast<const uint4 *>(a), static_cast<const uint4 *>(b), static_cast<uint4 *>(out),
-            nvec, act, binop, b_period);
+            nvec, act, binop, b_period, b_outer);
     }
     B200_LAUNCH_CHECK();
     return B200_OK;

@@ -339,6 +339,12 @@ int b200_binary(int binop, int dtype, const void *a, const void *b, void *out, s
 int b200_binary_bcast(int binop, int dtype, const void *a, const void *b, size_t b_count, void *out, size_t count,
                       float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
                       void *stream);
+/* the same with one instance of the second operand's period per `a_per_instance` elements of the first: an
+ * activation of shape [N, C, 1, 1] against [N, C, H, W] (a_per_instance = H * W * cp, b_count = cp) -- the per-image,
+ * per-channel case of shl_ref_diso_broadcast_base (source/reference/utils.c:83), e.g. a squeeze-and-excitation scale */
+int b200_binary_bcast_nc(int binop, int dtype, const void *a, const void *b, size_t b_count, size_t a_per_instance, void *out,
+                         size_t count, float s_a, int zp_a, float s_b, int zp_b, float s_out, int zp_out,
+                         const int8_t *post_lut, int act, void *stream);
 int b200_add(int dtype, const void *a, const void *b, void *out, size_t count, float s_a, int zp_a,
              float s_b, int zp_b, float s_out, int zp_out, const int8_t *post_lut, int act,
              void *stream);

@@ -1002,6 +1002,28 @@ def test_fullyconnected_fp16_activations_int8_weights(b200, rng):
     f16_close(got, want)  # exact integer weights in fp16 + per-channel scale in the f32 epilogue: the fp16 path's 1e-3
 
 
+from test_oracle import SE_CASES, se_case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,op", SE_CASES, ids=["add", "mul", "sub"])
+def test_binary_ops_between_an_activation_and_a_per_image_per_channel_activation(kind, op, b200, oracle, rng):
+    """[N, C, H, W] (op) [N, C, 1, 1] with both operands produced by earlier layers (a squeeze-and-excitation scale): the second
+    operand is indexed (image, channel) -- b200_binary_bcast_nc; int8 bit-exact in graph mode, fp16 within tolerance"""
+    for shape in ((2, 24, 5, 7), (3, 64, 9, 9)):
+        x, layers, want = se_case(kind, op, False, oracle, rng, shape=shape)
+        got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.04, zp_in=3, run_mode=RM_GRAPH)
+        assert np.array_equal(got, want), (shape, int(np.count_nonzero(got != want)))
+    from shl import H_GAP
+    shape = (2, 24, 5, 7)
+    xh = rng.standard_normal(shape).astype(np.float16)
+    layers = [Layer(H_RELU, shape), Layer(H_GAP, (2, 24, 1, 1), kernel=(5, 7)), Layer(kind, shape, in0=1, in1=2)]
+    got = b200.run(DT_F16, shape, layers, xh, run_mode=RM_GRAPH)
+    r = np.maximum(xh.astype(np.float32), 0)
+    g = r.mean(axis=(2, 3), keepdims=True).astype(np.float16).astype(np.float32)
+    f16_close(got, {0: r + g, 1: r - g, 2: r * g}[op])
+
+
 from test_oracle import SPLIT_CASES, split_case
 
 

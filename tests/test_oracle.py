@@ -447,6 +447,34 @@ def test_binary_ops_with_a_constant_operand_oracle_equals_the_reference(kind, op
     assert np.array_equal(got, want)
 
 
+def se_case(kind, op, shared, oracle, rng, shape=(2, 24, 5, 7)):
+    """x (op) g with g = global average pool of relu(x) (one value per image and channel, [N, C, 1, 1]) -- the
+    squeeze-and-excitation pattern; `shared`: g comes from a [1, C, 1, 1] tensor instead (image 0's pool)"""
+    from shl import H_GAP
+    n, c, h, w = shape
+    x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+    layers = [Layer(H_RELU, shape, s_out=0.021, zp_out=-128),
+              Layer(H_GAP, (n, c, 1, 1), s_out=0.011, zp_out=-100, kernel=(h, w)),
+              Layer(kind, shape, in0=1, in1=2, s_out=0.05 if op != 2 else 0.002, zp_out=-11)]
+    r = oracle.relu_i8(x, ACT_RELU, 0.04, 3, 0.021, -128)
+    g = oracle.pool_i8(r, (n, c, 1, 1), avg=True, kernel=(h, w), stride=(1, 1), pad=(0,) * 4, count_include_pad=0, s_in=0.021,
+                       zp_in=-128, s_out=0.011, zp_out=-100)
+    gb = np.ascontiguousarray(np.broadcast_to(g, shape))
+    want = oracle.binary_i8(op, r, gb, 0.021, -128, 0.011, -100, layers[2].s_out, -11)
+    return x, layers, want
+
+
+SE_CASES = [(H_ADD, 0), (18, 2), (17, 1)]
+
+
+@pytest.mark.parametrize("kind,op", SE_CASES, ids=["add", "mul", "sub"])
+def test_binary_ops_between_an_activation_and_its_pooled_self_oracle_equals_the_reference(kind, op, ref, oracle, rng):
+    """[N, C, H, W] (op) [N, C, 1, 1], both activations: shl_ref_diso_broadcast_base (source/reference/utils.c:83)"""
+    x, layers, want = se_case(kind, op, False, oracle, rng)
+    got = ref.run(DT_INT8, x.shape, layers, x, s_in=0.04, zp_in=3, run_mode=RM_GRAPH)
+    assert np.array_equal(got, want)
+
+
 def test_reference_takes_int8_weights_under_fp16_activations(ref, oracle, rng):
     """CSINN_QUANT_FLOAT16_W_INT8 through the unmodified reference (kernel transform source/nn2/utils.c:920-931):
     the harness path the GPU test compares against equals an f32 conv on (q - zp) * scale weights"""
