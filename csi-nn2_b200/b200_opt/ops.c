@@ -716,7 +716,7 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
             return CSINN_TRUE;
         }
         case B200_OPK_SOFTMAX:
-            DEV_CHECK(b200_softmax(op->dtype, in0->d, out->d, in0->n, in0->c, in0->cp, out->cp,
+            DEV_CHECK(b200_softmax(op->dtype, in0->d, out->d, in0->n * in0->h * in0->w, in0->c, in0->cp, out->cp,
                                    op->s_in, op->zp_in, op->s_out, op->zp_out, stream));
             return CSINN_TRUE;
         case B200_OPK_TENSOR:
@@ -1438,8 +1438,11 @@ int shl_b200_softmax_init(struct csinn_tensor *input, struct csinn_tensor *outpu
 {
     b200_dt din;
     int axis = params->axis < 0 ? params->axis + input->dim_count : params->axis;
-    if (!b200_dt_from_tensor(&din, input) || din.h * din.w != 1 || axis != 1) {
-        b200_fail("softmax: only axis 1 of an [N][C] (or N x C x 1 x 1) tensor is supported");
+    /* axis 1 = the channel axis: on the pixel-major device layout every (image, y, x) position's channels are one contiguous
+     * row, so an N x C x H x W softmax is N * H * W rows of the [N][C] kernel (the reference walks them in the same order,
+     * source/reference/softmax.c:42-63) */
+    if (!b200_dt_from_tensor(&din, input) || axis != 1) {
+        b200_fail("softmax: only axis 1 (channels) of a rank 2..4 tensor is supported");
         return CSINN_FALSE;
     }
     b200_op *op = op_new(&params->base, B200_OPK_SOFTMAX, input->dtype, "b200_softmax");

@@ -368,6 +368,22 @@ def test_softmax_int8_bit_exact(b200, oracle, rng):
     assert np.array_equal(got, oracle.softmax_i8(x, 0.08, 10, 1.0 / 256, -128))
 
 
+def test_softmax_over_channels_of_a_feature_map(b200, oracle, rng):
+    """axis 1 of N x C x H x W: N * H * W rows of the pixel-major layout (int8 bit-exact in both modes, fp16 in tolerance)"""
+    from test_oracle import softmax_nchw
+    for shape in ((2, 21, 5, 7), (1, 150, 3, 3)):
+        x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+        layer = Layer(H_SOFTMAX, shape, s_out=1.0 / 256, zp_out=-128, axis=1)
+        want = softmax_nchw(oracle, x, 0.08, 10, 1.0 / 256, -128)
+        for mode in (RM_LAYER, RM_GRAPH):
+            got = b200.run(DT_INT8, shape, [layer], x, s_in=0.08, zp_in=10, run_mode=mode)
+            assert np.array_equal(got, want), (shape, mode)
+    xh = rng.standard_normal((2, 21, 5, 7)).astype(np.float16)
+    got = b200.run(DT_F16, xh.shape, [Layer(H_SOFTMAX, xh.shape, axis=1)], xh).astype(np.float32)
+    e = np.exp(xh.astype(np.float32) - xh.astype(np.float32).max(axis=1, keepdims=True))
+    assert np.max(np.abs(got - e / e.sum(axis=1, keepdims=True))) < 1e-3
+
+
 def test_golden_vectors_of_the_reference(golden, b200):
     """the reference's own known answers, through the GPU path: fp16 conv / dw / fc / pools / relu
     (tests/unit_test/valid_data/*.dat) and the int8 maxpool + relu vectors it ships"""

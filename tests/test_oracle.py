@@ -213,6 +213,21 @@ def test_softmax_bit_exact(ref, oracle, rng):
     assert np.array_equal(got, oracle.softmax_i8(x, 0.08, 10, 1.0 / 256, -128))
 
 
+def softmax_nchw(oracle, x, s_in, zp_in, s_out, zp_out):
+    """softmax over the channel axis of an N x C x H x W tensor with the [rows][C] oracle"""
+    n, c, h, w = x.shape
+    rows = np.ascontiguousarray(x.transpose(0, 2, 3, 1).reshape(-1, c))
+    return np.ascontiguousarray(oracle.softmax_i8(rows, s_in, zp_in, s_out, zp_out).reshape(n, h, w, c).transpose(0, 3, 1, 2))
+
+
+def test_softmax_over_channels_of_a_feature_map_bit_exact(ref, oracle, rng):
+    """axis 1 of N x C x H x W (source/reference/softmax.c:30-63: outer = N, inner = H * W)"""
+    x = rng.integers(-128, 128, size=(2, 21, 5, 7), dtype=np.int8)
+    layer = Layer(H_SOFTMAX, x.shape, s_out=1.0 / 256, zp_out=-128, axis=1)
+    got = ref.run(DT_INT8, x.shape, [layer], x, s_in=0.08, zp_in=10)
+    assert np.array_equal(got, softmax_nchw(oracle, x, 0.08, 10, 1.0 / 256, -128))
+
+
 def test_f16_conversions_match_reference(ref, oracle, rng):
     """f32 -> f16 of the reference is round-half-up on the magnitude (source/nn2/utils.c:576-620),
     not IEEE round-half-even; f16 -> f32 is exact.  Checked through a 1x1 identity conv in f16."""
