@@ -393,6 +393,8 @@ static size_t matmul_scratch(const b200_op *op, size_t *off_b, size_t *off_o, si
 size_t b200_op_scratch_bytes(const b200_op *op, const b200_dt *in0, const b200_dt *out)
 {
     if (op->kind == B200_OPK_TENSOR && op->t_op == B200_T_MATMUL) return matmul_scratch(op, NULL, NULL, NULL);
+    if (op->kind == B200_OPK_COPY && op->direct == 2) /* general reshape: the tensor in NCHW order in between */
+        return ((size_t)in0->n * in0->c * in0->h * in0->w * in0->eb + 255) & ~(size_t)255;
     if (op->kind != B200_OPK_CONV && op->kind != B200_OPK_FC) return 0;
     size_t bytes = im2col_bytes(op, in0, out);
     if (op->d_wzp) bytes += (size_t)out->n * out->h * out->w * sizeof(int32_t);
@@ -722,8 +724,18 @@ int b200_op_run(b200_op *op, int part, const b200_dt *in0, const b200_dt *in1, c
         case B200_OPK_TENSOR:
             return run_tensor_op(op, in0, in1, out, scratch, stream);
         case B200_OPK_COPY:
-            if (op->direct) { /* flatten of an N x C x H x W tensor: back to NCHW order = the flattened rows */
+            if (op->direct == 1) { /* flatten of an N x C x H x W tensor: back to NCHW order = the flattened rows */
                 DEV_CHECK(b200_nhwc_to_nchw(in0->d, out->d, in0->n, in0->c, in0->h, in0->w, in0->cp, in0->eb, stream));
+                return CSINN_TRUE;
+            }
+            if (op->direct == 2) { /* any other reshape: pixel-major -> NCHW order (= the API's row-major bytes, which a
+                                    * reshape keeps) -> pixel-major of the new shape */
+                if (!scratch) {
+                    b200_fail("reshape: no scratch buffer planned");
+                    return CSINN_FALSE;
+                }
+                DEV_CHECK(b200_nhwc_to_nchw(in0->d, scratch, in0->n, in0->c, in0->h, in0->w, in0->cp, in0->eb, stream));
+                DEV_CHECK(b200_nchw_to_nhwc(scratch, out->d, out->n, out->c, out->h, out->w, out->cp, out->eb, 0, stream));
                 return CSINN_TRUE;
             }
             if (b200_dt_bytes(in0) != b200_dt_bytes(out)) {
@@ -1478,18 +1490,21 @@ int shl_b200_reshape_init(struct csinn_tensor *input, struct csinn_tensor *outpu
     /* N x C x 1 x 1 <-> N x C: the pixel-major buffer already is the result.  N x C x H x W -> N x (C*H*W) (the
      * flatten in front of a VGG / AlexNet classifier; source/reference/flatten.c / reshape.c copy the NCHW bytes):
      * the pixel-major buffer is permuted back into NCHW order, which IS the flattened row when C*H*W fills the
-     * output's row pitch.  Other reshapes with H*W > 1 would need a general permutation and are refused. */
+     * output's row pitch.  Other reshapes take the same permutation there and a second one back (direct = 2). */
     const int plain = din.h * din.w == 1 && dout.h * dout.w == 1 && din.n == dout.n && din.c == dout.c;
     const long long flat = (long long)din.c * din.h * din.w;
     const int to_rows = !plain && dout.h * dout.w == 1 && din.n == dout.n && flat == dout.c && dout.cp == dout.c;
-    if (!plain && !to_rows) {
-        b200_fail("reshape/flatten: only N x C x 1 x 1 <-> N x C, or N x C x H x W -> N x (C*H*W) with C*H*W a multiple of "
-                  "%d, is supported on the device layout", 16 / din.eb);
+    const long long e_in = (long long)din.n * din.c * din.h * din.w, e_out = (long long)dout.n * dout.c * dout.h * dout.w;
+    if (e_in != e_out) {
+        b200_fail("reshape/flatten: %lld elements in, %lld out", e_in, e_out);
         return CSINN_FALSE;
     }
-    b200_op *op = op_new(base, B200_OPK_COPY, input->dtype, to_rows ? "b200_flatten_to_nchw" : "b200_reshape_copy");
+    /* anything else goes through the NCHW order in a scratch buffer (two layout kernels): slow, general */
+    const int general = !plain && !to_rows;
+    b200_op *op = op_new(base, B200_OPK_COPY, input->dtype,
+                         to_rows ? "b200_flatten_to_nchw" : (general ? "b200_reshape_permute" : "b200_reshape_copy"));
     if (!op) return CSINN_FALSE;
-    op->direct = to_rows; /* B200_OPK_COPY: 1 = permute pixel-major -> NCHW order */
+    op->direct = to_rows ? 1 : (general ? 2 : 0); /* B200_OPK_COPY: 1 = permute pixel-major -> NCHW order, 2 = there and back */
     b200_op_bind(params, op);
     base->cb->exec = (int (*)())shl_b200_reshape;
     return CSINN_TRUE;

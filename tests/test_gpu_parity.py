@@ -1149,3 +1149,21 @@ def test_flatten_of_a_feature_map_feeds_fullyconnected(mode, b200, oracle, rng):
     want = nets.oracle_forward(SimpleNamespace(layers=layers, orc=oracle, dtype=DT_INT8, s_in=0.02, zp_in=-3), x)
     got = b200.run(DT_INT8, x.shape, layers, x, s_in=0.02, zp_in=-3, run_mode=mode)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [RM_LAYER, RM_GRAPH], ids=["layer", "graph"])
+def test_general_reshape_keeps_the_row_major_bytes(mode, b200, rng):
+    """csinn_reshape between shapes that are neither N x C x 1 x 1 <-> N x C nor the flatten (source/reference/reshape.c
+    copies the NCHW bytes): on the device the tensor goes through NCHW order in a scratch buffer and back into the
+    pixel-major layout of the new shape; the result read back must be the input's bytes under the new shape"""
+    from shl import H_RESHAPE
+    for shape, new in (((2, 24, 5, 6), (2, 8, 15, 6)), ((1, 6, 4, 10), (1, 40, 2, 3)), ((3, 16, 2, 2), (3, 4, 4, 4)),
+                       ((2, 12, 3, 7), (2, 252))):
+        x = rng.integers(-128, 128, size=shape, dtype=np.int8)
+        layers = [Layer(H_RELU, shape, s_out=0.02, zp_out=-128), Layer(H_RESHAPE, new, s_out=0.02, zp_out=-128)]
+        got = b200.run(DT_INT8, shape, layers, x, s_in=0.02, zp_in=-128, run_mode=mode)
+        assert np.array_equal(got, np.maximum(x, -128).reshape(new)), (shape, new)
+        xh = rng.standard_normal(shape).astype(np.float16)
+        goth = b200.run(DT_F16, shape, [Layer(H_RELU, shape), Layer(H_RESHAPE, new)], xh, run_mode=mode)
+        assert np.array_equal(goth.view(np.uint16), np.maximum(xh, np.float16(0)).reshape(new).view(np.uint16)), (shape, new)
