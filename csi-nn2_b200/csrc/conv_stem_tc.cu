@@ -15,7 +15,7 @@
 // output for 3x3x3 -> 32 channels, 136 us at batch 256, six times its HBM floor.  On the tensor
 // core the per-output cost is the epilogue alone; the gather is paid once per pixel, not per channel.
 //
-// CTA = 4 or 5 worker groups of 4 warps + 1 MMA warp, one CTA per SM, persistent.  A group owns one A tile, two staging
+// CTA = 4 or 6 worker groups of 4 warps + 1 MMA warp, one CTA per SM, persistent.  A group owns one A tile, two staging
 // buffers and two TMEM accumulators and software-pipelines itself: wait for tile i's rows -> gather -> signal the MMA warp
 // -> epilogue of tile i-1 (whose MMA ran meanwhile; the A tile is free again by then), with tile i+1's TMA in flight.  The
 // groups run staggered, so the gather of one overlaps the epilogue of another; no CTA-wide barrier inside the loop.
@@ -30,7 +30,7 @@
 
 namespace b200 {
 
-// worker groups per CTA: 5 when the tiles are small (K <= 128, N <= 32: 20 worker warps keep the
+// worker groups per CTA: 6 when the tiles are small (K <= 128, N <= 32: 24 worker warps keep the
 // schedulers busy through the shared-memory and TMEM latencies of gather and epilogue), else 4
 // (TMEM: groups x 2 x N columns <= 512; shared memory: groups x (A tile + 2 staging buffers))
 __host__ __device__ constexpr int stem_groups(int k, int nch) { return (k <= 128 && nch <= 2) ? 6 : 4; }
